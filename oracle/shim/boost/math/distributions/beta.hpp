@@ -1,0 +1,5 @@
+/* oracle/shim: stand-in for <boost/math/distributions/beta.hpp> -- TEST INFRASTRUCTURE (see orc_boost_shim.hpp). */
+#ifndef ORC_SHIM_BOOST_MATH_DISTRIBUTIONS_BETA_HPP
+#define ORC_SHIM_BOOST_MATH_DISTRIBUTIONS_BETA_HPP
+#include <orc_boost_shim.hpp>
+#endif
