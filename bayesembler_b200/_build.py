@@ -1,0 +1,59 @@
+"""In-tree build of the CUDA extension (sm_100a only) with plain nvcc.
+
+    python -m bayesembler_b200._build        # -> bayesembler_b200/libbayesembler_b200.so
+
+The shared library carries the C ABI of include/bayesembler_b200.h.  It is built in-tree so that it travels to
+the GPU box with the repo snapshot; nvcc cross-compiles without a GPU.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libbayesembler_b200.so")
+SOURCES = ["capi.cu", "gibbs_kernel.cu", "host_steps.cpp", "pack.cpp"]
+HEADERS = ["internal.h", "layout.h", "rng.cuh", os.path.join("..", "..", "include", "bayesembler_b200.h")]
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def nvcc_command(out=LIB, extra=()):
+    # -fmad=false: keep the sampler's own double arithmetic un-contracted so that it rounds like the CPU oracle
+    # (the CUDA math library's log/exp/cos use explicit fma internally and are unaffected).
+    cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
+           "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-shared", "-o", out]
+    cmd += list(extra)
+    cmd += [os.path.join(CSRC, s) for s in SOURCES]
+    return cmd
+
+
+def stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return LIB
+    cmd = nvcc_command(extra=("-Xptxas", "-v") if verbose else ())
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building %s" % LIB)
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force=True, verbose=True)
+    print(LIB)

@@ -1,0 +1,241 @@
+// Counter-based random numbers and uniform->variate transforms of the B200 sampler.
+//
+// The reference draws through Boost.Random on one sequential mt19937 per locus (assignmentGenerator.cpp:37-40,
+// expressionGenerator.cpp:37-40, simplexSizeGenerator.cpp:39-42).  A sequential stream cannot feed thousands of
+// threads, so every draw SITE owns a Philox4x32-10 stream instead (Salmon et al., SC'11):
+//     block j of site (phase, iteration, index, sub) = philox(key, {(sub << 12) | j, index, iteration, phase})
+// and the transforms are the published algorithms spelled out in DESIGN.md ("Variates"): Lemire multiply-shift
+// uniform_int, Marsaglia-Tsang gamma over a Box-Muller normal, BINV / BTRD binomial.  The CPU oracle implements the
+// same specification independently (oracle/orc_rng.h); parity tests compare the two draw for draw.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BAYES_HD __host__ __device__ __forceinline__
+#define BAYES_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define BAYES_HD inline
+#define BAYES_HD_NOINLINE inline
+#endif
+
+namespace bayes {
+
+enum Phase : uint32_t {
+    PH_COVER = 1,        // calcMinimumReadCover tie break, index = greedy round
+    PH_INIT_ASSIGN = 2,  // initAssignment chain, index = row, sub = column
+    PH_SIMPLEX = 3,      // simplex-size uniform of the iteration that uses b
+    PH_GAMMA = 4,        // expression gamma draw, index = transcript
+    PH_NULLPICK = 5,     // null-transcript pick, index = pick ordinal
+    PH_ASSIGN = 6        // generateAssignment, index = row, sub = column (chain) or 0 (uniforms)
+};
+
+struct u32x4 {
+    uint32_t x, y, z, w;
+};
+
+BAYES_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+BAYES_HD u32x4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    u32x4 o = {c0, c1, c2, c3};
+    return o;
+}
+
+// Draw site: key + the three fixed counter words; block(j) yields 4 fresh words.
+struct Site {
+    uint32_t k0, k1, sub12, index, iteration, phase;
+    BAYES_HD u32x4 block(uint32_t j) const { return philox4x32_10(k0, k1, sub12 | j, index, iteration, phase); }
+};
+
+BAYES_HD Site make_site(uint64_t key, uint32_t phase, uint32_t iteration, uint32_t index, uint32_t sub) {
+    Site s = {(uint32_t)key, (uint32_t)(key >> 32), sub << 12, index, iteration, phase};
+    return s;
+}
+
+// uniform_01<mt19937*>: one 32-bit word -> [0,1)
+BAYES_HD double u01(uint32_t w) { return (double)w * 2.3283064365386963e-10; }
+BAYES_HD double u32_open(uint32_t w) { return ((double)w + 0.5) * 2.3283064365386963e-10; }
+BAYES_HD double u53(uint32_t hi, uint32_t lo) {
+    const uint64_t x = (((uint64_t)hi << 32) | lo) >> 11;
+    return ((double)x + 0.5) * 1.1102230246251565e-16;
+}
+
+// uniform_int_distribution(0, n-1): words 0,1,2,... of the site (unbiased multiply-shift)
+BAYES_HD uint32_t uniform_int(const Site &s, uint32_t n) {
+    if (n <= 1) return 0;
+    uint32_t k = 0;
+    u32x4 b = s.block(0);
+    uint64_t m = (uint64_t)b.x * n;
+    uint32_t l = (uint32_t)m;
+    if (l < n) {
+        const uint32_t t = (0u - n) % n;
+        while (l < t) {
+            k++;
+            if ((k & 3u) == 0) b = s.block(k >> 2);
+            const uint32_t w = (k & 3u) == 1 ? b.y : (k & 3u) == 2 ? b.z : (k & 3u) == 3 ? b.w : b.x;
+            m = (uint64_t)w * n;
+            l = (uint32_t)m;
+        }
+    }
+    return (uint32_t)(m >> 32);
+}
+
+BAYES_HD double cos_2pi(double f) {
+#if defined(__CUDA_ARCH__)
+    return cospi(2.0 * f);
+#else
+    return cos(6.283185307179586 * f);
+#endif
+}
+
+// gamma_distribution(alpha, 1): one block per attempt (expressionGenerator.cpp:89-92, 100-113)
+BAYES_HD double gamma_variate(const Site &s, double alpha) {
+    uint32_t j = 0;
+    if (alpha == 1.0) {
+        const u32x4 b = s.block(0);
+        return -log(u53(b.x, b.y));
+    }
+    double boost = 1.0, a = alpha;
+    if (alpha < 1.0) {
+        const u32x4 b = s.block(j++);
+        boost = exp(log(u53(b.x, b.y)) / alpha);
+        a = alpha + 1.0;
+    }
+    const double d = a - 1.0 / 3.0;
+    const double c = 1.0 / sqrt(9.0 * d);
+    for (;;) {
+        const u32x4 b = s.block(j++);
+        const double u1 = u53(b.x, b.y);
+        const double x = sqrt(-2.0 * log(u1)) * cos_2pi(u01(b.z));
+        double v = 1.0 + c * x;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        const double u = u32_open(b.w);
+        const double x2 = x * x;
+        if (u < 1.0 - 0.0331 * x2 * x2) return d * v * boost;
+        if (log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) return d * v * boost;
+    }
+}
+
+BAYES_HD double stirling_fc(int k) {
+    double r;
+    switch (k) {
+        case 0: r = 0.08106146679532726; break;
+        case 1: r = 0.04134069595540929; break;
+        case 2: r = 0.02767792568499834; break;
+        case 3: r = 0.02079067210376509; break;
+        case 4: r = 0.01664469118982119; break;
+        case 5: r = 0.01387612882307075; break;
+        case 6: r = 0.01189670994589177; break;
+        case 7: r = 0.01041126526197209; break;
+        case 8: r = 0.009255462182712733; break;
+        case 9: r = 0.008330563433362871; break;
+        default: {
+            const double kp1 = (double)k + 1.0, kp1sq = kp1 * kp1;
+            r = (1.0 / 12 - (1.0 / 360 - 1.0 / 1260 / kp1sq) / kp1sq) / kp1;
+        }
+    }
+    return r;
+}
+
+// BTRD (Hoermann 1993), q <= 0.5, n*q >= 10; one block per attempt
+BAYES_HD_NOINLINE int binomial_btrd(const Site &s, int n, double q) {
+    const double npq = n * q * (1.0 - q);
+    const double spq = sqrt(npq);
+    const double bb = 1.15 + 2.53 * spq;
+    const double a = -0.0873 + 0.0248 * bb + 0.01 * q;
+    const double c = n * q + 0.5;
+    const double v_r = 0.92 - 4.2 / bb;
+    const double r = q / (1.0 - q);
+    const double alpha = (2.83 + 5.1 / bb) * spq;
+    const int m = (int)floor((n + 1) * q);
+    const double nr = (n + 1) * r;
+    for (uint32_t j = 0;; j++) {
+        const u32x4 b = s.block(j);
+        double v = u53(b.x, b.y);
+        const double u2 = u53(b.z, b.w);
+        double u;
+        if (v <= 0.86 * v_r) {
+            u = v / v_r - 0.43;
+            return (int)floor((2.0 * a / (0.5 - fabs(u)) + bb) * u + c);
+        }
+        if (v >= v_r) {
+            u = u2 - 0.5;
+        } else {
+            u = v / v_r - 0.93;
+            u = (u < 0.0 ? -0.5 : 0.5) - u;
+            v = u2 * v_r;
+        }
+        const double us = 0.5 - fabs(u);
+        const double kd = floor((2.0 * a / us + bb) * u + c);
+        if (kd < 0.0 || kd > (double)n) continue;
+        const int k = (int)kd;
+        v = v * alpha / (a / (us * us) + bb);
+        const int km = k > m ? k - m : m - k;
+        if (km <= 15) {
+            double f = 1.0;
+            if (m < k) {
+                for (int i = m + 1; i <= k; i++) f *= (nr / i - r);
+            } else if (m > k) {
+                for (int i = k + 1; i <= m; i++) v *= (nr / i - r);
+            }
+            if (v <= f) return k;
+            continue;
+        }
+        v = log(v);
+        const double kmd = (double)km;
+        const double rho = (kmd / npq) * (((kmd / 3.0 + 0.625) * kmd + 1.0 / 6.0) / npq + 0.5);
+        const double t = -kmd * kmd / (2.0 * npq);
+        if (v < t - rho) return k;
+        if (v > t + rho) continue;
+        const double nm = (double)(n - m + 1);
+        const double h = (m + 0.5) * log((m + 1) / (r * nm)) + stirling_fc(m) + stirling_fc(n - m);
+        const double nk = (double)(n - k + 1);
+        if (v <= h + (n + 1) * log(nm / nk) + (k + 0.5) * log(nk * r / (k + 1)) - stirling_fc(k) - stirling_fc(n - k)) return k;
+    }
+}
+
+// binomial_distribution(n, p) (assignmentGenerator.cpp:230-233, 346-349)
+BAYES_HD int binomial_variate(const Site &s, int n, double p) {
+    if (n <= 0 || !(p > 0.0)) return 0;
+    if (p >= 1.0) return n;
+    const bool flip = p > 0.5;
+    const double q = flip ? 1.0 - p : p;
+    int k;
+    if ((double)n * q < 10.0) {
+        const u32x4 b = s.block(0);
+        double u = u53(b.x, b.y);
+        const double sr = q / (1.0 - q);
+        const double a = (double)(n + 1) * sr;
+        double r = exp((double)n * log1p(-q));
+        k = 0;
+        while (u > r && k < n) {
+            u -= r;
+            k++;
+            r *= (a / (double)k - sr);
+        }
+    } else {
+        k = binomial_btrd(s, n, q);
+    }
+    return flip ? n - k : k;
+}
+
+}  // namespace bayes

@@ -1,0 +1,154 @@
+/*
+ * bayesembler_b200.h -- C ABI of the B200-native per-locus Gibbs sampler.
+ *
+ * Drop-in boundary for ONE path of bioinformatics-centre/bayesembler v1.2.0: the block
+ * assembler.cpp:1548-1609 inside Assembler::bayesemblerCallback, i.e. everything between "a CollapsedMap
+ * exists" and "GibbsOutput holds the posterior".  The reference has no FFI of its own; each entry point
+ * below names the reference interface it stands in for (paths relative to the reference's src/).
+ *
+ * Plain C, no C++/torch types.  Every function returns 0 on success or a negative BAYES_E_* code and never
+ * throws; bayes_last_error() gives the message of the calling thread's last failure.  There is no CPU
+ * fallback: without a usable CUDA device bayes_gibbs_create() fails.
+ *
+ * Usage (one context per GPU, the reference's N worker threads become one batched call):
+ *     bayes_gibbs_create(device, &ctx);
+ *     bayes_gibbs_submit(ctx, n, loci, &first_id);      // pack + min read cover + simplex tables (host, threaded)
+ *     bayes_gibbs_upload(ctx);                          // H2D, async on the context stream
+ *     bayes_gibbs_run(ctx);                             // all Gibbs iterations of all (locus, chain) jobs, async
+ *     bayes_gibbs_download(ctx);                        // D2H of the accumulators, async
+ *     bayes_gibbs_sync(ctx);
+ *     bayes_gibbs_fetch(ctx, id, chain, occ, mean, m2); // GibbsOutput state of one job
+ *     bayes_gibbs_destroy(ctx);
+ */
+#ifndef BAYESEMBLER_B200_H
+#define BAYESEMBLER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BAYES_OK 0
+#define BAYES_E_INVALID (-1)  /* bad argument / malformed locus      */
+#define BAYES_E_CUDA (-2)     /* CUDA runtime error                  */
+#define BAYES_E_STATE (-3)    /* call out of order                   */
+#define BAYES_E_NOMEM (-4)
+#define BAYES_E_NODEVICE (-5) /* no CUDA device: there is no CPU path */
+
+typedef struct bayes_gibbs_ctx bayes_gibbs_ctx;
+
+/*
+ * One locus = one CollapsedMap (utils.h:129-136) plus the sampler arguments the call site derives for it.
+ * The probability matrix is passed as CSR over its non-zero cells (the reference stores it dense,
+ * column-major, zeros = incompatible); columns must be strictly ascending inside a row, every row needs at
+ * least one cell >= DBL_MIN and a count >= 1.
+ */
+typedef struct {
+    int32_t T;                  /* candidates = probability_matrix.cols()                                   */
+    int32_t R;                  /* collapsed rows = probability_matrix.rows() = counts.size()               */
+    const int32_t *row_ptr;     /* R+1                                                                      */
+    const int32_t *col_idx;     /* nnz                                                                      */
+    const double *val;          /* nnz, CollapsedMap::probability_matrix(i,j)                               */
+    const int32_t *row_count;   /* R,   CollapsedMap::counts                                                */
+    const double *efflen;       /* T,   new_idx_to_old_idx_effective_length[t].second                       */
+    double total_num_fragments; /* adjusted_fragment_count; truncated to int as GibbsSampler's ctor does
+                                   (gibbsSampler.h:51, assembler.cpp:1577)                                  */
+    double gamma;               /* --dirichlet-parameter (assembler.cpp:1569)                               */
+    double pi;                  /* < 0: derive from the minimum read cover (assembler.cpp:1551-1559), the
+                                   reference's behaviour; otherwise use this value                          */
+    int32_t burn_in;            /* gibbs_burn_in  (assembler.cpp:1598)                                      */
+    int32_t samples;            /* gibbs_samples  (assembler.cpp:1599)                                      */
+    uint64_t seed;              /* graph_seed (assembler.cpp:1437); Philox key of chain c is derived from
+                                   (seed, c) by bayes_chain_key()                                           */
+    int32_t n_chains;           /* independent chains of this locus (reference: 1)                          */
+    int32_t reserved;
+} bayes_locus_desc;
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+int bayes_gibbs_create(int device, bayes_gibbs_ctx **out);
+void bayes_gibbs_destroy(bayes_gibbs_ctx *ctx);
+/* launch on a caller-owned cudaStream_t (e.g. torch.cuda.Stream().cuda_stream) instead of the context's own */
+int bayes_gibbs_set_stream(bayes_gibbs_ctx *ctx, void *cuda_stream);
+void *bayes_gibbs_get_stream(bayes_gibbs_ctx *ctx);
+/* host worker threads used by submit (0 = all hardware threads) */
+int bayes_gibbs_set_host_threads(bayes_gibbs_ctx *ctx, int n_threads);
+const char *bayes_last_error(void);
+
+/* ---- the sampler (replaces the objects built at assembler.cpp:1548-1577 and GibbsSampler::runSampler,
+ *      gibbsSampler.cpp:55-148, for a whole batch of loci) ------------------------------------------------ */
+/* Host side of K0: folds/sorts/packs the rows, runs AssignmentGenerator::calcMinimumReadCover
+ * (assignmentGenerator.cpp:52-96) when pi < 0 and builds the FixedBinomialFixedGammaSimplexSizeGenerator
+ * CDF table (simplexSizeGenerator.cpp:117-187).  Input buffers may be freed when it returns.  Locus ids are
+ * consecutive from *first_id. */
+int bayes_gibbs_submit(bayes_gibbs_ctx *ctx, int32_t n_loci, const bayes_locus_desc *loci, int64_t *first_id);
+int bayes_gibbs_upload(bayes_gibbs_ctx *ctx);
+/* initAssignment (assignmentGenerator.cpp:213-260), initSimplexSize (simplexSizeGenerator.cpp:201-206) and
+ * burn_in + samples iterations of generateExpression / generateAssignment / generateSimplexSize / addSample
+ * per job, one thread block per (locus, chain).  May be called repeatedly; every call restarts all chains. */
+int bayes_gibbs_run(bayes_gibbs_ctx *ctx);
+int bayes_gibbs_download(bayes_gibbs_ctx *ctx);
+int bayes_gibbs_sync(bayes_gibbs_ctx *ctx);
+/* submit + upload + run + download + sync in one call (the end-to-end path with host buffers) */
+int bayes_gibbs_run_batch(bayes_gibbs_ctx *ctx, int32_t n_loci, const bayes_locus_desc *loci, int64_t *first_id);
+/* forget all submitted loci (device buffers are kept for reuse) */
+int bayes_gibbs_clear(bayes_gibbs_ctx *ctx);
+
+/* GibbsOutput's state (gibbsOutput.cpp:40-75): marginal_occurence, marginal_mean_cumulant,
+ * marginal_var_cumulant, T entries each; any pointer may be NULL.  final_counts = map_counts after the
+ * last iteration (gibbsSampler.cpp:145). */
+int bayes_gibbs_fetch(bayes_gibbs_ctx *ctx, int64_t locus_id, int32_t chain, int32_t *occ, double *mean, double *m2,
+                      int32_t *final_counts);
+/* pi actually used, |minimum read cover| (0 when pi was given), folded single-cell rows */
+int bayes_gibbs_locus_info(bayes_gibbs_ctx *ctx, int64_t locus_id, double *pi, int32_t *cover_size, int32_t *rows_folded);
+int64_t bayes_gibbs_num_loci(bayes_gibbs_ctx *ctx);
+int64_t bayes_gibbs_num_jobs(bayes_gibbs_ctx *ctx);
+/* kernels launched by the last bayes_gibbs_run() */
+int32_t bayes_gibbs_last_launches(bayes_gibbs_ctx *ctx);
+
+/* Replay/debug: record theta and map_counts of the first trace_iters iterations of one job during the next
+ * run (call after submit, before upload).  theta_trace / counts_trace: trace_iters*T, b_trace: trace_iters,
+ * init_counts: T (initAssignment's result). */
+int bayes_gibbs_set_trace(bayes_gibbs_ctx *ctx, int64_t locus_id, int32_t chain, int32_t trace_iters);
+int bayes_gibbs_fetch_trace(bayes_gibbs_ctx *ctx, double *theta_trace, int32_t *counts_trace, int32_t *b_trace,
+                            int32_t *init_counts);
+
+/* GibbsOutput::getTopMarginals (gibbsOutput.cpp:77-106) on fetched accumulators; returns the number kept */
+int bayes_top_marginals(int32_t T, int32_t samples, const int32_t *occ, const double *mean, const double *m2,
+                        double marginal_threshold, int32_t *idx_out, double *mean_out, double *sd_out);
+
+/* ---- single sampler steps on the GPU, for step-level parity (same device code as bayes_gibbs_run) ------- */
+/* AssignmentGenerator::generateAssignment(expression) (assignmentGenerator.cpp:263-373): theta[T] in,
+ * counts_out[T]; draw sites keyed (ASSIGN, iteration, row, col) under `key`. */
+int bayes_step_generate_assignment(int device, const bayes_locus_desc *locus, const double *theta, uint64_t key,
+                                   uint32_t iteration, int32_t *counts_out);
+/* AssignmentGenerator::initAssignment (assignmentGenerator.cpp:213-260) */
+int bayes_step_init_assignment(int device, const bayes_locus_desc *locus, uint64_t key, int32_t *counts_out);
+/* ExpressionGenerator::generateExpression(b, gamma, map_counts) (expressionGenerator.cpp:77-132) */
+int bayes_step_generate_expression(int device, int32_t T, const int32_t *counts, int32_t b, double gamma, uint64_t key,
+                                   uint32_t iteration, double *theta_out);
+/* raw variates, n draws; draw i uses site (phase, 0, i, 0): gamma -> PH_GAMMA, binomial -> PH_ASSIGN,
+ * uniform_int -> PH_NULLPICK */
+int bayes_step_variates(int device, int kind, double a, double p, uint64_t key, int32_t n, double *out);
+
+/* ---- host-side pieces of the path (C++, no GPU needed) -------------------------------------------------- */
+/* AssignmentGenerator::calcMinimumReadCover + getMinimumReadCoverSize (assignmentGenerator.cpp:52-96);
+ * tie breaks from sites (COVER, 0, round) under `key`.  in_cover: T flags or NULL.  Returns |cover| or <0. */
+int bayes_min_read_cover(const bayes_locus_desc *locus, uint64_t key, int32_t *in_cover);
+/* FixedBinomialFixedGammaSimplexSizeGenerator ctor (simplexSizeGenerator.cpp:117-187): row k-1 (|S+| = k)
+ * is table[row_off[k-1] .. row_off[k]).  Call with table == NULL to size it: returns total entries. */
+int64_t bayes_simplex_table(double pi, double gamma, int32_t T, int32_t num_fragments, int64_t *row_off, double *table);
+/* Philox key of chain c of a locus seeded with `seed` */
+uint64_t bayes_chain_key(uint64_t seed, int32_t chain);
+/* cost model used to order jobs and to shard loci across GPUs: iterations * (cells + rows + candidates) */
+double bayes_locus_cost(const bayes_locus_desc *locus);
+/* cost-balanced greedy (LPT) partition of n items into n_parts (mirrors the reference's largest-first work
+ * queue, assembler.cpp:1886-1916); part_out[i] in [0, n_parts) */
+int bayes_partition_lpt(int64_t n, const double *cost, int32_t n_parts, int32_t *part_out);
+/* Philox4x32-10 block (known-answer tests) */
+void bayes_philox4x32(uint64_t key, const uint32_t ctr[4], uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAYESEMBLER_B200_H */

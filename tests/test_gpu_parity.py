@@ -1,0 +1,147 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, draw for draw.
+
+Both sides draw from the same site-keyed Philox streams (DESIGN.md "Replay"); integer results must be identical and
+floating point must agree to 1e-9 relative (north_star asks for 1e-6).
+"""
+import numpy as np
+import pytest
+
+from oracle.oracle_py import SITE, random_locus
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def _theta_for(rng, loc):
+    th = rng.dirichlet(np.ones(loc.T) * 0.7)
+    if loc.T > 3:
+        th[rng.choice(loc.T, size=loc.T // 3, replace=False)] = 0.0
+    P = np.zeros((loc.R, loc.T))
+    for i in range(loc.R):
+        s, e = loc.row_ptr[i], loc.row_ptr[i + 1]
+        P[i, loc.col_idx[s:e]] = loc.val[s:e]
+    bad = (P * th).sum(1) <= 0
+    for i in np.nonzero(bad)[0]:
+        th[loc.col_idx[loc.row_ptr[i]]] = rng.random() + 0.01
+    return th / th.sum()
+
+
+@pytest.mark.parametrize("alpha", [1.0, 0.3, 1.7, 12.0, 5000.5])
+def test_gamma_variates(lib, oracle, alpha):
+    key = 0xA5A5A5A512345678
+    g = lib.step_variates("gamma", alpha, 0.0, key, 20000)
+    o = oracle.gamma(alpha, SITE, key, 20000)
+    np.testing.assert_allclose(g, o, rtol=1e-12)
+
+
+@pytest.mark.parametrize("n,p", [(1, 0.3), (19, 0.5), (25, 0.07), (40, 0.93), (300, 0.2), (5000, 0.5), (100000, 0.999), (7, 1e-9)])
+def test_binomial_variates(lib, oracle, n, p):
+    key = 0x0123456789ABCDEF
+    g = lib.step_variates("binomial", n, p, key, 20000).astype(np.int64)
+    o = oracle.binomial(n, p, SITE, key, 20000)
+    assert np.array_equal(g, o)
+
+
+@pytest.mark.parametrize("rng_n", [2, 3, 7, 1000, 4000000000])
+def test_uniform_int_variates(lib, oracle, rng_n):
+    key = 77
+    g = lib.step_variates("uniform_int", rng_n, 0.0, key, 20000).astype(np.int64)
+    o = oracle.uniform_int(rng_n, SITE, key, 20000).astype(np.int64) & 0xFFFFFFFF
+    assert np.array_equal(g, o)
+
+
+SHAPES = [(2, 5, 30), (3, 40, 60), (10, 150, 300), (31, 400, 100), (33, 300, 2000), (100, 700, 50), (257, 200, 500)]
+
+
+@pytest.mark.parametrize("T,R,mc", SHAPES)
+def test_step_init_assignment(lib, oracle, T, R, mc):
+    rng = np.random.default_rng(T * 1000 + R)
+    loc = random_locus(rng, T, R, max_count=mc)
+    key = int(rng.integers(1, 2 ** 62))
+    g = lib.step_init_assignment(loc, key)
+    o, _ = oracle.init_assignment(loc, SITE, key)
+    assert g.sum() == loc.n_frag
+    assert np.array_equal(g, o)
+
+
+@pytest.mark.parametrize("T,R,mc", SHAPES)
+def test_step_generate_assignment(lib, oracle, T, R, mc):
+    rng = np.random.default_rng(T * 77 + R)
+    loc = random_locus(rng, T, R, max_count=mc)
+    key = int(rng.integers(1, 2 ** 62))
+    for it in (0, 5, 123456):
+        th = _theta_for(rng, loc)
+        g = lib.step_generate_assignment(loc, th, key, it)
+        o, _ = oracle.generate_assignment(loc, th, SITE, key, it)
+        assert g.sum() == loc.n_frag
+        assert np.array_equal(g, o)
+
+
+@pytest.mark.parametrize("T,gamma", [(2, 1.0), (7, 1.0), (32, 0.5), (33, 1.0), (100, 2.5), (1000, 1.0)])
+def test_step_generate_expression(lib, oracle, T, gamma):
+    rng = np.random.default_rng(T)
+    key = int(rng.integers(1, 2 ** 62))
+    for it in (0, 9):
+        counts = (rng.random(T) < 0.5) * rng.integers(1, 500, T)
+        counts[rng.integers(T)] = 17
+        n_plus = int((counts > 0).sum())
+        for b in sorted({n_plus, min(T, n_plus + 1), min(T, n_plus + 5), T}):
+            g = lib.step_generate_expression(counts, b, gamma, key, it)
+            o, order, _ = oracle.generate_expression(counts, b, gamma, SITE, key, it)
+            assert np.array_equal(g > 0, o > 0)
+            assert (g > 0).sum() == b
+            np.testing.assert_allclose(g, o, rtol=RTOL)
+            assert abs(g.sum() - 1) < 1e-12
+
+
+@pytest.mark.parametrize("T,R,mc,gamma", [(2, 6, 40, 1.0), (3, 30, 60, 1.0), (8, 120, 400, 1.0), (12, 60, 100, 0.5),
+                                          (30, 500, 80, 1.0), (40, 200, 3000, 2.0), (100, 300, 50, 1.0)])
+def test_full_chain_replay(lib, oracle, T, R, mc, gamma):
+    rng = np.random.default_rng(T * 31 + R)
+    loc = random_locus(rng, T, R, max_count=mc, gamma=gamma)
+    seed = int(rng.integers(1, 2 ** 62))
+    burn, samples = 60 + 3 * T, 600 + 30 * T
+    total = burn + samples
+    ctx = lib.GibbsContext(0)
+    descs = lib.make_desc_array([loc], [burn], [samples], [seed])
+    ctx.submit(descs)
+    ctx.set_trace(0, 0, total)
+    ctx.upload(); ctx.run(); ctx.download(); ctx.sync()
+    g = ctx.fetch(0)
+    tr = ctx.fetch_trace()
+    info = ctx.locus_info(0)
+    ctx.close()
+    o = oracle.run_sampler(loc, burn, samples, SITE, lib.chain_key(seed, 0), trace_iters=total)
+    assert info["pi"] == o["pi"]
+    assert np.array_equal(tr["init_counts"], o["init_counts"])
+    assert np.array_equal(tr["b_trace"], o["b_trace"])
+    assert np.array_equal(tr["counts_trace"], o["counts_trace"])
+    np.testing.assert_allclose(tr["theta_trace"], o["theta_trace"], rtol=RTOL, atol=0)
+    assert np.array_equal(g["occ"], o["occ"])
+    np.testing.assert_allclose(g["mean"], o["mean"], rtol=RTOL)
+    np.testing.assert_allclose(g["m2"], o["m2"], rtol=1e-7, atol=1e-9 * np.abs(o["mean"]).max() ** 2)
+    assert g["final_counts"].sum() == loc.n_frag
+    assert np.array_equal(g["final_counts"], o["counts_trace"][-1])
+
+
+def test_batch_mixed_loci_and_chains(lib, oracle):
+    rng = np.random.default_rng(2024)
+    shapes = [(1, 4, 30), (5, 50, 100), (2, 3, 10), (20, 90, 40), (1, 1, 5), (9, 33, 25), (64, 150, 60), (3, 1000, 30)]
+    loci = [random_locus(rng, T, R, max_count=mc) for (T, R, mc) in shapes]
+    seeds = [int(s) for s in rng.integers(1, 2 ** 62, len(loci))]
+    burn = [50 + 5 * l.T for l in loci]
+    samples = [10 * b for b in burn]
+    chains = [1, 3, 2, 1, 2, 4, 1, 2]
+    ctx = lib.GibbsContext(0)
+    descs = lib.make_desc_array(loci, burn, samples, seeds, n_chains=chains)
+    ctx.run_batch(descs)
+    for i, loc in enumerate(loci):
+        for c in range(chains[i]):
+            g = ctx.fetch(i, c)
+            o = oracle.run_sampler(loc, burn[i], samples[i], SITE, lib.chain_key(seeds[i], c),
+                                   pi=-1.0 if c == 0 else ctx.locus_info(i)["pi"])
+            assert np.array_equal(g["occ"], o["occ"]), (i, c)
+            np.testing.assert_allclose(g["mean"], o["mean"], rtol=RTOL)
+            assert g["final_counts"].sum() == loc.n_frag
+    ctx.close()
