@@ -16,6 +16,7 @@ EXPORTED_SYMBOLS = [
     "bayes_gibbs_create", "bayes_gibbs_destroy", "bayes_gibbs_set_stream", "bayes_gibbs_get_stream",
     "bayes_gibbs_set_host_threads", "bayes_last_error", "bayes_gibbs_submit", "bayes_gibbs_upload", "bayes_gibbs_run",
     "bayes_gibbs_download", "bayes_gibbs_sync", "bayes_gibbs_run_batch", "bayes_gibbs_clear", "bayes_gibbs_fetch",
+    "bayes_gibbs_fetch_all",
     "bayes_gibbs_locus_info", "bayes_gibbs_num_loci", "bayes_gibbs_num_jobs", "bayes_gibbs_last_launches",
     "bayes_gibbs_set_trace", "bayes_gibbs_fetch_trace", "bayes_top_marginals", "bayes_step_generate_assignment",
     "bayes_step_init_assignment", "bayes_step_generate_expression", "bayes_step_variates", "bayes_min_read_cover",
@@ -87,6 +88,7 @@ def load_library(path=None):
         "bayes_gibbs_run_batch": (C.c_int, [vp, i32, vp, C.POINTER(i64)]),
         "bayes_gibbs_clear": (C.c_int, [vp]),
         "bayes_gibbs_fetch": (C.c_int, [vp, i64, i32, vp, vp, vp, vp]),
+        "bayes_gibbs_fetch_all": (C.c_int, [vp, vp, vp, vp, vp]),
         "bayes_gibbs_locus_info": (C.c_int, [vp, i64, C.POINTER(dbl), C.POINTER(i32), C.POINTER(i32)]),
         "bayes_gibbs_num_loci": (i64, [vp]),
         "bayes_gibbs_num_jobs": (i64, [vp]),
@@ -169,13 +171,20 @@ class GibbsContext(object):
         except Exception:
             pass
 
-    def submit(self, desc_array):
-        first = C.c_int64(0)
-        _check(self.lib.bayes_gibbs_submit(self.h, len(desc_array), C.cast(desc_array, C.c_void_p), C.byref(first)),
-               "bayes_gibbs_submit")
+    def _note(self, desc_array):
+        if isinstance(desc_array, np.ndarray):  # structured array laid out as bayes_locus_desc[] (synth.DESC_DTYPE)
+            self._T.extend(int(t) for t in desc_array["T"])
+            self._chains.extend(int(c) for c in desc_array["n_chains"])
+            return C.c_void_p(desc_array.ctypes.data)
         for d in desc_array:
             self._T.append(d.T)
             self._chains.append(d.n_chains)
+        return C.cast(desc_array, C.c_void_p)
+
+    def submit(self, desc_array):
+        first = C.c_int64(0)
+        ptr = self._note(desc_array)
+        _check(self.lib.bayes_gibbs_submit(self.h, len(desc_array), ptr, C.byref(first)), "bayes_gibbs_submit")
         return first.value
 
     def upload(self):
@@ -192,12 +201,19 @@ class GibbsContext(object):
 
     def run_batch(self, desc_array):
         first = C.c_int64(0)
-        _check(self.lib.bayes_gibbs_run_batch(self.h, len(desc_array), C.cast(desc_array, C.c_void_p), C.byref(first)),
-               "bayes_gibbs_run_batch")
-        for d in desc_array:
-            self._T.append(d.T)
-            self._chains.append(d.n_chains)
+        ptr = self._note(desc_array)
+        _check(self.lib.bayes_gibbs_run_batch(self.h, len(desc_array), ptr, C.byref(first)), "bayes_gibbs_run_batch")
         return first.value
+
+    def fetch_all(self):
+        """Accumulators of every (locus, chain 0..) as flat arrays in submission order."""
+        n = sum(t * c for t, c in zip(self._T, self._chains))
+        occ = np.zeros(n, np.int32)
+        mean = np.zeros(n)
+        m2 = np.zeros(n)
+        counts = np.zeros(n, np.int32)
+        _check(self.lib.bayes_gibbs_fetch_all(self.h, _ptr(occ), _ptr(mean), _ptr(m2), _ptr(counts)), "bayes_gibbs_fetch_all")
+        return dict(occ=occ, mean=mean, m2=m2, final_counts=counts)
 
     def clear(self):
         _check(self.lib.bayes_gibbs_clear(self.h), "bayes_gibbs_clear")

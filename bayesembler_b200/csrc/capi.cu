@@ -1,13 +1,15 @@
-// C ABI of the B200 Gibbs sampler (include/bayesembler_b200.h): context, host packing on a thread pool, device
-// buffers, launches.  Everything that computes on the device is in gibbs_kernel.cu; nothing here falls back to the CPU.
+// C ABI of the B200 Gibbs sampler (include/bayesembler_b200.h): context, host preparation on a thread pool, unit
+// formation, device buffers, launches.  Everything that computes on the device is in gibbs_kernel.cu; nothing here
+// falls back to the CPU.
 #include <cuda_runtime.h>
 #include <string.h>
 
 #include <algorithm>
 #include <atomic>
-#include <mutex>
+#include <map>
 #include <numeric>
 #include <thread>
+#include <tuple>
 
 #include "internal.h"
 
@@ -78,20 +80,10 @@ struct PinBuf {
     }
 };
 
-struct LocusHost {
-    int32_t T, n_chains, samples, cover, folded;
-    double pi;
-    int64_t first_job;
-    // T == 1 closed form (gibbsSampler.cpp:57-67): no device work
-    bool closed_form;
-    double single_fpkm;
-    int32_t n_frag;
-};
-
 struct Launch {
-    int64_t job_base, n_jobs;
+    int64_t unit_base, n_units;
     int block;
-    bool mat_smem;
+    bool wide, mat_smem;
     size_t smem;
 };
 
@@ -101,43 +93,71 @@ struct Launch {
 using namespace bayes;
 
 struct bayes_gibbs_ctx {
-    int device = 0;
+    int device = 0, sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     int host_threads = 0;
     bool uploaded = false, ran = false, downloaded = false;
 
-    // staging (pinned), concatenated over loci
-    PinBuf<LocusDev> h_loci;
-    PinBuf<JobDev> h_jobs;
+    std::vector<PreLocus> loci;     // per submitted locus
+    std::vector<int64_t> out_base;  // locus -> offset of chain 0 in the outputs (chains of a locus are contiguous)
+    int64_t out_len = 0;            // total T over all (locus, chain)
+
+    // staging (pinned), concatenated over units
+    PinBuf<UnitDev> h_units;
     PinBuf<double> h_val, h_efflen, h_tab_val;
     PinBuf<uint16_t> h_col;
-    PinBuf<int32_t> h_slab, h_row_n, h_row_nnz, h_row_id, h_base, h_tab_row;
+    PinBuf<int32_t> h_slab, h_row_n, h_row_nnz, h_base, h_tab_row;
+    PinBuf<uint32_t> h_row_info;
     // results (pinned)
     PinBuf<int32_t> h_occ, h_counts;
     PinBuf<double> h_mean, h_m2;
 
-    DevBuf<LocusDev> d_loci;
-    DevBuf<JobDev> d_jobs;
+    DevBuf<UnitDev> d_units;
     DevBuf<double> d_val, d_efflen, d_tab_val, d_mean, d_m2, d_tr_theta;
     DevBuf<uint16_t> d_col;
-    DevBuf<int32_t> d_slab, d_row_n, d_row_nnz, d_row_id, d_base, d_tab_row, d_occ, d_counts, d_tr_counts, d_tr_b, d_tr_init;
+    DevBuf<int32_t> d_slab, d_row_n, d_row_nnz, d_base, d_tab_row, d_occ, d_counts, d_tr_counts, d_tr_b, d_tr_init;
+    DevBuf<uint32_t> d_row_info;
 
-    std::vector<LocusHost> loci;       // per submitted locus
-    std::vector<int32_t> dev_index;    // locus -> index in h_loci (-1 for closed form)
-    std::vector<double> job_cost;      // per job, submission order
-    std::vector<int32_t> job_block;
     std::vector<Launch> launches;
-    int64_t out_len = 0;               // total T over jobs
     int32_t last_launches = 0;
 
     int64_t trace_locus = -1;
-    int32_t trace_chain = 0, trace_iters = 0, trace_T = 0;
-    int64_t trace_job_sorted = -1;
+    int32_t trace_chain = 0, trace_iters = 0, trace_T = 0, trace_slot = 0;
+    int64_t trace_unit = -1;
+
+    // launch classes run concurrently: each on its own auxiliary stream, forked from / joined to `stream` by events
+    std::vector<cudaStream_t> aux;
+    std::vector<cudaEvent_t> join_ev;
+    cudaEvent_t fork_ev = nullptr;
 };
 
 namespace {
 
 int use_device(bayes_gibbs_ctx *ctx) { return cuda_rc(cudaSetDevice(ctx->device), "cudaSetDevice"); }
+
+int host_thread_count(const bayes_gibbs_ctx *ctx, int64_t work) {
+    int n = ctx->host_threads > 0 ? ctx->host_threads : (int)std::thread::hardware_concurrency();
+    return (int)std::max<int64_t>(1, std::min<int64_t>(n, work));
+}
+
+template <typename F>
+void parallel_for(int n_threads, int64_t n, F fn) {
+    if (n_threads <= 1) {
+        for (int64_t i = 0; i < n; i++) fn(i);
+        return;
+    }
+    std::atomic<int64_t> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int64_t i = next.fetch_add(1);
+            if (i >= n) return;
+            fn(i);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; t++) pool.emplace_back(work);
+    for (auto &t : pool) t.join();
+}
 
 template <typename T>
 int append(PinBuf<T> &dst, const std::vector<T> &src) {
@@ -156,61 +176,130 @@ int h2d(DevBuf<T> &d, const PinBuf<T> &h, cudaStream_t st) {
     return BAYES_OK;
 }
 
-// Order jobs so that each launch is one (block size, matrix placement) class with its most expensive jobs first: the
-// hardware block scheduler hands blocks out in index order, which makes this the largest-first queue of the reference
-// (assembler.cpp:1886-1916).
-int plan_launches(bayes_gibbs_ctx *ctx) {
-    const int64_t n = (int64_t)ctx->h_jobs.n;
-    std::vector<int64_t> order(n);
-    std::iota(order.begin(), order.end(), 0);
-    JobDev *jobs = ctx->h_jobs.p;
-    const LocusDev *loci = ctx->h_loci.p;
-    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
-        const LocusDev &la = loci[jobs[a].locus], &lb = loci[jobs[b].locus];
-        if (la.mat_smem != lb.mat_smem) return la.mat_smem < lb.mat_smem;  // streaming (largest) loci first
-        if (ctx->job_block[a] != ctx->job_block[b]) return ctx->job_block[a] > ctx->job_block[b];
-        return ctx->job_cost[a] > ctx->job_cost[b];
-    });
-    std::vector<JobDev> sorted(n);
-    std::vector<double> cost(n);
-    std::vector<int32_t> block(n);
-    for (int64_t i = 0; i < n; i++) {
-        sorted[i] = jobs[order[i]];
-        cost[i] = ctx->job_cost[order[i]];
-        block[i] = ctx->job_block[order[i]];
-    }
-    memcpy(jobs, sorted.data(), n * sizeof(JobDev));
-    ctx->job_cost.swap(cost);
-    ctx->job_block.swap(block);
+int append_unit(bayes_gibbs_ctx *ctx, PackedUnit &U) {
+    int rc;
+    U.d.slab_off = (int64_t)ctx->h_slab.n;
+    U.d.cell_off = (int64_t)ctx->h_val.n;
+    U.d.row_off = (int64_t)ctx->h_row_n.n;
+    U.d.lane_off = (int64_t)ctx->h_efflen.n;
+    U.d.tab_off = (int64_t)ctx->h_tab_val.n;
+    U.d.tabrow_off = (int64_t)ctx->h_tab_row.n;
+    if ((rc = append(ctx->h_slab, U.slab_cell_off)) || (rc = append(ctx->h_val, U.val)) || (rc = append(ctx->h_col, U.col)) ||
+        (rc = append(ctx->h_row_n, U.row_n)) || (rc = append(ctx->h_row_nnz, U.row_nnz)) || (rc = append(ctx->h_row_info, U.row_info)) ||
+        (rc = append(ctx->h_efflen, U.efflen)) || (rc = append(ctx->h_base, U.base_counts)) ||
+        (rc = append(ctx->h_tab_val, U.tab_val)) || (rc = append(ctx->h_tab_row, U.tab_row)))
+        return rc;
+    const size_t ui = ctx->h_units.n;
+    if ((rc = ctx->h_units.resize(ui + 1))) return rc;
+    ctx->h_units.p[ui] = U.d;
+    return BAYES_OK;
+}
+
+// Form the units: every (locus, chain) with more than one candidate is a slot; slots with T <= 32 that share Tpad and
+// the iteration counts are bundled side by side (most expensive first, so a bundle's slots finish together), the
+// others get a wide unit each.  Units are then ordered so that each launch is one (kernel, block size, matrix
+// placement) class with its most expensive units first: the hardware block scheduler hands blocks out in index order,
+// which makes this the largest-first queue of the reference (assembler.cpp:1886-1916).
+int build_units(bayes_gibbs_ctx *ctx) {
+    ctx->h_units.n = ctx->h_val.n = ctx->h_efflen.n = ctx->h_tab_val.n = ctx->h_col.n = 0;
+    ctx->h_slab.n = ctx->h_row_n.n = ctx->h_row_nnz.n = ctx->h_row_info.n = ctx->h_base.n = ctx->h_tab_row.n = 0;
     ctx->launches.clear();
-    for (int64_t i = 0; i < n;) {
-        const LocusDev &l0 = loci[jobs[i].locus];
+    ctx->trace_unit = -1;
+
+    std::vector<std::vector<SlotRef> > groups;  // one per unit
+    std::vector<char> group_wide;
+    typedef std::tuple<int, int, int> BundleKey;  // (Tpad, burn, samples)
+    std::map<BundleKey, std::vector<SlotRef> > pools;
+    for (size_t l = 0; l < ctx->loci.size(); l++) {
+        const PreLocus &L = ctx->loci[l];
+        if (L.T == 1) continue;  // closed form on the host (gibbsSampler.cpp:57-67)
+        for (int c = 0; c < L.n_chains; c++) {
+            SlotRef s{&L, c, ctx->out_base[l] + (int64_t)c * L.T};
+            const int tp = slot_lanes(L.T);
+            if (tp == 0) {
+                groups.push_back(std::vector<SlotRef>(1, s));
+                group_wide.push_back(1);
+            } else {
+                pools[BundleKey(tp, L.burn, L.samples)].push_back(s);
+            }
+        }
+    }
+    for (auto &kv : pools) {
+        std::vector<SlotRef> &v = kv.second;
+        const int per = 32 / std::get<0>(kv.first);
+        std::stable_sort(v.begin(), v.end(), [](const SlotRef &a, const SlotRef &b) { return a.locus->cost > b.locus->cost; });
+        for (size_t i = 0; i < v.size(); i += per) {
+            groups.push_back(std::vector<SlotRef>(v.begin() + i, v.begin() + std::min(v.size(), i + per)));
+            group_wide.push_back(0);
+        }
+    }
+    const int64_t n_units = (int64_t)groups.size();
+    std::vector<PackedUnit> packed(n_units);
+    parallel_for(host_thread_count(ctx, n_units), n_units, [&](int64_t i) { pack_unit(groups[i], group_wide[i] != 0, &packed[i]); });
+
+    // Warps per unit.  A block alternates between the one-warp E-step and the row-parallel A-step, so every extra warp
+    // spends much of its life parked at the block barrier while still holding registers.  Throughput is therefore best
+    // with ONE warp per unit (it simply walks all slabs); extra warps only buy latency, which matters for the units
+    // that would otherwise outlast the rest of the batch.  A unit gets more warps only when its estimated one-warp time
+    // exceeds half of the batch's ideal makespan (total work / warps the GPU keeps resident).
+    {
+        double total = 0;
+        for (const PackedUnit &u : packed) total += u.cost;
+        const double ideal = total / ((double)ctx->sm_count * 16.0);
+        for (PackedUnit &u : packed) {
+            int warps = 1;
+            const double want = ideal > 0 ? u.cost / (0.5 * ideal) : 1e9;
+            while (2 * warps <= kMaxBlock / 32 && warps < u.d.n_slabs && 2 * warps <= want) warps *= 2;
+            u.d.block = 32 * warps;
+        }
+    }
+
+    std::vector<int64_t> order(n_units);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+        const UnitDev &ua = packed[a].d, &ub = packed[b].d;
+        if (ua.mat_smem != ub.mat_smem) return ua.mat_smem < ub.mat_smem;  // streaming (largest) units first
+        if (ua.wide != ub.wide) return ua.wide > ub.wide;
+        if (ua.block != ub.block) return ua.block > ub.block;
+        return packed[a].cost > packed[b].cost;
+    });
+    int rc;
+    for (int64_t i = 0; i < n_units; i++)
+        if ((rc = append_unit(ctx, packed[order[i]]))) return rc;
+    const UnitDev *units = ctx->h_units.p;
+    for (int64_t i = 0; i < n_units;) {
         int64_t j = i;
         size_t smem = 0;
-        while (j < n && ctx->job_block[j] == ctx->job_block[i] && loci[jobs[j].locus].mat_smem == l0.mat_smem) {
-            smem = std::max(smem, (size_t)loci[jobs[j].locus].smem_bytes);
+        while (j < n_units && units[j].block == units[i].block && units[j].wide == units[i].wide && units[j].mat_smem == units[i].mat_smem) {
+            smem = std::max(smem, (size_t)units[j].smem_bytes);
             j++;
         }
-        ctx->launches.push_back(Launch{i, j - i, ctx->job_block[i], l0.mat_smem != 0, smem});
+        ctx->launches.push_back(Launch{i, j - i, units[i].block, units[i].wide != 0, units[i].mat_smem != 0, smem});
         i = j;
     }
-    // first_job / trace bookkeeping refer to (locus, chain): rebuild the lookup
-    ctx->trace_job_sorted = -1;
-    for (auto &l : ctx->loci) l.first_job = -1;
+    if (ctx->trace_locus >= 0) {
+        const int64_t want = ctx->out_base[ctx->trace_locus] + (int64_t)ctx->trace_chain * ctx->trace_T;
+        for (int64_t i = 0; i < n_units && ctx->trace_unit < 0; i++)
+            for (int g = 0; g < units[i].n_slots; g++)
+                if (units[i].out_off[g] == want) {
+                    ctx->trace_unit = i;
+                    ctx->trace_slot = g;
+                    break;
+                }
+    }
     return BAYES_OK;
 }
 
 KernelArgs kernel_args(bayes_gibbs_ctx *ctx) {
     KernelArgs a;
     memset(&a, 0, sizeof(a));
-    a.loci = ctx->d_loci.p;
-    a.jobs = ctx->d_jobs.p;
+    a.units = ctx->d_units.p;
     a.val = ctx->d_val.p;
     a.col = ctx->d_col.p;
     a.slab_cell_off = ctx->d_slab.p;
     a.row_n = ctx->d_row_n.p;
     a.row_nnz = ctx->d_row_nnz.p;
-    a.row_id = ctx->d_row_id.p;
+    a.row_info = ctx->d_row_info.p;
     a.efflen = ctx->d_efflen.p;
     a.base_counts = ctx->d_base.p;
     a.tab_val = ctx->d_tab_val.p;
@@ -219,13 +308,26 @@ KernelArgs kernel_args(bayes_gibbs_ctx *ctx) {
     a.out_mean = ctx->d_mean.p;
     a.out_m2 = ctx->d_m2.p;
     a.out_counts = ctx->d_counts.p;
-    a.trace_job = ctx->trace_job_sorted;
+    a.trace_unit = ctx->trace_unit;
+    a.trace_slot = ctx->trace_slot;
     a.trace_iters = ctx->trace_iters;
     a.tr_theta = ctx->d_tr_theta.p;
     a.tr_counts = ctx->d_tr_counts.p;
     a.tr_b = ctx->d_tr_b.p;
     a.tr_init = ctx->d_tr_init.p;
     return a;
+}
+
+int upload_units(bayes_gibbs_ctx *ctx) {
+    int rc;
+    cudaStream_t st = ctx->stream;
+    if ((rc = h2d(ctx->d_units, ctx->h_units, st)) || (rc = h2d(ctx->d_val, ctx->h_val, st)) || (rc = h2d(ctx->d_col, ctx->h_col, st)) ||
+        (rc = h2d(ctx->d_slab, ctx->h_slab, st)) || (rc = h2d(ctx->d_row_n, ctx->h_row_n, st)) ||
+        (rc = h2d(ctx->d_row_nnz, ctx->h_row_nnz, st)) || (rc = h2d(ctx->d_row_info, ctx->h_row_info, st)) ||
+        (rc = h2d(ctx->d_efflen, ctx->h_efflen, st)) || (rc = h2d(ctx->d_base, ctx->h_base, st)) ||
+        (rc = h2d(ctx->d_tab_val, ctx->h_tab_val, st)) || (rc = h2d(ctx->d_tab_row, ctx->h_tab_row, st)))
+        return rc;
+    return BAYES_OK;
 }
 
 }  // namespace
@@ -262,6 +364,7 @@ int bayes_gibbs_create(int device, bayes_gibbs_ctx **out) {
     bayes_gibbs_ctx *ctx = new (std::nothrow) bayes_gibbs_ctx();
     if (!ctx) return BAYES_E_NOMEM;
     ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     rc = cuda_rc(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     if (rc) {
         delete ctx;
@@ -276,14 +379,16 @@ void bayes_gibbs_destroy(bayes_gibbs_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->h_loci.release(); ctx->h_jobs.release(); ctx->h_val.release(); ctx->h_efflen.release(); ctx->h_tab_val.release();
-    ctx->h_col.release(); ctx->h_slab.release(); ctx->h_row_n.release(); ctx->h_row_nnz.release(); ctx->h_row_id.release();
-    ctx->h_base.release(); ctx->h_tab_row.release(); ctx->h_occ.release(); ctx->h_counts.release(); ctx->h_mean.release();
-    ctx->h_m2.release();
-    ctx->d_loci.release(); ctx->d_jobs.release(); ctx->d_val.release(); ctx->d_efflen.release(); ctx->d_tab_val.release();
-    ctx->d_mean.release(); ctx->d_m2.release(); ctx->d_tr_theta.release(); ctx->d_col.release(); ctx->d_slab.release();
-    ctx->d_row_n.release(); ctx->d_row_nnz.release(); ctx->d_row_id.release(); ctx->d_base.release(); ctx->d_tab_row.release();
-    ctx->d_occ.release(); ctx->d_counts.release(); ctx->d_tr_counts.release(); ctx->d_tr_b.release(); ctx->d_tr_init.release();
+    ctx->h_units.release(); ctx->h_val.release(); ctx->h_efflen.release(); ctx->h_tab_val.release(); ctx->h_col.release();
+    ctx->h_slab.release(); ctx->h_row_n.release(); ctx->h_row_nnz.release(); ctx->h_row_info.release(); ctx->h_base.release();
+    ctx->h_tab_row.release(); ctx->h_occ.release(); ctx->h_counts.release(); ctx->h_mean.release(); ctx->h_m2.release();
+    ctx->d_units.release(); ctx->d_val.release(); ctx->d_efflen.release(); ctx->d_tab_val.release(); ctx->d_mean.release();
+    ctx->d_m2.release(); ctx->d_tr_theta.release(); ctx->d_col.release(); ctx->d_slab.release(); ctx->d_row_n.release();
+    ctx->d_row_nnz.release(); ctx->d_row_info.release(); ctx->d_base.release(); ctx->d_tab_row.release(); ctx->d_occ.release();
+    ctx->d_counts.release(); ctx->d_tr_counts.release(); ctx->d_tr_b.release(); ctx->d_tr_init.release();
+    for (cudaStream_t st : ctx->aux) cudaStreamDestroy(st);
+    for (cudaEvent_t ev : ctx->join_ev) cudaEventDestroy(ev);
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -307,17 +412,14 @@ int bayes_gibbs_clear(bayes_gibbs_ctx *ctx) {
     int rc = use_device(ctx);
     if (rc) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->h_loci.n = ctx->h_jobs.n = ctx->h_val.n = ctx->h_efflen.n = ctx->h_tab_val.n = ctx->h_col.n = 0;
-    ctx->h_slab.n = ctx->h_row_n.n = ctx->h_row_nnz.n = ctx->h_row_id.n = ctx->h_base.n = ctx->h_tab_row.n = 0;
     ctx->loci.clear();
-    ctx->dev_index.clear();
-    ctx->job_cost.clear();
-    ctx->job_block.clear();
-    ctx->launches.clear();
+    ctx->out_base.clear();
     ctx->out_len = 0;
+    ctx->h_units.n = 0;
+    ctx->launches.clear();
     ctx->uploaded = ctx->ran = ctx->downloaded = false;
     ctx->trace_locus = -1;
-    ctx->trace_job_sorted = -1;
+    ctx->trace_unit = -1;
     ctx->trace_iters = 0;
     return BAYES_OK;
 }
@@ -331,87 +433,22 @@ int bayes_gibbs_submit(bayes_gibbs_ctx *ctx, int32_t n_loci, const bayes_locus_d
         set_error("bayes_gibbs_submit: batch already uploaded; call bayes_gibbs_clear first");
         return BAYES_E_STATE;
     }
-    int rc = use_device(ctx);
-    if (rc) return rc;
     if (first_id) *first_id = (int64_t)ctx->loci.size();
-
-    // pack on a thread pool (set cover + CDF table + SELL packing are independent per locus)
-    std::vector<PackedLocus> packed(n_loci);
+    // fold rows, read cover, CDF table: independent per locus
+    std::vector<PreLocus> pre(n_loci);
     std::vector<int> prc(n_loci, 0);
     std::vector<std::string> perr(n_loci);
-    int n_thr = ctx->host_threads > 0 ? ctx->host_threads : (int)std::thread::hardware_concurrency();
-    n_thr = std::max(1, std::min(n_thr, (int)n_loci));
-    std::atomic<int32_t> next(0);
-    auto work = [&]() {
-        for (;;) {
-            const int32_t i = next.fetch_add(1);
-            if (i >= n_loci) return;
-            prc[i] = pack_locus(loci[i], &packed[i], &perr[i]);
-        }
-    };
-    if (n_thr == 1) work();
-    else {
-        std::vector<std::thread> pool;
-        for (int t = 0; t < n_thr; t++) pool.emplace_back(work);
-        for (auto &t : pool) t.join();
-    }
+    parallel_for(host_thread_count(ctx, n_loci), n_loci, [&](int64_t i) { prc[i] = prepare_locus(loci[i], &pre[i], &perr[i]); });
     for (int32_t i = 0; i < n_loci; i++)
         if (prc[i] != BAYES_OK) {
             set_error("bayes_gibbs_submit: locus " + std::to_string(i) + ": " + perr[i]);
             return prc[i];
         }
-
+    ctx->loci.reserve(ctx->loci.size() + n_loci);
     for (int32_t i = 0; i < n_loci; i++) {
-        PackedLocus &P = packed[i];
-        LocusHost lh;
-        lh.T = P.d.T;
-        lh.n_chains = P.n_chains;
-        lh.samples = P.d.samples;
-        lh.cover = P.cover;
-        lh.folded = P.folded;
-        lh.pi = P.pi;
-        lh.first_job = -1;
-        lh.n_frag = P.d.N_f;
-        lh.closed_form = P.d.T == 1;
-        lh.single_fpkm = 0;
-        if (lh.closed_form) {
-            // gibbsSampler.cpp:57-67: (num_fragments * 1e9) / (total_num_fragments * effective_length)
-            lh.single_fpkm = (P.d.N_f * 1e9) / (P.d.N_total * P.efflen[0]);
-            ctx->dev_index.push_back(-1);
-            ctx->loci.push_back(lh);
-            continue;
-        }
-        P.d.slab_off = (int64_t)ctx->h_slab.n;
-        P.d.cell_off = (int64_t)ctx->h_val.n;
-        P.d.row_off = (int64_t)ctx->h_row_n.n;
-        P.d.t_off = (int64_t)ctx->h_efflen.n;
-        P.d.tab_off = (int64_t)ctx->h_tab_val.n;
-        P.d.tabrow_off = (int64_t)ctx->h_tab_row.n;
-        if ((rc = append(ctx->h_slab, P.slab_cell_off)) || (rc = append(ctx->h_val, P.val)) || (rc = append(ctx->h_col, P.col)) ||
-            (rc = append(ctx->h_row_n, P.row_n)) || (rc = append(ctx->h_row_nnz, P.row_nnz)) || (rc = append(ctx->h_row_id, P.row_id)) ||
-            (rc = append(ctx->h_efflen, P.efflen)) || (rc = append(ctx->h_base, P.base_counts)) ||
-            (rc = append(ctx->h_tab_val, P.tab_val)) || (rc = append(ctx->h_tab_row, P.tab_row)))
-            return rc;
-        const int32_t li = (int32_t)ctx->h_loci.n;
-        if ((rc = ctx->h_loci.resize(li + 1))) return rc;
-        ctx->h_loci.p[li] = P.d;
-        ctx->dev_index.push_back(li);
-        const int64_t locus_id = (int64_t)ctx->loci.size();
-        for (int32_t c = 0; c < P.n_chains; c++) {
-            const size_t j = ctx->h_jobs.n;
-            if ((rc = ctx->h_jobs.resize(j + 1))) return rc;
-            JobDev jd;
-            jd.locus = li;
-            jd.chain = c;
-            jd.key = bayes_chain_key(P.seed, c);
-            jd.out_off = ctx->out_len;
-            ctx->h_jobs.p[j] = jd;
-            ctx->out_len += P.d.T;
-            ctx->job_cost.push_back(P.cost);
-            ctx->job_block.push_back(P.block);
-        }
-        (void)locus_id;
-        ctx->loci.push_back(lh);
+        ctx->out_base.push_back(ctx->out_len);
+        ctx->out_len += (int64_t)pre[i].T * pre[i].n_chains;
+        ctx->loci.push_back(std::move(pre[i]));
     }
     return BAYES_OK;
 }
@@ -420,32 +457,14 @@ int bayes_gibbs_upload(bayes_gibbs_ctx *ctx) {
     if (!ctx) return BAYES_E_INVALID;
     int rc = use_device(ctx);
     if (rc) return rc;
-    if ((rc = plan_launches(ctx))) return rc;
-    // (locus, chain) -> sorted job index: out_off is stable, so fetch looks results up through the host copy of jobs
-    const int64_t n_jobs = (int64_t)ctx->h_jobs.n;
-    std::vector<int64_t> first(ctx->h_loci.n, -1);
-    for (int64_t j = 0; j < n_jobs; j++) {
-        const JobDev &jd = ctx->h_jobs.p[j];
-        if (jd.chain == 0) first[jd.locus] = jd.out_off;
-    }
-    for (size_t l = 0; l < ctx->loci.size(); l++)
-        if (ctx->dev_index[l] >= 0) ctx->loci[l].first_job = first[ctx->dev_index[l]];
+    if ((rc = build_units(ctx))) return rc;
     if (ctx->trace_locus >= 0) {
-        const int32_t li = ctx->dev_index[ctx->trace_locus];
-        for (int64_t j = 0; j < n_jobs; j++)
-            if (ctx->h_jobs.p[j].locus == li && ctx->h_jobs.p[j].chain == ctx->trace_chain) ctx->trace_job_sorted = j;
         const size_t n = (size_t)ctx->trace_iters * ctx->trace_T;
         if ((rc = ctx->d_tr_theta.reserve(n)) || (rc = ctx->d_tr_counts.reserve(n)) || (rc = ctx->d_tr_b.reserve(ctx->trace_iters)) ||
             (rc = ctx->d_tr_init.reserve(ctx->trace_T)))
             return rc;
     }
-    cudaStream_t st = ctx->stream;
-    if ((rc = h2d(ctx->d_loci, ctx->h_loci, st)) || (rc = h2d(ctx->d_jobs, ctx->h_jobs, st)) || (rc = h2d(ctx->d_val, ctx->h_val, st)) ||
-        (rc = h2d(ctx->d_col, ctx->h_col, st)) || (rc = h2d(ctx->d_slab, ctx->h_slab, st)) || (rc = h2d(ctx->d_row_n, ctx->h_row_n, st)) ||
-        (rc = h2d(ctx->d_row_nnz, ctx->h_row_nnz, st)) || (rc = h2d(ctx->d_row_id, ctx->h_row_id, st)) ||
-        (rc = h2d(ctx->d_efflen, ctx->h_efflen, st)) || (rc = h2d(ctx->d_base, ctx->h_base, st)) ||
-        (rc = h2d(ctx->d_tab_val, ctx->h_tab_val, st)) || (rc = h2d(ctx->d_tab_row, ctx->h_tab_row, st)))
-        return rc;
+    if ((rc = upload_units(ctx))) return rc;
     const size_t n_out = (size_t)ctx->out_len;
     if ((rc = ctx->d_occ.reserve(n_out)) || (rc = ctx->d_counts.reserve(n_out)) || (rc = ctx->d_mean.reserve(n_out)) ||
         (rc = ctx->d_m2.reserve(n_out)))
@@ -468,8 +487,27 @@ int bayes_gibbs_run(bayes_gibbs_ctx *ctx) {
     if (rc) return rc;
     const KernelArgs args = kernel_args(ctx);
     ctx->last_launches = 0;
-    for (const Launch &l : ctx->launches) {
-        if ((rc = launch_gibbs(args, l.job_base, l.n_jobs, l.block, l.mat_smem, l.smem, ctx->stream))) return rc;
+    const size_t n_l = ctx->launches.size();
+    if (!ctx->fork_ev) CU(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+    while (ctx->aux.size() < n_l) {
+        cudaStream_t st;
+        cudaEvent_t ev;
+        CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->aux.push_back(st);
+        ctx->join_ev.push_back(ev);
+    }
+    // the block scheduler drains launches roughly in issue order, so the classes with the longest chains go first
+    if (n_l > 1) CU(cudaEventRecord(ctx->fork_ev, ctx->stream));
+    for (size_t i = 0; i < n_l; i++) {
+        const Launch &l = ctx->launches[i];
+        cudaStream_t st = n_l > 1 ? ctx->aux[i] : ctx->stream;
+        if (n_l > 1) CU(cudaStreamWaitEvent(st, ctx->fork_ev, 0));
+        if ((rc = launch_units(args, l.unit_base, l.n_units, l.block, l.wide, l.mat_smem, l.smem, st))) return rc;
+        if (n_l > 1) {
+            CU(cudaEventRecord(ctx->join_ev[i], st));
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[i], 0));
+        }
         ctx->last_launches++;
     }
     ctx->ran = true;
@@ -519,28 +557,44 @@ int bayes_gibbs_fetch(bayes_gibbs_ctx *ctx, int64_t locus_id, int32_t chain, int
         set_error("bayes_gibbs_fetch: bad locus id");
         return BAYES_E_INVALID;
     }
-    const LocusHost &lh = ctx->loci[locus_id];
-    if (chain < 0 || chain >= lh.n_chains) {
+    const PreLocus &L = ctx->loci[locus_id];
+    if (chain < 0 || chain >= L.n_chains) {
         set_error("bayes_gibbs_fetch: bad chain");
         return BAYES_E_INVALID;
     }
-    if (lh.closed_form) {
-        // every one of the `samples` identical samples is accumulated (gibbsSampler.cpp:63-66, gibbsOutput.cpp:51-75)
-        if (occ) occ[0] = lh.samples;
-        if (mean) mean[0] = lh.single_fpkm;
+    if (L.T == 1) {
+        // gibbsSampler.cpp:57-67: `samples` identical samples of (num_fragments * 1e9) / (total_num_fragments * efflen)
+        // accumulated by addSample (gibbsOutput.cpp:51-75): mean = that value, M2 = 0
+        if (occ) occ[0] = L.samples;
+        if (mean) mean[0] = (L.n_frag * 1e9) / (L.N_total * L.efflen[0]);
         if (m2) m2[0] = 0.0;
-        if (final_counts) final_counts[0] = lh.n_frag;
+        if (final_counts) final_counts[0] = L.n_frag;
         return BAYES_OK;
     }
     if (!ctx->downloaded) {
         set_error("bayes_gibbs_fetch: results not downloaded (run, download, sync first)");
         return BAYES_E_STATE;
     }
-    const int64_t off = lh.first_job + (int64_t)chain * lh.T;  // chains of a locus are contiguous in the outputs
-    if (occ) memcpy(occ, ctx->h_occ.p + off, lh.T * sizeof(int32_t));
-    if (mean) memcpy(mean, ctx->h_mean.p + off, lh.T * sizeof(double));
-    if (m2) memcpy(m2, ctx->h_m2.p + off, lh.T * sizeof(double));
-    if (final_counts) memcpy(final_counts, ctx->h_counts.p + off, lh.T * sizeof(int32_t));
+    const int64_t off = ctx->out_base[locus_id] + (int64_t)chain * L.T;
+    if (occ) memcpy(occ, ctx->h_occ.p + off, L.T * sizeof(int32_t));
+    if (mean) memcpy(mean, ctx->h_mean.p + off, L.T * sizeof(double));
+    if (m2) memcpy(m2, ctx->h_m2.p + off, L.T * sizeof(double));
+    if (final_counts) memcpy(final_counts, ctx->h_counts.p + off, L.T * sizeof(int32_t));
+    return BAYES_OK;
+}
+
+int bayes_gibbs_fetch_all(bayes_gibbs_ctx *ctx, int32_t *occ, double *mean, double *m2, int32_t *final_counts) {
+    if (!ctx) return BAYES_E_INVALID;
+    int64_t at = 0;
+    for (int64_t l = 0; l < (int64_t)ctx->loci.size(); l++) {
+        const PreLocus &L = ctx->loci[l];
+        for (int32_t c = 0; c < L.n_chains; c++) {
+            int rc = bayes_gibbs_fetch(ctx, l, c, occ ? occ + at : nullptr, mean ? mean + at : nullptr, m2 ? m2 + at : nullptr,
+                                       final_counts ? final_counts + at : nullptr);
+            if (rc) return rc;
+            at += L.T;
+        }
+    }
     return BAYES_OK;
 }
 
@@ -549,15 +603,20 @@ int bayes_gibbs_locus_info(bayes_gibbs_ctx *ctx, int64_t locus_id, double *pi, i
         set_error("bayes_gibbs_locus_info: bad locus id");
         return BAYES_E_INVALID;
     }
-    const LocusHost &lh = ctx->loci[locus_id];
-    if (pi) *pi = lh.pi;
-    if (cover_size) *cover_size = lh.cover;
-    if (rows_folded) *rows_folded = lh.folded;
+    const PreLocus &L = ctx->loci[locus_id];
+    if (pi) *pi = L.pi;
+    if (cover_size) *cover_size = L.cover;
+    if (rows_folded) *rows_folded = L.folded;
     return BAYES_OK;
 }
 
 int64_t bayes_gibbs_num_loci(bayes_gibbs_ctx *ctx) { return ctx ? (int64_t)ctx->loci.size() : 0; }
-int64_t bayes_gibbs_num_jobs(bayes_gibbs_ctx *ctx) { return ctx ? (int64_t)ctx->h_jobs.n : 0; }
+int64_t bayes_gibbs_num_jobs(bayes_gibbs_ctx *ctx) {
+    if (!ctx) return 0;
+    int64_t n = 0;
+    for (const PreLocus &L : ctx->loci) n += L.n_chains;
+    return n;
+}
 int32_t bayes_gibbs_last_launches(bayes_gibbs_ctx *ctx) { return ctx ? ctx->last_launches : 0; }
 
 int bayes_gibbs_set_trace(bayes_gibbs_ctx *ctx, int64_t locus_id, int32_t chain, int32_t trace_iters) {
@@ -569,15 +628,15 @@ int bayes_gibbs_set_trace(bayes_gibbs_ctx *ctx, int64_t locus_id, int32_t chain,
         set_error("bayes_gibbs_set_trace: must be called before bayes_gibbs_upload");
         return BAYES_E_STATE;
     }
-    const LocusHost &lh = ctx->loci[locus_id];
-    if (lh.closed_form || chain < 0 || chain >= lh.n_chains) {
+    const PreLocus &L = ctx->loci[locus_id];
+    if (L.T == 1 || chain < 0 || chain >= L.n_chains) {
         set_error("bayes_gibbs_set_trace: locus has no device job for that chain");
         return BAYES_E_INVALID;
     }
     ctx->trace_locus = locus_id;
     ctx->trace_chain = chain;
     ctx->trace_iters = trace_iters;
-    ctx->trace_T = lh.T;
+    ctx->trace_T = L.T;
     return BAYES_OK;
 }
 
@@ -607,41 +666,30 @@ static int step_assignment(int device, const bayes_locus_desc *locus, const doub
     bayes_gibbs_ctx *ctx = nullptr;
     int rc = bayes_gibbs_create(device, &ctx);
     if (rc) return rc;
+    auto fail = [&](int code) { bayes_gibbs_destroy(ctx); return code; };
     bayes_locus_desc d = *locus;
     if (d.pi < 0) d.pi = 0.5;  // the cover is not part of this step
     d.n_chains = 1;
     if (d.burn_in < 0) d.burn_in = 0;
     if (d.samples < 1) d.samples = 1;
-    PackedLocus P;
+    d.seed = key;  // chain 0 uses the seed itself as its Philox key
+    PreLocus P;
     std::string err;
-    if ((rc = pack_locus(d, &P, &err))) {
+    if ((rc = prepare_locus(d, &P, &err))) {
         set_error("bayes_step_*_assignment: " + err);
-        bayes_gibbs_destroy(ctx);
-        return rc;
+        return fail(rc);
     }
     const int T = d.T;
-    auto fail = [&](int code) { bayes_gibbs_destroy(ctx); return code; };
-    P.d.slab_off = P.d.cell_off = P.d.row_off = P.d.t_off = P.d.tab_off = P.d.tabrow_off = 0;
-    JobDev jd;
-    jd.locus = 0; jd.chain = 0; jd.key = key; jd.out_off = 0;
-    if ((rc = ctx->h_loci.resize(1)) || (rc = ctx->h_jobs.resize(1))) return fail(rc);
-    ctx->h_loci.p[0] = P.d;
-    ctx->h_jobs.p[0] = jd;
-    if ((rc = append(ctx->h_slab, P.slab_cell_off)) || (rc = append(ctx->h_val, P.val)) || (rc = append(ctx->h_col, P.col)) ||
-        (rc = append(ctx->h_row_n, P.row_n)) || (rc = append(ctx->h_row_nnz, P.row_nnz)) || (rc = append(ctx->h_row_id, P.row_id)) ||
-        (rc = append(ctx->h_base, P.base_counts)))
-        return fail(rc);
+    PackedUnit U;
+    pack_unit(std::vector<SlotRef>(1, SlotRef{&P, 0, 0}), true, &U);  // wide layout: columns stay candidate indices
+    if ((rc = append_unit(ctx, U))) return fail(rc);
+    if ((rc = upload_units(ctx))) return fail(rc);
     cudaStream_t st = ctx->stream;
-    if ((rc = h2d(ctx->d_loci, ctx->h_loci, st)) || (rc = h2d(ctx->d_jobs, ctx->h_jobs, st)) || (rc = h2d(ctx->d_val, ctx->h_val, st)) ||
-        (rc = h2d(ctx->d_col, ctx->h_col, st)) || (rc = h2d(ctx->d_slab, ctx->h_slab, st)) || (rc = h2d(ctx->d_row_n, ctx->h_row_n, st)) ||
-        (rc = h2d(ctx->d_row_nnz, ctx->h_row_nnz, st)) || (rc = h2d(ctx->d_row_id, ctx->h_row_id, st)) ||
-        (rc = h2d(ctx->d_base, ctx->h_base, st)))
-        return fail(rc);
     if ((rc = ctx->d_mean.reserve(T)) || (rc = ctx->d_occ.reserve(T))) return fail(rc);
     if (!init && (rc = cuda_rc(cudaMemcpyAsync(ctx->d_mean.p, theta, T * sizeof(double), cudaMemcpyHostToDevice, st), "theta H2D")))
         return fail(rc);
     const KernelArgs args = kernel_args(ctx);
-    if ((rc = launch_step_assignment(args, init, ctx->d_mean.p, iteration, ctx->d_occ.p, 12 * (size_t)T + 16, st))) return fail(rc);
+    if ((rc = launch_step_assignment(args, init, ctx->d_mean.p, iteration, ctx->d_occ.p, 12 * (size_t)T + 32, st))) return fail(rc);
     if ((rc = cuda_rc(cudaMemcpyAsync(counts_out, ctx->d_occ.p, T * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "counts D2H")))
         return fail(rc);
     if ((rc = cuda_rc(cudaStreamSynchronize(st), "step sync"))) return fail(rc);

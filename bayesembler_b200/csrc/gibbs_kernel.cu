@@ -1,7 +1,7 @@
-// Persistent per-(locus, chain) Gibbs sampler for sm_100a.
+// Persistent Gibbs sampler kernels for sm_100a: one thread block per UNIT for ALL of its iterations.
 //
-// One thread block owns one chain of one locus for ALL of its iterations (17 600 .. 671 000 dependent iterations per
-// locus; a launch per iteration would be launch-bound).  Per iteration (gibbsSampler.cpp:103-141):
+// A chain is 17 600 .. 671 000 strictly dependent iterations (gibbsSampler.cpp:103-141), so a launch per iteration
+// would be launch-bound; instead a block keeps everything it needs in shared memory / registers and loops:
 //   E  warp 0:  |S+| from the counts, simplex size b (1 uniform + CDF search, simplexSizeGenerator.cpp:214-224), the
 //               b-|S+| null picks (expressionGenerator.cpp:104-127), one Gamma draw per member of the simplex, warp
 //               shuffle reduction of the sum, theta = g / sum (expressionGenerator.cpp:77-132), FPKM + Welford update
@@ -9,15 +9,27 @@
 //   A  all threads, one thread per collapsed row, 32 rows of a SELL-32 slab per warp: Z = sum_j P_ij theta_j, then
 //               either n < 20 uniforms located in the row's CDF or the chain of conditional binomials
 //               (assignmentGenerator.cpp:263-373); counts accumulate with shared-memory atomics.
-// The locus' matrix, theta, counts, the CDF table and the accumulators live in shared memory for the whole chain;
-// loci too large for that stream their cells from L2/HBM with fully coalesced slab-column reads.
-// No tensor cores: there is no dense contraction anywhere on this path.
+// Two unit shapes (internal.h):
+//   bundle  up to 16 chains (of different loci) whose candidates sit side by side in the 32 lanes of warp 0; the
+//           E-step is segmented by slot and keeps all per-candidate state in registers; rows of all slots are pooled,
+//           so the data-dependent branches of the A-step find many more lanes taking the same path;
+//   wide    one chain of a locus with more than 32 candidates; the E-step loops over 32-candidate chunks with the
+//           per-candidate state in shared memory.
+// The matrix, theta, counts and the CDF tables live in shared memory for the whole chain; units too large for that
+// stream their cells from L2/HBM with fully coalesced slab-column reads.  No tensor cores: nothing here is a dense
+// contraction.
 #include <cuda_runtime.h>
 #include <float.h>
 
 #include "internal.h"
 #include "layout.h"
 #include "rng.cuh"
+
+// Registers per thread = 65536 / (kMaxBlock * BAYES_MIN_BLOCKS): 4 -> 64 registers, i.e. 32 resident one-warp units per SM
+// (the hardware limit of 32 blocks per SM); measured best against 3 (80) and 2 (128), see profiles/.
+#ifndef BAYES_MIN_BLOCKS
+#define BAYES_MIN_BLOCKS 4
+#endif
 
 namespace bayes {
 
@@ -36,96 +48,210 @@ struct MatView {
     const int32_t *slab;     // n_slabs + 1 cell offsets
     const int32_t *row_n;
     const int32_t *row_nnz;
-    const int32_t *row_id;
+    const uint32_t *row_info;  // slot << 27 | original row index
     int n_slabs;
 };
 
 // ------------------------------------------------------------------------------------------------------------------
-// A-step.  INIT = AssignmentGenerator::initAssignment (assignmentGenerator.cpp:213-260): binomial chain on P_ij itself,
-// no row normalisation.  Otherwise generateAssignment (:263-373).
+// A-step.  init = AssignmentGenerator::initAssignment (assignmentGenerator.cpp:213-260): binomial chain on P_ij itself,
+// no row normalisation; the caller passes theta == 1 (P_ij * 1.0 is P_ij exactly) and Z is pinned to 1, so that the one
+// copy of this code (instruction-cache footprint) serves both.  Otherwise generateAssignment (:263-373).
 // ------------------------------------------------------------------------------------------------------------------
-template <bool INIT>
-__device__ __forceinline__ void assign_rows(const MatView &M, const double *theta, int32_t *counts, uint64_t key, uint32_t iteration) {
+__device__ __forceinline__ void assign_rows(const MatView &M, const double *theta, int32_t *counts, const uint64_t *skey,
+                                            int lanes_per_slot, uint32_t iteration, const bool init) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const uint32_t phase = INIT ? PH_INIT_ASSIGN : PH_ASSIGN;
-    for (int s = warp; s < M.n_slabs; s += n_warps) {
+    const uint32_t phase = init ? PH_INIT_ASSIGN : PH_ASSIGN;
+    // slabs are ordered heaviest first; warp 0 (which also runs the E-step) starts from the lightest one
+    for (int s = M.n_slabs - 1 - warp; s >= 0; s -= n_warps) {
         const int r = s * 32 + lane;
         const int n = M.row_n[r];
         const int nnz = M.row_nnz[r];
         if (nnz == 0) continue;  // padding lane of the last slab
-        const uint32_t id = (uint32_t)M.row_id[r];
+        const uint32_t info = M.row_info[r];
+        const uint32_t id = info & ((1u << kRowSlotShift) - 1u);
         const double *val = M.val + M.slab[s] + lane;
         const uint16_t *col = M.col + M.slab[s] + lane;
+        const bool chain = init || n >= kSmallCount;
 
-        double Z = 1.0;
-        if (!INIT) {
-            Z = 0.0;
-            for (int k = 0; k < nnz; k++) Z += val[32 * k] * theta[col[32 * k]];  // :280-282
+        // Z = sum_j P_ij theta_j (:280-282) and the first / last cell that can receive fragments.  A cell is in play
+        // when its normalised probability is > 0 (CDF walk, :304-306) resp. >= double_underflow (chain, :344).
+        double Z = 0.0;
+        int kf = nnz, kl = -1;
+        bool tiny = false;
+        for (int k = 0; k < nnz; k++) {
+            const double p = val[32 * k] * theta[col[32 * k]];
+            Z += p;
+            if (p != 0.0) {
+                tiny |= p < 1e-300;
+                if (kf == nnz) kf = k;
+                kl = k;
+            }
         }
-
-        if (!INIT && n < kSmallCount) {
-            // :289-334.  The reference sorts the n uniforms and walks the CDF once; which column a uniform lands in
-            // does not depend on the order they are visited in, so they are taken four at a time (one Philox block).
-            const Site site = make_site(key, phase, iteration, id, 0);
-            for (int j = 0; 4 * j < n; j++) {
-                const u32x4 w = site.block((uint32_t)j);
-                const int left = n - 4 * j;
-                double cum = 0.0;
-                int below_prev = 0;
-                for (int k = 0; k < nnz; k++) {
-                    const int c = col[32 * k];
-                    cum += (val[32 * k] * theta[c]) / Z;                        // :304
-                    // u = w * 2^-32 < cum  <=>  w < ceil(cum * 2^32)            // :306
-                    const unsigned long long thr = __double2ull_ru(cum * 4294967296.0);
-                    int below = (int)((unsigned long long)w.x < thr);
-                    below += (left > 1) & (int)((unsigned long long)w.y < thr);
-                    below += (left > 2) & (int)((unsigned long long)w.z < thr);
-                    below += (left > 3) & (int)((unsigned long long)w.w < thr);
-                    const int got = below - below_prev;
-                    if (got > 0) atomicAdd(&counts[c], got);                     // :323-324
-                    below_prev = below;
-                    if (below >= (left < 4 ? left : 4)) break;                   // :327-331
+        if (init) Z = 1.0;  // initAssignment uses P_ij as it is (:226)
+        if (chain && tiny) {  // exact rule for denormal-range cells: in play iff p / Z >= double_underflow
+            kf = nnz;
+            kl = -1;
+            for (int k = 0; k < nnz; k++) {
+                const double p = val[32 * k] * theta[col[32 * k]];
+                if (p != 0.0 && p / Z >= DBL_MIN) {
+                    if (kf == nnz) kf = k;
+                    kl = k;
                 }
             }
-        } else {
-            // :336-365 (INIT: :222-251)
-            double divider = 1.0;
-            int rem = n, last = -1;
-            for (int k = 0; k < nnz && rem > 0; k++) {
-                const int c = col[32 * k];
-                const double np = INIT ? val[32 * k] : (val[32 * k] * theta[c]) / Z;
-                if (np >= DBL_MIN) {
-                    const Site site = make_site(key, phase, iteration, id, (uint32_t)c);
+        }
+        if (kl < 0) continue;  // reference: assert(normalisation_constant >= double_underflow) (:284)
+        const int c_last = col[32 * kl];
+
+        // Whatever the cells before the last one in play do not take ends up in that last cell: in the chain the
+        // reference asserts that nothing is left after it (:253, :363), and in the CDF walk its cumulative sum is 1 up
+        // to rounding while every uniform is <= 1 - 2^-32.  So the last cell never needs a draw of its own.
+        int rem = n;
+        if (kf < kl) {
+            const uint32_t slot = info >> kRowSlotShift;
+            const uint64_t key = skey[slot];
+            const int col0 = (int)slot * lanes_per_slot;  // lane of the slot's candidate 0 (0 in a wide unit)
+            if (!chain) {
+                // :289-334.  The reference sorts the n uniforms and walks the CDF once; which column a uniform lands
+                // in does not depend on the visiting order, so they are taken four at a time (one Philox block).
+                const Site site = make_site(key, phase, iteration, id, 0);
+                for (int j = 0; 4 * j < n; j++) {
+                    const u32x4 w = site.block((uint32_t)j);
+                    const int left = n - 4 * j < 4 ? n - 4 * j : 4;
+                    double cum = 0.0;
+                    int below_prev = 0;
+                    for (int k = kf; k < kl; k++) {
+                        const int c = col[32 * k];
+                        const double p = val[32 * k] * theta[c];
+                        if (p == 0.0) continue;
+                        cum += p / Z;                                                 // :304
+                        // u = w * 2^-32 < cum  <=>  w < ceil(cum * 2^32)              // :306
+                        const unsigned long long thr = __double2ull_ru(cum * 4294967296.0);
+                        int below = (int)((unsigned long long)w.x < thr);
+                        below += (left > 1) & (int)((unsigned long long)w.y < thr);
+                        below += (left > 2) & (int)((unsigned long long)w.z < thr);
+                        below += (left > 3) & (int)((unsigned long long)w.w < thr);
+                        const int got = below - below_prev;
+                        if (got > 0) atomicAdd(&counts[c], got);                      // :323-324
+                        rem -= got;
+                        below_prev = below;
+                        if (below >= left) break;                                     // :327-331
+                    }
+                }
+            } else {
+                // :336-365 (INIT: :222-251)
+                // Every lane first skips ahead to ITS next cell in play and only then do the lanes meet again for the
+                // binomial, so a warp runs the (expensive, divergent) draw once per in-play cell of its deepest row
+                // instead of once per stored cell.
+                double divider = 1.0;
+                int k = kf;
+                while (rem > 0) {
+                    int c = 0;
+                    double np = 0.0;
+                    for (; k < kl; k++) {
+                        c = col[32 * k];
+                        const double p = val[32 * k] * theta[c];
+                        if (p == 0.0) continue;
+                        np = p / Z;
+                        if (np >= DBL_MIN) break;
+                        divider -= np;  // below double_underflow: no draw, but the divider still shrinks (:360)
+                    }
+                    if (k >= kl) break;
+                    const Site site = make_site(key, phase, iteration, id, (uint32_t)(c - col0));
                     const int got = binomial_variate(site, rem, np / divider);
                     if (got > 0) atomicAdd(&counts[c], got);
                     rem -= got;
-                    last = c;
+                    divider -= np;
+                    k++;
                 }
-                divider -= np;
             }
-            // the reference asserts nothing is left (:253, :363); keep the total conserved instead of aborting
-            if (rem > 0 && last >= 0) atomicAdd(&counts[last], rem);
         }
+        if (rem > 0) atomicAdd(&counts[c_last], rem);
     }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// E-step pieces (warp 0 only; all 32 lanes execute the scalar parts redundantly, so nothing is broadcast)
-// ------------------------------------------------------------------------------------------------------------------
-// FixedBinomialFixedGammaSimplexSizeGenerator::sampleSimplexSize (simplexSizeGenerator.cpp:214-224)
+// FixedBinomialFixedGammaSimplexSizeGenerator::sampleSimplexSize (simplexSizeGenerator.cpp:214-224): one uniform_01,
+// std::upper_bound on the CDF row of |S+|, + |S+|
 __device__ __forceinline__ int sample_simplex(const double *tab_val, const int32_t *tab_row, int n_plus, uint64_t key, uint32_t iteration) {
     const double u = u01(make_site(key, PH_SIMPLEX, iteration, 0, 0).block(0).x);
     int lo = tab_row[n_plus - 1];
     const int first = lo;
     int hi = tab_row[n_plus];
-    while (lo < hi) {  // std::upper_bound: first entry > u
+    while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (u < tab_val[mid]) hi = mid; else lo = mid + 1;
     }
     return (lo - first) + n_plus;
 }
 
-struct EState {
+// ------------------------------------------------------------------------------------------------------------------
+// E-step of a bundle (warp 0): lane = slot * Tpad + t.  Per-lane constants and the posterior accumulators live in
+// registers for the whole chain.
+// ------------------------------------------------------------------------------------------------------------------
+struct BundleLane {
+    // constants
+    uint64_t key;        // Philox key of the lane's slot
+    double gamma, den;   // den = efflen * N_total (valueContainer.cpp:235)
+    const int32_t *trow; // CDF row offsets of the slot
+    uint32_t segmask;    // lanes of the slot
+    uint32_t validmask;  // lanes of the slot that hold a candidate
+    int32_t Tg, t, base, N_f;
+    int32_t half;        // Tpad / 2: first xor distance of the segmented sum
+    bool valid;          // lane holds a candidate
+    // state: GibbsOutput accumulators (gibbsOutput.cpp:40-75)
+    int32_t occ;
+    double mean, m2;
+};
+
+// ExpressionGenerator::generateExpression (expressionGenerator.cpp:77-132) for every slot of the bundle at once,
+// + getFPKM / addSample when sampling.  Returns the simplex size used by the lane's slot.
+__device__ __forceinline__ int bundle_e_step(BundleLane &L, double *theta, int32_t *counts, const double *tab_val, uint32_t iteration,
+                                             bool sampling) {
+    const int lane = threadIdx.x & 31;
+    const int cnt = counts[lane];
+    const uint32_t pm = __ballot_sync(0xffffffffu, L.valid && cnt > 0) & L.segmask;
+    const int n_plus = __popc(pm);
+    int b = 0, n_pick = 0;
+    if (L.Tg > 0) {
+        b = sample_simplex(tab_val, L.trow, n_plus, L.key, iteration);
+        n_pick = b - n_plus;
+    }
+    // expressionGenerator.cpp:104-127: one uniform_int over the current ascending null list per extra slot
+    uint32_t sel = 0u;
+    const int max_pick = __reduce_max_sync(0xffffffffu, n_pick);
+    for (int k = 0; k < max_pick; k++) {
+        if (k < n_pick) {
+            const uint32_t s = uniform_int(make_site(L.key, PH_NULLPICK, iteration, (uint32_t)k, 0), (uint32_t)(L.Tg - n_plus - k));
+            const uint32_t nullm = L.validmask & ~(pm | sel);
+            sel |= 1u << __fns(nullm, 0, (int)s + 1);
+        }
+    }
+    // :85-98 and :113: Gamma(count + gamma) on S+, Gamma(gamma) on the picked nulls
+    const bool active = ((pm | sel) >> lane) & 1u;
+    double g = 0.0;
+    if (active) g = gamma_variate(make_site(L.key, PH_GAMMA, iteration, (uint32_t)L.t, 0), (double)cnt + L.gamma);
+    double norm = g;
+    for (int o = L.half; o > 0; o >>= 1) norm += __shfl_xor_sync(0xffffffffu, norm, o);
+    const double th = active ? g / norm : 0.0;  // valueContainer.cpp:216-224
+    theta[lane] = th;
+    counts[lane] = L.base;  // fresh CountValueContainer for the next assignment (:266) + folded rows
+    if (sampling && active) {
+        const double fpkm = (th * (double)L.N_f * 1e9) / L.den;  // valueContainer.cpp:235
+        const int o = ++L.occ;                                   // gibbsOutput.cpp:60
+        if (o == 1) {
+            L.mean = fpkm;
+        } else {
+            const double delta = fpkm - L.mean;
+            L.mean += delta / o;
+            L.m2 += delta * (fpkm - L.mean);
+        }
+    }
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// E-step of a wide unit (warp 0, 32 candidates per chunk, state in shared memory)
+// ------------------------------------------------------------------------------------------------------------------
+struct WideState {
     double *theta, *den, *mean, *m2;
     int32_t *counts, *occ;
     const int32_t *base;
@@ -136,9 +262,7 @@ struct EState {
     double gamma;
 };
 
-// ExpressionGenerator::generateExpression (expressionGenerator.cpp:77-132) + getFPKM / addSample when sampling.
-// Returns the simplex size used (for the trace).
-__device__ __forceinline__ int e_step(const EState &E, uint64_t key, uint32_t iteration, bool sampling, double *tr_theta) {
+__device__ __forceinline__ int wide_e_step(const WideState &E, uint64_t key, uint32_t iteration, bool sampling, double *tr_theta) {
     const int lane = threadIdx.x & 31;
     const int T = E.T, nch = E.nch;
     int n_plus = 0;
@@ -150,8 +274,6 @@ __device__ __forceinline__ int e_step(const EState &E, uint64_t key, uint32_t it
     }
     __syncwarp();
     const int b = sample_simplex(E.tab_val, E.tab_row, n_plus, key, iteration);
-
-    // expressionGenerator.cpp:104-127: one uniform_int over the current ascending null list per extra slot
     const int n_null = T - n_plus;
     for (int k = 0; k < b - n_plus; k++) {
         uint32_t rem = uniform_int(make_site(key, PH_NULLPICK, iteration, (uint32_t)k, 0), (uint32_t)(n_null - k));
@@ -167,8 +289,6 @@ __device__ __forceinline__ int e_step(const EState &E, uint64_t key, uint32_t it
         if (lane == 0 && pick >= 0) E.mask[nch + (pick >> 5)] |= 1u << (pick & 31);
         __syncwarp();
     }
-
-    // :85-98 and :113: Gamma(count + gamma) on S+, Gamma(gamma) on the picked nulls
     double part = 0.0;
     for (int c = 0; c < nch; c++) {
         const int t = c * 32 + lane;
@@ -183,13 +303,13 @@ __device__ __forceinline__ int e_step(const EState &E, uint64_t key, uint32_t it
         const int t = c * 32 + lane;
         if (t < T) {
             const double g = E.theta[t];
-            const double th = g != 0.0 ? g / norm : 0.0;  // valueContainer.cpp:216-224
+            const double th = g != 0.0 ? g / norm : 0.0;
             E.theta[t] = th;
-            E.counts[t] = E.base[t];  // fresh CountValueContainer for the next assignment (:266) + folded rows
+            E.counts[t] = E.base[t];
             if (tr_theta) tr_theta[t] = th;
             if (sampling && g != 0.0) {
-                const double fpkm = (th * (double)E.N_f * 1e9) / E.den[t];  // valueContainer.cpp:235
-                const int o = ++E.occ[t];                                    // gibbsOutput.cpp:60
+                const double fpkm = (th * (double)E.N_f * 1e9) / E.den[t];
+                const int o = ++E.occ[t];
                 if (o == 1) {
                     E.mean[t] = fpkm;
                 } else {
@@ -209,17 +329,135 @@ __device__ __forceinline__ void block_copy(T *dst, const T *src, int n) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
+template <bool MAT_SMEM>
+__device__ __forceinline__ MatView stage_matrix(const KernelArgs &A, const UnitDev &U, const SmemLayout &lay, unsigned char *smem) {
+    MatView M;
+    M.n_slabs = U.n_slabs;
+    if (MAT_SMEM) {
+        double *sv = (double *)(smem + lay.val);
+        uint16_t *sc = (uint16_t *)(smem + lay.col);
+        int32_t *ss = (int32_t *)(smem + lay.slab);
+        int32_t *rn = (int32_t *)(smem + lay.row_n);
+        int32_t *rz = (int32_t *)(smem + lay.row_nnz);
+        uint32_t *ri = (uint32_t *)(smem + lay.row_info);
+        block_copy(sv, A.val + U.cell_off, U.n_cells);
+        block_copy(sc, A.col + U.cell_off, U.n_cells);
+        block_copy(ss, A.slab_cell_off + U.slab_off, U.n_slabs + 1);
+        block_copy(rn, A.row_n + U.row_off, U.n_slabs * 32);
+        block_copy(rz, A.row_nnz + U.row_off, U.n_slabs * 32);
+        block_copy(ri, A.row_info + U.row_off, U.n_slabs * 32);
+        M.val = sv; M.col = sc; M.slab = ss; M.row_n = rn; M.row_nnz = rz; M.row_info = ri;
+    } else {
+        M.val = A.val + U.cell_off;
+        M.col = A.col + U.cell_off;
+        M.slab = A.slab_cell_off + U.slab_off;
+        M.row_n = A.row_n + U.row_off;
+        M.row_nnz = A.row_nnz + U.row_off;
+        M.row_info = A.row_info + U.row_off;
+    }
+    return M;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 template <bool MAT_SMEM>
-__global__ void __launch_bounds__(kMaxBlock) gibbs_chain_kernel(const __grid_constant__ KernelArgs A, const int64_t job_base) {
+__global__ void __launch_bounds__(kMaxBlock, BAYES_MIN_BLOCKS) gibbs_bundle_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int64_t job_idx = job_base + blockIdx.x;
-    const JobDev job = A.jobs[job_idx];
-    const LocusDev L = A.loci[job.locus];
-    const int T = L.T;
-    const SmemLayout lay = smem_layout(T, L.n_slabs, L.n_cells, L.tab_len, L.tab_smem != 0, MAT_SMEM);
+    const int64_t ui = unit_base + blockIdx.x;
+    const UnitDev &U = A.units[ui];
+    const int n_slots = U.n_slots, Tpad = U.Tpad;
+    const SmemLayout lay = unit_layout(false, 32, n_slots, Tpad, U.n_slabs, U.n_cells, U.tab_len, U.tab_smem != 0, MAT_SMEM);
+    double *theta = (double *)(smem + lay.theta);
+    int32_t *counts = (int32_t *)(smem + lay.counts);
+    uint64_t *skey = (uint64_t *)(smem + lay.key);
+    const double *tab_val;
+    const int32_t *tab_row;
+    if (U.tab_smem) {
+        double *tv = (double *)(smem + lay.tab_val);
+        int32_t *tr = (int32_t *)(smem + lay.tab_row);
+        block_copy(tv, A.tab_val + U.tab_off, U.tab_len);
+        block_copy(tr, A.tab_row + U.tabrow_off, n_slots * (Tpad + 1));
+        tab_val = tv;
+        tab_row = tr;
+    } else {
+        tab_val = A.tab_val + U.tab_off;
+        tab_row = A.tab_row + U.tabrow_off;
+    }
+    const MatView M = stage_matrix<MAT_SMEM>(A, U, lay, smem);
+    if (threadIdx.x < (unsigned)n_slots) skey[threadIdx.x] = U.key[threadIdx.x];
 
-    EState E;
+    // lane constants of warp 0
+    const int lane = threadIdx.x & 31;
+    BundleLane L;
+    int g = 0;
+    {
+        int sh = 1;
+        while ((1 << sh) < Tpad) sh++;
+        g = lane >> sh;
+        L.t = lane & (Tpad - 1);
+        const bool slot_ok = g < n_slots;
+        L.Tg = slot_ok ? U.T[g] : 0;
+        L.valid = L.t < L.Tg;
+        L.key = slot_ok ? U.key[g] : 0ull;
+        L.gamma = slot_ok ? U.gamma[g] : 1.0;
+        L.N_f = slot_ok ? U.N_f[g] : 0;
+        L.den = A.efflen[U.lane_off + lane] * (double)(slot_ok ? U.N_total[g] : 1);
+        L.base = A.base_counts[U.lane_off + lane];
+        L.trow = tab_row + (slot_ok ? g : 0) * (Tpad + 1);
+        L.segmask = Tpad == 32 ? 0xffffffffu : (((1u << Tpad) - 1u) << (g * Tpad));
+        L.validmask = L.Tg == 32 ? 0xffffffffu : (((1u << L.Tg) - 1u) << (g * Tpad));
+        L.half = Tpad >> 1;
+        L.occ = 0;
+        L.mean = 0.0;
+        L.m2 = 0.0;
+    }
+    if (threadIdx.x < 32) {
+        theta[lane] = 1.0;  // initAssignment runs the A-step on P_ij itself
+        counts[lane] = L.base;
+    }
+    __syncthreads();
+
+    const bool tracing = A.trace_unit == ui;
+    const bool my_trace = tracing && threadIdx.x < 32 && g == A.trace_slot && L.valid;
+    const int total = U.burn + U.samples, burn = U.burn;
+
+    assign_rows(M, theta, counts, skey, Tpad, 0u, true);  // gibbsSampler.cpp:90
+    __syncthreads();
+    if (my_trace) A.tr_init[L.t] = counts[lane];
+
+    for (int it = 0; it < total; it++) {
+        if (threadIdx.x < 32) {
+            if (my_trace && it > 0 && it - 1 < A.trace_iters) A.tr_counts[(size_t)(it - 1) * L.Tg + L.t] = counts[lane];
+            const int b = bundle_e_step(L, theta, counts, tab_val, (uint32_t)it, it >= burn);
+            if (my_trace && it < A.trace_iters) {
+                A.tr_theta[(size_t)it * L.Tg + L.t] = theta[lane];
+                if (L.t == 0) A.tr_b[it] = b;
+            }
+        }
+        __syncthreads();
+        assign_rows(M, theta, counts, skey, Tpad, (uint32_t)it, false);
+        __syncthreads();
+    }
+    if (my_trace && total - 1 < A.trace_iters) A.tr_counts[(size_t)(total - 1) * L.Tg + L.t] = counts[lane];
+
+    if (threadIdx.x < 32 && L.valid) {
+        const int64_t o = U.out_off[g] + L.t;
+        A.out_occ[o] = L.occ;
+        A.out_mean[o] = L.mean;
+        A.out_m2[o] = L.m2;
+        A.out_counts[o] = counts[lane];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+template <bool MAT_SMEM>
+__global__ void __launch_bounds__(kMaxBlock, BAYES_MIN_BLOCKS) gibbs_wide_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int64_t ui = unit_base + blockIdx.x;
+    const UnitDev &U = A.units[ui];
+    const int T = U.T[0];
+    const SmemLayout lay = unit_layout(true, T, 1, U.Tpad, U.n_slabs, U.n_cells, U.tab_len, U.tab_smem != 0, MAT_SMEM);
+
+    WideState E;
     E.theta = (double *)(smem + lay.theta);
     E.den = (double *)(smem + lay.den);
     E.mean = (double *)(smem + lay.mean);
@@ -231,61 +469,41 @@ __global__ void __launch_bounds__(kMaxBlock) gibbs_chain_kernel(const __grid_con
     E.mask = (uint32_t *)(smem + lay.mask);
     E.T = T;
     E.nch = (T + 31) >> 5;
-    E.N_f = L.N_f;
-    E.gamma = L.gamma;
+    E.N_f = U.N_f[0];
+    E.gamma = U.gamma[0];
+    uint64_t *skey = (uint64_t *)(smem + lay.key);
+    const uint64_t key = U.key[0];
+    if (threadIdx.x == 0) skey[0] = key;
 
-    // stage the locus
+    const double n_total = (double)U.N_total[0];
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
-        const int32_t bc = A.base_counts[L.t_off + t];
+        const int32_t bc = A.base_counts[U.lane_off + t];
         base[t] = bc;
         E.counts[t] = bc;
         E.occ[t] = 0;
         E.mean[t] = 0.0;
         E.m2[t] = 0.0;
-        E.theta[t] = 0.0;
-        E.den[t] = A.efflen[L.t_off + t] * (double)L.N_total;  // valueContainer.cpp:235 denominator
+        E.theta[t] = 1.0;  // initAssignment runs the A-step on P_ij itself
+        E.den[t] = A.efflen[U.lane_off + t] * n_total;  // valueContainer.cpp:235 denominator
     }
-    if (L.tab_smem) {
+    if (U.tab_smem) {
         double *tv = (double *)(smem + lay.tab_val);
         int32_t *tr = (int32_t *)(smem + lay.tab_row);
-        block_copy(tv, A.tab_val + L.tab_off, L.tab_len);
-        block_copy(tr, A.tab_row + L.tabrow_off, T + 1);
+        block_copy(tv, A.tab_val + U.tab_off, U.tab_len);
+        block_copy(tr, A.tab_row + U.tabrow_off, T + 1);
         E.tab_val = tv;
         E.tab_row = tr;
     } else {
-        E.tab_val = A.tab_val + L.tab_off;
-        E.tab_row = A.tab_row + L.tabrow_off;
+        E.tab_val = A.tab_val + U.tab_off;
+        E.tab_row = A.tab_row + U.tabrow_off;
     }
-    MatView M;
-    M.n_slabs = L.n_slabs;
-    if (MAT_SMEM) {
-        double *sv = (double *)(smem + lay.val);
-        uint16_t *sc = (uint16_t *)(smem + lay.col);
-        int32_t *ss = (int32_t *)(smem + lay.slab);
-        int32_t *rn = (int32_t *)(smem + lay.row_n);
-        int32_t *rz = (int32_t *)(smem + lay.row_nnz);
-        int32_t *ri = (int32_t *)(smem + lay.row_id);
-        block_copy(sv, A.val + L.cell_off, L.n_cells);
-        block_copy(sc, A.col + L.cell_off, L.n_cells);
-        block_copy(ss, A.slab_cell_off + L.slab_off, L.n_slabs + 1);
-        block_copy(rn, A.row_n + L.row_off, L.n_slabs * 32);
-        block_copy(rz, A.row_nnz + L.row_off, L.n_slabs * 32);
-        block_copy(ri, A.row_id + L.row_off, L.n_slabs * 32);
-        M.val = sv; M.col = sc; M.slab = ss; M.row_n = rn; M.row_nnz = rz; M.row_id = ri;
-    } else {
-        M.val = A.val + L.cell_off;
-        M.col = A.col + L.cell_off;
-        M.slab = A.slab_cell_off + L.slab_off;
-        M.row_n = A.row_n + L.row_off;
-        M.row_nnz = A.row_nnz + L.row_off;
-        M.row_id = A.row_id + L.row_off;
-    }
+    const MatView M = stage_matrix<MAT_SMEM>(A, U, lay, smem);
     __syncthreads();
 
-    const bool tracing = A.trace_job == job_idx;
-    const int total = L.burn + L.samples;
+    const bool tracing = A.trace_unit == ui;
+    const int total = U.burn + U.samples, burn = U.burn;
 
-    assign_rows<true>(M, E.theta, E.counts, job.key, 0u);  // gibbsSampler.cpp:90
+    assign_rows(M, E.theta, E.counts, skey, 0, 0u, true);  // gibbsSampler.cpp:90
     __syncthreads();
     if (tracing)
         for (int t = threadIdx.x; t < T; t += blockDim.x) A.tr_init[t] = E.counts[t];
@@ -295,21 +513,22 @@ __global__ void __launch_bounds__(kMaxBlock) gibbs_chain_kernel(const __grid_con
             const bool tr = tracing && it < A.trace_iters;
             if (tracing && it > 0 && it - 1 < A.trace_iters)
                 for (int t = threadIdx.x; t < T; t += 32) A.tr_counts[(size_t)(it - 1) * T + t] = E.counts[t];
-            const int b = e_step(E, job.key, (uint32_t)it, it >= L.burn, tr ? A.tr_theta + (size_t)it * T : nullptr);
+            const int b = wide_e_step(E, key, (uint32_t)it, it >= burn, tr ? A.tr_theta + (size_t)it * T : nullptr);
             if (tr && threadIdx.x == 0) A.tr_b[it] = b;
         }
         __syncthreads();
-        assign_rows<false>(M, E.theta, E.counts, job.key, (uint32_t)it);
+        assign_rows(M, E.theta, E.counts, skey, 0, (uint32_t)it, false);
         __syncthreads();
     }
     if (tracing && total - 1 < A.trace_iters)
         for (int t = threadIdx.x; t < T; t += blockDim.x) A.tr_counts[(size_t)(total - 1) * T + t] = E.counts[t];
 
+    const int64_t o = U.out_off[0];
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
-        A.out_occ[job.out_off + t] = E.occ[t];
-        A.out_mean[job.out_off + t] = E.mean[t];
-        A.out_m2[job.out_off + t] = E.m2[t];
-        A.out_counts[job.out_off + t] = E.counts[t];
+        A.out_occ[o + t] = E.occ[t];
+        A.out_mean[o + t] = E.mean[t];
+        A.out_m2[o + t] = E.m2[t];
+        A.out_counts[o + t] = E.counts[t];
     }
 }
 
@@ -317,53 +536,67 @@ __global__ void __launch_bounds__(kMaxBlock) gibbs_chain_kernel(const __grid_con
 template <bool INIT>
 __global__ void step_assignment_kernel(const __grid_constant__ KernelArgs A, const double *theta_in, uint32_t iteration, int32_t *counts_out) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const LocusDev L = A.loci[0];
-    const JobDev job = A.jobs[0];
+    const UnitDev &U = A.units[0];
+    const int T = U.T[0];
     double *theta = (double *)smem;
-    int32_t *counts = (int32_t *)(theta + L.T);
-    for (int t = threadIdx.x; t < L.T; t += blockDim.x) {
-        theta[t] = INIT ? 0.0 : theta_in[t];
-        counts[t] = A.base_counts[L.t_off + t];
+    uint64_t *skey = (uint64_t *)(theta + T);
+    int32_t *counts = (int32_t *)(skey + 1);
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        theta[t] = INIT ? 1.0 : theta_in[t];
+        counts[t] = A.base_counts[U.lane_off + t];
     }
+    if (threadIdx.x == 0) skey[0] = U.key[0];
     MatView M;
-    M.n_slabs = L.n_slabs;
-    M.val = A.val + L.cell_off;
-    M.col = A.col + L.cell_off;
-    M.slab = A.slab_cell_off + L.slab_off;
-    M.row_n = A.row_n + L.row_off;
-    M.row_nnz = A.row_nnz + L.row_off;
-    M.row_id = A.row_id + L.row_off;
+    M.n_slabs = U.n_slabs;
+    M.val = A.val + U.cell_off;
+    M.col = A.col + U.cell_off;
+    M.slab = A.slab_cell_off + U.slab_off;
+    M.row_n = A.row_n + U.row_off;
+    M.row_nnz = A.row_nnz + U.row_off;
+    M.row_info = A.row_info + U.row_off;
     __syncthreads();
-    assign_rows<INIT>(M, theta, counts, job.key, iteration);
+    assign_rows(M, theta, counts, skey, 0, iteration, INIT);
     __syncthreads();
-    for (int t = threadIdx.x; t < L.T; t += blockDim.x) counts_out[t] = counts[t];
+    for (int t = threadIdx.x; t < T; t += blockDim.x) counts_out[t] = counts[t];
 }
 
+// generateExpression with a GIVEN simplex size b: a one-row CDF table ((b - |S+|) zeros, then 2.0) makes the upper bound
+// of any uniform land on b.  T <= 32 runs the bundle E-step (one slot), larger T the wide E-step.
 __global__ void step_expression_kernel(int T, const int32_t *counts_in, int b, double gamma, uint64_t key, uint32_t iteration, double *theta_out) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int nch = (T + 31) >> 5;
+    const int nT = T <= 32 ? 32 : T;
+    const int nch = (nT + 31) >> 5;
     double *theta = (double *)smem;
-    double *tab = theta + T;      // T + 2 entries: a one-row CDF table that forces the simplex size to b
+    double *tab = theta + nT;  // T + 2 entries
     int32_t *counts = (int32_t *)(tab + T + 2);
-    int32_t *base = counts + T;
-    int32_t *tab_row = base + T;  // T + 1
+    int32_t *base = counts + nT;
+    int32_t *tab_row = base + nT;  // T + 1
     uint32_t *mask = (uint32_t *)(tab_row + T + 1);
     const int lane = threadIdx.x;
-    for (int t = lane; t < T; t += 32) { counts[t] = counts_in[t]; base[t] = 0; theta[t] = 0.0; }
+    for (int t = lane; t < nT; t += 32) { counts[t] = t < T ? counts_in[t] : 0; base[t] = 0; theta[t] = 0.0; }
     __syncwarp();
     int n_plus = 0;
     for (int t = 0; t < T; t++) n_plus += counts[t] > 0;
-    // row |S+|-1 = (b - |S+|) zeros, then 2.0: the upper bound of any u in [0,1) is at offset b - |S+|
     const int extra = b - n_plus;
     for (int t = lane; t <= T; t += 32) tab_row[t] = t >= n_plus ? extra + 1 : 0;
     for (int t = lane; t <= extra; t += 32) tab[t] = t == extra ? 2.0 : 0.0;
     __syncwarp();
-    EState E;
-    E.theta = theta; E.den = theta; E.mean = theta; E.m2 = theta;
-    E.counts = counts; E.occ = counts; E.base = base; E.mask = mask;
-    E.tab_val = tab; E.tab_row = tab_row;
-    E.T = T; E.nch = nch; E.N_f = 0; E.gamma = gamma;
-    e_step(E, key, iteration, false, theta_out);
+    if (T <= 32) {
+        BundleLane L;
+        L.key = key; L.gamma = gamma; L.den = 1.0; L.trow = tab_row; L.segmask = 0xffffffffu;
+        L.validmask = T == 32 ? 0xffffffffu : (1u << T) - 1u;
+        L.Tg = T; L.t = lane; L.base = 0; L.N_f = 0; L.half = 16; L.valid = lane < T; L.occ = 0; L.mean = 0.0; L.m2 = 0.0;
+        bundle_e_step(L, theta, counts, tab, iteration, false);
+        __syncwarp();
+        if (lane < T) theta_out[lane] = theta[lane];
+    } else {
+        WideState E;
+        E.theta = theta; E.den = theta; E.mean = theta; E.m2 = theta;
+        E.counts = counts; E.occ = counts; E.base = base; E.mask = mask;
+        E.tab_val = tab; E.tab_row = tab_row;
+        E.T = T; E.nch = nch; E.N_f = 0; E.gamma = gamma;
+        wide_e_step(E, key, iteration, false, theta_out);
+    }
 }
 
 __global__ void step_variates_kernel(int kind, double a, double p, uint64_t key, int n, double *out) {
@@ -383,21 +616,28 @@ static int check(cudaError_t e, const char *what) {
 }
 
 int configure_kernels() {
-    int rc = check(cudaFuncSetAttribute(gibbs_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "cudaFuncSetAttribute");
-    if (rc) return rc;
-    rc = check(cudaFuncSetAttribute(gibbs_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "cudaFuncSetAttribute");
-    if (rc) return rc;
-    rc = check(cudaFuncSetAttribute(step_assignment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "cudaFuncSetAttribute");
-    if (rc) return rc;
+    int rc;
+    if ((rc = check(cudaFuncSetAttribute(gibbs_bundle_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "cudaFuncSetAttribute"))) return rc;
+    if ((rc = check(cudaFuncSetAttribute(gibbs_bundle_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "cudaFuncSetAttribute"))) return rc;
+    if ((rc = check(cudaFuncSetAttribute(gibbs_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "cudaFuncSetAttribute"))) return rc;
+    if ((rc = check(cudaFuncSetAttribute(gibbs_wide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "cudaFuncSetAttribute"))) return rc;
+    if ((rc = check(cudaFuncSetAttribute(step_assignment_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "cudaFuncSetAttribute"))) return rc;
     return check(cudaFuncSetAttribute(step_assignment_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "cudaFuncSetAttribute");
 }
 
-int launch_gibbs(const KernelArgs &args, int64_t job_base, int64_t n_jobs, int block, bool mat_smem, size_t smem_bytes, void *stream) {
-    if (n_jobs <= 0) return BAYES_OK;
+int launch_units(const KernelArgs &args, int64_t unit_base, int64_t n_units, int block, bool wide, bool mat_smem, size_t smem_bytes,
+                 void *stream) {
+    if (n_units <= 0) return BAYES_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    if (mat_smem) gibbs_chain_kernel<true><<<(unsigned)n_jobs, block, smem_bytes, st>>>(args, job_base);
-    else gibbs_chain_kernel<false><<<(unsigned)n_jobs, block, smem_bytes, st>>>(args, job_base);
-    return check(cudaGetLastError(), "gibbs_chain_kernel launch");
+    const unsigned grid = (unsigned)n_units;
+    if (wide) {
+        if (mat_smem) gibbs_wide_kernel<true><<<grid, block, smem_bytes, st>>>(args, unit_base);
+        else gibbs_wide_kernel<false><<<grid, block, smem_bytes, st>>>(args, unit_base);
+    } else {
+        if (mat_smem) gibbs_bundle_kernel<true><<<grid, block, smem_bytes, st>>>(args, unit_base);
+        else gibbs_bundle_kernel<false><<<grid, block, smem_bytes, st>>>(args, unit_base);
+    }
+    return check(cudaGetLastError(), "gibbs kernel launch");
 }
 
 int launch_step_assignment(const KernelArgs &args, bool init, const double *d_theta, uint32_t iteration, int32_t *d_counts_out,
@@ -410,7 +650,8 @@ int launch_step_assignment(const KernelArgs &args, bool init, const double *d_th
 
 int launch_step_expression(int T, const int32_t *d_counts, int b, double gamma, uint64_t key, uint32_t iteration, double *d_theta,
                            void *stream) {
-    const size_t smem = 8 * (2 * (size_t)T + 2) + 4 * (3 * (size_t)T + 1) + 4 * (2 * (((size_t)T + 31) / 32) + 2) + 16;
+    const size_t nT = T <= 32 ? 32 : (size_t)T;
+    const size_t smem = 8 * (nT + (size_t)T + 2) + 4 * (2 * nT + (size_t)T + 1) + 4 * (2 * ((nT + 31) / 32) + 2) + 16;
     step_expression_kernel<<<1, 32, smem, (cudaStream_t)stream>>>(T, d_counts, b, gamma, key, iteration, d_theta);
     return check(cudaGetLastError(), "step_expression_kernel launch");
 }

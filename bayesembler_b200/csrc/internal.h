@@ -1,4 +1,11 @@
 // Internal structures shared by the host packer, the C ABI and the CUDA kernels.
+//
+// Terminology
+//   slot  one chain of one locus: the unit of the reference's runSampler call (gibbsSampler.cpp:55-148)
+//   unit  what ONE thread block runs: either one slot with any number of candidates ("wide" unit), or up to 16 slots
+//         whose candidates fit side by side in the 32 lanes of a warp ("bundle"): slot g owns lanes
+//         [g * Tpad, (g + 1) * Tpad), Tpad = power of two >= T.  Rows of all slots of a unit are pooled and sorted
+//         together so that the 32 rows a warp walks are alike, whichever locus they came from.
 #pragma once
 
 #include <stdint.h>
@@ -10,51 +17,51 @@
 
 namespace bayes {
 
-constexpr int kMaxT = 4096;          // per-transcript state lives in shared memory (44 B per candidate)
-constexpr int kMaxBlock = 256;       // threads per (locus, chain) block: one thread per packed row up to this many
-constexpr int kSmallCount = 20;      // assignmentGenerator.cpp:289: rows with fewer fragments draw uniforms
-constexpr int kTableSmemEntries = 1024;   // simplex CDF tables up to this many entries are staged in shared memory
-constexpr int kMatrixSmemBytes = 96 * 1024;  // loci whose packed matrix exceeds this stream it from L2/HBM
+constexpr int kMaxT = 4096;             // candidates per locus (per-candidate state lives in shared memory)
+constexpr int kMaxBlock = 256;          // threads per unit
+constexpr int kMaxSlots = 16;           // slots per bundle (T = 2 -> Tpad = 2 -> 16 slots)
+constexpr int kSmallCount = 20;         // assignmentGenerator.cpp:289: rows with fewer fragments draw uniforms
+constexpr int kTableSmemEntries = 2048; // simplex CDF tables up to this many entries are staged in shared memory
+constexpr int kMatrixSmemBytes = 96 * 1024;  // units whose packed matrix exceeds this stream it from L2/HBM
+constexpr uint32_t kRowSlotShift = 27;  // row_info = slot << 27 | original row index
 
-// Device-side descriptor of one packed locus.  All *_off fields index the context-wide concatenated arrays.
-struct LocusDev {
-    int32_t T;          // candidates
-    int32_t R;          // packed rows (rows with >= 2 cells; single-cell rows are folded into base counts)
-    int32_t n_slabs;    // ceil(R / 32) slabs of 32 rows, stored column-major inside a slab (SELL-32)
-    int32_t N_f;        // fragments in the locus (sum of all row counts, folded rows included)
-    int32_t N_total;    // (int) total_num_fragments
+// Device-side descriptor of one unit.  All *_off fields index the context-wide concatenated arrays.
+struct UnitDev {
+    int32_t n_slots;    // 1 for a wide unit
+    int32_t Tpad;       // lanes per slot (bundle) or T (wide unit)
+    int32_t wide;       // 1: wide unit (gibbs_wide_kernel), 0: bundle (gibbs_bundle_kernel)
+    int32_t n_slabs;    // ceil(pooled rows / 32) slabs of 32 rows, column-major inside a slab (SELL-32)
+    int32_t n_cells;    // padded cells = 32 * sum of slab widths
     int32_t burn;
     int32_t samples;
-    int32_t tab_len;    // entries in the simplex CDF table
-    int32_t n_cells;    // padded cells = 32 * sum of slab widths
+    int32_t tab_len;    // entries of all simplex CDF tables of the unit
     int32_t mat_smem;   // 1: matrix staged in shared memory
-    int32_t tab_smem;   // 1: CDF table staged in shared memory
-    int32_t smem_bytes; // dynamic shared memory this locus needs
-    double gamma;
+    int32_t tab_smem;   // 1: CDF tables staged in shared memory
+    int32_t smem_bytes; // dynamic shared memory this unit needs
+    int32_t block;      // threads
     int64_t slab_off;   // -> slab_cell_off[n_slabs + 1] (cell offsets relative to cell_off)
     int64_t cell_off;   // -> val / col
-    int64_t row_off;    // -> row_n / row_nnz / row_id   (n_slabs * 32 entries, padded rows have n = nnz = 0)
-    int64_t t_off;      // -> efflen / base_counts
-    int64_t tab_off;    // -> tab_val
-    int64_t tabrow_off; // -> tab_row[T + 1]
-};
-
-struct JobDev {
-    int32_t locus;
-    int32_t chain;
-    uint64_t key;       // Philox key of the chain
-    int64_t out_off;    // -> out_occ / out_mean / out_m2 / out_counts (T entries each)
+    int64_t row_off;    // -> row_n / row_nnz / row_info (n_slabs * 32 entries, padded rows have n = nnz = 0)
+    int64_t lane_off;   // -> efflen / base_counts: 32 entries (bundle, by lane) or T entries (wide)
+    int64_t tab_off;    // -> tab_val (tables of the slots back to back)
+    int64_t tabrow_off; // -> tab_row: slot g at g * (Tpad + 1), T + 1 offsets relative to the unit's tab_off
+    // per slot
+    int32_t T[kMaxSlots];
+    int32_t N_f[kMaxSlots];      // fragments of the locus (folded rows included)
+    int32_t N_total[kMaxSlots];  // (int) total_num_fragments
+    double gamma[kMaxSlots];
+    uint64_t key[kMaxSlots];     // Philox key of the chain
+    int64_t out_off[kMaxSlots];  // -> out_occ / out_mean / out_m2 / out_counts (T entries)
 };
 
 struct KernelArgs {
-    const LocusDev *loci;
-    const JobDev *jobs;
+    const UnitDev *units;
     const double *val;
     const uint16_t *col;
     const int32_t *slab_cell_off;
     const int32_t *row_n;
     const int32_t *row_nnz;
-    const int32_t *row_id;
+    const uint32_t *row_info;
     const double *efflen;
     const int32_t *base_counts;
     const double *tab_val;
@@ -63,8 +70,9 @@ struct KernelArgs {
     double *out_mean;
     double *out_m2;
     int32_t *out_counts;
-    // replay trace of one job (trace_job < 0: off)
-    int64_t trace_job;
+    // replay trace of one slot (trace_unit < 0: off)
+    int64_t trace_unit;
+    int32_t trace_slot;
     int32_t trace_iters;
     double *tr_theta;
     int32_t *tr_counts;
@@ -72,33 +80,49 @@ struct KernelArgs {
     int32_t *tr_init;
 };
 
-// Host-side result of packing one locus.
-struct PackedLocus {
-    LocusDev d;
-    std::vector<double> val;
-    std::vector<uint16_t> col;
-    std::vector<int32_t> slab_cell_off, row_n, row_nnz, row_id, base_counts, tab_row;
-    std::vector<double> efflen, tab_val;
-    double pi = 0;
-    int32_t cover = 0;
-    int32_t folded = 0;
-    int32_t n_chains = 1;
+// Host-side result of preparing one locus (everything that does not depend on which unit it lands in).
+struct PreLocus {
+    int32_t T = 0, n_frag = 0, N_total = 0, burn = 0, samples = 0, n_chains = 1, cover = 0, folded = 0;
+    double gamma = 1, pi = 0;
     uint64_t seed = 0;
+    std::vector<double> efflen, tab_val;
+    std::vector<int32_t> base_counts, tab_row;
+    // multi-cell rows in processing order (binomial-chain rows first, wider first, larger counts first)
+    std::vector<int32_t> row_id, row_n, row_ptr;  // row_ptr: rows + 1
+    std::vector<int32_t> cell_col;
+    std::vector<double> cell_val;
+    double cost = 0;  // per chain
+};
+
+struct SlotRef {
+    const PreLocus *locus;
+    int32_t chain;
+    int64_t out_off;
+};
+
+// Host-side packed unit.
+struct PackedUnit {
+    UnitDev d;
+    std::vector<double> val, efflen, tab_val;
+    std::vector<uint16_t> col;
+    std::vector<int32_t> slab_cell_off, row_n, row_nnz, base_counts, tab_row;
+    std::vector<uint32_t> row_info;
     double cost = 0;
-    int32_t block = 32;  // threads per block chosen for this locus
 };
 
 // pack.cpp
-int pack_locus(const bayes_locus_desc &in, PackedLocus *out, std::string *err);
 int validate_locus(const bayes_locus_desc &in, std::string *err);
-size_t locus_smem_bytes(const LocusDev &d);
+int prepare_locus(const bayes_locus_desc &in, PreLocus *out, std::string *err);
+int slot_lanes(int T);  // Tpad of a bundle slot (power of two >= T), 0 when T > 32
+void pack_unit(const std::vector<SlotRef> &slots, bool wide, PackedUnit *out);
 
 // host_steps.cpp
 int min_read_cover(const bayes_locus_desc &in, uint64_t key, int32_t *in_cover);
 void simplex_table(double pi, double gamma, int T, int num_fragments, std::vector<int32_t> *row_off, std::vector<double> *table);
 
 // gibbs_kernel.cu
-int launch_gibbs(const KernelArgs &args, int64_t job_base, int64_t n_jobs, int block, bool mat_smem, size_t smem_bytes, void *stream);
+int launch_units(const KernelArgs &args, int64_t unit_base, int64_t n_units, int block, bool wide, bool mat_smem, size_t smem_bytes,
+                 void *stream);
 int launch_step_assignment(const KernelArgs &args, bool init, const double *d_theta, uint32_t iteration, int32_t *d_counts_out,
                            size_t smem_bytes, void *stream);
 int launch_step_expression(int T, const int32_t *d_counts, int b, double gamma, uint64_t key, uint32_t iteration, double *d_theta,

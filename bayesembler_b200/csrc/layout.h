@@ -1,4 +1,4 @@
-// Shared-memory carve-up of one (locus, chain) thread block; used by the host (to size the launch) and by the kernel.
+// Shared-memory carve-up of one unit's thread block; used by the host (to size the launch) and by the kernels.
 #pragma once
 
 #include <stdint.h>
@@ -13,31 +13,36 @@ namespace bayes {
 
 struct SmemLayout {
     // byte offsets from the start of dynamic shared memory; 8-byte members first
-    uint32_t theta, den, mean, m2, tab_val, val;        // double
-    uint32_t counts, base, occ, tab_row, mask, slab, row_n, row_nnz, row_id;  // int32
-    uint32_t col;                                       // uint16
+    uint32_t theta, den, mean, m2, tab_val, val, key;                      // double / uint64
+    uint32_t counts, base, occ, tab_row, mask, slab, row_n, row_nnz, row_info;  // int32
+    uint32_t col;                                                          // uint16
     uint32_t total;
 };
 
-BAYES_LAYOUT_HD SmemLayout smem_layout(int T, int n_slabs, int n_cells, int tab_len, bool tab_smem, bool mat_smem) {
+// nT: per-candidate entries (32 for a bundle, T for a wide unit); wide units also keep den / mean / m2 / base / occ and
+// the S+ / picked masks in shared memory, a bundle keeps them in the registers of warp 0.
+BAYES_LAYOUT_HD SmemLayout unit_layout(bool wide, int nT, int n_slots, int Tpad, int n_slabs, int n_cells, int tab_len, bool tab_smem,
+                                       bool mat_smem) {
     SmemLayout L;
-    const uint32_t uT = (uint32_t)T, Rp = (uint32_t)n_slabs * 32u, nch = (uT + 31u) / 32u;
+    const uint32_t uT = (uint32_t)nT, Rp = (uint32_t)n_slabs * 32u, nch = (uT + 31u) / 32u;
+    const uint32_t n_tabrow = (uint32_t)n_slots * ((uint32_t)Tpad + 1u);
     uint32_t o = 0;
     L.theta = o; o += 8u * uT;
-    L.den = o; o += 8u * uT;
-    L.mean = o; o += 8u * uT;
-    L.m2 = o; o += 8u * uT;
+    L.den = o; o += wide ? 8u * uT : 0u;
+    L.mean = o; o += wide ? 8u * uT : 0u;
+    L.m2 = o; o += wide ? 8u * uT : 0u;
     L.tab_val = o; o += tab_smem ? 8u * (uint32_t)tab_len : 0u;
     L.val = o; o += mat_smem ? 8u * (uint32_t)n_cells : 0u;
+    L.key = o; o += 8u * (uint32_t)n_slots;
     L.counts = o; o += 4u * uT;
-    L.base = o; o += 4u * uT;
-    L.occ = o; o += 4u * uT;
-    L.tab_row = o; o += tab_smem ? 4u * (uT + 1u) : 0u;
-    L.mask = o; o += 4u * (2u * nch + 2u);
+    L.base = o; o += wide ? 4u * uT : 0u;
+    L.occ = o; o += wide ? 4u * uT : 0u;
+    L.tab_row = o; o += tab_smem ? 4u * n_tabrow : 0u;
+    L.mask = o; o += wide ? 4u * (2u * nch + 2u) : 0u;
     L.slab = o; o += mat_smem ? 4u * ((uint32_t)n_slabs + 1u) : 0u;
     L.row_n = o; o += mat_smem ? 4u * Rp : 0u;
     L.row_nnz = o; o += mat_smem ? 4u * Rp : 0u;
-    L.row_id = o; o += mat_smem ? 4u * Rp : 0u;
+    L.row_info = o; o += mat_smem ? 4u * Rp : 0u;
     L.col = o; o += mat_smem ? 2u * (uint32_t)n_cells : 0u;
     L.total = (o + 15u) & ~15u;
     return L;

@@ -1,13 +1,18 @@
-// Host packer: one CollapsedMap (CSR) -> the device layout of the Gibbs kernel.
+// Host packer: CollapsedMaps (CSR) -> the device layout of the Gibbs kernels.
 //
+// prepare_locus (per locus, thread pool):
 //  * rows with a single cell always send all their fragments to that cell's candidate (p/Z == 1 in
 //    generateAssignment, assignmentGenerator.cpp:280-334/346-349; in initAssignment whatever the binomial leaves is
 //    the row's own remainder), so they are folded into per-candidate base counts and never visited again;
-//  * the remaining rows are ordered by (binomial-chain rows first, wider rows first, larger counts first) so that the
-//    32 rows a warp walks together take the same branch and have similar lengths;
+//  * minimum read cover -> pi (assembler.cpp:1551-1559) and the simplex-size CDF table (simplexSizeGenerator.cpp:117-187).
+// pack_unit (per thread block):
+//  * the rows of all slots of the unit are pooled and ordered by (binomial-chain rows first, wider rows first, larger
+//    counts first) so that the 32 rows a warp walks together take the same branch and have similar lengths;
 //  * 32 consecutive rows form a slab stored column-major (cell k of lane l at slab + 32 k + l, SELL-32), so a warp
 //    reading "cell k of my row" touches 32 consecutive doubles / 32 consecutive uint16 columns: conflict-free in
-//    shared memory, fully coalesced from L2/HBM.
+//    shared memory, fully coalesced from L2/HBM;
+//  * in a bundle the column of a cell is the LANE of its candidate (slot * Tpad + t), so the assignment step indexes
+//    one pooled theta / counts vector whichever locus a row belongs to.
 #include <float.h>
 #include <math.h>
 
@@ -40,12 +45,14 @@ int validate_locus(const bayes_locus_desc &in, std::string *err) {
     return BAYES_OK;
 }
 
-// Same carve-up as the kernel uses (layout.h).
-size_t locus_smem_bytes(const LocusDev &d) {
-    return smem_layout(d.T, d.n_slabs, d.n_cells, d.tab_len, d.tab_smem != 0, d.mat_smem != 0).total;
+int slot_lanes(int T) {
+    if (T > 32) return 0;
+    int p = 2;
+    while (p < T) p *= 2;
+    return p;
 }
 
-int pack_locus(const bayes_locus_desc &in, PackedLocus *out, std::string *err) {
+int prepare_locus(const bayes_locus_desc &in, PreLocus *out, std::string *err) {
     int rc = validate_locus(in, err);
     if (rc != 0) return rc;
     if (in.T > kMaxT) { *err = "T exceeds the supported maximum (4096 candidates)"; return BAYES_E_INVALID; }
@@ -54,11 +61,17 @@ int pack_locus(const bayes_locus_desc &in, PackedLocus *out, std::string *err) {
     if (in.burn_in < 0 || in.samples < 1) { *err = "need burn_in >= 0 and samples >= 1"; return BAYES_E_INVALID; }
     if (!(in.total_num_fragments >= 1.0) || in.total_num_fragments > 2147483647.0) { *err = "total_num_fragments out of int range"; return BAYES_E_INVALID; }
     if (in.n_chains < 1) { *err = "n_chains < 1"; return BAYES_E_INVALID; }
+    if (in.R >= (1 << kRowSlotShift)) { *err = "too many rows"; return BAYES_E_INVALID; }
 
     const int T = in.T, R = in.R;
-    PackedLocus &P = *out;
-    P = PackedLocus();
+    PreLocus &P = *out;
+    P = PreLocus();
+    P.T = T;
+    P.N_total = (int32_t)in.total_num_fragments;
+    P.burn = in.burn_in;
+    P.samples = in.samples;
     P.n_chains = in.n_chains;
+    P.gamma = in.gamma;
     P.seed = in.seed;
     P.efflen.assign(in.efflen, in.efflen + T);
     P.base_counts.assign(T, 0);
@@ -76,41 +89,23 @@ int pack_locus(const bayes_locus_desc &in, PackedLocus *out, std::string *err) {
         else rows.push_back(Row{i, in.row_count[i], nz});
     }
     if (n_frag > 2147483647) { *err = "more than 2^31-1 fragments in one locus"; return BAYES_E_INVALID; }
+    P.n_frag = (int32_t)n_frag;
     std::stable_sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) {
         const bool ca = a.n >= kSmallCount, cb = b.n >= kSmallCount;
         if (ca != cb) return ca;
         if (a.nnz != b.nnz) return a.nnz > b.nnz;
         return a.n > b.n;
     });
-
-    const int Rm = (int)rows.size();
-    const int n_slabs = (Rm + 31) / 32;
-    P.slab_cell_off.assign(n_slabs + 1, 0);
-    P.row_n.assign((size_t)n_slabs * 32, 0);
-    P.row_nnz.assign((size_t)n_slabs * 32, 0);
-    P.row_id.assign((size_t)n_slabs * 32, 0);
-    for (int s = 0; s < n_slabs; s++) {
-        int w = 0;
-        for (int l = 0; l < 32 && s * 32 + l < Rm; l++) w = std::max(w, rows[s * 32 + l].nnz);
-        P.slab_cell_off[s + 1] = P.slab_cell_off[s] + 32 * w;
-    }
-    const int n_cells = P.slab_cell_off[n_slabs];
-    P.val.assign(n_cells, 0.0);
-    P.col.assign(n_cells, 0);
-    for (int r = 0; r < Rm; r++) {
-        const Row &row = rows[r];
-        const int s = r / 32, l = r % 32;
-        P.row_n[r] = row.n;
-        P.row_nnz[r] = row.nnz;
-        P.row_id[r] = row.id;
-        int k2 = 0;
+    P.row_ptr.assign(1, 0);
+    for (const Row &row : rows) {
+        P.row_id.push_back(row.id);
+        P.row_n.push_back(row.n);
         for (int k = in.row_ptr[row.id]; k < in.row_ptr[row.id + 1]; k++) {
             if (in.val[k] == 0.0) continue;
-            const size_t at = (size_t)P.slab_cell_off[s] + 32 * (size_t)k2 + l;
-            P.val[at] = in.val[k];
-            P.col[at] = (uint16_t)in.col_idx[k];
-            k2++;
+            P.cell_col.push_back(in.col_idx[k]);
+            P.cell_val.push_back(in.val[k]);
         }
+        P.row_ptr.push_back((int32_t)P.cell_val.size());
     }
 
     // pi from the minimum read cover unless supplied (assembler.cpp:1551-1559)
@@ -125,31 +120,102 @@ int pack_locus(const bayes_locus_desc &in, PackedLocus *out, std::string *err) {
     if (!(pi >= DBL_MIN) || !(pi <= 1.0 - DBL_EPSILON)) { *err = "pi out of (0, 1-eps]"; return BAYES_E_INVALID; }
     P.pi = pi;
     if (T > 1) simplex_table(pi, in.gamma, T, (int)n_frag, &P.tab_row, &P.tab_val);
-    else { P.tab_row.assign(2, 0); }
+    else P.tab_row.assign(2, 0);
 
-    LocusDev &d = P.d;
-    d = LocusDev();
-    d.T = T;
-    d.R = Rm;
+    const double iters = (double)in.burn_in + in.samples;
+    P.cost = iters * ((double)P.cell_val.size() + 8.0 * rows.size() + 16.0 * T + 64.0);
+    return BAYES_OK;
+}
+
+void pack_unit(const std::vector<SlotRef> &slots, bool wide, PackedUnit *out) {
+    PackedUnit &U = *out;
+    U = PackedUnit();
+    const int n_slots = (int)slots.size();
+    const PreLocus &L0 = *slots[0].locus;
+    const int Tpad = wide ? L0.T : slot_lanes(L0.T);
+    const int nT = wide ? L0.T : 32;
+
+    struct Row { int32_t slot, r, n, nnz; };
+    std::vector<Row> rows;
+    for (int g = 0; g < n_slots; g++) {
+        const PreLocus &L = *slots[g].locus;
+        for (size_t r = 0; r < L.row_id.size(); r++) rows.push_back(Row{g, (int32_t)r, L.row_n[r], L.row_ptr[r + 1] - L.row_ptr[r]});
+    }
+    if (n_slots > 1)
+        std::stable_sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) {
+            const bool ca = a.n >= kSmallCount, cb = b.n >= kSmallCount;
+            if (ca != cb) return ca;
+            if (a.nnz != b.nnz) return a.nnz > b.nnz;
+            return a.n > b.n;
+        });
+    const int Rm = (int)rows.size();
+    const int n_slabs = (Rm + 31) / 32;
+    U.slab_cell_off.assign(n_slabs + 1, 0);
+    U.row_n.assign((size_t)n_slabs * 32, 0);
+    U.row_nnz.assign((size_t)n_slabs * 32, 0);
+    U.row_info.assign((size_t)n_slabs * 32, 0);
+    for (int s = 0; s < n_slabs; s++) {
+        int w = 0;
+        for (int l = 0; l < 32 && s * 32 + l < Rm; l++) w = std::max(w, rows[s * 32 + l].nnz);
+        U.slab_cell_off[s + 1] = U.slab_cell_off[s] + 32 * w;
+    }
+    const int n_cells = U.slab_cell_off[n_slabs];
+    U.val.assign(n_cells, 0.0);
+    U.col.assign(n_cells, 0);
+    for (int r = 0; r < Rm; r++) {
+        const Row &row = rows[r];
+        const PreLocus &L = *slots[row.slot].locus;
+        const int s = r / 32, l = r % 32;
+        U.row_n[r] = row.n;
+        U.row_nnz[r] = row.nnz;
+        U.row_info[r] = ((uint32_t)row.slot << kRowSlotShift) | (uint32_t)L.row_id[row.r];
+        const int lane0 = wide ? 0 : row.slot * Tpad;
+        for (int k = 0; k < row.nnz; k++) {
+            const size_t at = (size_t)U.slab_cell_off[s] + 32 * (size_t)k + l;
+            U.val[at] = L.cell_val[L.row_ptr[row.r] + k];
+            U.col[at] = (uint16_t)(lane0 + L.cell_col[L.row_ptr[row.r] + k]);
+        }
+    }
+
+    U.efflen.assign(nT, 1.0);
+    U.base_counts.assign(nT, 0);
+    U.tab_row.assign((size_t)n_slots * (Tpad + 1), 0);
+    UnitDev &d = U.d;
+    d = UnitDev();
+    for (int g = 0; g < n_slots; g++) {
+        const PreLocus &L = *slots[g].locus;
+        const int lane0 = wide ? 0 : g * Tpad;
+        for (int t = 0; t < L.T; t++) {
+            U.efflen[lane0 + t] = L.efflen[t];
+            U.base_counts[lane0 + t] = L.base_counts[t];
+        }
+        const int32_t tab_base = (int32_t)U.tab_val.size();
+        for (int t = 0; t <= L.T; t++) U.tab_row[(size_t)g * (Tpad + 1) + t] = tab_base + L.tab_row[t];
+        U.tab_val.insert(U.tab_val.end(), L.tab_val.begin(), L.tab_val.end());
+        d.T[g] = L.T;
+        d.N_f[g] = L.n_frag;
+        d.N_total[g] = L.N_total;
+        d.gamma[g] = L.gamma;
+        d.key[g] = bayes_chain_key(L.seed, slots[g].chain);
+        d.out_off[g] = slots[g].out_off;
+        U.cost = std::max(U.cost, L.cost);
+    }
+    U.cost *= 1.0 + 0.25 * (n_slots - 1);
+    d.n_slots = n_slots;
+    d.Tpad = Tpad;
+    d.wide = wide ? 1 : 0;
     d.n_slabs = n_slabs;
-    d.N_f = (int32_t)n_frag;
-    d.N_total = (int32_t)in.total_num_fragments;
-    d.burn = in.burn_in;
-    d.samples = in.samples;
-    d.tab_len = (int32_t)P.tab_val.size();
     d.n_cells = n_cells;
-    d.gamma = in.gamma;
+    d.burn = L0.burn;
+    d.samples = L0.samples;
+    d.tab_len = (int32_t)U.tab_val.size();
     d.tab_smem = d.tab_len <= kTableSmemEntries;
     const size_t mat_bytes = (size_t)n_cells * 10 + (size_t)n_slabs * 32 * 12 + 4 * ((size_t)n_slabs + 1);
     d.mat_smem = mat_bytes <= (size_t)kMatrixSmemBytes;
-    d.smem_bytes = (int32_t)locus_smem_bytes(d);
-
+    d.smem_bytes = (int32_t)unit_layout(wide, nT, n_slots, Tpad, n_slabs, n_cells, d.tab_len, d.tab_smem != 0, d.mat_smem != 0).total;
     int block = 32;
     while (block < Rm && block < kMaxBlock) block *= 2;
-    P.block = block;
-    const double iters = (double)in.burn_in + in.samples;
-    P.cost = iters * ((double)n_cells + 8.0 * Rm + 16.0 * T + 64.0);
-    return BAYES_OK;
+    d.block = block;
 }
 
 }  // namespace bayes

@@ -43,8 +43,9 @@ BAYES_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 
-BAYES_HD u32x4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
-#pragma unroll
+// Out of line on purpose (as are the log, the gamma and the binomial below): the sampler's hot loop has to fit the
+// 32 KB instruction cache, and six inlined copies of the ten rounds alone were 7 KB.
+BAYES_HD_NOINLINE u32x4 philox4x32_10(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
     for (int r = 0; r < 10; r++) {
         const uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
@@ -98,6 +99,9 @@ BAYES_HD uint32_t uniform_int(const Site &s, uint32_t n) {
     return (uint32_t)(m >> 32);
 }
 
+// one shared copy of the double-precision log (about 100 instructions when inlined)
+BAYES_HD_NOINLINE double dlog(double x) { return log(x); }
+
 BAYES_HD double cos_2pi(double f) {
 #if defined(__CUDA_ARCH__)
     return cospi(2.0 * f);
@@ -107,16 +111,16 @@ BAYES_HD double cos_2pi(double f) {
 }
 
 // gamma_distribution(alpha, 1): one block per attempt (expressionGenerator.cpp:89-92, 100-113)
-BAYES_HD double gamma_variate(const Site &s, double alpha) {
+BAYES_HD_NOINLINE double gamma_variate(const Site &s, double alpha) {
     uint32_t j = 0;
     if (alpha == 1.0) {
         const u32x4 b = s.block(0);
-        return -log(u53(b.x, b.y));
+        return -dlog(u53(b.x, b.y));
     }
     double boost = 1.0, a = alpha;
     if (alpha < 1.0) {
         const u32x4 b = s.block(j++);
-        boost = exp(log(u53(b.x, b.y)) / alpha);
+        boost = exp(dlog(u53(b.x, b.y)) / alpha);
         a = alpha + 1.0;
     }
     const double d = a - 1.0 / 3.0;
@@ -124,48 +128,62 @@ BAYES_HD double gamma_variate(const Site &s, double alpha) {
     for (;;) {
         const u32x4 b = s.block(j++);
         const double u1 = u53(b.x, b.y);
-        const double x = sqrt(-2.0 * log(u1)) * cos_2pi(u01(b.z));
+        const double x = sqrt(-2.0 * dlog(u1)) * cos_2pi(u01(b.z));
         double v = 1.0 + c * x;
         if (v <= 0.0) continue;
         v = v * v * v;
         const double u = u32_open(b.w);
         const double x2 = x * x;
         if (u < 1.0 - 0.0331 * x2 * x2) return d * v * boost;
-        if (log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) return d * v * boost;
+        if (dlog(u) < 0.5 * x2 + d * (1.0 - v + dlog(v))) return d * v * boost;
     }
 }
 
 BAYES_HD double stirling_fc(int k) {
-    double r;
-    switch (k) {
-        case 0: r = 0.08106146679532726; break;
-        case 1: r = 0.04134069595540929; break;
-        case 2: r = 0.02767792568499834; break;
-        case 3: r = 0.02079067210376509; break;
-        case 4: r = 0.01664469118982119; break;
-        case 5: r = 0.01387612882307075; break;
-        case 6: r = 0.01189670994589177; break;
-        case 7: r = 0.01041126526197209; break;
-        case 8: r = 0.009255462182712733; break;
-        case 9: r = 0.008330563433362871; break;
-        default: {
-            const double kp1 = (double)k + 1.0, kp1sq = kp1 * kp1;
-            r = (1.0 / 12 - (1.0 / 360 - 1.0 / 1260 / kp1sq) / kp1sq) / kp1;
-        }
+    if (k < 10) {
+        // 1/(12(k+1)) - 1/(360(k+1)^3) + ... is not accurate enough below 10: tabulated (Hoermann 1993, table 1)
+        const double t0 = 0.08106146679532726, t1 = 0.04134069595540929, t2 = 0.02767792568499834, t3 = 0.02079067210376509,
+                     t4 = 0.01664469118982119, t5 = 0.01387612882307075, t6 = 0.01189670994589177, t7 = 0.01041126526197209,
+                     t8 = 0.009255462182712733, t9 = 0.008330563433362871;
+        const double lo = k < 1 ? t0 : k < 2 ? t1 : k < 3 ? t2 : k < 4 ? t3 : t4;
+        const double hi = k < 6 ? t5 : k < 7 ? t6 : k < 8 ? t7 : k < 9 ? t8 : t9;
+        return k < 5 ? lo : hi;
     }
-    return r;
+    const double kp1 = (double)k + 1.0, kp1sq = kp1 * kp1;
+    return (1.0 / 12 - (1.0 / 360 - 1.0 / 1260 / kp1sq) / kp1sq) / kp1;
 }
 
-// BTRD (Hoermann 1993), q <= 0.5, n*q >= 10; one block per attempt
-BAYES_HD_NOINLINE int binomial_btrd(const Site &s, int n, double q) {
+BAYES_HD double recip(double x) {
+#if defined(__CUDA_ARCH__)
+    return __drcp_rn(x);  // correctly rounded, i.e. the same double as 1.0 / x on the host
+#else
+    return 1.0 / x;
+#endif
+}
+
+// (1-q)^n by binary exponentiation (IEEE multiplications only: bit-identical to the oracle's orc_ipow)
+BAYES_HD double ipow(double base, int n) {
+    double result = 1.0;
+    while (n > 0) {
+        if (n & 1) result *= base;
+        base *= base;
+        n >>= 1;
+    }
+    return result;
+}
+
+// BTRD (Hoermann 1993), q <= 0.5, n*q >= 10; one block per attempt.  Same operation order as oracle/orc_rng.h.
+BAYES_HD int binomial_btrd(const Site &s, int n, double q) {
     const double npq = n * q * (1.0 - q);
     const double spq = sqrt(npq);
     const double bb = 1.15 + 2.53 * spq;
+    const double inv_bb = recip(bb);
     const double a = -0.0873 + 0.0248 * bb + 0.01 * q;
     const double c = n * q + 0.5;
-    const double v_r = 0.92 - 4.2 / bb;
+    const double v_r = 0.92 - 4.2 * inv_bb;
+    const double inv_vr = recip(v_r);
     const double r = q / (1.0 - q);
-    const double alpha = (2.83 + 5.1 / bb) * spq;
+    const double alpha = (2.83 + 5.1 * inv_bb) * spq;
     const int m = (int)floor((n + 1) * q);
     const double nr = (n + 1) * r;
     for (uint32_t j = 0;; j++) {
@@ -174,13 +192,13 @@ BAYES_HD_NOINLINE int binomial_btrd(const Site &s, int n, double q) {
         const double u2 = u53(b.z, b.w);
         double u;
         if (v <= 0.86 * v_r) {
-            u = v / v_r - 0.43;
+            u = v * inv_vr - 0.43;
             return (int)floor((2.0 * a / (0.5 - fabs(u)) + bb) * u + c);
         }
         if (v >= v_r) {
             u = u2 - 0.5;
         } else {
-            u = v / v_r - 0.93;
+            u = v * inv_vr - 0.93;
             u = (u < 0.0 ? -0.5 : 0.5) - u;
             v = u2 * v_r;
         }
@@ -191,46 +209,47 @@ BAYES_HD_NOINLINE int binomial_btrd(const Site &s, int n, double q) {
         v = v * alpha / (a / (us * us) + bb);
         const int km = k > m ? k - m : m - k;
         if (km <= 15) {
-            double f = 1.0;
+            double num = 1.0, den = 1.0;
             if (m < k) {
-                for (int i = m + 1; i <= k; i++) f *= (nr / i - r);
-            } else if (m > k) {
-                for (int i = k + 1; i <= m; i++) v *= (nr / i - r);
+                for (int i = m + 1; i <= k; i++) { num *= (nr - r * i); den *= (double)i; }
+                if (v * den <= num) return k;
+            } else {
+                for (int i = k + 1; i <= m; i++) { num *= (nr - r * i); den *= (double)i; }
+                if (v * num <= den) return k;
             }
-            if (v <= f) return k;
             continue;
         }
-        v = log(v);
+        v = dlog(v);
         const double kmd = (double)km;
         const double rho = (kmd / npq) * (((kmd / 3.0 + 0.625) * kmd + 1.0 / 6.0) / npq + 0.5);
         const double t = -kmd * kmd / (2.0 * npq);
         if (v < t - rho) return k;
         if (v > t + rho) continue;
         const double nm = (double)(n - m + 1);
-        const double h = (m + 0.5) * log((m + 1) / (r * nm)) + stirling_fc(m) + stirling_fc(n - m);
+        const double h = (m + 0.5) * dlog((m + 1) / (r * nm)) + stirling_fc(m) + stirling_fc(n - m);
         const double nk = (double)(n - k + 1);
-        if (v <= h + (n + 1) * log(nm / nk) + (k + 0.5) * log(nk * r / (k + 1)) - stirling_fc(k) - stirling_fc(n - k)) return k;
+        if (v <= h + (n + 1) * dlog(nm / nk) + (k + 0.5) * dlog(nk * r / (k + 1)) - stirling_fc(k) - stirling_fc(n - k)) return k;
     }
 }
 
 // binomial_distribution(n, p) (assignmentGenerator.cpp:230-233, 346-349)
-BAYES_HD int binomial_variate(const Site &s, int n, double p) {
+BAYES_HD_NOINLINE int binomial_variate(const Site &s, int n, double p) {
     if (n <= 0 || !(p > 0.0)) return 0;
     if (p >= 1.0) return n;
     const bool flip = p > 0.5;
     const double q = flip ? 1.0 - p : p;
     int k;
     if ((double)n * q < 10.0) {
+        // BINV: P(0) = (1-q)^n, P(k) = P(k-1) s (n-k+1) / k
         const u32x4 b = s.block(0);
         double u = u53(b.x, b.y);
         const double sr = q / (1.0 - q);
-        const double a = (double)(n + 1) * sr;
-        double r = exp((double)n * log1p(-q));
+        double r = ipow(1.0 - q, n);
         k = 0;
         while (u > r && k < n) {
             u -= r;
             k++;
-            r *= (a / (double)k - sr);
+            r = (r * ((double)(n - k + 1) * sr)) * recip((double)k);
         }
     } else {
         k = binomial_btrd(s, n, q);

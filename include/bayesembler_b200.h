@@ -99,6 +99,9 @@ int bayes_gibbs_clear(bayes_gibbs_ctx *ctx);
  * last iteration (gibbsSampler.cpp:145). */
 int bayes_gibbs_fetch(bayes_gibbs_ctx *ctx, int64_t locus_id, int32_t chain, int32_t *occ, double *mean, double *m2,
                       int32_t *final_counts);
+/* The same for every job at once: locus after locus in submission order, chains of a locus back to back, T entries
+ * per job (what the reference's output thread would drain, assembler.cpp:1746-1839). */
+int bayes_gibbs_fetch_all(bayes_gibbs_ctx *ctx, int32_t *occ, double *mean, double *m2, int32_t *final_counts);
 /* pi actually used, |minimum read cover| (0 when pi was given), folded single-cell rows */
 int bayes_gibbs_locus_info(bayes_gibbs_ctx *ctx, int64_t locus_id, double *pi, int32_t *cover_size, int32_t *rows_folded);
 int64_t bayes_gibbs_num_loci(bayes_gibbs_ctx *ctx);

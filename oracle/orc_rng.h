@@ -228,16 +228,32 @@ static inline double orc_stirling_fc(int k) {
     return (1.0 / 12 - (1.0 / 360 - 1.0 / 1260 / kp1sq) / kp1sq) / kp1;
 }
 
-/* BTRD, Hoermann 1993; requires q <= 0.5 and n*q >= 10; one 4-word block per attempt */
+/* (1-q)^n by binary exponentiation, least significant bit first: IEEE multiplications only, so the CUDA product
+ * reproduces it bit for bit (no libm call whose last bit could differ between host and device) */
+static inline double orc_ipow(double base, int n) {
+    double result = 1.0;
+    while (n > 0) {
+        if (n & 1) result *= base;
+        base *= base;
+        n >>= 1;
+    }
+    return result;
+}
+
+/* BTRD, Hoermann 1993; requires q <= 0.5 and n*q >= 10; one 4-word block per attempt.  Divisions that share a
+ * denominator are written as one reciprocal and multiplications, and the recursive evaluation of f(k)/f(m) (step 3.1)
+ * keeps numerator and denominator separately: the algorithm is unchanged, it is only cheaper on the GPU. */
 static inline int orc_btrd(orc_ws *w, int n, double q) {
-    const double spq = sqrt(n * q * (1.0 - q));
     const double npq = n * q * (1.0 - q);
+    const double spq = sqrt(npq);
     const double bb = 1.15 + 2.53 * spq;
+    const double inv_bb = 1.0 / bb;
     const double a = -0.0873 + 0.0248 * bb + 0.01 * q;
     const double c = n * q + 0.5;
-    const double v_r = 0.92 - 4.2 / bb;
+    const double v_r = 0.92 - 4.2 * inv_bb;
+    const double inv_vr = 1.0 / v_r;
     const double r = q / (1.0 - q);
-    const double alpha = (2.83 + 5.1 / bb) * spq;
+    const double alpha = (2.83 + 5.1 * inv_bb) * spq;
     const int m = (int)floor((n + 1) * q);
     const double nr = (n + 1) * r;
     uint32_t b[4];
@@ -247,13 +263,13 @@ static inline int orc_btrd(orc_ws *w, int n, double q) {
         double u2 = orc_u53(b[2], b[3]);
         double u;
         if (v <= 0.86 * v_r) {
-            u = v / v_r - 0.43;
+            u = v * inv_vr - 0.43;
             return (int)floor((2.0 * a / (0.5 - fabs(u)) + bb) * u + c);
         }
         if (v >= v_r) {
             u = u2 - 0.5;
         } else {
-            u = v / v_r - 0.93;
+            u = v * inv_vr - 0.93;
             u = (u < 0.0 ? -0.5 : 0.5) - u;
             v = u2 * v_r;
         }
@@ -264,10 +280,15 @@ static inline int orc_btrd(orc_ws *w, int n, double q) {
         v = v * alpha / (a / (us * us) + bb);
         int km = k > m ? k - m : m - k;
         if (km <= 15) {
-            double f = 1.0;
-            if (m < k) { for (int i = m + 1; i <= k; i++) f *= (nr / i - r); }
-            else if (m > k) { for (int i = k + 1; i <= m; i++) v *= (nr / i - r); }
-            if (v <= f) return k;
+            /* f(k)/f(m) = prod (nr/i - r) = prod (nr - r i) / prod i */
+            double num = 1.0, den = 1.0;
+            if (m < k) {
+                for (int i = m + 1; i <= k; i++) { num *= (nr - r * i); den *= (double)i; }
+                if (v * den <= num) return k;
+            } else {
+                for (int i = k + 1; i <= m; i++) { num *= (nr - r * i); den *= (double)i; }
+                if (v * num <= den) return k;
+            }
             continue;
         }
         v = log(v);
@@ -292,17 +313,17 @@ static inline int orc_binomial(orc_ws *w, int n, double p) {
     const double q = flip ? 1.0 - p : p;
     int k;
     if ((double)n * q < 10.0) {
+        /* BINV: sequential search from 0 with P(0) = (1-q)^n, P(k) = P(k-1) s (n-k+1) / k, s = q/(1-q) */
         uint32_t b[4];
         orc_ws_block(w, b);
         double u = orc_u53(b[0], b[1]);
         const double s = q / (1.0 - q);
-        const double a = (double)(n + 1) * s;
-        double r = exp((double)n * log1p(-q));
+        double r = orc_ipow(1.0 - q, n);
         k = 0;
         while (u > r && k < n) {
             u -= r;
             k++;
-            r *= (a / (double)k - s);
+            r = (r * ((double)(n - k + 1) * s)) * (1.0 / (double)k);
         }
     } else {
         k = orc_btrd(w, n, q);
