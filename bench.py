@@ -201,21 +201,17 @@ def main():
 
     # workload: world * per_gpu loci; every rank generates its own contiguous block, costs are exchanged, the LPT
     # partition is computed identically everywhere and each rank regenerates exactly the loci assigned to it
+    from bayesembler_b200 import shard
     block = synth.SynthBatch(cfg, n_loci=per_gpu, first=rank * per_gpu, n_threads=host_threads)
     descs = block.desc_array(n_chains=n_chains)
-    lib = bb.load_library()
-    import ctypes as C
-    cost_local = np.array([lib.bayes_locus_cost(C.cast(descs[i:i + 1].ctypes.data, C.POINTER(bb.LocusDesc))) for i in range(len(descs))])
+    cost_local = shard.desc_costs(descs)
     if world > 1:
-        t = torch.from_numpy(cost_local).cuda()
-        gathered = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(gathered, t)
-        cost_all = torch.cat(gathered).cpu().numpy()
-        part = bb.partition_lpt(cost_all, world)
-        mine = np.nonzero(part == rank)[0]
+        cost_all = shard.gather_costs(cost_local, dist, device="cuda")
+        mine, load = shard.shard_loci(cost_all, world, rank)
         batch = synth.SynthBatch(cfg, ids=mine, n_threads=host_threads)
         descs = batch.desc_array(n_chains=n_chains)
-        shard_cost = [float(cost_all[part == r].sum()) for r in range(world)]
+        cost_local = cost_all[mine]
+        shard_cost = [float(x) for x in load]
     else:
         batch = block
         shard_cost = [float(cost_local.sum())]
