@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = [
     "bayes_gibbs_set_host_threads", "bayes_last_error", "bayes_gibbs_submit", "bayes_gibbs_upload", "bayes_gibbs_run",
     "bayes_gibbs_download", "bayes_gibbs_sync", "bayes_gibbs_run_batch", "bayes_gibbs_clear", "bayes_gibbs_fetch",
     "bayes_gibbs_fetch_all",
-    "bayes_gibbs_locus_info", "bayes_gibbs_num_loci", "bayes_gibbs_num_jobs", "bayes_gibbs_last_launches",
+    "bayes_gibbs_locus_info", "bayes_gibbs_chain_info", "bayes_gibbs_num_loci", "bayes_gibbs_num_jobs", "bayes_gibbs_last_launches",
     "bayes_gibbs_set_trace", "bayes_gibbs_fetch_trace", "bayes_top_marginals", "bayes_step_generate_assignment",
     "bayes_step_init_assignment", "bayes_step_generate_expression", "bayes_step_variates", "bayes_min_read_cover",
     "bayes_simplex_table", "bayes_chain_key", "bayes_locus_cost", "bayes_partition_lpt", "bayes_philox4x32",
@@ -90,6 +90,7 @@ def load_library(path=None):
         "bayes_gibbs_fetch": (C.c_int, [vp, i64, i32, vp, vp, vp, vp]),
         "bayes_gibbs_fetch_all": (C.c_int, [vp, vp, vp, vp, vp]),
         "bayes_gibbs_locus_info": (C.c_int, [vp, i64, C.POINTER(dbl), C.POINTER(i32), C.POINTER(i32)]),
+        "bayes_gibbs_chain_info": (C.c_int, [vp, i64, i32, C.POINTER(dbl), C.POINTER(i32)]),
         "bayes_gibbs_num_loci": (i64, [vp]),
         "bayes_gibbs_num_jobs": (i64, [vp]),
         "bayes_gibbs_last_launches": (i32, [vp]),
@@ -237,6 +238,12 @@ class GibbsContext(object):
         _check(self.lib.bayes_gibbs_locus_info(self.h, locus_id, C.byref(pi), C.byref(cover), C.byref(folded)),
                "bayes_gibbs_locus_info")
         return dict(pi=pi.value, cover=cover.value, folded=folded.value)
+
+    def chain_info(self, locus_id, chain):
+        pi = C.c_double(0)
+        cover = C.c_int32(0)
+        _check(self.lib.bayes_gibbs_chain_info(self.h, locus_id, chain, C.byref(pi), C.byref(cover)), "bayes_gibbs_chain_info")
+        return dict(pi=pi.value, cover=cover.value)
 
     def num_jobs(self):
         return self.lib.bayes_gibbs_num_jobs(self.h)

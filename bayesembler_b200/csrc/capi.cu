@@ -604,9 +604,20 @@ int bayes_gibbs_locus_info(bayes_gibbs_ctx *ctx, int64_t locus_id, double *pi, i
         return BAYES_E_INVALID;
     }
     const PreLocus &L = ctx->loci[locus_id];
-    if (pi) *pi = L.pi;
-    if (cover_size) *cover_size = L.cover;
+    if (pi) *pi = L.prior(0).pi;
+    if (cover_size) *cover_size = L.prior(0).cover;
     if (rows_folded) *rows_folded = L.folded;
+    return BAYES_OK;
+}
+
+int bayes_gibbs_chain_info(bayes_gibbs_ctx *ctx, int64_t locus_id, int32_t chain, double *pi, int32_t *cover_size) {
+    if (!ctx || locus_id < 0 || locus_id >= (int64_t)ctx->loci.size() || chain < 0 || chain >= ctx->loci[locus_id].n_chains) {
+        set_error("bayes_gibbs_chain_info: bad locus id / chain");
+        return BAYES_E_INVALID;
+    }
+    const SimplexPrior &sp = ctx->loci[locus_id].prior(chain);
+    if (pi) *pi = sp.pi;
+    if (cover_size) *cover_size = sp.cover;
     return BAYES_OK;
 }
 

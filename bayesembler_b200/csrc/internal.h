@@ -81,12 +81,25 @@ struct KernelArgs {
 };
 
 // Host-side result of preparing one locus (everything that does not depend on which unit it lands in).
+// Simplex-size prior of a chain: pi and the CDF table built from it.  Every chain is one independent run of the
+// reference's call site, so (unless the caller fixes pi) chain c derives pi from ITS OWN minimum read cover, whose
+// random tie breaks are keyed by the chain (assembler.cpp:1551-1559); chains with equal cover size share a table.
+struct SimplexPrior {
+    double pi = 0;
+    int32_t cover = 0;
+    std::vector<double> tab_val;
+    std::vector<int32_t> tab_row;
+};
+
 struct PreLocus {
-    int32_t T = 0, n_frag = 0, N_total = 0, burn = 0, samples = 0, n_chains = 1, cover = 0, folded = 0;
-    double gamma = 1, pi = 0;
+    int32_t T = 0, n_frag = 0, N_total = 0, burn = 0, samples = 0, n_chains = 1, folded = 0;
+    double gamma = 1;
     uint64_t seed = 0;
-    std::vector<double> efflen, tab_val;
-    std::vector<int32_t> base_counts, tab_row;
+    std::vector<double> efflen;
+    std::vector<int32_t> base_counts;
+    std::vector<SimplexPrior> priors;   // distinct priors of the locus
+    std::vector<int32_t> chain_prior;   // chain -> index into priors
+    const SimplexPrior &prior(int chain) const { return priors[chain_prior[chain]]; }
     // multi-cell rows in processing order (binomial-chain rows first, wider first, larger counts first)
     std::vector<int32_t> row_id, row_n, row_ptr;  // row_ptr: rows + 1
     std::vector<int32_t> cell_col;

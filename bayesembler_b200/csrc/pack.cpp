@@ -108,19 +108,33 @@ int prepare_locus(const bayes_locus_desc &in, PreLocus *out, std::string *err) {
         P.row_ptr.push_back((int32_t)P.cell_val.size());
     }
 
-    // pi from the minimum read cover unless supplied (assembler.cpp:1551-1559)
-    double pi = in.pi;
-    if (pi < 0) {
-        const int cover = min_read_cover(in, bayes_chain_key(in.seed, 0), nullptr);
-        if (cover < 0) { *err = "minimum read cover failed"; return BAYES_E_INVALID; }
-        P.cover = cover;
-        pi = (double)cover / T;
-        if (pi > 1.0 - DBL_EPSILON) pi = 1.0 - DBL_EPSILON;
+    // pi from the minimum read cover unless supplied (assembler.cpp:1551-1559), one cover per chain
+    P.chain_prior.assign(in.n_chains, 0);
+    auto add_prior = [&](double pi, int cover, std::string *e) -> int {
+        if (!(pi >= DBL_MIN) || !(pi <= 1.0 - DBL_EPSILON)) { *e = "pi out of (0, 1-eps]"; return -1; }
+        for (size_t i = 0; i < P.priors.size(); i++)
+            if (P.priors[i].pi == pi && P.priors[i].cover == cover) return (int)i;
+        P.priors.push_back(SimplexPrior());
+        SimplexPrior &sp = P.priors.back();
+        sp.pi = pi;
+        sp.cover = cover;
+        if (T > 1) simplex_table(pi, in.gamma, T, (int)n_frag, &sp.tab_row, &sp.tab_val);
+        else sp.tab_row.assign(2, 0);
+        return (int)P.priors.size() - 1;
+    };
+    if (in.pi < 0) {
+        for (int c = 0; c < in.n_chains; c++) {
+            const int cover = min_read_cover(in, bayes_chain_key(in.seed, c), nullptr);
+            if (cover < 0) { *err = "minimum read cover failed"; return BAYES_E_INVALID; }
+            double pi = (double)cover / T;
+            if (pi > 1.0 - DBL_EPSILON) pi = 1.0 - DBL_EPSILON;
+            const int idx = add_prior(pi, cover, err);
+            if (idx < 0) return BAYES_E_INVALID;
+            P.chain_prior[c] = idx;
+        }
+    } else {
+        if (add_prior(in.pi, 0, err) < 0) return BAYES_E_INVALID;
     }
-    if (!(pi >= DBL_MIN) || !(pi <= 1.0 - DBL_EPSILON)) { *err = "pi out of (0, 1-eps]"; return BAYES_E_INVALID; }
-    P.pi = pi;
-    if (T > 1) simplex_table(pi, in.gamma, T, (int)n_frag, &P.tab_row, &P.tab_val);
-    else P.tab_row.assign(2, 0);
 
     const double iters = (double)in.burn_in + in.samples;
     P.cost = iters * ((double)P.cell_val.size() + 8.0 * rows.size() + 16.0 * T + 64.0);
@@ -189,9 +203,10 @@ void pack_unit(const std::vector<SlotRef> &slots, bool wide, PackedUnit *out) {
             U.efflen[lane0 + t] = L.efflen[t];
             U.base_counts[lane0 + t] = L.base_counts[t];
         }
+        const SimplexPrior &sp = L.prior(slots[g].chain);
         const int32_t tab_base = (int32_t)U.tab_val.size();
-        for (int t = 0; t <= L.T; t++) U.tab_row[(size_t)g * (Tpad + 1) + t] = tab_base + L.tab_row[t];
-        U.tab_val.insert(U.tab_val.end(), L.tab_val.begin(), L.tab_val.end());
+        for (int t = 0; t <= L.T; t++) U.tab_row[(size_t)g * (Tpad + 1) + t] = tab_base + sp.tab_row[t];
+        U.tab_val.insert(U.tab_val.end(), sp.tab_val.begin(), sp.tab_val.end());
         d.T[g] = L.T;
         d.N_f[g] = L.n_frag;
         d.N_total[g] = L.N_total;

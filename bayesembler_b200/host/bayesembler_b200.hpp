@@ -1,0 +1,392 @@
+// Host-side mirror of the reference's sampler interface on top of the C ABI (include/bayesembler_b200.h).
+//
+// Same class names, constructor argument order and meaning, and error behaviour as the reference objects built at the
+// hot-path call site, assembler.cpp:1548-1609, so that Assembler::bayesemblerCallback keeps its shape:
+//
+//   reference (src/)                                                      here
+//   AssignmentGenerator(mt_rng_pt_t, Eigen::MatrixXd*, vector<int>*)      AssignmentGenerator(mt_rng_pt_t, const Matrix*, const vector<int>*)
+//     (assignmentGenerator.h:48)                                            Matrix: anything with rows(), cols(), operator()(i, j) -- Eigen::MatrixXd works
+//   FixedBinomialFixedGammaSimplexSizeGenerator(pi, gamma, T, rng, N_f)   same (simplexSizeGenerator.h:67)
+//   FixedGammaGenerator(gamma)                                            same (gammaGenerator.h:71)
+//   ExpressionGenerator(N_f, T, rng)                                      same (expressionGenerator.h:45)
+//   GibbsSampler(ssg*, gg*, eg*, ag*, idx->(old idx, efflen), N_total,    same (gibbsSampler.h:51); `int` truncation of N_total kept
+//                N_f, T, rng, assignment_minimum)
+//   GibbsOutput(samples, T), getTopMarginals, writeEnsembleGtf,           same (gibbsOutput.h:46-50); Ensemble holds std::vector<double>
+//   writeCandidateGtf                                                      instead of Eigen::VectorXd
+//   void GibbsSampler::runSampler(GibbsOutput*, burn, samples, log)       same, synchronous, ONE locus on the GPU (correct, latency-bound);
+//                                                                         GibbsBatch::add(...) + run() is the batched form the GPU wants
+//
+// The one type that changes is the random engine: the reference hands every generator a boost::random::mt19937*
+// seeded with graph_seed (assembler.cpp:1437-1445); a sequential engine cannot feed a GPU, so mt_rng_t here only
+// carries the seed and the device derives counter-based Philox streams from it.
+//
+// Header-only; link against bayesembler_b200/libbayesembler_b200.so.  There is no CPU sampler behind these classes:
+// without a CUDA device runSampler / GibbsBatch::run throw std::runtime_error carrying bayes_last_error().
+#ifndef BAYESEMBLER_B200_HPP
+#define BAYESEMBLER_B200_HPP
+
+#include <math.h>
+#include <stdint.h>
+
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/bayesembler_b200.h"
+
+namespace bayesembler_b200 {
+
+// ---- utils.h:85-136 ------------------------------------------------------------------------------------------------
+struct Ensemble {  // utils.h:91-97
+    std::vector<int> indices;
+    std::vector<double> means;
+    std::vector<double> sd;
+};
+struct Vertex {  // utils.h:100-106
+    std::string reference;
+    std::string strand;
+    int start;
+    int end;
+};
+struct Candidate {  // utils.h:109-117
+    int idx;
+    std::string name;
+    std::string graph_name;
+    int length;
+    std::vector<Vertex> vertices;
+    bool isPreMrna;
+};
+typedef std::map<int, std::pair<int, double> > IdxMap;  // new idx -> (old idx, effective length); reference: tr1::unordered_map
+
+// Stand-in for boost::random::mt19937: carries graph_seed only (see header comment).
+struct mt_rng_t {
+    uint64_t graph_seed;
+    mt_rng_t() : graph_seed(5489u) {}
+    explicit mt_rng_t(uint64_t s) : graph_seed(s) {}
+    void seed(uint64_t s) { graph_seed = s; }
+};
+typedef mt_rng_t *mt_rng_pt_t;
+
+inline void check(int rc, const char *what) {
+    if (rc < 0) throw std::runtime_error(std::string(what) + ": " + bayes_last_error());
+}
+
+// ---- assignmentGenerator.h -------------------------------------------------------------------------------------------
+class AssignmentGenerator {
+   public:
+    template <class Matrix>
+    AssignmentGenerator(mt_rng_pt_t rng, const Matrix *collapsed_map, const std::vector<int> *collapsed_counts)
+        : mt_rng_pt(rng), num_rows((int)collapsed_map->rows()), num_transcripts((int)collapsed_map->cols()), cover_size(-1) {
+        // dense (zeros = incompatible, utils.h:131) -> CSR over the non-zero cells, columns ascending
+        row_ptr.assign(1, 0);
+        for (int i = 0; i < num_rows; i++) {
+            for (int j = 0; j < num_transcripts; j++) {
+                const double v = (*collapsed_map)(i, j);
+                if (v != 0.0) {
+                    col_idx.push_back(j);
+                    val.push_back(v);
+                }
+            }
+            row_ptr.push_back((int32_t)val.size());
+        }
+        row_count.assign(collapsed_counts->begin(), collapsed_counts->end());
+    }
+    // CSR form, for callers that never materialise the dense matrix
+    AssignmentGenerator(mt_rng_pt_t rng, int T, const std::vector<int32_t> &row_ptr_in, const std::vector<int32_t> &col_idx_in,
+                        const std::vector<double> &val_in, const std::vector<int32_t> &counts)
+        : mt_rng_pt(rng), num_rows((int)counts.size()), num_transcripts(T), cover_size(-1), row_ptr(row_ptr_in), col_idx(col_idx_in),
+          val(val_in), row_count(counts) {}
+
+    // assignmentGenerator.cpp:52-91
+    void calcMinimumReadCover(std::stringstream &log_stream) {
+        bayes_locus_desc d = desc();
+        const int n = bayes_min_read_cover(&d, bayes_chain_key(mt_rng_pt->graph_seed, 0), 0);
+        check(n, "calcMinimumReadCover");
+        cover_size = n;
+        log_stream << "[bayesembler_b200] Minimum read cover size: " << cover_size << std::endl;
+    }
+    int getMinimumReadCoverSize() const { return cover_size; }  // :93-96
+
+    bayes_locus_desc desc() const {
+        bayes_locus_desc d;
+        d.T = num_transcripts;
+        d.R = num_rows;
+        d.row_ptr = row_ptr.data();
+        d.col_idx = col_idx.data();
+        d.val = val.data();
+        d.row_count = row_count.data();
+        d.efflen = 0;
+        d.total_num_fragments = 1;
+        d.gamma = 1;
+        d.pi = -1;
+        d.burn_in = 0;
+        d.samples = 1;
+        d.seed = mt_rng_pt->graph_seed;
+        d.n_chains = 1;
+        d.reserved = 0;
+        return d;
+    }
+    int getNumFragments() const {
+        long n = 0;
+        for (size_t i = 0; i < row_count.size(); i++) n += row_count[i];
+        return (int)n;
+    }
+
+   private:
+    mt_rng_pt_t mt_rng_pt;
+    int num_rows, num_transcripts, cover_size;
+    std::vector<int32_t> row_ptr, col_idx;
+    std::vector<double> val;
+    std::vector<int32_t> row_count;
+};
+
+// ---- simplexSizeGenerator.h ------------------------------------------------------------------------------------------
+class SimplexSizeGenerator {
+   public:
+    virtual std::string getParameterString() = 0;
+    virtual double getPi() const = 0;
+    bool isFixed() const { return true; }
+    virtual ~SimplexSizeGenerator() {}
+};
+
+class FixedBinomialFixedGammaSimplexSizeGenerator : public SimplexSizeGenerator {
+   public:
+    FixedBinomialFixedGammaSimplexSizeGenerator(double pi_in, double gamma_in, int num_transcripts_in, mt_rng_pt_t, int num_fragments_in)
+        : pi(pi_in), gamma(gamma_in), num_transcripts(num_transcripts_in), num_fragments(num_fragments_in) {}
+    std::string getParameterString() {  // simplexSizeGenerator.cpp:189-199
+        std::stringstream s;
+        s << "FixedBinomialFixedGamma simplex size generator (pi=" << pi << ", gamma=" << gamma << ")";
+        return s.str();
+    }
+    double getPi() const { return pi; }
+    // the CDF table of the ctor (simplexSizeGenerator.cpp:117-187), row k-1 = |S+| = k
+    std::vector<std::vector<double> > simplexProbMatrix() const {
+        std::vector<int64_t> off(num_transcripts + 1);
+        const int64_t n = bayes_simplex_table(pi, gamma, num_transcripts, num_fragments, 0, 0);
+        check((int)n, "bayes_simplex_table");
+        std::vector<double> tab(n);
+        bayes_simplex_table(pi, gamma, num_transcripts, num_fragments, off.data(), tab.data());
+        std::vector<std::vector<double> > rows(num_transcripts);
+        for (int k = 0; k < num_transcripts; k++) rows[k].assign(tab.begin() + off[k], tab.begin() + off[k + 1]);
+        return rows;
+    }
+
+   private:
+    double pi, gamma;
+    int num_transcripts, num_fragments;
+};
+
+// ---- gammaGenerator.h --------------------------------------------------------------------------------------------------
+class GammaGenerator {
+   public:
+    virtual double initGamma() = 0;
+    bool isFixed() const { return true; }
+    virtual ~GammaGenerator() {}
+};
+class FixedGammaGenerator : public GammaGenerator {  // gammaGenerator.cpp:159-171
+   public:
+    explicit FixedGammaGenerator(double gamma_in) : gamma(gamma_in) {}
+    double initGamma() { return gamma; }
+
+   private:
+    double gamma;
+};
+
+// ---- expressionGenerator.h ---------------------------------------------------------------------------------------------
+class ExpressionGenerator {
+   public:
+    ExpressionGenerator(int num_fragments_in, int num_transcripts_in, mt_rng_pt_t) : num_transcripts(num_transcripts_in), num_fragments(num_fragments_in) {}
+    int numTranscripts() const { return num_transcripts; }
+    int numFragments() const { return num_fragments; }
+
+   private:
+    int num_transcripts, num_fragments;
+};
+
+// ---- gibbsOutput.h -----------------------------------------------------------------------------------------------------
+class GibbsOutput {
+    int num_iterations, num_transcripts;
+
+   public:
+    GibbsOutput(int num_iterations_in, int num_transcripts_in)  // gibbsOutput.cpp:40-49
+        : num_iterations(num_iterations_in), num_transcripts(num_transcripts_in), marginal_occurence(num_transcripts_in, 0),
+          marginal_mean_cumulant(num_transcripts_in, 0.0), marginal_var_cumulant(num_transcripts_in, 0.0) {}
+
+    // gibbsOutput.cpp:51-75 (host form; the device runs the same recurrence fused into its E-step)
+    void addSample(std::vector<int> plus, const std::vector<double> &values) {
+        for (size_t i = 0; i < plus.size(); i++) {
+            const int idx = plus[i];
+            marginal_occurence[idx]++;
+            if (marginal_occurence[idx] == 1) {
+                marginal_mean_cumulant[idx] = values[idx];
+            } else {
+                const double delta = values[idx] - marginal_mean_cumulant[idx];
+                marginal_mean_cumulant[idx] += delta / marginal_occurence[idx];
+                marginal_var_cumulant[idx] += delta * (values[idx] - marginal_mean_cumulant[idx]);
+            }
+        }
+    }
+
+    Ensemble getTopMarginals(double marginal_threshold) const {  // gibbsOutput.cpp:77-106
+        Ensemble e;
+        e.indices.resize(num_transcripts);
+        e.means.resize(num_transcripts);
+        e.sd.resize(num_transcripts);
+        const int n = bayes_top_marginals(num_transcripts, num_iterations, marginal_occurence.data(), marginal_mean_cumulant.data(),
+                                          marginal_var_cumulant.data(), marginal_threshold, e.indices.data(), e.means.data(), e.sd.data());
+        e.indices.resize(n);
+        e.means.resize(n);
+        e.sd.resize(n);
+        return e;
+    }
+
+    // gibbsOutput.cpp:109-141.  total_num_fragments is an int here exactly as in the reference signature.
+    std::string writeEnsembleGtf(const Ensemble &top_ensemble, const std::vector<Candidate> &candidates, const IdxMap &idx_map,
+                                 int total_num_fragments, double count_threshold) const {
+        std::stringstream out;
+        for (size_t i = 0; i < top_ensemble.indices.size(); i++) {
+            const int new_idx = top_ensemble.indices[i];
+            const std::pair<int, double> &m = idx_map.at(new_idx);
+            const double expected_count = top_ensemble.means[i] * m.second * total_num_fragments / 1e9;
+            if (expected_count < count_threshold) continue;
+            const Candidate &c = candidates[m.first];
+            if (c.idx != m.first) throw std::logic_error("writeEnsembleGtf: candidate index mismatch");  // reference: assert :127
+            if (c.isPreMrna) continue;
+            for (size_t j = 0; j < c.vertices.size(); j++)
+                exon_line(out, c, c.vertices[j], (double)marginal_occurence[new_idx] / num_iterations, top_ensemble.means[i],
+                          top_ensemble.sd[i], expected_count);
+        }
+        return out.str();
+    }
+
+    // gibbsOutput.cpp:143-166
+    std::string writeCandidateGtf(const std::vector<Candidate> &candidates, const IdxMap &idx_map, int total_num_fragments) const {
+        std::stringstream out;
+        for (int i = 0; i < num_transcripts; i++) {
+            const std::pair<int, double> &m = idx_map.at(i);
+            const double expected_count = marginal_mean_cumulant[i] * m.second * total_num_fragments / 1e9;
+            const Candidate &c = candidates[m.first];
+            if (c.idx != m.first) throw std::logic_error("writeCandidateGtf: candidate index mismatch");
+            for (size_t j = 0; j < c.vertices.size(); j++)
+                exon_line(out, c, c.vertices[j], (double)marginal_occurence[i] / num_iterations, marginal_mean_cumulant[i],
+                          sqrt(marginal_var_cumulant[i] / (marginal_occurence[i] - 1)), expected_count);
+        }
+        return out.str();
+    }
+
+    int numIterations() const { return num_iterations; }
+    int numTranscripts() const { return num_transcripts; }
+    std::vector<int32_t> marginal_occurence;
+    std::vector<double> marginal_mean_cumulant;
+    std::vector<double> marginal_var_cumulant;
+
+   private:
+    static void exon_line(std::stringstream &out, const Candidate &c, const Vertex &v, double confidence, double fpkm, double fpkm_sd,
+                          double expected_count) {
+        out << v.reference << "\tBayesembler\texon\t" << v.start << "\t" << v.end << "\t.\t" << v.strand << "\t.\tgene_id \"" << c.graph_name
+            << "\"; transcript_id \"" << c.name << "\"; transcript_confidence \"" << confidence << "\"; FPKM \"" << fpkm << "\"; FPKM_sd \""
+            << fpkm_sd << "\"; expected_count \"" << expected_count << "\";" << std::endl;
+    }
+};
+
+// ---- gibbsSampler.h ----------------------------------------------------------------------------------------------------
+class GibbsSampler {
+   public:
+    GibbsSampler(SimplexSizeGenerator *ssg, GammaGenerator *gg, ExpressionGenerator *eg, AssignmentGenerator *ag, const IdxMap &idx_map,
+                 int total_num_fragments_in, int num_fragments_in, int num_transcripts_in, mt_rng_pt_t rng, bool assignment_minimum_in)
+        : simplex_size_generator(ssg), gamma_generator(gg), expression_generator(eg), assignment_generator(ag),
+          new_idx_to_old_idx_effective_length(idx_map), total_num_fragments(total_num_fragments_in), num_fragments(num_fragments_in),
+          num_transcripts(num_transcripts_in), mt_rng_pt(rng), assignment_minimum(assignment_minimum_in) {
+        if (assignment_minimum) throw std::invalid_argument("GibbsSampler: assignment_minimum is unreachable in v1.2.0 (assembler.cpp:1577) and not built");
+        efflen.resize(num_transcripts);
+        for (int t = 0; t < num_transcripts; t++) efflen[t] = idx_map.at(t).second;  // gibbsSampler.cpp:73-78
+    }
+
+    // bayes_locus_desc of this sampler: what the reference's objects at assembler.cpp:1548-1577 hold between them
+    bayes_locus_desc desc(int burn_in, int samples, int n_chains = 1) const {
+        bayes_locus_desc d = assignment_generator->desc();
+        d.efflen = efflen.data();
+        d.total_num_fragments = (double)total_num_fragments;
+        d.gamma = gamma_generator->initGamma();
+        d.pi = simplex_size_generator->getPi();
+        d.burn_in = burn_in;
+        d.samples = samples;
+        d.seed = mt_rng_pt->graph_seed;
+        d.n_chains = n_chains;
+        return d;
+    }
+
+    // gibbsSampler.cpp:55-148 for ONE locus on device `device`: correct, but a single dependent chain cannot fill a GPU --
+    // use GibbsBatch wherever the caller can defer reading the GibbsOutput.
+    void runSampler(GibbsOutput *gibbs_output, int burn_in, int samples, std::stringstream &log_stream, int device = 0) const {
+        bayes_gibbs_ctx *ctx = 0;
+        check(bayes_gibbs_create(device, &ctx), "bayes_gibbs_create");
+        bayes_locus_desc d = desc(burn_in, samples);
+        int64_t id = 0;
+        int rc = bayes_gibbs_run_batch(ctx, 1, &d, &id);
+        if (rc == 0)
+            rc = bayes_gibbs_fetch(ctx, id, 0, gibbs_output->marginal_occurence.data(), gibbs_output->marginal_mean_cumulant.data(),
+                                   gibbs_output->marginal_var_cumulant.data(), 0);
+        std::string err = rc ? bayes_last_error() : "";
+        bayes_gibbs_destroy(ctx);
+        if (rc) throw std::runtime_error("runSampler: " + err);
+        log_stream << "[bayesembler_b200] Gibbs sampler: " << burn_in << " burn-in + " << samples << " sampling iterations on device " << device
+                   << std::endl;
+    }
+
+    int numTranscripts() const { return num_transcripts; }
+
+   private:
+    SimplexSizeGenerator *simplex_size_generator;
+    GammaGenerator *gamma_generator;
+    ExpressionGenerator *expression_generator;
+    AssignmentGenerator *assignment_generator;
+    IdxMap new_idx_to_old_idx_effective_length;
+    int total_num_fragments;  // int on purpose: gibbsSampler.h:51 truncates the caller's double
+    int num_fragments;
+    int num_transcripts;
+    mt_rng_pt_t mt_rng_pt;
+    bool assignment_minimum;
+    std::vector<double> efflen;
+};
+
+// The batched form: the reference's N worker threads each run one locus start to finish (assembler.cpp:2017-2026); a GPU
+// wants all loci of a pass at once.  add() copies what the sampler needs (the generator objects may die afterwards),
+// run() executes every queued sampler in one submit/upload/run/download and fills the GibbsOutputs.
+class GibbsBatch {
+   public:
+    explicit GibbsBatch(int device = 0) : ctx(0) { check(bayes_gibbs_create(device, &ctx), "bayes_gibbs_create"); }
+    ~GibbsBatch() { bayes_gibbs_destroy(ctx); }
+    void add(const GibbsSampler &sampler, GibbsOutput *out, int burn_in, int samples) {
+        bayes_locus_desc d = sampler.desc(burn_in, samples);
+        int64_t id = 0;
+        check(bayes_gibbs_submit(ctx, 1, &d, &id), "bayes_gibbs_submit");  // packs now; the caller's buffers are free again
+        outputs.push_back(out);
+    }
+    void run() {
+        check(bayes_gibbs_upload(ctx), "bayes_gibbs_upload");
+        check(bayes_gibbs_run(ctx), "bayes_gibbs_run");
+        check(bayes_gibbs_download(ctx), "bayes_gibbs_download");
+        check(bayes_gibbs_sync(ctx), "bayes_gibbs_sync");
+        for (size_t i = 0; i < outputs.size(); i++)
+            check(bayes_gibbs_fetch(ctx, (int64_t)i, 0, outputs[i]->marginal_occurence.data(), outputs[i]->marginal_mean_cumulant.data(),
+                                    outputs[i]->marginal_var_cumulant.data(), 0),
+                  "bayes_gibbs_fetch");
+        check(bayes_gibbs_clear(ctx), "bayes_gibbs_clear");
+        outputs.clear();
+    }
+    size_t size() const { return outputs.size(); }
+
+   private:
+    GibbsBatch(const GibbsBatch &);
+    GibbsBatch &operator=(const GibbsBatch &);
+    bayes_gibbs_ctx *ctx;
+    std::vector<GibbsOutput *> outputs;
+};
+
+}  // namespace bayesembler_b200
+
+#endif  // BAYESEMBLER_B200_HPP

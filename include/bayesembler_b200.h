@@ -61,7 +61,8 @@ typedef struct {
     int32_t samples;            /* gibbs_samples  (assembler.cpp:1599)                                      */
     uint64_t seed;              /* graph_seed (assembler.cpp:1437); Philox key of chain c is derived from
                                    (seed, c) by bayes_chain_key()                                           */
-    int32_t n_chains;           /* independent chains of this locus (reference: 1)                          */
+    int32_t n_chains;           /* independent chains of this locus (reference: 1); each chain is a complete
+                                   independent run (own read cover when pi < 0, own Philox key)             */
     int32_t reserved;
 } bayes_locus_desc;
 
@@ -102,8 +103,11 @@ int bayes_gibbs_fetch(bayes_gibbs_ctx *ctx, int64_t locus_id, int32_t chain, int
 /* The same for every job at once: locus after locus in submission order, chains of a locus back to back, T entries
  * per job (what the reference's output thread would drain, assembler.cpp:1746-1839). */
 int bayes_gibbs_fetch_all(bayes_gibbs_ctx *ctx, int32_t *occ, double *mean, double *m2, int32_t *final_counts);
-/* pi actually used, |minimum read cover| (0 when pi was given), folded single-cell rows */
+/* pi actually used by chain 0, its |minimum read cover| (0 when pi was given), folded single-cell rows */
 int bayes_gibbs_locus_info(bayes_gibbs_ctx *ctx, int64_t locus_id, double *pi, int32_t *cover_size, int32_t *rows_folded);
+/* Every chain is one independent run of the reference's call site: unless pi was given, chain c derives pi from its
+ * own minimum read cover (tie breaks keyed by bayes_chain_key(seed, c), assembler.cpp:1551-1559). */
+int bayes_gibbs_chain_info(bayes_gibbs_ctx *ctx, int64_t locus_id, int32_t chain, double *pi, int32_t *cover_size);
 int64_t bayes_gibbs_num_loci(bayes_gibbs_ctx *ctx);
 int64_t bayes_gibbs_num_jobs(bayes_gibbs_ctx *ctx);
 /* kernels launched by the last bayes_gibbs_run() */

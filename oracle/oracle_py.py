@@ -200,6 +200,42 @@ class Oracle(object):
         return out
 
 
+GTF_ARGTYPES = [C.c_int, C.c_int, C.c_int, _i32p, _f64p, C.c_int, _i32p, _i32p, _i32p, _i32p, _i32p, _f64p, C.c_int, C.c_double,
+                C.c_double, C.c_int, C.c_char_p, C.c_int]
+
+
+def call_gtf(fn, case, mode):
+    """Shared argument marshalling of ref_gtf (oracle/_ref) and facade_gtf (tests/cpp/facade_driver.cpp)."""
+    buf = C.create_string_buffer(1 << 20)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)  # noqa: E731
+    n = fn(case["T"], case["samples"], len(case["mask"]), i32(case["mask"]), np.ascontiguousarray(case["values"], np.float64),
+           len(case["n_vert"]), i32(case["n_vert"]), i32(case["starts"]), i32(case["ends"]), i32(case["premrna"]), i32(case["old_idx"]),
+           np.ascontiguousarray(case["efflen"], np.float64), int(case["total_num_fragments"]), float(case["count_threshold"]),
+           float(case["marginal_threshold"]), mode, buf, len(buf))
+    assert n >= 0
+    return buf.value.decode()
+
+
+def gtf_case(seed, T=7, samples=40, n_cand=9):
+    """Deterministic GibbsOutput + candidate set for the GTF writers."""
+    rng = np.random.default_rng(seed)
+    mask = (rng.random((samples, T)) < rng.random(T)[None, :]).astype(np.int32)
+    mask[:, 0] = 1
+    values = rng.gamma(2.0, 20.0, (samples, T)) * rng.random(T)[None, :]
+    n_vert = rng.integers(1, 6, n_cand)
+    starts, ends = [], []
+    for nv in n_vert:
+        pos = 1000 + np.cumsum(rng.integers(50, 4000, 2 * nv))
+        starts += pos[0::2].tolist()
+        ends += pos[1::2].tolist()
+    premrna = np.zeros(n_cand, np.int32)
+    premrna[rng.integers(n_cand)] = 1
+    old_idx = np.sort(rng.choice(n_cand, T, replace=False))
+    return dict(T=T, samples=samples, mask=mask, values=values, n_vert=n_vert, starts=starts, ends=ends, premrna=premrna,
+                old_idx=old_idx, efflen=rng.uniform(300, 4000, T), total_num_fragments=2000000, count_threshold=12.0,
+                marginal_threshold=0.5)
+
+
 class Reference(object):
     """The unmodified reference sampler TUs behind oracle/ref_driver.cpp (sequential MT19937 only)."""
 
@@ -226,6 +262,8 @@ class Reference(object):
         L.ref_sample_simplex.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_uint32]
         L.ref_top_marginals.restype = C.c_int
         L.ref_top_marginals.argtypes = [C.c_int, C.c_int, _i32p, _f64p, _f64p, C.c_double, _i32p, _f64p, _f64p]
+        L.ref_gtf.restype = C.c_int
+        L.ref_gtf.argtypes = GTF_ARGTYPES
         L.ref_run_batch.restype = C.c_double
         L.ref_run_batch.argtypes = [C.c_int, _i32p, C.c_void_p, C.c_void_p, C.c_void_p, _i32p, _i32p, _f64p, _i32p, _f64p,
                                     C.c_double, C.c_double, _u32p, _i32p, _i32p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -289,6 +327,9 @@ class Reference(object):
         n = self.lib.ref_top_marginals(T, samples, np.ascontiguousarray(occ, np.int32), np.ascontiguousarray(mean),
                                        np.ascontiguousarray(m2), threshold, idx, mo, sd)
         return idx[:n], mo[:n], sd[:n]
+
+    def gtf(self, case, mode):
+        return call_gtf(self.lib.ref_gtf, case, mode)
 
     def run_batch(self, loci, seeds, burn, samples, n_threads, want_output=False):
         """CPU baseline: thread pool over loci (assembler.cpp:2017-2026). Returns (seconds, outputs|None)."""

@@ -16,6 +16,7 @@
  * popping loci from a queue like assembler.cpp:1422-1439 / 2017-2026.
  */
 #include <chrono>
+#include <cstring>
 #include <mutex>
 #include <sstream>
 #include <stdint.h>
@@ -195,6 +196,48 @@ int ref_top_marginals(int T, int samples, const int *occ, const double *mean, co
         sd_out[i] = e.sd(i);
     }
     return (int)e.indices.size();
+}
+
+/* GibbsOutput::addSample (gibbsOutput.cpp:51-75) n_add times, then getTopMarginals + writeEnsembleGtf (mode 0,
+ * gibbsOutput.cpp:109-141) or writeCandidateGtf (mode 1, :143-166) on candidates built from flat arrays.
+ * Returns the text length, or -(needed) when cap is too small. */
+int ref_gtf(int T, int samples, int n_add, const int *mask, const double *values, int n_cand, const int *n_vert, const int *starts,
+            const int *ends, const int *premrna, const int *old_idx, const double *efflen, int total_num_fragments,
+            double count_threshold, double marginal_threshold, int mode, char *out, int cap) {
+    GibbsOutput go(samples, T);
+    for (int s = 0; s < n_add; s++) {
+        vector<int> plus;
+        for (int t = T - 1; t >= 0; t--)
+            if (mask[(size_t)s * T + t]) plus.push_back(t);
+        go.addSample(plus, vector<double>(values + (size_t)s * T, values + (size_t)(s + 1) * T));
+    }
+    tr1::unordered_map<int, pair<int, double> > idx_map;
+    for (int t = 0; t < T; t++) idx_map[t] = pair<int, double>(old_idx[t], efflen[t]);
+    vector<Candidate> cands(n_cand);
+    int at = 0;
+    for (int i = 0; i < n_cand; i++) {
+        stringstream nm;
+        nm << "graph1_cand" << i;
+        cands[i].idx = i;
+        cands[i].name = nm.str();
+        cands[i].graph_name = "graph1";
+        cands[i].length = 0;
+        cands[i].isPreMrna = premrna[i] != 0;
+        for (int j = 0; j < n_vert[i]; j++, at++) {
+            Vertex v;
+            v.reference = "chr1";
+            v.strand = (i & 1) ? "-" : "+";
+            v.start = starts[at];
+            v.end = ends[at];
+            cands[i].vertices.push_back(v);
+            cands[i].length += ends[at] - starts[at] + 1;
+        }
+    }
+    string text = mode == 0 ? go.writeEnsembleGtf(go.getTopMarginals(marginal_threshold), cands, idx_map, total_num_fragments, count_threshold)
+                            : go.writeCandidateGtf(cands, idx_map, total_num_fragments);
+    if ((int)text.size() + 1 > cap) return -(int)text.size() - 1;
+    memcpy(out, text.c_str(), text.size() + 1);
+    return (int)text.size();
 }
 
 /*

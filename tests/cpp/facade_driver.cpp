@@ -1,0 +1,147 @@
+// C-callable test driver around the C++ host facade (bayesembler_b200/host/bayesembler_b200.hpp); built by
+// tests/test_host_facade.py with g++ and linked against libbayesembler_b200.so.  facade_run_loci() is written the way
+// Assembler::bayesemblerCallback builds and runs its sampler objects (assembler.cpp:1548-1609).
+#include <string.h>
+
+#include "../../bayesembler_b200/host/bayesembler_b200.hpp"
+
+using namespace bayesembler_b200;
+
+namespace {
+
+// dense matrix with the accessors AssignmentGenerator's templated ctor needs (what Eigen::MatrixXd offers)
+struct Dense {
+    int R, T;
+    std::vector<double> a;
+    Dense(int R_, int T_) : R(R_), T(T_), a((size_t)R_ * T_, 0.0) {}
+    int rows() const { return R; }
+    int cols() const { return T; }
+    double operator()(int i, int j) const { return a[(size_t)j * R + i]; }
+    double &operator()(int i, int j) { return a[(size_t)j * R + i]; }
+};
+
+std::vector<Candidate> make_candidates(int n_cand, const int *n_vert, const int *starts, const int *ends, const int *premrna) {
+    std::vector<Candidate> c(n_cand);
+    int at = 0;
+    for (int i = 0; i < n_cand; i++) {
+        std::stringstream nm;
+        nm << "graph1_cand" << i;
+        c[i].idx = i;
+        c[i].name = nm.str();
+        c[i].graph_name = "graph1";
+        c[i].length = 0;
+        c[i].isPreMrna = premrna[i] != 0;
+        for (int j = 0; j < n_vert[i]; j++, at++) {
+            Vertex v;
+            v.reference = "chr1";
+            v.strand = (i & 1) ? "-" : "+";
+            v.start = starts[at];
+            v.end = ends[at];
+            c[i].vertices.push_back(v);
+            c[i].length += ends[at] - starts[at] + 1;
+        }
+    }
+    return c;
+}
+
+}  // namespace
+
+extern "C" {
+
+// GibbsOutput: n_add addSample calls (mask/values rows of length T), then getTopMarginals + writeEnsembleGtf (mode 0) or
+// writeCandidateGtf (mode 1).  Returns the text length (or -needed when cap is too small).
+int facade_gtf(int T, int samples, int n_add, const int *mask, const double *values, int n_cand, const int *n_vert, const int *starts,
+               const int *ends, const int *premrna, const int *old_idx, const double *efflen, int total_num_fragments,
+               double count_threshold, double marginal_threshold, int mode, char *out, int cap) {
+    GibbsOutput go(samples, T);
+    for (int s = 0; s < n_add; s++) {
+        std::vector<int> plus;
+        for (int t = T - 1; t >= 0; t--)
+            if (mask[(size_t)s * T + t]) plus.push_back(t);
+        go.addSample(plus, std::vector<double>(values + (size_t)s * T, values + (size_t)(s + 1) * T));
+    }
+    IdxMap idx_map;
+    for (int t = 0; t < T; t++) idx_map[t] = std::make_pair(old_idx[t], efflen[t]);
+    const std::vector<Candidate> cands = make_candidates(n_cand, n_vert, starts, ends, premrna);
+    const std::string text = mode == 0 ? go.writeEnsembleGtf(go.getTopMarginals(marginal_threshold), cands, idx_map, total_num_fragments, count_threshold)
+                                       : go.writeCandidateGtf(cands, idx_map, total_num_fragments);
+    if ((int)text.size() + 1 > cap) return -(int)text.size() - 1;
+    memcpy(out, text.c_str(), text.size() + 1);
+    return (int)text.size();
+}
+
+// n loci (concatenated CSR, per-locus row_ptr with R+1 entries at row_off[l] + l), each driven like
+// assembler.cpp:1548-1609.  batched = 0: GibbsSampler::runSampler per locus; 1: GibbsBatch.  Returns 0 or -1 (message in err).
+int facade_run_loci(int n, const int *T_arr, const int64_t *row_off, const int64_t *cell_off, const int64_t *t_off, const int *row_ptr,
+                    const int *col_idx, const double *val, const int *row_count, const double *efflen, double adjusted_fragment_count,
+                    double gamma, const uint64_t *seeds, const int *burn, const int *samples, int batched, int *occ, double *mean,
+                    double *m2, double *pi_out, char *err, int err_cap) {
+    try {
+        GibbsBatch *batch = batched ? new GibbsBatch(0) : 0;
+        std::vector<GibbsOutput *> outs;
+        for (int l = 0; l < n; l++) {
+            const int T = T_arr[l], R = (int)(row_off[l + 1] - row_off[l]);
+            const int *rp = row_ptr + row_off[l] + l;
+            Dense P(R, T);
+            for (int i = 0; i < R; i++)
+                for (int k = rp[i]; k < rp[i + 1]; k++) P(i, col_idx[cell_off[l] + k]) = val[cell_off[l] + k];
+            std::vector<int> counts(row_count + row_off[l], row_count + row_off[l + 1]);
+            IdxMap idx_map;
+            for (int t = 0; t < T; t++) idx_map[t] = std::make_pair(t, efflen[t_off[l] + t]);
+            int num_fragments = 0;
+            for (int i = 0; i < R; i++) num_fragments += counts[i];
+            std::stringstream log;
+
+            mt_rng_t mt_rng;
+            mt_rng.seed(seeds[l]);
+            AssignmentGenerator assignment_generator(&mt_rng, &P, &counts);
+            assignment_generator.calcMinimumReadCover(log);
+            double msc_to_all_ratio = double(assignment_generator.getMinimumReadCoverSize()) / T;
+            if (msc_to_all_ratio > 1.0 - 2.220446049250313e-16) msc_to_all_ratio = 1.0 - 2.220446049250313e-16;
+            FixedBinomialFixedGammaSimplexSizeGenerator fixed_simplex_size_generator(msc_to_all_ratio, gamma, T, &mt_rng, num_fragments);
+            FixedGammaGenerator fixed_gamma_generator(gamma);
+            ExpressionGenerator expression_generator(num_fragments, T, &mt_rng);
+            GibbsSampler gibbs_sampler(&fixed_simplex_size_generator, &fixed_gamma_generator, &expression_generator, &assignment_generator,
+                                       idx_map, adjusted_fragment_count, num_fragments, T, &mt_rng, false);
+            GibbsOutput *gibbs_output = new GibbsOutput(samples[l], T);
+            outs.push_back(gibbs_output);
+            if (batch) batch->add(gibbs_sampler, gibbs_output, burn[l], samples[l]);
+            else gibbs_sampler.runSampler(gibbs_output, burn[l], samples[l], log);
+            if (pi_out) pi_out[l] = msc_to_all_ratio;
+        }
+        if (batch) {
+            batch->run();
+            delete batch;
+        }
+        for (int l = 0; l < n; l++) {
+            for (int t = 0; t < T_arr[l]; t++) {
+                occ[t_off[l] + t] = outs[l]->marginal_occurence[t];
+                mean[t_off[l] + t] = outs[l]->marginal_mean_cumulant[t];
+                m2[t_off[l] + t] = outs[l]->marginal_var_cumulant[t];
+            }
+            delete outs[l];
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        if (err && err_cap > 0) {
+            strncpy(err, e.what(), err_cap - 1);
+            err[err_cap - 1] = 0;
+        }
+        return -1;
+    }
+}
+
+// the CDF table as the facade's FixedBinomialFixedGammaSimplexSizeGenerator exposes it (row lengths only + flat values)
+int facade_simplex_rows(double pi, double gamma, int T, int num_fragments, int *row_len, double *flat) {
+    mt_rng_t rng;
+    FixedBinomialFixedGammaSimplexSizeGenerator g(pi, gamma, T, &rng, num_fragments);
+    std::vector<std::vector<double> > rows = g.simplexProbMatrix();
+    int at = 0;
+    for (int k = 0; k < T; k++) {
+        row_len[k] = (int)rows[k].size();
+        for (size_t j = 0; j < rows[k].size(); j++) flat[at++] = rows[k][j];
+    }
+    return at;
+}
+
+}  // extern "C"

@@ -12,6 +12,7 @@ Contents (all produced by reference code on a sequential MT19937, seeds below):
                  pi, and the number of 32-bit RNG words each call consumed
   table{j}_*     FixedBinomialFixedGammaSimplexSizeGenerator CDF tables
   top_*          getTopMarginals on fixed accumulators
+  gtf{k}_*       writeEnsembleGtf / writeCandidateGtf text for oracle_py.gtf_case(100 + k, ...)
 """
 import os
 import sys
@@ -87,6 +88,10 @@ def main():
     idx, mo, sd = ref.top_marginals(100, occ, mean, m2, 0.5)
     out["top_occ"], out["top_mean"], out["top_m2"] = occ, mean, m2
     out["top_idx"], out["top_mean_out"], out["top_sd_out"] = idx, mo, sd
+    for gi in range(4):
+        case = oracle_py.gtf_case(100 + gi, T=[7, 3, 12, 1][gi], samples=[40, 25, 60, 10][gi], n_cand=[9, 3, 20, 2][gi])
+        out["gtf%d_ensemble" % gi] = np.frombuffer(ref.gtf(case, 0).encode(), np.uint8)
+        out["gtf%d_candidates" % gi] = np.frombuffer(ref.gtf(case, 1).encode(), np.uint8)
     np.savez_compressed(OUT, **out)
     print("wrote %s (%d arrays, %d bytes)" % (OUT, len(out), os.path.getsize(OUT)))
 

@@ -139,8 +139,8 @@ def test_batch_mixed_loci_and_chains(lib, oracle):
     for i, loc in enumerate(loci):
         for c in range(chains[i]):
             g = ctx.fetch(i, c)
-            o = oracle.run_sampler(loc, burn[i], samples[i], SITE, lib.chain_key(seeds[i], c),
-                                   pi=-1.0 if c == 0 else ctx.locus_info(i)["pi"])
+            o = oracle.run_sampler(loc, burn[i], samples[i], SITE, lib.chain_key(seeds[i], c))  # own read cover per chain
+            assert o["pi"] == ctx.chain_info(i, c)["pi"]
             assert np.array_equal(g["occ"], o["occ"]), (i, c)
             np.testing.assert_allclose(g["mean"], o["mean"], rtol=RTOL)
             assert g["final_counts"].sum() == loc.n_frag

@@ -1,0 +1,124 @@
+"""The C++ host facade (bayesembler_b200/host/bayesembler_b200.hpp) -- the reference's class surface on top of the C ABI.
+
+CPU: the GTF writers and getTopMarginals against text recorded from the reference's own GibbsOutput
+(tests/golden/ref_vectors.npz, gibbsOutput.cpp:77-166) and against the live reference where oracle/_ref exists; the
+facade refuses to sample without a GPU.  GPU: a worker written like assembler.cpp:1548-1609 on the facade classes gives
+the same accumulators as the C ABI called directly, in both the per-locus and the batched form.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import oracle_py
+from oracle.oracle_py import random_locus
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "facade_driver.cpp")
+HPP = os.path.join(ROOT, "bayesembler_b200", "host", "bayesembler_b200.hpp")
+OUT = os.path.join(ROOT, "tests", "cpp", "libfacade_test.so")
+GOLD = os.path.join(ROOT, "tests", "golden", "ref_vectors.npz")
+GTF_SHAPES = [dict(T=7, samples=40, n_cand=9), dict(T=3, samples=25, n_cand=3), dict(T=12, samples=60, n_cand=20),
+              dict(T=1, samples=10, n_cand=2)]
+
+
+@pytest.fixture(scope="module")
+def facade(lib):
+    libdir = os.path.join(ROOT, "bayesembler_b200")
+    newest = max(os.path.getmtime(p) for p in (SRC, HPP, os.path.join(ROOT, "include", "bayesembler_b200.h")))
+    if not os.path.exists(OUT) or os.path.getmtime(OUT) < newest:
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=gnu++17", "-fPIC", "-shared", "-Wall", "-Werror", "-o", OUT, SRC,
+                               "-L" + libdir, "-lbayesembler_b200", "-Wl,-rpath," + libdir])
+    lib.load_library()
+    L = C.CDLL(OUT)
+    L.facade_gtf.restype = C.c_int
+    L.facade_gtf.argtypes = oracle_py.GTF_ARGTYPES
+    return L
+
+
+@pytest.mark.parametrize("gi", range(4))
+def test_gtf_text_matches_reference_golden(facade, gi):
+    g = np.load(GOLD)
+    case = oracle_py.gtf_case(100 + gi, **GTF_SHAPES[gi])
+    assert oracle_py.call_gtf(facade.facade_gtf, case, 0) == bytes(g["gtf%d_ensemble" % gi]).decode()
+    assert oracle_py.call_gtf(facade.facade_gtf, case, 1) == bytes(g["gtf%d_candidates" % gi]).decode()
+
+
+def test_gtf_text_matches_live_reference(facade, reference):
+    for seed in range(20):
+        case = oracle_py.gtf_case(seed, T=1 + seed % 9, samples=10 + 7 * seed, n_cand=10)
+        case["count_threshold"] = [0.0, 12.0, 500.0][seed % 3]
+        for mode in (0, 1):
+            assert oracle_py.call_gtf(facade.facade_gtf, case, mode) == reference.gtf(case, mode)
+
+
+def test_facade_simplex_table(facade, oracle):
+    pi, gamma, T, nf = 0.2, 1.0, 25, 800
+    rl = np.zeros(T, np.int32)
+    flat = np.zeros(T * T)
+    facade.facade_simplex_rows.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    n = facade.facade_simplex_rows(pi, gamma, T, nf, rl.ctypes.data, flat.ctypes.data)
+    otab, orl = oracle.simplex_table(pi, gamma, T, nf)
+    assert np.array_equal(rl, orl) and n == orl.sum()
+    at = 0
+    for k in range(T):
+        assert np.array_equal(flat[at:at + rl[k]], otab[k, :rl[k]])
+        at += rl[k]
+
+
+def _run_loci(facade, loci, seeds, burn, samples, batched):
+    n = len(loci)
+    T_arr = np.array([l.T for l in loci], np.int32)
+    row_off = np.zeros(n + 1, np.int64)
+    cell_off = np.zeros(n + 1, np.int64)
+    t_off = np.zeros(n + 1, np.int64)
+    for i, l in enumerate(loci):
+        row_off[i + 1], cell_off[i + 1], t_off[i + 1] = row_off[i] + l.R, cell_off[i] + l.nnz, t_off[i] + l.T
+    cat = lambda xs, dt: np.ascontiguousarray(np.concatenate(xs), dt)  # noqa: E731
+    row_ptr, col, val = cat([l.row_ptr for l in loci], np.int32), cat([l.col_idx for l in loci], np.int32), cat([l.val for l in loci], np.float64)
+    cnt, eff = cat([l.row_count for l in loci], np.int32), cat([l.efflen for l in loci], np.float64)
+    occ, mean, m2, pi = np.zeros(t_off[-1], np.int32), np.zeros(t_off[-1]), np.zeros(t_off[-1]), np.zeros(n)
+    err = C.create_string_buffer(512)
+    vp = C.c_void_p
+    facade.facade_run_loci.restype = C.c_int
+    facade.facade_run_loci.argtypes = [C.c_int] + [vp] * 9 + [C.c_double, C.c_double, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_char_p, C.c_int]
+    p = lambda a: a.ctypes.data  # noqa: E731
+    rc = facade.facade_run_loci(n, p(T_arr), p(row_off), p(cell_off), p(t_off), p(row_ptr), p(col), p(val), p(cnt), p(eff),
+                                loci[0].n_total, loci[0].gamma, p(np.ascontiguousarray(seeds, np.uint64)),
+                                p(np.ascontiguousarray(burn, np.int32)), p(np.ascontiguousarray(samples, np.int32)), int(batched),
+                                p(occ), p(mean), p(m2), p(pi), err, len(err))
+    return rc, err.value.decode(), [dict(occ=occ[t_off[i]:t_off[i + 1]], mean=mean[t_off[i]:t_off[i + 1]], m2=m2[t_off[i]:t_off[i + 1]],
+                                         pi=pi[i]) for i in range(n)]
+
+
+def test_facade_has_no_cpu_sampler(facade):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    rng = np.random.default_rng(0)
+    for batched in (0, 1):
+        rc, err, _ = _run_loci(facade, [random_locus(rng, 3, 6)], [1], [5], [50], batched)
+        assert rc == -1 and "no CPU path" in err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batched", [0, 1])
+def test_facade_worker_matches_c_abi(facade, lib, batched):
+    rng = np.random.default_rng(77)
+    shapes = [(1, 3, 9), (2, 6, 40), (5, 50, 100), (12, 70, 30), (40, 120, 200)]
+    loci = [random_locus(rng, T, R, max_count=mc) for (T, R, mc) in shapes]
+    seeds = [int(s) for s in rng.integers(1, 2 ** 31, len(loci))]
+    burn = [30 + 3 * l.T for l in loci]
+    samples = [10 * b for b in burn]
+    rc, err, got = _run_loci(facade, loci, seeds, burn, samples, batched)
+    assert rc == 0, err
+    ctx = lib.GibbsContext(0)
+    ctx.run_batch(lib.make_desc_array(loci, burn, samples, seeds))
+    for i in range(len(loci)):
+        want = ctx.fetch(i)
+        assert got[i]["pi"] == ctx.locus_info(i)["pi"]
+        assert np.array_equal(got[i]["occ"], want["occ"])
+        assert np.array_equal(got[i]["mean"], want["mean"]) and np.array_equal(got[i]["m2"], want["m2"])
+    ctx.close()

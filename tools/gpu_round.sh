@@ -1,0 +1,39 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, the bench line, the ncu launch list of the same bench command and one
+# `--set full` capture of the dominant kernel.  Run from the repo root under gpurun:
+#     gpurun --timeout 1500 -- 'bash tools/gpu_round.sh r1'
+# Outputs land in gpurun_out/ (scratch); tools/summarise_profile.py turns them into profiles/<tag>_*.
+set -u
+TAG=${1:-r1}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/${TAG}_smi.csv 2>&1
+
+python -m pytest tests -m gpu -x -q > $OUT/${TAG}_pytest.log 2>&1
+echo "pytest rc=$?" | tee -a $OUT/${TAG}_pytest.log
+tail -3 $OUT/${TAG}_pytest.log
+
+python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1
+echo "smoke rc=$?" | tee -a $OUT/${TAG}_smoke.log
+
+python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
+rc=$?
+echo "bench rc=$rc"
+cat $OUT/${TAG}_bench.json
+python bench.py --impl reference --steps 1 --warmup 0 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err
+echo "bench ref rc=$?"
+cat $OUT/${TAG}_bench_ref.json
+
+if [ $rc -eq 0 ]; then
+  # launch list of the same command (cold-cache, serialised: compare shares, not absolutes)
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
+      python bench.py --no-cpu-baseline > $OUT/${TAG}_ncu_launches.log 2>&1
+  echo "ncu launches rc=$?"
+fi
+
+# the dominant kernel, full set, on a 2000-locus slice of the same workload
+SMALL="python bench.py --loci 2000 --steps 1 --warmup 1 --no-cpu-baseline"
+$SMALL > $OUT/${TAG}_small.json 2> $OUT/${TAG}_small.err && \
+ncu --set full --clock-control none --import-source on -k regex:gibbs_ -c 6 -f -o $OUT/${TAG}_prof \
+    $SMALL > $OUT/${TAG}_ncu_full.log 2>&1
+echo "ncu full rc=$?"
