@@ -31,6 +31,8 @@ def nvcc_command(out=LIB, extra=()):
            "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-shared", "-o", out]
     if os.environ.get("BAYES_MIN_BLOCKS"):  # experiment knob: registers per thread = 65536 / (256 * this)
         cmd += ["-DBAYES_MIN_BLOCKS=" + os.environ["BAYES_MIN_BLOCKS"]]
+    if os.environ.get("BAYES_NVCC_FLAGS"):  # experiment knob, e.g. -DBAYES_BINV_NQ=24.0
+        cmd += os.environ["BAYES_NVCC_FLAGS"].split()
     cmd += list(extra)
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     return cmd

@@ -2,12 +2,14 @@
 // formation, device buffers, launches.  Everything that computes on the device is in gibbs_kernel.cu; nothing here
 // falls back to the CPU.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <atomic>
 #include <map>
 #include <numeric>
+#include <queue>
 #include <thread>
 #include <tuple>
 
@@ -117,6 +119,7 @@ struct bayes_gibbs_ctx {
     DevBuf<uint16_t> d_col;
     DevBuf<int32_t> d_slab, d_row_n, d_row_nnz, d_base, d_tab_row, d_occ, d_counts, d_tr_counts, d_tr_b, d_tr_init;
     DevBuf<uint32_t> d_row_info;
+    DevBuf<uint64_t> d_unit_clock;
 
     std::vector<Launch> launches;
     int32_t last_launches = 0;
@@ -234,33 +237,170 @@ int build_units(bayes_gibbs_ctx *ctx) {
         }
     }
     const int64_t n_units = (int64_t)groups.size();
-    std::vector<PackedUnit> packed(n_units);
-    parallel_for(host_thread_count(ctx, n_units), n_units, [&](int64_t i) { pack_unit(groups[i], group_wide[i] != 0, &packed[i]); });
 
-    // Warps per unit.  A block alternates between the one-warp E-step and the row-parallel A-step, so every extra warp
-    // spends much of its life parked at the block barrier while still holding registers.  Throughput is therefore best
-    // with ONE warp per unit (it simply walks all slabs); extra warps only buy latency, which matters for the units
-    // that would otherwise outlast the rest of the batch.  A unit gets more warps only when its estimated one-warp time
-    // exceeds half of the batch's ideal makespan (total work / warps the GPU keeps resident).
+    // ---- shape of every unit before it is packed: its A-step items in processing order (chain items, then uniform
+    // items, pack.cpp) -> slab widths for any slab height
+    struct Shape {
+        std::vector<int32_t> nnz;     // per item
+        std::vector<int32_t> blocks;  // per item: Philox blocks of a uniform item
+        int n_chain = 0;
+        double iters = 0;
+    };
+    std::vector<Shape> shapes(n_units);
+    parallel_for(host_thread_count(ctx, n_units), n_units, [&](int64_t i) {
+        Shape &S = shapes[i];
+        std::vector<ItemShape> items;
+        build_items(groups[i], &items, &S.n_chain);
+        S.nnz.reserve(items.size());
+        S.blocks.reserve(items.size());
+        for (const ItemShape &it : items) {
+            S.nnz.push_back(it.nnz);
+            S.blocks.push_back(it.blocks);
+        }
+        S.iters = (double)groups[i][0].locus->burn + groups[i][0].locus->samples;
+    });
+    // Time model in microseconds per iteration, fitted on B200 to loci running alone (profiles/README.md).  A chain slab
+    // costs chain_us(h) per column (one conditional binomial of its slowest lane per step: fewer lanes, fewer divergent
+    // paths), a uniform slab a fixed part (row sum) plus, per Philox block of its busiest lane, a fixed part and a little
+    // per column; the one-warp E-step and the two block barriers cost kEstepUs.  The warps of a unit take slabs from a
+    // shared counter, heaviest first (greedy list scheduling).
+    auto chain_us = [](int h) { return h >= 32 ? 1.7 : h >= 16 ? 1.5 : h >= 8 ? 1.2 : 1.1; };
+    const double kEstepUs = 4.0, kUniformSlabUs = 0.3, kUniformBlockUs = 0.25, kUniformColumnUs = 0.05;
+    auto slab_layout = [](const Shape &S, int h, int *chain_slabs, int *n_slabs) {
+        const int n_items = (int)S.nnz.size();
+        *chain_slabs = (S.n_chain + h - 1) / h;
+        *n_slabs = *chain_slabs + (n_items - S.n_chain + h - 1) / h;
+    };
+    auto iteration_us = [&](const Shape &S, int warps, int h) {
+        int chain_slabs, n_slabs;
+        slab_layout(S, h, &chain_slabs, &n_slabs);
+        const int n_items = (int)S.nnz.size();
+        std::vector<double> load(warps, 0.0);  // list scheduling in slab order
+        double worst = 0;
+        for (int s = 0; s < n_slabs; s++) {
+            const bool chain = s < chain_slabs;
+            const int first = chain ? s * h : S.n_chain + (s - chain_slabs) * h, last = chain ? S.n_chain : n_items;
+            int width = 0, blocks = 0;
+            for (int l = 0; l < h && first + l < last; l++) {
+                width = std::max(width, S.nnz[first + l]);
+                blocks = std::max(blocks, S.blocks[first + l]);
+            }
+            const double us = chain ? width * chain_us(h) : kUniformSlabUs + blocks * (kUniformBlockUs + width * kUniformColumnUs);
+            double &l0 = *std::min_element(load.begin(), load.end());
+            l0 += us;
+            worst = std::max(worst, l0);
+        }
+        return worst + kEstepUs;
+    };
+    auto unit_time = [&](const Shape &S, int warps, int h) { return 1e-6 * S.iters * iteration_us(S, warps, h); };
+    auto smem_estimate = [&](const Shape &S, int h) {
+        int chain_slabs, n_slabs;
+        slab_layout(S, h, &chain_slabs, &n_slabs);
+        const int n_items = (int)S.nnz.size();
+        double cells = 0;
+        for (int s = 0; s < n_slabs; s++) {
+            const bool chain = s < chain_slabs;
+            const int first = chain ? s * h : S.n_chain + (s - chain_slabs) * h, last = chain ? S.n_chain : n_items;
+            int width = 0;
+            for (int l = 0; l < h && first + l < last; l++) width = std::max(width, S.nnz[first + l]);
+            cells += (double)h * width;
+        }
+        return 10.0 * cells + 12.0 * h * n_slabs + 1024.0;
+    };
+
+    // Warps and slab height per unit.  Throughput is best with ONE warp per unit walking full 32-row slabs: every extra
+    // warp is parked at the block barrier during the one-warp E-step, and short slabs leave lanes idle.  Extra warps /
+    // shorter slabs only buy latency, which matters for the units that would otherwise outlast the rest of the batch.
+    // Greedy critical-path reduction: while the longest unit exceeds what the GPU needs for the whole batch anyway
+    // (occupied warp-seconds / warps it keeps resident), move that unit one step down the ladder below.
+    std::vector<int> unit_warps(n_units, 1), unit_h(n_units, 32);
     {
-        double total = 0;
-        for (const PackedUnit &u : packed) total += u.cost;
-        const double ideal = total / ((double)ctx->sm_count * 16.0);
-        for (PackedUnit &u : packed) {
-            int warps = 1;
-            const double want = ideal > 0 ? u.cost / (0.5 * ideal) : 1e9;
-            while (2 * warps <= kMaxBlock / 32 && warps < u.d.n_slabs && 2 * warps <= want) warps *= 2;
-            u.d.block = 32 * warps;
+        static const int ladder[][2] = {{1, 32}, {2, 32}, {4, 32}, {8, 32}, {8, 16}, {16, 16}, {16, 8}};
+        const int n_ladder = (int)(sizeof(ladder) / sizeof(ladder[0]));
+        const double capacity = (double)ctx->sm_count * 32.0;  // resident warps at 64 registers per thread
+        std::vector<int> step(n_units, 0);
+        std::vector<double> t(n_units);
+        double occupied = 0;  // sum of warps * time
+        typedef std::pair<double, int64_t> Item;
+        std::priority_queue<Item> heap;
+        for (int64_t i = 0; i < n_units; i++) {
+            // A unit's matrix sits in shared memory whatever its block size; the SM runs out of shared memory before it
+            // runs out of warp slots when units of much more than 227 KB / 32 keep one warp each, so such units start with as
+            // many warps as their footprint pays for (they are parked warps otherwise nobody could use).
+            const Shape &S = shapes[i];
+            int chain_slabs, n_slabs;
+            slab_layout(S, 32, &chain_slabs, &n_slabs);
+            const double smem_est = smem_estimate(S, 32);
+            int k = 0;
+            while (k + 1 < 4 && ladder[k][0] * 8192.0 < smem_est && ladder[k + 1][0] < 2 * n_slabs) k++;
+            step[i] = k;
+            t[i] = unit_time(S, ladder[k][0], ladder[k][1]);
+            occupied += ladder[k][0] * t[i];
+            heap.push(Item(t[i], i));
+        }
+        while (!heap.empty()) {
+            const Item top = heap.top();
+            const int64_t i = top.second;
+            if (top.first <= 1.25 * occupied / capacity) break;  // the batch is throughput-bound from here on
+            heap.pop();
+            // next rung that actually shortens the unit
+            int k = step[i] + 1;
+            double tk = 0;
+            for (; k < n_ladder; k++) {
+                int chain_slabs, n_slabs;
+                slab_layout(shapes[i], ladder[k][1], &chain_slabs, &n_slabs);
+                if (ladder[k][0] >= 2 * n_slabs && ladder[k][0] > ladder[step[i]][0]) continue;  // idle warps only
+                tk = unit_time(shapes[i], ladder[k][0], ladder[k][1]);
+                if (tk < 0.93 * t[i]) break;
+            }
+            if (k >= n_ladder) continue;  // cannot be shortened further: it stays out of the heap
+            occupied += ladder[k][0] * tk - ladder[step[i]][0] * t[i];
+            step[i] = k;
+            t[i] = tk;
+            heap.push(Item(tk, i));
+        }
+        const char *fw = getenv("BAYES_FORCE_WARPS"), *fh = getenv("BAYES_FORCE_H");  // experiment knobs
+        for (int64_t i = 0; i < n_units; i++) {
+            unit_warps[i] = fw ? std::max(1, std::min(atoi(fw), kMaxBlock / 32)) : ladder[step[i]][0];
+            unit_h[i] = fh ? atoi(fh) : ladder[step[i]][1];
         }
     }
 
+    std::vector<PackedUnit> packed(n_units);
+    parallel_for(host_thread_count(ctx, n_units), n_units, [&](int64_t i) {
+        pack_unit(groups[i], group_wide[i] != 0, unit_h[i], &packed[i]);
+        packed[i].d.block = 32 * unit_warps[i];
+        packed[i].cost = unit_time(shapes[i], unit_warps[i], unit_h[i]);  // estimated duration: the launch-order key
+    });
+
+    // One launch per class = (kernel, block size, matrix placement, shared-memory bucket).  The bucket matters: a launch
+    // has ONE dynamic shared-memory size, and sizing it for the largest unit of a broad class would cut the number of
+    // resident units per SM several-fold.  Classes are issued in order of their longest unit and units inside a class
+    // longest first: the hardware block scheduler hands blocks out in that order, which makes this the largest-first
+    // queue of the reference (assembler.cpp:1886-1916).
+    auto smem_bucket = [](int32_t bytes) -> int32_t {
+        int32_t step = bytes <= 16 * 1024 ? 1024 : bytes <= 64 * 1024 ? 4096 : 16 * 1024;
+        return (bytes + step - 1) / step * step;
+    };
+    typedef std::tuple<int, int, int, int> ClassKey;  // (wide, mat_smem, block, smem bucket)
+    auto class_of = [&](const PackedUnit &u) { return ClassKey(u.d.wide, u.d.mat_smem, u.d.block, smem_bucket(u.d.smem_bytes)); };
+    std::map<ClassKey, double> class_max;
+    for (const PackedUnit &u : packed) {
+        double &m = class_max[class_of(u)];
+        m = std::max(m, u.cost);
+    }
     std::vector<int64_t> order(n_units);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
-        const UnitDev &ua = packed[a].d, &ub = packed[b].d;
-        if (ua.mat_smem != ub.mat_smem) return ua.mat_smem < ub.mat_smem;  // streaming (largest) units first
-        if (ua.wide != ub.wide) return ua.wide > ub.wide;
-        if (ua.block != ub.block) return ua.block > ub.block;
+        const ClassKey ka = class_of(packed[a]), kb = class_of(packed[b]);
+        if (ka != kb) {
+            // widened units are the ones on the critical path, and a large block only fits an SM that is still
+            // nearly empty: largest blocks first, then the class with the longest unit
+            if (std::get<2>(ka) != std::get<2>(kb)) return std::get<2>(ka) > std::get<2>(kb);
+            const double ma = class_max[ka], mb = class_max[kb];
+            if (ma != mb) return ma > mb;
+            return ka < kb;
+        }
         return packed[a].cost > packed[b].cost;
     });
     int rc;
@@ -269,12 +409,9 @@ int build_units(bayes_gibbs_ctx *ctx) {
     const UnitDev *units = ctx->h_units.p;
     for (int64_t i = 0; i < n_units;) {
         int64_t j = i;
-        size_t smem = 0;
-        while (j < n_units && units[j].block == units[i].block && units[j].wide == units[i].wide && units[j].mat_smem == units[i].mat_smem) {
-            smem = std::max(smem, (size_t)units[j].smem_bytes);
-            j++;
-        }
-        ctx->launches.push_back(Launch{i, j - i, units[i].block, units[i].wide != 0, units[i].mat_smem != 0, smem});
+        const ClassKey k = class_of(packed[order[i]]);
+        while (j < n_units && class_of(packed[order[j]]) == k) j++;
+        ctx->launches.push_back(Launch{i, j - i, units[i].block, units[i].wide != 0, units[i].mat_smem != 0, (size_t)std::get<3>(k)});
         i = j;
     }
     if (ctx->trace_locus >= 0) {
@@ -308,6 +445,7 @@ KernelArgs kernel_args(bayes_gibbs_ctx *ctx) {
     a.out_mean = ctx->d_mean.p;
     a.out_m2 = ctx->d_m2.p;
     a.out_counts = ctx->d_counts.p;
+    a.unit_clock = ctx->d_unit_clock.p;
     a.trace_unit = ctx->trace_unit;
     a.trace_slot = ctx->trace_slot;
     a.trace_iters = ctx->trace_iters;
@@ -385,6 +523,7 @@ void bayes_gibbs_destroy(bayes_gibbs_ctx *ctx) {
     ctx->d_units.release(); ctx->d_val.release(); ctx->d_efflen.release(); ctx->d_tab_val.release(); ctx->d_mean.release();
     ctx->d_m2.release(); ctx->d_tr_theta.release(); ctx->d_col.release(); ctx->d_slab.release(); ctx->d_row_n.release();
     ctx->d_row_nnz.release(); ctx->d_row_info.release(); ctx->d_base.release(); ctx->d_tab_row.release(); ctx->d_occ.release();
+    ctx->d_unit_clock.release();
     ctx->d_counts.release(); ctx->d_tr_counts.release(); ctx->d_tr_b.release(); ctx->d_tr_init.release();
     for (cudaStream_t st : ctx->aux) cudaStreamDestroy(st);
     for (cudaEvent_t ev : ctx->join_ev) cudaEventDestroy(ev);
@@ -465,6 +604,7 @@ int bayes_gibbs_upload(bayes_gibbs_ctx *ctx) {
             return rc;
     }
     if ((rc = upload_units(ctx))) return rc;
+    if ((rc = ctx->d_unit_clock.reserve(3 * ctx->h_units.n + 3))) return rc;
     const size_t n_out = (size_t)ctx->out_len;
     if ((rc = ctx->d_occ.reserve(n_out)) || (rc = ctx->d_counts.reserve(n_out)) || (rc = ctx->d_mean.reserve(n_out)) ||
         (rc = ctx->d_m2.reserve(n_out)))
@@ -490,9 +630,14 @@ int bayes_gibbs_run(bayes_gibbs_ctx *ctx) {
     const size_t n_l = ctx->launches.size();
     if (!ctx->fork_ev) CU(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
     while (ctx->aux.size() < n_l) {
+        // launch i carries the class with the i-th longest unit: the earlier the launch, the higher the stream priority,
+        // so that the block scheduler places the units on the critical path before it fills the SMs with short ones
         cudaStream_t st;
         cudaEvent_t ev;
-        CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        int least = 0, greatest = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        const int prio = std::min(least, greatest + (int)ctx->aux.size());
+        CU(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio));
         CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         ctx->aux.push_back(st);
         ctx->join_ev.push_back(ev);
@@ -621,6 +766,30 @@ int bayes_gibbs_chain_info(bayes_gibbs_ctx *ctx, int64_t locus_id, int32_t chain
     return BAYES_OK;
 }
 
+// Diagnostics of the last run: per unit {wide, block, n_slots, n_slabs, n_cells, iterations, T of slot 0, mat_smem} and
+// {start ns, end ns, SM id}.  Returns the number of units (call with NULL pointers to size the buffers).
+int64_t bayes_gibbs_unit_stats(bayes_gibbs_ctx *ctx, int32_t *shape8, uint64_t *clock3) {
+    if (!ctx) return BAYES_E_INVALID;
+    const int64_t n = (int64_t)ctx->h_units.n;
+    if (!shape8 && !clock3) return n;
+    if (!ctx->ran) {
+        set_error("bayes_gibbs_unit_stats: no run yet");
+        return BAYES_E_STATE;
+    }
+    if (use_device(ctx)) return BAYES_E_CUDA;
+    if (cuda_rc(cudaStreamSynchronize(ctx->stream), "sync")) return BAYES_E_CUDA;
+    if (shape8)
+        for (int64_t i = 0; i < n; i++) {
+            const UnitDev &u = ctx->h_units.p[i];
+            int32_t *o = shape8 + 8 * i;
+            o[0] = u.wide; o[1] = u.block; o[2] = u.n_slots; o[3] = u.n_slabs; o[4] = u.n_cells; o[5] = u.burn + u.samples; o[6] = u.T[0];
+            o[7] = u.mat_smem | (u.slab_h << 8);
+        }
+    if (clock3 && n && cuda_rc(cudaMemcpy(clock3, ctx->d_unit_clock.p, 3 * n * sizeof(uint64_t), cudaMemcpyDeviceToHost), "unit clock D2H"))
+        return BAYES_E_CUDA;
+    return n;
+}
+
 int64_t bayes_gibbs_num_loci(bayes_gibbs_ctx *ctx) { return ctx ? (int64_t)ctx->loci.size() : 0; }
 int64_t bayes_gibbs_num_jobs(bayes_gibbs_ctx *ctx) {
     if (!ctx) return 0;
@@ -692,7 +861,7 @@ static int step_assignment(int device, const bayes_locus_desc *locus, const doub
     }
     const int T = d.T;
     PackedUnit U;
-    pack_unit(std::vector<SlotRef>(1, SlotRef{&P, 0, 0}), true, &U);  // wide layout: columns stay candidate indices
+    pack_unit(std::vector<SlotRef>(1, SlotRef{&P, 0, 0}), true, 32, &U);  // wide layout: columns stay candidate indices
     if ((rc = append_unit(ctx, U))) return fail(rc);
     if ((rc = upload_units(ctx))) return fail(rc);
     cudaStream_t st = ctx->stream;

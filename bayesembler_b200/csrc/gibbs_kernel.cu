@@ -35,6 +35,17 @@ namespace bayes {
 
 namespace {
 
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ uint32_t sm_id() {
+    uint32_t s;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
+    return s;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -50,28 +61,52 @@ struct MatView {
     const int32_t *row_nnz;
     const uint32_t *row_info;  // slot << 27 | original row index
     int n_slabs;
+    int h;  // rows per slab (lanes >= h idle in the A-step)
 };
 
 // ------------------------------------------------------------------------------------------------------------------
-// A-step.  init = AssignmentGenerator::initAssignment (assignmentGenerator.cpp:213-260): binomial chain on P_ij itself,
-// no row normalisation; the caller passes theta == 1 (P_ij * 1.0 is P_ij exactly) and Z is pinned to 1, so that the one
-// copy of this code (instruction-cache footprint) serves both.  Otherwise generateAssignment (:263-373).
+// A-step.  One lane per collapsed row ("item", internal.h): a row with n >= 20 fragments runs the conditional binomials
+// of assignmentGenerator.cpp:336-365, a row with n < 20 locates its n uniforms in the row's CDF (:289-334), one Philox
+// block = four uniforms at a time.  Rows of one kind fill whole slabs and are sorted by length / block count, so the
+// lanes of a warp run the same code about the same number of times.
+// init = AssignmentGenerator::initAssignment (:213-260): binomial chain on P_ij itself for EVERY row, no row
+// normalisation; the caller passes theta == 1 (P_ij * 1.0 is P_ij exactly) and Z is pinned to 1, so that the one copy of
+// this code (instruction-cache footprint) serves both.
 // ------------------------------------------------------------------------------------------------------------------
+
+// p / Z, correctly rounded, from rZ = RN(1 / Z): quotient estimate, exact residual, one fused correction (Markstein).
+// One reciprocal per row replaces a division per cell.
+__device__ __forceinline__ double div_by(double p, double Z, double rZ) {
+    const double q0 = p * rZ;
+    return __fma_rn(__fma_rn(-q0, Z, p), rZ, q0);
+}
+
 __device__ __forceinline__ void assign_rows(const MatView &M, const double *theta, int32_t *counts, const uint64_t *skey,
-                                            int lanes_per_slot, uint32_t iteration, const bool init) {
+                                            int lanes_per_slot, uint32_t iteration, const bool init, int *next_slab) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const uint32_t phase = init ? PH_INIT_ASSIGN : PH_ASSIGN;
-    // slabs are ordered heaviest first; warp 0 (which also runs the E-step) starts from the lightest one
-    for (int s = M.n_slabs - 1 - warp; s >= 0; s -= n_warps) {
-        const int r = s * 32 + lane;
-        const int n = M.row_n[r];
-        const int nnz = M.row_nnz[r];
-        if (nnz == 0) continue;  // padding lane of the last slab
+    const int H = M.h;
+    // Slabs are ordered heaviest first.  A one-warp unit walks them all; the warps of a larger unit take the next slab
+    // from a shared counter as they become free (the draws are site-keyed and the counts integer atomics, so who
+    // processes which slab does not change the result).
+    const bool dynamic = next_slab != nullptr && n_warps > 1;
+    for (int s = dynamic ? 0 : warp;; s += n_warps) {
+        if (dynamic) {
+            if (lane == 0) s = atomicAdd(next_slab, 1);
+            s = __shfl_sync(0xffffffffu, s, 0);
+        }
+        if (s >= M.n_slabs) break;
+        if (lane >= H) continue;
+        const int r = s * H + lane;
+        const uint32_t item = (uint32_t)M.row_nnz[r];
+        const int nnz = (int)(item & kItemNnzMask);
+        if (nnz == 0) continue;  // padding lane
+        const bool chain = init || ((item >> kItemChainShift) & 1u);
+        const int n = M.row_n[r];  // fragments of the row
         const uint32_t info = M.row_info[r];
         const uint32_t id = info & ((1u << kRowSlotShift) - 1u);
         const double *val = M.val + M.slab[s] + lane;
         const uint16_t *col = M.col + M.slab[s] + lane;
-        const bool chain = init || n >= kSmallCount;
 
         // Z = sum_j P_ij theta_j (:280-282) and the first / last cell that can receive fragments.  A cell is in play
         // when its normalised probability is > 0 (CDF walk, :304-306) resp. >= double_underflow (chain, :344).
@@ -79,7 +114,7 @@ __device__ __forceinline__ void assign_rows(const MatView &M, const double *thet
         int kf = nnz, kl = -1;
         bool tiny = false;
         for (int k = 0; k < nnz; k++) {
-            const double p = val[32 * k] * theta[col[32 * k]];
+            const double p = val[H * k] * theta[col[H * k]];
             Z += p;
             if (p != 0.0) {
                 tiny |= p < 1e-300;
@@ -88,11 +123,12 @@ __device__ __forceinline__ void assign_rows(const MatView &M, const double *thet
             }
         }
         if (init) Z = 1.0;  // initAssignment uses P_ij as it is (:226)
+        tiny |= !(Z >= 1e-300);
         if (chain && tiny) {  // exact rule for denormal-range cells: in play iff p / Z >= double_underflow
             kf = nnz;
             kl = -1;
             for (int k = 0; k < nnz; k++) {
-                const double p = val[32 * k] * theta[col[32 * k]];
+                const double p = val[H * k] * theta[col[H * k]];
                 if (p != 0.0 && p / Z >= DBL_MIN) {
                     if (kf == nnz) kf = k;
                     kl = k;
@@ -100,58 +136,70 @@ __device__ __forceinline__ void assign_rows(const MatView &M, const double *thet
             }
         }
         if (kl < 0) continue;  // reference: assert(normalisation_constant >= double_underflow) (:284)
-        const int c_last = col[32 * kl];
+        const int c_last = col[H * kl];
+        const double rZ = __drcp_rn(Z);
 
         // Whatever the cells before the last one in play do not take ends up in that last cell: in the chain the
         // reference asserts that nothing is left after it (:253, :363), and in the CDF walk its cumulative sum is 1 up
         // to rounding while every uniform is <= 1 - 2^-32.  So the last cell never needs a draw of its own.
-        int rem = n;
-        if (kf < kl) {
-            const uint32_t slot = info >> kRowSlotShift;
-            const uint64_t key = skey[slot];
-            const int col0 = (int)slot * lanes_per_slot;  // lane of the slot's candidate 0 (0 in a wide unit)
-            if (!chain) {
-                // :289-334.  The reference sorts the n uniforms and walks the CDF once; which column a uniform lands
-                // in does not depend on the visiting order, so they are taken four at a time (one Philox block).
+        const uint32_t slot = info >> kRowSlotShift;
+        const uint64_t key = skey[slot];
+        if (!chain) {
+            // :289-334.  The reference sorts the n uniforms and walks the CDF once; which column a uniform lands in does
+            // not depend on the visiting order, so they are taken four at a time (one Philox block).
+            int rem = n;
+            if (kf < kl) {
                 const Site site = make_site(key, phase, iteration, id, 0);
-                for (int j = 0; 4 * j < n; j++) {
+                const int blocks = (int)((item >> kItemBlockShift) & 7u);
+                for (int j = 0; j < blocks; j++) {
                     const u32x4 w = site.block((uint32_t)j);
                     const int left = n - 4 * j < 4 ? n - 4 * j : 4;
                     double cum = 0.0;
-                    int below_prev = 0;
-                    for (int k = kf; k < kl; k++) {
-                        const int c = col[32 * k];
-                        const double p = val[32 * k] * theta[c];
-                        if (p == 0.0) continue;
-                        cum += p / Z;                                                 // :304
-                        // u = w * 2^-32 < cum  <=>  w < ceil(cum * 2^32)              // :306
-                        const unsigned long long thr = __double2ull_ru(cum * 4294967296.0);
-                        int below = (int)((unsigned long long)w.x < thr);
-                        below += (left > 1) & (int)((unsigned long long)w.y < thr);
-                        below += (left > 2) & (int)((unsigned long long)w.z < thr);
-                        below += (left > 3) & (int)((unsigned long long)w.w < thr);
-                        const int got = below - below_prev;
-                        if (got > 0) atomicAdd(&counts[c], got);                      // :323-324
-                        rem -= got;
-                        below_prev = below;
-                        if (below >= left) break;                                     // :327-331
+                    int prev = 0;
+                    // every lane first skips ahead to ITS next cell with a non-zero probability (theta is zero outside
+                    // the current simplex) and only then do the lanes meet for the threshold arithmetic
+                    for (int k = kf;; k++) {
+                        int c = 0;
+                        double p = 0.0;
+                        for (; k < kl; k++) {
+                            c = col[H * k];
+                            p = val[H * k] * theta[c];
+                            if (p != 0.0) break;
+                        }
+                        if (k >= kl) break;
+                        cum += tiny ? p / Z : div_by(p, Z, rZ);                                   // :304
+                        // u = w * 2^-32 < cum  <=>  w < ceil(cum * 2^32)  <=>  w <= ceil(cum * 2^32 - 1)   // :306
+                        // (the conversion saturates, so cum >= 1 gives 0xffffffff: every word is below)
+                        const uint32_t t = __double2uint_ru(__fma_rn(cum, 4294967296.0, -1.0));
+                        int below = 0;
+                        if (cum > 0.0)
+                            below = (int)(w.x <= t) + ((left > 1) & (int)(w.y <= t)) + ((left > 2) & (int)(w.z <= t)) + ((left > 3) & (int)(w.w <= t));
+                        if (below > prev) atomicAdd(&counts[c], below - prev);              // :323-324
+                        rem -= below - prev;
+                        prev = below;
+                        if (below >= left) break;                                             // :327-331
                     }
                 }
-            } else {
-                // :336-365 (INIT: :222-251)
-                // Every lane first skips ahead to ITS next cell in play and only then do the lanes meet again for the
-                // binomial, so a warp runs the (expensive, divergent) draw once per in-play cell of its deepest row
-                // instead of once per stored cell.
+            }
+            if (rem > 0) atomicAdd(&counts[c_last], rem);
+        } else {
+            // :336-365 (INIT: :222-251)
+            // Every lane first skips ahead to ITS next cell in play and only then do the lanes meet again for the
+            // binomial, so a warp runs the (expensive, divergent) draw once per in-play cell of its deepest row
+            // instead of once per stored cell.
+            int rem = n;
+            if (kf < kl) {
+                const int col0 = (int)slot * lanes_per_slot;  // lane of the slot's candidate 0 (0 in a wide unit)
                 double divider = 1.0;
                 int k = kf;
                 while (rem > 0) {
                     int c = 0;
                     double np = 0.0;
                     for (; k < kl; k++) {
-                        c = col[32 * k];
-                        const double p = val[32 * k] * theta[c];
+                        c = col[H * k];
+                        const double p = val[H * k] * theta[c];
                         if (p == 0.0) continue;
-                        np = p / Z;
+                        np = tiny ? p / Z : div_by(p, Z, rZ);
                         if (np >= DBL_MIN) break;
                         divider -= np;  // below double_underflow: no draw, but the divider still shrinks (:360)
                     }
@@ -164,8 +212,8 @@ __device__ __forceinline__ void assign_rows(const MatView &M, const double *thet
                     k++;
                 }
             }
+            if (rem > 0) atomicAdd(&counts[c_last], rem);
         }
-        if (rem > 0) atomicAdd(&counts[c_last], rem);
     }
 }
 
@@ -215,12 +263,18 @@ __device__ __forceinline__ int bundle_e_step(BundleLane &L, double *theta, int32
         b = sample_simplex(tab_val, L.trow, n_plus, L.key, iteration);
         n_pick = b - n_plus;
     }
-    // expressionGenerator.cpp:104-127: one uniform_int over the current ascending null list per extra slot
+    // expressionGenerator.cpp:104-127: one uniform_int over the current ascending null list per extra slot.  The draws
+    // themselves are independent (site = pick ordinal), so lane t of the slot makes the draw of pick t and only the
+    // cheap selection below is sequential.
+    uint32_t my_pick = 0u;
+    if (L.valid && L.t < n_pick)
+        my_pick = uniform_int(make_site(L.key, PH_NULLPICK, iteration, (uint32_t)L.t, 0), (uint32_t)(L.Tg - n_plus - L.t));
     uint32_t sel = 0u;
     const int max_pick = __reduce_max_sync(0xffffffffu, n_pick);
+    const int lane0 = lane - L.t;  // first lane of the slot
     for (int k = 0; k < max_pick; k++) {
+        const uint32_t s = __shfl_sync(0xffffffffu, my_pick, (lane0 + k) & 31);
         if (k < n_pick) {
-            const uint32_t s = uniform_int(make_site(L.key, PH_NULLPICK, iteration, (uint32_t)k, 0), (uint32_t)(L.Tg - n_plus - k));
             const uint32_t nullm = L.validmask & ~(pm | sel);
             sel |= 1u << __fns(nullm, 0, (int)s + 1);
         }
@@ -275,19 +329,27 @@ __device__ __forceinline__ int wide_e_step(const WideState &E, uint64_t key, uin
     __syncwarp();
     const int b = sample_simplex(E.tab_val, E.tab_row, n_plus, key, iteration);
     const int n_null = T - n_plus;
-    for (int k = 0; k < b - n_plus; k++) {
-        uint32_t rem = uniform_int(make_site(key, PH_NULLPICK, iteration, (uint32_t)k, 0), (uint32_t)(n_null - k));
-        int pick = -1;
-        for (int c = 0; c < nch; c++) {
-            uint32_t w = ~(E.mask[c] | E.mask[nch + c]);
-            if (c == nch - 1 && (T & 31)) w &= (1u << (T & 31)) - 1u;
-            const uint32_t pc = (uint32_t)__popc(w);
-            if (rem < pc) { pick = c * 32 + (int)__fns(w, 0, (int)rem + 1); break; }
-            rem -= pc;
+    const int n_pick = b - n_plus;
+    // the draws are independent (site = pick ordinal): 32 at a time, one per lane; the selection is sequential
+    for (int k0 = 0; k0 < n_pick; k0 += 32) {
+        uint32_t my_pick = 0u;
+        if (k0 + lane < n_pick)
+            my_pick = uniform_int(make_site(key, PH_NULLPICK, iteration, (uint32_t)(k0 + lane), 0), (uint32_t)(n_null - k0 - lane));
+        const int kn = n_pick - k0 < 32 ? n_pick - k0 : 32;
+        for (int k = 0; k < kn; k++) {
+            uint32_t rem = __shfl_sync(0xffffffffu, my_pick, k);
+            int pick = -1;
+            for (int c = 0; c < nch; c++) {
+                uint32_t w = ~(E.mask[c] | E.mask[nch + c]);
+                if (c == nch - 1 && (T & 31)) w &= (1u << (T & 31)) - 1u;
+                const uint32_t pc = (uint32_t)__popc(w);
+                if (rem < pc) { pick = c * 32 + (int)__fns(w, 0, (int)rem + 1); break; }
+                rem -= pc;
+            }
+            __syncwarp();
+            if (lane == 0 && pick >= 0) E.mask[nch + (pick >> 5)] |= 1u << (pick & 31);
+            __syncwarp();
         }
-        __syncwarp();
-        if (lane == 0 && pick >= 0) E.mask[nch + (pick >> 5)] |= 1u << (pick & 31);
-        __syncwarp();
     }
     double part = 0.0;
     for (int c = 0; c < nch; c++) {
@@ -333,6 +395,7 @@ template <bool MAT_SMEM>
 __device__ __forceinline__ MatView stage_matrix(const KernelArgs &A, const UnitDev &U, const SmemLayout &lay, unsigned char *smem) {
     MatView M;
     M.n_slabs = U.n_slabs;
+    M.h = U.slab_h;
     if (MAT_SMEM) {
         double *sv = (double *)(smem + lay.val);
         uint16_t *sc = (uint16_t *)(smem + lay.col);
@@ -343,9 +406,9 @@ __device__ __forceinline__ MatView stage_matrix(const KernelArgs &A, const UnitD
         block_copy(sv, A.val + U.cell_off, U.n_cells);
         block_copy(sc, A.col + U.cell_off, U.n_cells);
         block_copy(ss, A.slab_cell_off + U.slab_off, U.n_slabs + 1);
-        block_copy(rn, A.row_n + U.row_off, U.n_slabs * 32);
-        block_copy(rz, A.row_nnz + U.row_off, U.n_slabs * 32);
-        block_copy(ri, A.row_info + U.row_off, U.n_slabs * 32);
+        block_copy(rn, A.row_n + U.row_off, U.n_slabs * U.slab_h);
+        block_copy(rz, A.row_nnz + U.row_off, U.n_slabs * U.slab_h);
+        block_copy(ri, A.row_info + U.row_off, U.n_slabs * U.slab_h);
         M.val = sv; M.col = sc; M.slab = ss; M.row_n = rn; M.row_nnz = rz; M.row_info = ri;
     } else {
         M.val = A.val + U.cell_off;
@@ -360,15 +423,17 @@ __device__ __forceinline__ MatView stage_matrix(const KernelArgs &A, const UnitD
 
 // ------------------------------------------------------------------------------------------------------------------
 template <bool MAT_SMEM>
-__global__ void __launch_bounds__(kMaxBlock, BAYES_MIN_BLOCKS) gibbs_bundle_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
+__global__ void __launch_bounds__(kMaxBlock, 1) gibbs_bundle_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int64_t ui = unit_base + blockIdx.x;
+    if (threadIdx.x == 0) A.unit_clock[3 * ui] = global_ns();
     const UnitDev &U = A.units[ui];
     const int n_slots = U.n_slots, Tpad = U.Tpad;
-    const SmemLayout lay = unit_layout(false, 32, n_slots, Tpad, U.n_slabs, U.n_cells, U.tab_len, U.tab_smem != 0, MAT_SMEM);
+    const SmemLayout lay = unit_layout(false, 32, n_slots, Tpad, U.n_slabs, U.slab_h, U.n_cells, U.tab_len, U.tab_smem != 0, MAT_SMEM);
     double *theta = (double *)(smem + lay.theta);
     int32_t *counts = (int32_t *)(smem + lay.counts);
     uint64_t *skey = (uint64_t *)(smem + lay.key);
+    int *next_slab = (int *)(smem + lay.next_slab);
     const double *tab_val;
     const int32_t *tab_row;
     if (U.tab_smem) {
@@ -414,18 +479,16 @@ __global__ void __launch_bounds__(kMaxBlock, BAYES_MIN_BLOCKS) gibbs_bundle_kern
         theta[lane] = 1.0;  // initAssignment runs the A-step on P_ij itself
         counts[lane] = L.base;
     }
-    __syncthreads();
 
     const bool tracing = A.trace_unit == ui;
     const bool my_trace = tracing && threadIdx.x < 32 && g == A.trace_slot && L.valid;
     const int total = U.burn + U.samples, burn = U.burn;
 
-    assign_rows(M, theta, counts, skey, Tpad, 0u, true);  // gibbsSampler.cpp:90
-    __syncthreads();
-    if (my_trace) A.tr_init[L.t] = counts[lane];
-
-    for (int it = 0; it < total; it++) {
-        if (threadIdx.x < 32) {
+    // it == -1 is initAssignment (gibbsSampler.cpp:90): the same A-step code on theta == 1, no E-step before it
+    for (int it = -1; it < total; it++) {
+        if (threadIdx.x == 0) *next_slab = 0;
+        if (it >= 0 && threadIdx.x < 32) {
+            if (my_trace && it == 0) A.tr_init[L.t] = counts[lane];
             if (my_trace && it > 0 && it - 1 < A.trace_iters) A.tr_counts[(size_t)(it - 1) * L.Tg + L.t] = counts[lane];
             const int b = bundle_e_step(L, theta, counts, tab_val, (uint32_t)it, it >= burn);
             if (my_trace && it < A.trace_iters) {
@@ -434,7 +497,7 @@ __global__ void __launch_bounds__(kMaxBlock, BAYES_MIN_BLOCKS) gibbs_bundle_kern
             }
         }
         __syncthreads();
-        assign_rows(M, theta, counts, skey, Tpad, (uint32_t)it, false);
+        assign_rows(M, theta, counts, skey, Tpad, (uint32_t)(it < 0 ? 0 : it), it < 0, next_slab);
         __syncthreads();
     }
     if (my_trace && total - 1 < A.trace_iters) A.tr_counts[(size_t)(total - 1) * L.Tg + L.t] = counts[lane];
@@ -446,16 +509,21 @@ __global__ void __launch_bounds__(kMaxBlock, BAYES_MIN_BLOCKS) gibbs_bundle_kern
         A.out_m2[o] = L.m2;
         A.out_counts[o] = counts[lane];
     }
+    if (threadIdx.x == 0) {
+        A.unit_clock[3 * ui + 1] = global_ns();
+        A.unit_clock[3 * ui + 2] = sm_id();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 template <bool MAT_SMEM>
-__global__ void __launch_bounds__(kMaxBlock, BAYES_MIN_BLOCKS) gibbs_wide_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
+__global__ void __launch_bounds__(kMaxBlock, 1) gibbs_wide_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int64_t ui = unit_base + blockIdx.x;
+    if (threadIdx.x == 0) A.unit_clock[3 * ui] = global_ns();
     const UnitDev &U = A.units[ui];
     const int T = U.T[0];
-    const SmemLayout lay = unit_layout(true, T, 1, U.Tpad, U.n_slabs, U.n_cells, U.tab_len, U.tab_smem != 0, MAT_SMEM);
+    const SmemLayout lay = unit_layout(true, T, 1, U.Tpad, U.n_slabs, U.slab_h, U.n_cells, U.tab_len, U.tab_smem != 0, MAT_SMEM);
 
     WideState E;
     E.theta = (double *)(smem + lay.theta);
@@ -472,6 +540,7 @@ __global__ void __launch_bounds__(kMaxBlock, BAYES_MIN_BLOCKS) gibbs_wide_kernel
     E.N_f = U.N_f[0];
     E.gamma = U.gamma[0];
     uint64_t *skey = (uint64_t *)(smem + lay.key);
+    int *next_slab = (int *)(smem + lay.next_slab);
     const uint64_t key = U.key[0];
     if (threadIdx.x == 0) skey[0] = key;
 
@@ -498,26 +567,24 @@ __global__ void __launch_bounds__(kMaxBlock, BAYES_MIN_BLOCKS) gibbs_wide_kernel
         E.tab_row = A.tab_row + U.tabrow_off;
     }
     const MatView M = stage_matrix<MAT_SMEM>(A, U, lay, smem);
-    __syncthreads();
 
     const bool tracing = A.trace_unit == ui;
     const int total = U.burn + U.samples, burn = U.burn;
 
-    assign_rows(M, E.theta, E.counts, skey, 0, 0u, true);  // gibbsSampler.cpp:90
-    __syncthreads();
-    if (tracing)
-        for (int t = threadIdx.x; t < T; t += blockDim.x) A.tr_init[t] = E.counts[t];
-
-    for (int it = 0; it < total; it++) {
-        if (threadIdx.x < 32) {
+    // it == -1 is initAssignment (gibbsSampler.cpp:90): the same A-step code on theta == 1, no E-step before it
+    for (int it = -1; it < total; it++) {
+        if (threadIdx.x == 0) *next_slab = 0;
+        if (it >= 0 && threadIdx.x < 32) {
             const bool tr = tracing && it < A.trace_iters;
+            if (tracing && it == 0)
+                for (int t = threadIdx.x; t < T; t += 32) A.tr_init[t] = E.counts[t];
             if (tracing && it > 0 && it - 1 < A.trace_iters)
                 for (int t = threadIdx.x; t < T; t += 32) A.tr_counts[(size_t)(it - 1) * T + t] = E.counts[t];
             const int b = wide_e_step(E, key, (uint32_t)it, it >= burn, tr ? A.tr_theta + (size_t)it * T : nullptr);
             if (tr && threadIdx.x == 0) A.tr_b[it] = b;
         }
         __syncthreads();
-        assign_rows(M, E.theta, E.counts, skey, 0, (uint32_t)it, false);
+        assign_rows(M, E.theta, E.counts, skey, 0, (uint32_t)(it < 0 ? 0 : it), it < 0, next_slab);
         __syncthreads();
     }
     if (tracing && total - 1 < A.trace_iters)
@@ -529,6 +596,10 @@ __global__ void __launch_bounds__(kMaxBlock, BAYES_MIN_BLOCKS) gibbs_wide_kernel
         A.out_mean[o + t] = E.mean[t];
         A.out_m2[o + t] = E.m2[t];
         A.out_counts[o + t] = E.counts[t];
+    }
+    if (threadIdx.x == 0) {
+        A.unit_clock[3 * ui + 1] = global_ns();
+        A.unit_clock[3 * ui + 2] = sm_id();
     }
 }
 
@@ -548,6 +619,7 @@ __global__ void step_assignment_kernel(const __grid_constant__ KernelArgs A, con
     if (threadIdx.x == 0) skey[0] = U.key[0];
     MatView M;
     M.n_slabs = U.n_slabs;
+    M.h = U.slab_h;
     M.val = A.val + U.cell_off;
     M.col = A.col + U.cell_off;
     M.slab = A.slab_cell_off + U.slab_off;
@@ -555,7 +627,7 @@ __global__ void step_assignment_kernel(const __grid_constant__ KernelArgs A, con
     M.row_nnz = A.row_nnz + U.row_off;
     M.row_info = A.row_info + U.row_off;
     __syncthreads();
-    assign_rows(M, theta, counts, skey, 0, iteration, INIT);
+    assign_rows(M, theta, counts, skey, 0, iteration, INIT, nullptr);
     __syncthreads();
     for (int t = threadIdx.x; t < T; t += blockDim.x) counts_out[t] = counts[t];
 }
@@ -617,6 +689,12 @@ static int check(cudaError_t e, const char *what) {
 
 int configure_kernels() {
     int rc;
+    // every sampler kernel asks for the same (maximal) shared-memory carve-out, so launches of different classes can
+    // share an SM instead of waiting for it to drain and be reconfigured
+    if ((rc = check(cudaFuncSetAttribute(gibbs_bundle_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100), "carveout"))) return rc;
+    if ((rc = check(cudaFuncSetAttribute(gibbs_bundle_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100), "carveout"))) return rc;
+    if ((rc = check(cudaFuncSetAttribute(gibbs_wide_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100), "carveout"))) return rc;
+    if ((rc = check(cudaFuncSetAttribute(gibbs_wide_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100), "carveout"))) return rc;
     if ((rc = check(cudaFuncSetAttribute(gibbs_bundle_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "cudaFuncSetAttribute"))) return rc;
     if ((rc = check(cudaFuncSetAttribute(gibbs_bundle_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "cudaFuncSetAttribute"))) return rc;
     if ((rc = check(cudaFuncSetAttribute(gibbs_wide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "cudaFuncSetAttribute"))) return rc;

@@ -18,20 +18,26 @@
 namespace bayes {
 
 constexpr int kMaxT = 4096;             // candidates per locus (per-candidate state lives in shared memory)
-constexpr int kMaxBlock = 256;          // threads per unit
+constexpr int kMaxBlock = 1024;         // threads per unit
 constexpr int kMaxSlots = 16;           // slots per bundle (T = 2 -> Tpad = 2 -> 16 slots)
 constexpr int kSmallCount = 20;         // assignmentGenerator.cpp:289: rows with fewer fragments draw uniforms
 constexpr int kTableSmemEntries = 2048; // simplex CDF tables up to this many entries are staged in shared memory
 constexpr int kMatrixSmemBytes = 96 * 1024;  // units whose packed matrix exceeds this stream it from L2/HBM
 constexpr uint32_t kRowSlotShift = 27;  // row_info = slot << 27 | original row index
+// A-step work items (one lane each) = collapsed rows.  A row with n >= kSmallCount fragments is a chain item (one
+// conditional binomial per cell in play); a row with fewer is a uniform item that locates its n uniforms in the row's
+// CDF, four (one Philox block) at a time.  row_nnz word of an item: cells | Philox blocks << 16 | chain << 24
+constexpr uint32_t kItemNnzMask = 0xFFFFu;
+constexpr uint32_t kItemBlockShift = 16, kItemChainShift = 24;
 
 // Device-side descriptor of one unit.  All *_off fields index the context-wide concatenated arrays.
 struct UnitDev {
     int32_t n_slots;    // 1 for a wide unit
     int32_t Tpad;       // lanes per slot (bundle) or T (wide unit)
     int32_t wide;       // 1: wide unit (gibbs_wide_kernel), 0: bundle (gibbs_bundle_kernel)
-    int32_t n_slabs;    // ceil(pooled rows / 32) slabs of 32 rows, column-major inside a slab (SELL-32)
-    int32_t n_cells;    // padded cells = 32 * sum of slab widths
+    int32_t n_slabs;    // ceil(pooled rows / slab_h) slabs of slab_h rows, column-major inside a slab (SELL-h)
+    int32_t slab_h;     // rows per slab = lanes a warp uses in the A-step: 32, or 16 / 8 / 4 for latency-critical units
+    int32_t n_cells;    // padded cells = slab_h * sum of slab widths
     int32_t burn;
     int32_t samples;
     int32_t tab_len;    // entries of all simplex CDF tables of the unit
@@ -41,7 +47,7 @@ struct UnitDev {
     int32_t block;      // threads
     int64_t slab_off;   // -> slab_cell_off[n_slabs + 1] (cell offsets relative to cell_off)
     int64_t cell_off;   // -> val / col
-    int64_t row_off;    // -> row_n / row_nnz / row_info (n_slabs * 32 entries, padded rows have n = nnz = 0)
+    int64_t row_off;    // -> row_n / row_nnz / row_info (n_slabs * slab_h entries, padded rows have n = nnz = 0)
     int64_t lane_off;   // -> efflen / base_counts: 32 entries (bundle, by lane) or T entries (wide)
     int64_t tab_off;    // -> tab_val (tables of the slots back to back)
     int64_t tabrow_off; // -> tab_row: slot g at g * (Tpad + 1), T + 1 offsets relative to the unit's tab_off
@@ -70,6 +76,7 @@ struct KernelArgs {
     double *out_mean;
     double *out_m2;
     int32_t *out_counts;
+    uint64_t *unit_clock;  // per unit: globaltimer ns at block start, at block end, SM id (3 words)
     // replay trace of one slot (trace_unit < 0: off)
     int64_t trace_unit;
     int32_t trace_slot;
@@ -123,11 +130,18 @@ struct PackedUnit {
     double cost = 0;
 };
 
+// shape of one A-step item before packing (pack.cpp builds them, capi.cu sizes units with them)
+struct ItemShape {
+    int32_t slot, r, n, nnz, blocks;
+    bool chain;
+};
+
 // pack.cpp
+void build_items(const std::vector<SlotRef> &slots, std::vector<ItemShape> *items, int *n_chain);
 int validate_locus(const bayes_locus_desc &in, std::string *err);
 int prepare_locus(const bayes_locus_desc &in, PreLocus *out, std::string *err);
 int slot_lanes(int T);  // Tpad of a bundle slot (power of two >= T), 0 when T > 32
-void pack_unit(const std::vector<SlotRef> &slots, bool wide, PackedUnit *out);
+void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, PackedUnit *out);
 
 // host_steps.cpp
 int min_read_cover(const bayes_locus_desc &in, uint64_t key, int32_t *in_cover);

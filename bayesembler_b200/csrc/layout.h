@@ -14,17 +14,17 @@ namespace bayes {
 struct SmemLayout {
     // byte offsets from the start of dynamic shared memory; 8-byte members first
     uint32_t theta, den, mean, m2, tab_val, val, key;                      // double / uint64
-    uint32_t counts, base, occ, tab_row, mask, slab, row_n, row_nnz, row_info;  // int32
+    uint32_t counts, base, occ, tab_row, mask, slab, row_n, row_nnz, row_info, next_slab;  // int32
     uint32_t col;                                                          // uint16
     uint32_t total;
 };
 
 // nT: per-candidate entries (32 for a bundle, T for a wide unit); wide units also keep den / mean / m2 / base / occ and
 // the S+ / picked masks in shared memory, a bundle keeps them in the registers of warp 0.
-BAYES_LAYOUT_HD SmemLayout unit_layout(bool wide, int nT, int n_slots, int Tpad, int n_slabs, int n_cells, int tab_len, bool tab_smem,
-                                       bool mat_smem) {
+BAYES_LAYOUT_HD SmemLayout unit_layout(bool wide, int nT, int n_slots, int Tpad, int n_slabs, int slab_h, int n_cells, int tab_len,
+                                       bool tab_smem, bool mat_smem) {
     SmemLayout L;
-    const uint32_t uT = (uint32_t)nT, Rp = (uint32_t)n_slabs * 32u, nch = (uT + 31u) / 32u;
+    const uint32_t uT = (uint32_t)nT, Rp = (uint32_t)n_slabs * (uint32_t)slab_h, nch = (uT + 31u) / 32u;
     const uint32_t n_tabrow = (uint32_t)n_slots * ((uint32_t)Tpad + 1u);
     uint32_t o = 0;
     L.theta = o; o += 8u * uT;
@@ -34,6 +34,7 @@ BAYES_LAYOUT_HD SmemLayout unit_layout(bool wide, int nT, int n_slots, int Tpad,
     L.tab_val = o; o += tab_smem ? 8u * (uint32_t)tab_len : 0u;
     L.val = o; o += mat_smem ? 8u * (uint32_t)n_cells : 0u;
     L.key = o; o += 8u * (uint32_t)n_slots;
+    L.next_slab = o; o += 8u;
     L.counts = o; o += 4u * uT;
     L.base = o; o += wide ? 4u * uT : 0u;
     L.occ = o; o += wide ? 4u * uT : 0u;

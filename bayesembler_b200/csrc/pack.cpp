@@ -8,9 +8,9 @@
 // pack_unit (per thread block):
 //  * the rows of all slots of the unit are pooled and ordered by (binomial-chain rows first, wider rows first, larger
 //    counts first) so that the 32 rows a warp walks together take the same branch and have similar lengths;
-//  * 32 consecutive rows form a slab stored column-major (cell k of lane l at slab + 32 k + l, SELL-32), so a warp
-//    reading "cell k of my row" touches 32 consecutive doubles / 32 consecutive uint16 columns: conflict-free in
-//    shared memory, fully coalesced from L2/HBM;
+//  * h consecutive rows (h = 32, or 16 / 8 / 4 for latency-critical units that spread their rows over more warps) form
+//    a slab stored column-major (cell k of lane l at slab + h k + l, SELL-h), so a warp reading "cell k of my row"
+//    touches consecutive doubles / consecutive uint16 columns: conflict-free in shared memory, coalesced from L2/HBM;
 //  * in a bundle the column of a cell is the LANE of its candidate (slot * Tpad + t), so the assignment step indexes
 //    one pooled theta / counts vector whichever locus a row belongs to.
 #include <float.h>
@@ -141,7 +141,31 @@ int prepare_locus(const bayes_locus_desc &in, PreLocus *out, std::string *err) {
     return BAYES_OK;
 }
 
-void pack_unit(const std::vector<SlotRef> &slots, bool wide, PackedUnit *out) {
+// A-step items of a unit in processing order: chain items first (wider first, larger counts first: the number of
+// conditional binomials a lane runs is bounded by its cells), then uniform items (more Philox blocks first, then wider),
+// so that the lanes of a slab loop the same number of times.
+void build_items(const std::vector<SlotRef> &slots, std::vector<ItemShape> *items, int *n_chain) {
+    items->clear();
+    for (int g = 0; g < (int)slots.size(); g++) {
+        const PreLocus &L = *slots[g].locus;
+        for (size_t r = 0; r < L.row_id.size(); r++) {
+            const int32_t n = L.row_n[r], nnz = L.row_ptr[r + 1] - L.row_ptr[r];
+            const bool chain = n >= kSmallCount;
+            items->push_back(ItemShape{g, (int32_t)r, n, nnz, chain ? 0 : (n + 3) / 4, chain});
+        }
+    }
+    std::stable_sort(items->begin(), items->end(), [](const ItemShape &a, const ItemShape &b) {
+        if (a.chain != b.chain) return a.chain;
+        if (a.chain) return a.nnz != b.nnz ? a.nnz > b.nnz : a.n > b.n;
+        return a.blocks != b.blocks ? a.blocks > b.blocks : a.nnz > b.nnz;
+    });
+    int nc = 0;
+    for (const ItemShape &it : *items) nc += it.chain;
+    *n_chain = nc;
+}
+
+void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, PackedUnit *out) {
+    const int H = slab_h;
     PackedUnit &U = *out;
     U = PackedUnit();
     const int n_slots = (int)slots.size();
@@ -149,45 +173,36 @@ void pack_unit(const std::vector<SlotRef> &slots, bool wide, PackedUnit *out) {
     const int Tpad = wide ? L0.T : slot_lanes(L0.T);
     const int nT = wide ? L0.T : 32;
 
-    struct Row { int32_t slot, r, n, nnz; };
-    std::vector<Row> rows;
-    for (int g = 0; g < n_slots; g++) {
-        const PreLocus &L = *slots[g].locus;
-        for (size_t r = 0; r < L.row_id.size(); r++) rows.push_back(Row{g, (int32_t)r, L.row_n[r], L.row_ptr[r + 1] - L.row_ptr[r]});
-    }
-    if (n_slots > 1)
-        std::stable_sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) {
-            const bool ca = a.n >= kSmallCount, cb = b.n >= kSmallCount;
-            if (ca != cb) return ca;
-            if (a.nnz != b.nnz) return a.nnz > b.nnz;
-            return a.n > b.n;
-        });
-    const int Rm = (int)rows.size();
-    const int n_slabs = (Rm + 31) / 32;
+    std::vector<ItemShape> items;
+    int n_chain = 0;
+    build_items(slots, &items, &n_chain);
+    // chain items fill their own slabs; the uniform items start on a slab boundary (a slab is one kind of work)
+    const int n_items = (int)items.size();
+    const int chain_slabs = (n_chain + H - 1) / H, unif_slabs = (n_items - n_chain + H - 1) / H;
+    const int n_slabs = chain_slabs + unif_slabs;
+    auto position = [&](int i) { return i < n_chain ? i : chain_slabs * H + (i - n_chain); };  // item -> padded row
     U.slab_cell_off.assign(n_slabs + 1, 0);
-    U.row_n.assign((size_t)n_slabs * 32, 0);
-    U.row_nnz.assign((size_t)n_slabs * 32, 0);
-    U.row_info.assign((size_t)n_slabs * 32, 0);
-    for (int s = 0; s < n_slabs; s++) {
-        int w = 0;
-        for (int l = 0; l < 32 && s * 32 + l < Rm; l++) w = std::max(w, rows[s * 32 + l].nnz);
-        U.slab_cell_off[s + 1] = U.slab_cell_off[s] + 32 * w;
-    }
+    U.row_n.assign((size_t)n_slabs * H, 0);
+    U.row_nnz.assign((size_t)n_slabs * H, 0);
+    U.row_info.assign((size_t)n_slabs * H, 0);
+    std::vector<int> width(n_slabs, 0);
+    for (int i = 0; i < n_items; i++) width[position(i) / H] = std::max(width[position(i) / H], items[i].nnz);
+    for (int s = 0; s < n_slabs; s++) U.slab_cell_off[s + 1] = U.slab_cell_off[s] + H * width[s];
     const int n_cells = U.slab_cell_off[n_slabs];
     U.val.assign(n_cells, 0.0);
     U.col.assign(n_cells, 0);
-    for (int r = 0; r < Rm; r++) {
-        const Row &row = rows[r];
-        const PreLocus &L = *slots[row.slot].locus;
-        const int s = r / 32, l = r % 32;
-        U.row_n[r] = row.n;
-        U.row_nnz[r] = row.nnz;
-        U.row_info[r] = ((uint32_t)row.slot << kRowSlotShift) | (uint32_t)L.row_id[row.r];
-        const int lane0 = wide ? 0 : row.slot * Tpad;
-        for (int k = 0; k < row.nnz; k++) {
-            const size_t at = (size_t)U.slab_cell_off[s] + 32 * (size_t)k + l;
-            U.val[at] = L.cell_val[L.row_ptr[row.r] + k];
-            U.col[at] = (uint16_t)(lane0 + L.cell_col[L.row_ptr[row.r] + k]);
+    for (int i = 0; i < n_items; i++) {
+        const ItemShape &it = items[i];
+        const PreLocus &L = *slots[it.slot].locus;
+        const int r = position(i), s = r / H, l = r % H;
+        U.row_n[r] = it.n;
+        U.row_nnz[r] = (int32_t)((uint32_t)it.nnz | ((uint32_t)it.blocks << kItemBlockShift) | ((uint32_t)(it.chain ? 1 : 0) << kItemChainShift));
+        U.row_info[r] = ((uint32_t)it.slot << kRowSlotShift) | (uint32_t)L.row_id[it.r];
+        const int lane0 = wide ? 0 : it.slot * Tpad;
+        for (int k = 0; k < it.nnz; k++) {
+            const size_t at = (size_t)U.slab_cell_off[s] + H * (size_t)k + l;
+            U.val[at] = L.cell_val[L.row_ptr[it.r] + k];
+            U.col[at] = (uint16_t)(lane0 + L.cell_col[L.row_ptr[it.r] + k]);
         }
     }
 
@@ -220,17 +235,16 @@ void pack_unit(const std::vector<SlotRef> &slots, bool wide, PackedUnit *out) {
     d.Tpad = Tpad;
     d.wide = wide ? 1 : 0;
     d.n_slabs = n_slabs;
+    d.slab_h = H;
     d.n_cells = n_cells;
     d.burn = L0.burn;
     d.samples = L0.samples;
     d.tab_len = (int32_t)U.tab_val.size();
     d.tab_smem = d.tab_len <= kTableSmemEntries;
-    const size_t mat_bytes = (size_t)n_cells * 10 + (size_t)n_slabs * 32 * 12 + 4 * ((size_t)n_slabs + 1);
+    const size_t mat_bytes = (size_t)n_cells * 10 + (size_t)n_slabs * H * 12 + 4 * ((size_t)n_slabs + 1);
     d.mat_smem = mat_bytes <= (size_t)kMatrixSmemBytes;
-    d.smem_bytes = (int32_t)unit_layout(wide, nT, n_slots, Tpad, n_slabs, n_cells, d.tab_len, d.tab_smem != 0, d.mat_smem != 0).total;
-    int block = 32;
-    while (block < Rm && block < kMaxBlock) block *= 2;
-    d.block = block;
+    d.smem_bytes = (int32_t)unit_layout(wide, nT, n_slots, Tpad, n_slabs, H, n_cells, d.tab_len, d.tab_smem != 0, d.mat_smem != 0).total;
+    d.block = 32;  // build_units decides
 }
 
 }  // namespace bayes

@@ -232,6 +232,31 @@ BAYES_HD int binomial_btrd(const Site &s, int n, double q) {
     }
 }
 
+// n * min(p, 1-p) below this: inversion (BINV), else BTRD.  Hoermann's BTRD needs >= 10 (measured best switch point on B200: 32); inversion costs one short
+// loop iteration per unit of n*q but has a single, branch-free body, which is what 32 lanes in lockstep want.
+#ifndef BAYES_BINV_NQ
+#define BAYES_BINV_NQ 32.0
+#endif
+
+// 1/k for the inversion recurrence: the correctly rounded reciprocal, so a table entry is the same double as 1.0 / k
+#if defined(__CUDACC__)
+__constant__ double kInvTable[64] = {
+    0.0,      1.0 / 1,  1.0 / 2,  1.0 / 3,  1.0 / 4,  1.0 / 5,  1.0 / 6,  1.0 / 7,  1.0 / 8,  1.0 / 9,  1.0 / 10, 1.0 / 11, 1.0 / 12,
+    1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25,
+    1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32, 1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37, 1.0 / 38,
+    1.0 / 39, 1.0 / 40, 1.0 / 41, 1.0 / 42, 1.0 / 43, 1.0 / 44, 1.0 / 45, 1.0 / 46, 1.0 / 47, 1.0 / 48, 1.0 / 49, 1.0 / 50, 1.0 / 51,
+    1.0 / 52, 1.0 / 53, 1.0 / 54, 1.0 / 55, 1.0 / 56, 1.0 / 57, 1.0 / 58, 1.0 / 59, 1.0 / 60, 1.0 / 61, 1.0 / 62, 1.0 / 63};
+#endif
+
+BAYES_HD double inv_int(int k) {
+#if defined(__CUDA_ARCH__)
+    // lanes run the recurrence in lockstep from k = 1, so this is a uniform (broadcast) constant-bank read
+    return k < 64 ? kInvTable[k] : __drcp_rn((double)k);
+#else
+    return 1.0 / (double)k;
+#endif
+}
+
 // binomial_distribution(n, p) (assignmentGenerator.cpp:230-233, 346-349)
 BAYES_HD_NOINLINE int binomial_variate(const Site &s, int n, double p) {
     if (n <= 0 || !(p > 0.0)) return 0;
@@ -239,17 +264,20 @@ BAYES_HD_NOINLINE int binomial_variate(const Site &s, int n, double p) {
     const bool flip = p > 0.5;
     const double q = flip ? 1.0 - p : p;
     int k;
-    if ((double)n * q < 10.0) {
-        // BINV: P(0) = (1-q)^n, P(k) = P(k-1) s (n-k+1) / k
+    if ((double)n * q < BAYES_BINV_NQ) {
+        // BINV: P(0) = (1-q)^n, P(k) = P(k-1) * ((n-k+1) s / k).  The factor does not depend on P(k-1), so the
+        // dependent chain per step is one multiplication and one subtraction.
         const u32x4 b = s.block(0);
         double u = u53(b.x, b.y);
         const double sr = q / (1.0 - q);
         double r = ipow(1.0 - q, n);
+        double left = (double)n;  // n - k + 1 of the next step, kept as a double (exact) to save a conversion per step
         k = 0;
         while (u > r && k < n) {
             u -= r;
             k++;
-            r = (r * ((double)(n - k + 1) * sr)) * recip((double)k);
+            r = r * ((left * sr) * inv_int(k));
+            left -= 1.0;
         }
     } else {
         k = binomial_btrd(s, n, q);

@@ -110,6 +110,10 @@ int bayes_gibbs_locus_info(bayes_gibbs_ctx *ctx, int64_t locus_id, double *pi, i
 int bayes_gibbs_chain_info(bayes_gibbs_ctx *ctx, int64_t locus_id, int32_t chain, double *pi, int32_t *cover_size);
 int64_t bayes_gibbs_num_loci(bayes_gibbs_ctx *ctx);
 int64_t bayes_gibbs_num_jobs(bayes_gibbs_ctx *ctx);
+/* Scheduling diagnostics of the last run, one entry per thread-block unit: shape8 = {wide, threads, slots, row slabs,
+ * padded cells, iterations, T of slot 0, matrix in shared memory | rows per slab << 8}, clock3 = {start ns, end ns, SM id} (globaltimer).
+ * Returns the number of units; call with both pointers NULL to size the buffers. */
+int64_t bayes_gibbs_unit_stats(bayes_gibbs_ctx *ctx, int32_t *shape8, uint64_t *clock3);
 /* kernels launched by the last bayes_gibbs_run() */
 int32_t bayes_gibbs_last_launches(bayes_gibbs_ctx *ctx);
 

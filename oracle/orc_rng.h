@@ -305,6 +305,11 @@ static inline int orc_btrd(orc_ws *w, int n, double q) {
     }
 }
 
+/* n * min(p, 1-p) below this: inversion (BINV), else BTRD (which needs >= 10) */
+#ifndef ORC_BINV_NQ
+#define ORC_BINV_NQ 32.0
+#endif
+
 /* binomial_distribution(n, p)   (assignmentGenerator.cpp:230-233, 346-349) */
 static inline int orc_binomial(orc_ws *w, int n, double p) {
     if (n <= 0 || !(p > 0.0)) return 0; /* also NaN; nothing consumed */
@@ -312,8 +317,8 @@ static inline int orc_binomial(orc_ws *w, int n, double p) {
     const int flip = p > 0.5;
     const double q = flip ? 1.0 - p : p;
     int k;
-    if ((double)n * q < 10.0) {
-        /* BINV: sequential search from 0 with P(0) = (1-q)^n, P(k) = P(k-1) s (n-k+1) / k, s = q/(1-q) */
+    if ((double)n * q < ORC_BINV_NQ) {
+        /* BINV: sequential search from 0 with P(0) = (1-q)^n, P(k) = P(k-1) ((n-k+1) s (1/k)), s = q/(1-q) */
         uint32_t b[4];
         orc_ws_block(w, b);
         double u = orc_u53(b[0], b[1]);
@@ -323,7 +328,7 @@ static inline int orc_binomial(orc_ws *w, int n, double p) {
         while (u > r && k < n) {
             u -= r;
             k++;
-            r = (r * ((double)(n - k + 1) * s)) * (1.0 / (double)k);
+            r = r * (((double)(n - k + 1) * s) * (1.0 / (double)k));
         }
     } else {
         k = orc_btrd(w, n, q);

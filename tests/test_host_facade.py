@@ -85,9 +85,9 @@ def _run_loci(facade, loci, seeds, burn, samples, batched):
     facade.facade_run_loci.restype = C.c_int
     facade.facade_run_loci.argtypes = [C.c_int] + [vp] * 9 + [C.c_double, C.c_double, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_char_p, C.c_int]
     p = lambda a: a.ctypes.data  # noqa: E731
+    seeds_a, burn_a, samples_a = np.ascontiguousarray(seeds, np.uint64), np.ascontiguousarray(burn, np.int32), np.ascontiguousarray(samples, np.int32)
     rc = facade.facade_run_loci(n, p(T_arr), p(row_off), p(cell_off), p(t_off), p(row_ptr), p(col), p(val), p(cnt), p(eff),
-                                loci[0].n_total, loci[0].gamma, p(np.ascontiguousarray(seeds, np.uint64)),
-                                p(np.ascontiguousarray(burn, np.int32)), p(np.ascontiguousarray(samples, np.int32)), int(batched),
+                                loci[0].n_total, loci[0].gamma, p(seeds_a), p(burn_a), p(samples_a), int(batched),
                                 p(occ), p(mean), p(m2), p(pi), err, len(err))
     return rc, err.value.decode(), [dict(occ=occ[t_off[i]:t_off[i + 1]], mean=mean[t_off[i]:t_off[i + 1]], m2=m2[t_off[i]:t_off[i + 1]],
                                          pi=pi[i]) for i in range(n)]
@@ -119,6 +119,7 @@ def test_facade_worker_matches_c_abi(facade, lib, batched):
     for i in range(len(loci)):
         want = ctx.fetch(i)
         assert got[i]["pi"] == ctx.locus_info(i)["pi"]
-        assert np.array_equal(got[i]["occ"], want["occ"])
-        assert np.array_equal(got[i]["mean"], want["mean"]) and np.array_equal(got[i]["m2"], want["m2"])
+        assert np.array_equal(got[i]["occ"], want["occ"]), i
+        assert np.array_equal(got[i]["mean"], want["mean"]), (i, got[i]["mean"], want["mean"])
+        assert np.array_equal(got[i]["m2"], want["m2"]), (i, got[i]["m2"], want["m2"])
     ctx.close()
