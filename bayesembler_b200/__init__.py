@@ -17,7 +17,7 @@ EXPORTED_SYMBOLS = [
     "bayes_gibbs_set_host_threads", "bayes_last_error", "bayes_gibbs_submit", "bayes_gibbs_upload", "bayes_gibbs_run",
     "bayes_gibbs_download", "bayes_gibbs_sync", "bayes_gibbs_run_batch", "bayes_gibbs_clear", "bayes_gibbs_fetch",
     "bayes_gibbs_fetch_all",
-    "bayes_gibbs_locus_info", "bayes_gibbs_chain_info", "bayes_gibbs_num_loci", "bayes_gibbs_num_jobs", "bayes_gibbs_unit_stats", "bayes_gibbs_last_launches",
+    "bayes_gibbs_locus_info", "bayes_gibbs_chain_info", "bayes_gibbs_num_loci", "bayes_gibbs_num_jobs", "bayes_gibbs_unit_stats", "bayes_gibbs_phase_seconds", "bayes_gibbs_last_launches",
     "bayes_gibbs_set_trace", "bayes_gibbs_fetch_trace", "bayes_top_marginals", "bayes_step_generate_assignment",
     "bayes_step_init_assignment", "bayes_step_generate_expression", "bayes_step_variates", "bayes_min_read_cover",
     "bayes_simplex_table", "bayes_chain_key", "bayes_locus_cost", "bayes_partition_lpt", "bayes_philox4x32",
@@ -94,6 +94,7 @@ def load_library(path=None):
         "bayes_gibbs_num_loci": (i64, [vp]),
         "bayes_gibbs_num_jobs": (i64, [vp]),
         "bayes_gibbs_unit_stats": (i64, [vp, vp, vp]),
+        "bayes_gibbs_phase_seconds": (C.c_int, [vp, vp]),
         "bayes_gibbs_last_launches": (i32, [vp]),
         "bayes_gibbs_set_trace": (C.c_int, [vp, i64, i32, i32]),
         "bayes_gibbs_fetch_trace": (C.c_int, [vp, vp, vp, vp, vp]),
@@ -256,6 +257,11 @@ class GibbsContext(object):
         clock = np.zeros((n, 3), np.uint64)
         _check(self.lib.bayes_gibbs_unit_stats(self.h, _ptr(shape), _ptr(clock)), "bayes_gibbs_unit_stats")
         return shape, clock
+
+    def phase_seconds(self):
+        out = np.zeros(6)
+        _check(self.lib.bayes_gibbs_phase_seconds(self.h, _ptr(out)), "bayes_gibbs_phase_seconds")
+        return dict(zip(["prepare", "pack", "h2d_enqueue", "launch", "d2h_enqueue", "sync"], out.tolist()))
 
     def last_launches(self):
         return self.lib.bayes_gibbs_last_launches(self.h)

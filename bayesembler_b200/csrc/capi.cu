@@ -2,11 +2,13 @@
 // formation, device buffers, launches.  Everything that computes on the device is in gibbs_kernel.cu; nothing here
 // falls back to the CPU.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <map>
 #include <numeric>
 #include <queue>
@@ -123,6 +125,9 @@ struct bayes_gibbs_ctx {
 
     std::vector<Launch> launches;
     int32_t last_launches = 0;
+    // wall-clock seconds of the host phases of the last batch: prepare (fold, cover, tables), unit formation + packing,
+    // H2D enqueue, launch enqueue, D2H enqueue, final synchronise (= device time not hidden behind the host)
+    double phase_s[6] = {0, 0, 0, 0, 0, 0};
 
     int64_t trace_locus = -1;
     int32_t trace_chain = 0, trace_iters = 0, trace_T = 0, trace_slot = 0;
@@ -130,11 +135,14 @@ struct bayes_gibbs_ctx {
 
     // launch classes run concurrently: each on its own auxiliary stream, forked from / joined to `stream` by events
     std::vector<cudaStream_t> aux;
-    std::vector<cudaEvent_t> join_ev;
+    std::vector<cudaEvent_t> join_ev, gate_ev;
     cudaEvent_t fork_ev = nullptr;
+    cudaStream_t gate = nullptr;  // releases the class launches one by one (bayes_gibbs_run)
 };
 
 namespace {
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 int use_device(bayes_gibbs_ctx *ctx) { return cuda_rc(cudaSetDevice(ctx->device), "cudaSetDevice"); }
 
@@ -373,34 +381,28 @@ int build_units(bayes_gibbs_ctx *ctx) {
         packed[i].cost = unit_time(shapes[i], unit_warps[i], unit_h[i]);  // estimated duration: the launch-order key
     });
 
-    // One launch per class = (kernel, block size, matrix placement, shared-memory bucket).  The bucket matters: a launch
-    // has ONE dynamic shared-memory size, and sizing it for the largest unit of a broad class would cut the number of
-    // resident units per SM several-fold.  Classes are issued in order of their longest unit and units inside a class
-    // longest first: the hardware block scheduler hands blocks out in that order, which makes this the largest-first
-    // queue of the reference (assembler.cpp:1886-1916).
+    // One launch per class = (kernel, block size, matrix placement, shared-memory bucket) and duration band.  The bucket
+    // matters: a launch has ONE dynamic shared-memory size, and sizing it for the largest unit of a broad class would
+    // cut the number of resident units per SM several-fold.  The band matters: the hardware block scheduler hands
+    // blocks out launch by launch, so the launches are issued longest units first across ALL classes -- the
+    // largest-first queue of the reference (assembler.cpp:1886-1916) -- with the blocks of 8 or more warps, which only
+    // fit an SM that is still nearly empty, ahead of everything else.
     auto smem_bucket = [](int32_t bytes) -> int32_t {
-        int32_t step = bytes <= 16 * 1024 ? 1024 : bytes <= 64 * 1024 ? 4096 : 16 * 1024;
+        int32_t step = bytes <= 8 * 1024 ? 2048 : bytes <= 32 * 1024 ? 4096 : 16 * 1024;
         return (bytes + step - 1) / step * step;
     };
-    typedef std::tuple<int, int, int, int> ClassKey;  // (wide, mat_smem, block, smem bucket)
-    auto class_of = [&](const PackedUnit &u) { return ClassKey(u.d.wide, u.d.mat_smem, u.d.block, smem_bucket(u.d.smem_bytes)); };
-    std::map<ClassKey, double> class_max;
-    for (const PackedUnit &u : packed) {
-        double &m = class_max[class_of(u)];
-        m = std::max(m, u.cost);
-    }
+    auto band_of = [](const PackedUnit &u) -> int {
+        if (u.d.block >= 256) return 1000;                            // critical, hard to place later
+        return (int)floor(log(std::max(u.cost, 1e-6)) / log(1.4));   // +-18 % of duration per band
+    };
+    typedef std::tuple<int, int, int, int, int> ClassKey;  // (-band, wide, mat_smem, block, smem bucket)
+    auto class_of = [&](const PackedUnit &u) { return ClassKey(-band_of(u), u.d.wide, u.d.mat_smem, u.d.block, smem_bucket(u.d.smem_bytes)); };
+    std::vector<ClassKey> key(n_units);
+    for (int64_t i = 0; i < n_units; i++) key[i] = class_of(packed[i]);
     std::vector<int64_t> order(n_units);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
-        const ClassKey ka = class_of(packed[a]), kb = class_of(packed[b]);
-        if (ka != kb) {
-            // widened units are the ones on the critical path, and a large block only fits an SM that is still
-            // nearly empty: largest blocks first, then the class with the longest unit
-            if (std::get<2>(ka) != std::get<2>(kb)) return std::get<2>(ka) > std::get<2>(kb);
-            const double ma = class_max[ka], mb = class_max[kb];
-            if (ma != mb) return ma > mb;
-            return ka < kb;
-        }
+        if (key[a] != key[b]) return key[a] < key[b];
         return packed[a].cost > packed[b].cost;
     });
     int rc;
@@ -409,9 +411,9 @@ int build_units(bayes_gibbs_ctx *ctx) {
     const UnitDev *units = ctx->h_units.p;
     for (int64_t i = 0; i < n_units;) {
         int64_t j = i;
-        const ClassKey k = class_of(packed[order[i]]);
-        while (j < n_units && class_of(packed[order[j]]) == k) j++;
-        ctx->launches.push_back(Launch{i, j - i, units[i].block, units[i].wide != 0, units[i].mat_smem != 0, (size_t)std::get<3>(k)});
+        const ClassKey &k = key[order[i]];
+        while (j < n_units && key[order[j]] == k) j++;
+        ctx->launches.push_back(Launch{i, j - i, units[i].block, units[i].wide != 0, units[i].mat_smem != 0, (size_t)std::get<4>(k)});
         i = j;
     }
     if (ctx->trace_locus >= 0) {
@@ -527,6 +529,8 @@ void bayes_gibbs_destroy(bayes_gibbs_ctx *ctx) {
     ctx->d_counts.release(); ctx->d_tr_counts.release(); ctx->d_tr_b.release(); ctx->d_tr_init.release();
     for (cudaStream_t st : ctx->aux) cudaStreamDestroy(st);
     for (cudaEvent_t ev : ctx->join_ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->gate_ev) cudaEventDestroy(ev);
+    if (ctx->gate) cudaStreamDestroy(ctx->gate);
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -552,6 +556,7 @@ int bayes_gibbs_clear(bayes_gibbs_ctx *ctx) {
     if (rc) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->loci.clear();
+    ctx->phase_s[0] = 0;
     ctx->out_base.clear();
     ctx->out_len = 0;
     ctx->h_units.n = 0;
@@ -573,6 +578,7 @@ int bayes_gibbs_submit(bayes_gibbs_ctx *ctx, int32_t n_loci, const bayes_locus_d
         return BAYES_E_STATE;
     }
     if (first_id) *first_id = (int64_t)ctx->loci.size();
+    const double t0 = now_s();
     // fold rows, read cover, CDF table: independent per locus
     std::vector<PreLocus> pre(n_loci);
     std::vector<int> prc(n_loci, 0);
@@ -589,6 +595,7 @@ int bayes_gibbs_submit(bayes_gibbs_ctx *ctx, int32_t n_loci, const bayes_locus_d
         ctx->out_len += (int64_t)pre[i].T * pre[i].n_chains;
         ctx->loci.push_back(std::move(pre[i]));
     }
+    ctx->phase_s[0] += now_s() - t0;
     return BAYES_OK;
 }
 
@@ -596,7 +603,10 @@ int bayes_gibbs_upload(bayes_gibbs_ctx *ctx) {
     if (!ctx) return BAYES_E_INVALID;
     int rc = use_device(ctx);
     if (rc) return rc;
+    const double t0 = now_s();
     if ((rc = build_units(ctx))) return rc;
+    const double t1 = now_s();
+    ctx->phase_s[1] = t1 - t0;
     if (ctx->trace_locus >= 0) {
         const size_t n = (size_t)ctx->trace_iters * ctx->trace_T;
         if ((rc = ctx->d_tr_theta.reserve(n)) || (rc = ctx->d_tr_counts.reserve(n)) || (rc = ctx->d_tr_b.reserve(ctx->trace_iters)) ||
@@ -614,6 +624,7 @@ int bayes_gibbs_upload(bayes_gibbs_ctx *ctx) {
         return rc;
     ctx->uploaded = true;
     ctx->ran = ctx->downloaded = false;
+    ctx->phase_s[2] = now_s() - t1;
     return BAYES_OK;
 }
 
@@ -625,6 +636,7 @@ int bayes_gibbs_run(bayes_gibbs_ctx *ctx) {
     }
     int rc = use_device(ctx);
     if (rc) return rc;
+    const double t0 = now_s();
     const KernelArgs args = kernel_args(ctx);
     ctx->last_launches = 0;
     const size_t n_l = ctx->launches.size();
@@ -642,12 +654,31 @@ int bayes_gibbs_run(bayes_gibbs_ctx *ctx) {
         ctx->aux.push_back(st);
         ctx->join_ev.push_back(ev);
     }
-    // the block scheduler drains launches roughly in issue order, so the classes with the longest chains go first
-    if (n_l > 1) CU(cudaEventRecord(ctx->fork_ev, ctx->stream));
+    // The block scheduler hands out the blocks of concurrent launches in the order in which the launches become
+    // runnable, and the launches are sorted longest units first.  When the batch is queued behind other work all of
+    // them would become runnable at the same instant (and be served in no particular order), so a gate stream releases
+    // them one by one, a few microseconds apart: gate kernel i -> event i -> launch i on its own stream.
+    if (n_l > 1) {
+        if (!ctx->gate) CU(cudaStreamCreateWithFlags(&ctx->gate, cudaStreamNonBlocking));
+        while (ctx->gate_ev.size() < n_l) {
+            cudaEvent_t ev;
+            CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            ctx->gate_ev.push_back(ev);
+        }
+        CU(cudaEventRecord(ctx->fork_ev, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->gate, ctx->fork_ev, 0));
+    }
     for (size_t i = 0; i < n_l; i++) {
         const Launch &l = ctx->launches[i];
         cudaStream_t st = n_l > 1 ? ctx->aux[i] : ctx->stream;
-        if (n_l > 1) CU(cudaStreamWaitEvent(st, ctx->fork_ev, 0));
+        if (n_l > 1) {
+            if (i > 0) {
+                if ((rc = launch_stagger(3000u, ctx->gate))) return rc;
+                ctx->last_launches++;
+            }
+            CU(cudaEventRecord(ctx->gate_ev[i], ctx->gate));
+            CU(cudaStreamWaitEvent(st, ctx->gate_ev[i], 0));
+        }
         if ((rc = launch_units(args, l.unit_base, l.n_units, l.block, l.wide, l.mat_smem, l.smem, st))) return rc;
         if (n_l > 1) {
             CU(cudaEventRecord(ctx->join_ev[i], st));
@@ -657,6 +688,7 @@ int bayes_gibbs_run(bayes_gibbs_ctx *ctx) {
     }
     ctx->ran = true;
     ctx->downloaded = false;
+    ctx->phase_s[3] = now_s() - t0;
     return BAYES_OK;
 }
 
@@ -668,6 +700,7 @@ int bayes_gibbs_download(bayes_gibbs_ctx *ctx) {
     }
     int rc = use_device(ctx);
     if (rc) return rc;
+    const double t0 = now_s();
     const size_t n = (size_t)ctx->out_len;
     if (n) {
         CU(cudaMemcpyAsync(ctx->h_occ.p, ctx->d_occ.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -676,6 +709,7 @@ int bayes_gibbs_download(bayes_gibbs_ctx *ctx) {
         CU(cudaMemcpyAsync(ctx->h_counts.p, ctx->d_counts.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     }
     ctx->downloaded = true;
+    ctx->phase_s[4] = now_s() - t0;
     return BAYES_OK;
 }
 
@@ -683,7 +717,16 @@ int bayes_gibbs_sync(bayes_gibbs_ctx *ctx) {
     if (!ctx) return BAYES_E_INVALID;
     int rc = use_device(ctx);
     if (rc) return rc;
+    const double t0 = now_s();
     CU(cudaStreamSynchronize(ctx->stream));
+    ctx->phase_s[5] = now_s() - t0;
+    return BAYES_OK;
+}
+
+// wall-clock seconds of the host phases of the last batch (see bayes_gibbs_ctx::phase_s)
+int bayes_gibbs_phase_seconds(bayes_gibbs_ctx *ctx, double *out6) {
+    if (!ctx || !out6) return BAYES_E_INVALID;
+    for (int i = 0; i < 6; i++) out6[i] = ctx->phase_s[i];
     return BAYES_OK;
 }
 

@@ -718,6 +718,18 @@ int launch_units(const KernelArgs &args, int64_t unit_base, int64_t n_units, int
     return check(cudaGetLastError(), "gibbs kernel launch");
 }
 
+// One thread that waits `ns` nanoseconds: spaces the start of consecutive class launches (capi.cu, bayes_gibbs_run)
+__global__ void stagger_kernel(unsigned ns) {
+    const uint64_t t0 = global_ns();
+    while (global_ns() - t0 < ns) {
+    }
+}
+
+int launch_stagger(unsigned ns, void *stream) {
+    stagger_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ns);
+    return check(cudaGetLastError(), "stagger_kernel launch");
+}
+
 int launch_step_assignment(const KernelArgs &args, bool init, const double *d_theta, uint32_t iteration, int32_t *d_counts_out,
                            size_t smem_bytes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;

@@ -150,6 +150,7 @@ void simplex_table(double pi, double gamma, int T, int num_fragments, std::vecto
 // gibbs_kernel.cu
 int launch_units(const KernelArgs &args, int64_t unit_base, int64_t n_units, int block, bool wide, bool mat_smem, size_t smem_bytes,
                  void *stream);
+int launch_stagger(unsigned ns, void *stream);
 int launch_step_assignment(const KernelArgs &args, bool init, const double *d_theta, uint32_t iteration, int32_t *d_counts_out,
                            size_t smem_bytes, void *stream);
 int launch_step_expression(int T, const int32_t *d_counts, int b, double gamma, uint64_t key, uint32_t iteration, double *d_theta,

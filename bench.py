@@ -269,6 +269,7 @@ def main():
         ctx.run_batch(descs)
         out = ctx.fetch_all()
     t1 = time.perf_counter()
+    host_phases = ctx.phase_seconds()
     barrier()
     e2e_ms = 1e3 * (t1 - t0)
     assert int(out["occ"].astype(np.int64).sum()) == checksum  # same seeds -> same chains as the resident run
@@ -312,7 +313,8 @@ def main():
             "loci_per_sec": loci * args.steps / secs, "row_visits_per_sec": row_visits * args.steps / secs,
             "cell_visits_per_sec": cell_visits * args.steps / secs, "iterations_per_sec": iterations * args.steps / secs,
             "e2e": {"value": draws * e2e_steps / (e2e_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / e2e_steps, "loci_per_sec": loci * e2e_steps / (e2e_ms / 1e3)},
+                    "ms_per_step": e2e_ms / e2e_steps, "loci_per_sec": loci * e2e_steps / (e2e_ms / 1e3),
+                    "host_phases_s_rank0": host_phases},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,

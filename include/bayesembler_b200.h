@@ -114,6 +114,9 @@ int64_t bayes_gibbs_num_jobs(bayes_gibbs_ctx *ctx);
  * padded cells, iterations, T of slot 0, matrix in shared memory | rows per slab << 8}, clock3 = {start ns, end ns, SM id} (globaltimer).
  * Returns the number of units; call with both pointers NULL to size the buffers. */
 int64_t bayes_gibbs_unit_stats(bayes_gibbs_ctx *ctx, int32_t *shape8, uint64_t *clock3);
+/* Wall-clock seconds of the host phases of the last batch: {prepare (fold rows, read cover, CDF tables), unit formation
+ * and packing, H2D enqueue, launch enqueue, D2H enqueue, final synchronise}. */
+int bayes_gibbs_phase_seconds(bayes_gibbs_ctx *ctx, double *out6);
 /* kernels launched by the last bayes_gibbs_run() */
 int32_t bayes_gibbs_last_launches(bayes_gibbs_ctx *ctx);
 

@@ -1,0 +1,70 @@
+"""Full-size run of BASELINE.json configs[1] (20 000 loci, 20 M fragments, default sampler settings) through the C ABI:
+size-independent properties of the domain for every locus, run-to-run determinism, and a draw-for-draw spot check of a
+few loci against the CPU oracle (which needs seconds per locus, so it cannot check them all)."""
+import numpy as np
+import pytest
+
+from oracle.oracle_py import SITE
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def full_run(lib):
+    from bayesembler_b200 import synth
+    batch = synth.SynthBatch(2)
+    descs = batch.desc_array()
+    ctx = lib.GibbsContext(0)
+    ctx.run_batch(descs)
+    res = ctx.fetch_all()
+    yield batch, descs, ctx, res
+    ctx.close()
+
+
+def test_full_size_invariants(full_run):
+    batch, descs, ctx, res = full_run
+    assert batch.n == 20000 and 19_000_000 < batch.n_frag.sum() < 21_000_000
+    t_off = batch.t_off
+    seg = np.repeat(np.arange(batch.n), batch.T)
+    # every fragment is assigned to exactly one candidate after the last iteration (assignmentGenerator.cpp:363)
+    assert np.array_equal(np.bincount(seg, weights=res["final_counts"], minlength=batch.n).astype(np.int64), batch.n_frag)
+    samples = np.repeat(batch.samples, batch.T)
+    occ = res["occ"]
+    assert occ.min() >= 0 and np.all(occ <= samples)
+    # |S+_expr| >= 1 in every sampling iteration: the inclusion counts of a locus add up to at least `samples`
+    assert np.all(np.bincount(seg, weights=occ, minlength=batch.n) >= batch.samples)
+    # T == 1: closed form (gibbsSampler.cpp:57-67)
+    one = np.nonzero(batch.T == 1)[0]
+    assert np.array_equal(occ[t_off[one]], batch.samples[one])
+    want = batch.n_frag[one] * 1e9 / (np.trunc(batch.n_total) * batch.efflen[t_off[one]])
+    np.testing.assert_allclose(res["mean"][t_off[one]], want, rtol=1e-15)
+    assert np.all(res["m2"][t_off[one]] == 0)
+    # Welford accumulators: finite, mean > 0 where included, M2 >= 0, nothing where never included
+    assert np.all(np.isfinite(res["mean"])) and np.all(np.isfinite(res["m2"]))
+    assert np.all(res["mean"][occ > 0] > 0) and np.all(res["m2"] >= 0)
+    assert np.all(res["mean"][occ == 0] == 0) and np.all(res["m2"][occ <= 1] == 0)
+    # a candidate that holds fragments at the end was in the last simplex; folded single-cell rows pin a floor
+    assert ctx.last_launches() >= 1
+
+
+def test_full_size_deterministic(full_run, lib):
+    batch, descs, ctx, res = full_run
+    ctx.run()          # same seeds -> same chains, whatever the block scheduler did
+    ctx.download()
+    ctx.sync()
+    again = ctx.fetch_all()
+    for k in res:
+        assert np.array_equal(res[k], again[k]), k
+
+
+def test_full_size_spot_check_against_oracle(full_run, lib, oracle):
+    batch, descs, ctx, res = full_run
+    rng = np.random.default_rng(11)
+    multi = np.nonzero((batch.T > 1) & (batch.T <= 12))[0]
+    for i in rng.choice(multi, 5, replace=False):
+        i = int(i)
+        o = oracle.run_sampler(batch.locus(i), int(batch.burn[i]), int(batch.samples[i]), SITE, lib.chain_key(int(batch.seeds[i]), 0))
+        g = ctx.fetch(i)
+        assert np.array_equal(g["occ"], o["occ"]), i
+        np.testing.assert_allclose(g["mean"], o["mean"], rtol=1e-9)
+        np.testing.assert_allclose(g["m2"], o["m2"], rtol=1e-6, atol=1e-9 * np.abs(o["mean"]).max() ** 2)

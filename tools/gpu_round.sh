@@ -31,9 +31,11 @@ if [ $rc -eq 0 ]; then
   echo "ncu launches rc=$?"
 fi
 
-# the dominant kernel, full set, on a 2000-locus slice of the same workload
-SMALL="python bench.py --loci 2000 --steps 1 --warmup 1 --no-cpu-baseline"
+# the dominant kernel, full set: the first launch classes of a 1000-locus slice of the same workload ...
+SMALL="python bench.py --loci 1000 --steps 1 --warmup 1 --no-cpu-baseline"
 $SMALL > $OUT/${TAG}_small.json 2> $OUT/${TAG}_small.err && \
-ncu --set full --clock-control none --import-source on -k regex:gibbs_ -c 6 -f -o $OUT/${TAG}_prof \
+ncu --set full --clock-control none --import-source on -k regex:gibbs_ -c 3 -f -o $OUT/${TAG}_prof \
     $SMALL > $OUT/${TAG}_ncu_full.log 2>&1
 echo "ncu full rc=$?"
+# ... and the saturated regime: 4096 chains of one mid-size locus = ONE launch class that fills every SM
+bash tools/ncu_bulk.sh ${TAG}_bulk 1220 4096 1100

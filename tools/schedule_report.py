@@ -29,8 +29,17 @@ def main():
     ctx.upload()
     ctx.run()
     ctx.sync()
+    import time
+    t0 = time.perf_counter()
     ctx.run()
     ctx.sync()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    ctx.run()
+    ctx.run()
+    ctx.sync()
+    wall2_ms = 1e3 * (time.perf_counter() - t0) / 2
+    print("wall clock of one run() + sync: %.1f ms; two runs back to back: %.1f ms each" % (wall_ms, wall2_ms))
     shape, clock = ctx.unit_stats()
     slab_h = shape[:, 7] >> 8
     shape[:, 7] &= 1
@@ -40,6 +49,7 @@ def main():
     end = (clock[:, 1] - t0).astype(np.float64) * 1e-6
     dur = end - start
     span = end.max()
+    print("launches per run: %d" % ctx.last_launches())
     print("units %d  makespan %.1f ms  sum(unit time) %.1f ms  avg resident units %.0f (of %d SMs x 32)  draws/s %.3g" % (
         len(dur), span, dur.sum(), dur.sum() / span, len(np.unique(clock[:, 2])), st["draws"] / (span * 1e-3)))
     warps = shape[:, 1] // 32
