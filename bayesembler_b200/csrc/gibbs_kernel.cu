@@ -111,27 +111,35 @@ __device__ __forceinline__ void assign_rows(const MatView &M, const double *thet
         // Z = sum_j P_ij theta_j (:280-282) and the first / last cell that can receive fragments.  A cell is in play
         // when its normalised probability is > 0 (CDF walk, :304-306) resp. >= double_underflow (chain, :344).
         double Z = 0.0;
-        int kf = nnz, kl = -1;
-        bool tiny = false;
+        int kl = -1, in_play = 0;
         for (int k = 0; k < nnz; k++) {
             const double p = val[H * k] * theta[col[H * k]];
             Z += p;
             if (p != 0.0) {
-                tiny |= p < 1e-300;
-                if (kf == nnz) kf = k;
                 kl = k;
+                in_play++;
             }
         }
         if (init) Z = 1.0;  // initAssignment uses P_ij as it is (:226)
-        tiny |= !(Z >= 1e-300);
-        if (chain && tiny) {  // exact rule for denormal-range cells: in play iff p / Z >= double_underflow
-            kf = nnz;
-            kl = -1;
+        // Denormal-range cells (p < 1e-300 needs an input probability below ~1e-280, or a Dirichlet parameter < 1): the
+        // packer flags rows that can have them, and only those pay for the exact rule "in play iff p / Z >=
+        // double_underflow" with true divisions.
+        bool tiny = false;
+        if ((item >> kItemTinyShift) & 1u) {
+            tiny = !(Z >= 1e-300);
             for (int k = 0; k < nnz; k++) {
                 const double p = val[H * k] * theta[col[H * k]];
-                if (p != 0.0 && p / Z >= DBL_MIN) {
-                    if (kf == nnz) kf = k;
-                    kl = k;
+                tiny |= p != 0.0 && p < 1e-300;
+            }
+            if (chain && tiny) {
+                kl = -1;
+                in_play = 0;
+                for (int k = 0; k < nnz; k++) {
+                    const double p = val[H * k] * theta[col[H * k]];
+                    if (p != 0.0 && p / Z >= DBL_MIN) {
+                        kl = k;
+                        in_play++;
+                    }
                 }
             }
         }
@@ -148,7 +156,7 @@ __device__ __forceinline__ void assign_rows(const MatView &M, const double *thet
             // :289-334.  The reference sorts the n uniforms and walks the CDF once; which column a uniform lands in does
             // not depend on the visiting order, so they are taken four at a time (one Philox block).
             int rem = n;
-            if (kf < kl) {
+            if (in_play > 1) {  // with a single cell in play everything goes to it
                 const Site site = make_site(key, phase, iteration, id, 0);
                 const int blocks = (int)((item >> kItemBlockShift) & 7u);
                 for (int j = 0; j < blocks; j++) {
@@ -158,7 +166,7 @@ __device__ __forceinline__ void assign_rows(const MatView &M, const double *thet
                     int prev = 0;
                     // every lane first skips ahead to ITS next cell with a non-zero probability (theta is zero outside
                     // the current simplex) and only then do the lanes meet for the threshold arithmetic
-                    for (int k = kf;; k++) {
+                    for (int k = 0;; k++) {
                         int c = 0;
                         double p = 0.0;
                         for (; k < kl; k++) {
@@ -188,10 +196,10 @@ __device__ __forceinline__ void assign_rows(const MatView &M, const double *thet
             // binomial, so a warp runs the (expensive, divergent) draw once per in-play cell of its deepest row
             // instead of once per stored cell.
             int rem = n;
-            if (kf < kl) {
+            if (in_play > 1) {
                 const int col0 = (int)slot * lanes_per_slot;  // lane of the slot's candidate 0 (0 in a wide unit)
                 double divider = 1.0;
-                int k = kf;
+                int k = 0;
                 while (rem > 0) {
                     int c = 0;
                     double np = 0.0;

@@ -26,9 +26,10 @@ constexpr int kMatrixSmemBytes = 96 * 1024;  // units whose packed matrix exceed
 constexpr uint32_t kRowSlotShift = 27;  // row_info = slot << 27 | original row index
 // A-step work items (one lane each) = collapsed rows.  A row with n >= kSmallCount fragments is a chain item (one
 // conditional binomial per cell in play); a row with fewer is a uniform item that locates its n uniforms in the row's
-// CDF, four (one Philox block) at a time.  row_nnz word of an item: cells | Philox blocks << 16 | chain << 24
+// CDF, four (one Philox block) at a time.  row_nnz word of an item: cells | Philox blocks << 16 | chain << 24 |
+// may-have-denormal-range-cells << 25
 constexpr uint32_t kItemNnzMask = 0xFFFFu;
-constexpr uint32_t kItemBlockShift = 16, kItemChainShift = 24;
+constexpr uint32_t kItemBlockShift = 16, kItemChainShift = 24, kItemTinyShift = 25;
 
 // Device-side descriptor of one unit.  All *_off fields index the context-wide concatenated arrays.
 struct UnitDev {

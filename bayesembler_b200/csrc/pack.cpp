@@ -196,7 +196,12 @@ void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, PackedU
         const PreLocus &L = *slots[it.slot].locus;
         const int r = position(i), s = r / H, l = r % H;
         U.row_n[r] = it.n;
-        U.row_nnz[r] = (int32_t)((uint32_t)it.nnz | ((uint32_t)it.blocks << kItemBlockShift) | ((uint32_t)(it.chain ? 1 : 0) << kItemChainShift));
+        // a product P_ij theta_j can only reach the denormal range from a tiny P_ij, or from a tiny theta_j, which needs a
+        // Gamma(< 1) draw: flag those rows for the exact (slow) in-play rule of the A-step
+        bool may_be_tiny = L.gamma < 1.0;
+        for (int k = 0; k < it.nnz; k++) may_be_tiny |= L.cell_val[L.row_ptr[it.r] + k] < 1e-150;
+        U.row_nnz[r] = (int32_t)((uint32_t)it.nnz | ((uint32_t)it.blocks << kItemBlockShift) | ((uint32_t)(it.chain ? 1 : 0) << kItemChainShift) |
+                                 ((uint32_t)(may_be_tiny ? 1 : 0) << kItemTinyShift));
         U.row_info[r] = ((uint32_t)it.slot << kRowSlotShift) | (uint32_t)L.row_id[it.r];
         const int lane0 = wide ? 0 : it.slot * Tpad;
         for (int k = 0; k < it.nnz; k++) {

@@ -250,8 +250,7 @@ __constant__ double kInvTable[64] = {
 
 BAYES_HD double inv_int(int k) {
 #if defined(__CUDA_ARCH__)
-    // lanes run the recurrence in lockstep from k = 1, so this is a uniform (broadcast) constant-bank read
-    return k < 64 ? kInvTable[k] : __drcp_rn((double)k);
+    return __drcp_rn((double)k);
 #else
     return 1.0 / (double)k;
 #endif
@@ -273,6 +272,17 @@ BAYES_HD_NOINLINE int binomial_variate(const Site &s, int n, double p) {
         double r = ipow(1.0 - q, n);
         double left = (double)n;  // n - k + 1 of the next step, kept as a double (exact) to save a conversion per step
         k = 0;
+#if defined(__CUDA_ARCH__)
+        // the first 63 steps take 1/k from the constant table: lanes run the recurrence in lockstep from k = 1, so the
+        // read is a broadcast, and the loop body has no branch
+        const int k_tab = n < 63 ? n : 63;
+        while (u > r && k < k_tab) {
+            u -= r;
+            k++;
+            r = r * ((left * sr) * kInvTable[k]);
+            left -= 1.0;
+        }
+#endif
         while (u > r && k < n) {
             u -= r;
             k++;

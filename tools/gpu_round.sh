@@ -25,9 +25,10 @@ echo "bench ref rc=$?"
 cat $OUT/${TAG}_bench_ref.json
 
 if [ $rc -eq 0 ]; then
-  # launch list of the same command (cold-cache, serialised: compare shares, not absolutes)
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
-      python bench.py --no-cpu-baseline > $OUT/${TAG}_ncu_launches.log 2>&1
+  # launch list of the same command (cold-cache, serialised: compare shares, not absolutes) with the DRAM bytes of
+  # every launch; the first 400 launches = two full steps of the warm-up, the rest of the run is not profiled
+  ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv \
+      --log-file $OUT/${TAG}_launches.csv python bench.py --no-cpu-baseline > $OUT/${TAG}_ncu_launches.log 2>&1
   echo "ncu launches rc=$?"
 fi
 

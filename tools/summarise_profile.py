@@ -5,7 +5,8 @@
 Writes  profiles/<tag>_bench.json      the bench lines as printed (b200 arm, reference arm, 2000-locus slice)
         profiles/<tag>_launches.csv    per-kernel launch count / total / mean device time of the ncu launch list
         profiles/<tag>_ncu_full.csv    selected counters of the `--set full` capture, one row per captured launch
-        profiles/traffic.json          dram bytes per launch of the dominant kernel (read by bench.py -> roofline.traffic)
+        profiles/<tag>_bulk_ncu_full.csv  the same for the saturated single-launch capture (tools/ncu_bulk.sh)
+        profiles/traffic.json          DRAM bytes of one bench step's sampler launches (read by bench.py -> roofline.traffic)
 """
 import csv
 import io
@@ -37,30 +38,45 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
 
 
-def launches(tag):
+def launches(tag, launches_per_step):
+    """Per (kernel, block size): launch count, device time, DRAM bytes; plus the DRAM traffic of ONE bench step
+    (= launches_per_step consecutive launches of the sampler kernels, the unit bench.py's roofline.traffic refers to)."""
     p = os.path.join(OUT, tag + "_launches.csv")
     if not os.path.exists(p):
         return None
     lines = [l for l in open(p) if not l.startswith("==")]
     rows = list(csv.DictReader(io.StringIO("".join(lines))))
-    agg = {}
+    scale = {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9, "nsecond": 1, "usecond": 1e3, "msecond": 1e6, "second": 1e9,
+             "byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per_launch = {}
     for r in rows:
-        if r.get("Metric Name") != "gpu__time_duration.sum":
-            continue
-        v = float(r["Metric Value"].replace(",", ""))
-        unit = r.get("Metric Unit", "ns")
-        ns = v * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9, "nsecond": 1, "usecond": 1e3, "msecond": 1e6, "second": 1e9}.get(unit, 1)
-        name = r["Kernel Name"]
-        key = (name, r.get("Block Size", ""))
-        a = agg.setdefault(key, [0, 0.0])
+        v = float(r["Metric Value"].replace(",", "")) * scale.get(r.get("Metric Unit", ""), 1)
+        d = per_launch.setdefault(int(r["ID"]), {"name": r["Kernel Name"], "block": r.get("Block Size", ""), "ns": 0.0, "dram": 0.0})
+        if r["Metric Name"] == "gpu__time_duration.sum":
+            d["ns"] = v
+        elif r["Metric Name"].startswith("dram__bytes"):
+            d["dram"] += v
+    agg = {}
+    for d in per_launch.values():
+        a = agg.setdefault((d["name"], d["block"]), [0, 0.0, 0.0])
         a[0] += 1
-        a[1] += ns
+        a[1] += d["ns"]
+        a[2] += d["dram"]
     total = sum(a[1] for a in agg.values()) or 1.0
     out = os.path.join(PROF, tag + "_launches.csv")
     with open(out, "w") as f:
-        f.write("kernel,block,launches,total_ms,mean_ms,share\n")
+        f.write("kernel,block,launches,total_ms,mean_ms,share_of_device_time,dram_MB_per_launch\n")
         for (name, blk), a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            f.write('"%s","%s",%d,%.3f,%.3f,%.4f\n' % (name, blk, a[0], a[1] / 1e6, a[1] / 1e6 / a[0], a[1] / total))
+            f.write('"%s","%s",%d,%.3f,%.3f,%.4f,%.3f\n' % (name, blk, a[0], a[1] / 1e6, a[1] / 1e6 / a[0], a[1] / total, a[2] / 1e6 / a[0]))
+    ours = [d for _, d in sorted(per_launch.items()) if "gibbs_" in d["name"] or "stagger" in d["name"]]
+    if launches_per_step and len(ours) >= launches_per_step:
+        step = ours[:launches_per_step]
+        json.dump({"tag": tag, "what": "DRAM read+write bytes summed over the %d sampler launches of one bench step (ncu launch list, "
+                   "dram__bytes_read.sum + dram__bytes_write.sum per launch)" % launches_per_step,
+                   "dram_bytes_per_launch": sum(d["dram"] for d in step),
+                   "serialised_device_ms": sum(d["ns"] for d in step) / 1e6,
+                   "command": "python bench.py --no-cpu-baseline (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum)"},
+                  open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
     return out
 
 
@@ -79,20 +95,6 @@ def ncu_full(tag):
         w.writerow([units[i] for i in cols])
         for r in body:
             w.writerow([r[i] for i in cols])
-    # dram traffic per launch of the longest captured launch = the dominant kernel
-    ix = {h: i for i, h in enumerate(hdr)}
-
-    def val(r, name):
-        v = float(r[ix[name]].replace(",", ""))
-        u = units[ix[name]]
-        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9,
-                    "nsecond": 1, "usecond": 1e3, "msecond": 1e6, "second": 1e9}.get(u, 1)
-    top = max(body, key=lambda r: val(r, "gpu__time_duration.sum"))
-    traffic = val(top, "dram__bytes_read.sum") + val(top, "dram__bytes_write.sum")
-    json.dump({"tag": tag, "kernel": top[ix["Kernel Name"]], "grid": top[ix["Grid Size"]], "block": top[ix["Block Size"]],
-               "dram_bytes_per_launch": traffic, "duration_ns": val(top, "gpu__time_duration.sum"),
-               "command": "python bench.py --loci 2000 --steps 1 --warmup 1 --no-cpu-baseline (ncu --set full, 2000-locus slice of config 2)"},
-              open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
     return out
 
 
@@ -110,8 +112,15 @@ def main():
     if lines:
         json.dump(lines, open(os.path.join(PROF, tag + "_bench.json"), "w"), indent=1)
     print("bench lines:", list(lines))
-    print("launch list:", launches(tag))
+    per_step = 0
+    if "bench" in lines and lines["bench"].get("steps"):
+        per_step = int(lines["bench"]["gpu_launches"]) // int(lines["bench"]["steps"])
+    print("launch list:", launches(tag, per_step))
     print("ncu full   :", ncu_full(tag))
+    bulk = os.path.join(OUT, tag + "_bulk_prof.ncu-rep")
+    if os.path.exists(bulk):
+        global_tag = tag + "_bulk"
+        print("ncu bulk   :", ncu_full(global_tag))
 
 
 if __name__ == "__main__":
