@@ -29,8 +29,6 @@ def nvcc_command(out=LIB, extra=()):
     # (the CUDA math library's log/exp/cos use explicit fma internally and are unaffected).
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
            "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-shared", "-o", out]
-    if os.environ.get("BAYES_MIN_BLOCKS"):  # experiment knob: registers per thread = 65536 / (256 * this)
-        cmd += ["-DBAYES_MIN_BLOCKS=" + os.environ["BAYES_MIN_BLOCKS"]]
     if os.environ.get("BAYES_NVCC_FLAGS"):  # experiment knob, e.g. -DBAYES_BINV_NQ=24.0
         cmd += os.environ["BAYES_NVCC_FLAGS"].split()
     cmd += list(extra)

@@ -325,7 +325,7 @@ int build_units(bayes_gibbs_ctx *ctx) {
     {
         static const int ladder[][2] = {{1, 32}, {2, 32}, {4, 32}, {8, 32}, {8, 16}, {16, 16}, {16, 8}};
         const int n_ladder = (int)(sizeof(ladder) / sizeof(ladder[0]));
-        const double capacity = (double)ctx->sm_count * 32.0;  // resident warps at 64 registers per thread
+        const double capacity = (double)ctx->sm_count * kWarpsPerSM;  // resident warps at the kernels' register count
         std::vector<int> step(n_units, 0);
         std::vector<double> t(n_units);
         double occupied = 0;  // sum of warps * time

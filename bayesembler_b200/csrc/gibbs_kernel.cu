@@ -25,10 +25,11 @@
 #include "layout.h"
 #include "rng.cuh"
 
-// Registers per thread = 65536 / (kMaxBlock * BAYES_MIN_BLOCKS): 4 -> 64 registers, i.e. 32 resident one-warp units per SM
-// (the hardware limit of 32 blocks per SM); measured best against 3 (80) and 2 (128), see profiles/.
-#ifndef BAYES_MIN_BLOCKS
-#define BAYES_MIN_BLOCKS 4
+// Registers per thread: 72 keeps 28 warps per SM resident (internal.h: kWarpsPerSM) and removes most of the spills that 64
+// (32 warps) forces into the inner loops.  Measured on config 2: 64 -> 2.21 s per step, 72 -> 2.01 s, 80 -> 2.09 s,
+// 96 -> 2.16 s (gpurun_out/exp_regs.txt, profiles/README.md).
+#ifndef BAYES_MAXNREG
+#define BAYES_MAXNREG 72
 #endif
 
 namespace bayes {
@@ -431,7 +432,7 @@ __device__ __forceinline__ MatView stage_matrix(const KernelArgs &A, const UnitD
 
 // ------------------------------------------------------------------------------------------------------------------
 template <bool MAT_SMEM>
-__global__ void __launch_bounds__(kMaxBlock, 1) gibbs_bundle_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
+__global__ void __maxnreg__(BAYES_MAXNREG) gibbs_bundle_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int64_t ui = unit_base + blockIdx.x;
     if (threadIdx.x == 0) A.unit_clock[3 * ui] = global_ns();
@@ -525,7 +526,7 @@ __global__ void __launch_bounds__(kMaxBlock, 1) gibbs_bundle_kernel(const __grid
 
 // ------------------------------------------------------------------------------------------------------------------
 template <bool MAT_SMEM>
-__global__ void __launch_bounds__(kMaxBlock, 1) gibbs_wide_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
+__global__ void __maxnreg__(BAYES_MAXNREG) gibbs_wide_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int64_t ui = unit_base + blockIdx.x;
     if (threadIdx.x == 0) A.unit_clock[3 * ui] = global_ns();

@@ -18,7 +18,8 @@
 namespace bayes {
 
 constexpr int kMaxT = 4096;             // candidates per locus (per-candidate state lives in shared memory)
-constexpr int kMaxBlock = 1024;         // threads per unit
+constexpr int kMaxBlock = 512;          // threads per unit
+constexpr int kWarpsPerSM = 28;         // resident warps per SM at the kernels' 72 registers per thread
 constexpr int kMaxSlots = 16;           // slots per bundle (T = 2 -> Tpad = 2 -> 16 slots)
 constexpr int kSmallCount = 20;         // assignmentGenerator.cpp:289: rows with fewer fragments draw uniforms
 constexpr int kTableSmemEntries = 2048; // simplex CDF tables up to this many entries are staged in shared memory
