@@ -349,7 +349,7 @@ int build_units(bayes_gibbs_ctx *ctx) {
         while (!heap.empty()) {
             const Item top = heap.top();
             const int64_t i = top.second;
-            if (top.first <= 1.25 * occupied / capacity) break;  // the batch is throughput-bound from here on
+            if (top.first <= 1.0 * occupied / capacity) break;  // the batch is throughput-bound from here on
             heap.pop();
             // next rung that actually shortens the unit
             int k = step[i] + 1;

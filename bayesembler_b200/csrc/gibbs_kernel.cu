@@ -28,6 +28,11 @@
 // Registers per thread: 72 keeps 28 warps per SM resident (internal.h: kWarpsPerSM) and removes most of the spills that 64
 // (32 warps) forces into the inner loops.  Measured on config 2: 64 -> 2.21 s per step, 72 -> 2.01 s, 80 -> 2.09 s,
 // 96 -> 2.16 s (gpurun_out/exp_regs.txt, profiles/README.md).
+// Unroll factor of the row-sum loop: rows are short (a handful of cells), so the compiler's default 8-way unrolling with
+// its remainder loop only costs instruction-cache space: 1 measured best on config 2 (8: 2.04 s, 4: 1.98 s, 2: 1.94 s, 1: 1.91 s).
+#ifndef BAYES_Z_UNROLL
+#define BAYES_Z_UNROLL 1
+#endif
 #ifndef BAYES_MAXNREG
 #define BAYES_MAXNREG 72
 #endif
@@ -35,6 +40,8 @@
 namespace bayes {
 
 namespace {
+
+constexpr int kZUnroll = BAYES_Z_UNROLL;
 
 __device__ __forceinline__ uint64_t global_ns() {
     uint64_t t;
@@ -113,6 +120,7 @@ __device__ __forceinline__ void assign_rows(const MatView &M, const double *thet
         // when its normalised probability is > 0 (CDF walk, :304-306) resp. >= double_underflow (chain, :344).
         double Z = 0.0;
         int kl = -1, in_play = 0;
+#pragma unroll kZUnroll
         for (int k = 0; k < nnz; k++) {
             const double p = val[H * k] * theta[col[H * k]];
             Z += p;
