@@ -173,12 +173,7 @@ BAYES_HD double ipow(double base, int n) {
 }
 
 // BTRD (Hoermann 1993), q <= 0.5, n*q >= 10; one block per attempt.  Same operation order as oracle/orc_rng.h.
-#ifdef BAYES_BTRD_NOINLINE
-BAYES_HD_NOINLINE
-#else
-BAYES_HD
-#endif
-int binomial_btrd(const Site &s, int n, double q) {
+BAYES_HD int binomial_btrd(const Site &s, int n, double q) {
     const double npq = n * q * (1.0 - q);
     const double spq = sqrt(npq);
     const double bb = 1.15 + 2.53 * spq;
