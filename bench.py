@@ -12,8 +12,8 @@ process per GPU, no collective on the data path.
   value    draws/s with the packed loci already resident in HBM (kernel launches only, CUDA events on the launch stream)
   e2e      the same metric through the C ABI with HOST buffers: submit (pack, read cover, CDF tables) + H2D + kernels +
            D2H + fetch inside the timed region
-  roofline algorithmic bytes (12 nnz + 8 R + 24 T per iteration, + 40 T when sampling) / kernel time
-           against the measured HBM copy bandwidth
+  roofline algorithmic bytes (12 nnz + 8 R + 24 T per iteration, + 40 T when sampling) / device time of the
+           step's concurrent sampler launches, against the measured HBM copy bandwidth
   cpu_baseline / --impl reference: the UNMODIFIED reference sampler (oracle/_ref, built from /root/reference against
            the stand-in headers) or, where that .so is absent, the C restatement -- on the host cores of this box.
 """
@@ -318,8 +318,12 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "note": "algorithmic bytes per launch = sum over jobs of iters*(12 nnz + 8 R + 24 T) + samples*40 T "
-                                 "(f64/u32 reference-equivalent CSR); data is shared-memory resident, DRAM traffic is ~one read per locus"},
+                         "note": "dominant kernel = gibbs_bundle_kernel; one step issues its unit classes as concurrent launches of that "
+                                 "kernel, so 'per launch' here means per step: achieved = algorithmic bytes of the step (sum over jobs of "
+                                 "iters*(12 nnz + 8 R + 24 T) + samples*40 T, f64/u32 reference-equivalent CSR) / CUDA-event time of the step; "
+                                 "traffic = DRAM bytes summed over the same launches (profiles/traffic.json). The loci are shared-memory "
+                                 "resident, so DRAM traffic is about one read per locus and the kernel is issue/latency-bound, not HBM-bound "
+                                 "(DESIGN.md section 4)"},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
