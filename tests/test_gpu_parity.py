@@ -145,3 +145,55 @@ def test_batch_mixed_loci_and_chains(lib, oracle):
             np.testing.assert_allclose(g["mean"], o["mean"], rtol=RTOL)
             assert g["final_counts"].sum() == loc.n_frag
     ctx.close()
+
+
+def test_error_paths_and_call_order(lib):
+    """Status codes instead of the reference's asserts; calls out of order are refused."""
+    import ctypes as C
+    rng = np.random.default_rng(1)
+    loc = random_locus(rng, 4, 10)
+    L = lib.load_library()
+    ctx = lib.GibbsContext(0)
+    with pytest.raises(lib.BayesError, match="upload first"):
+        ctx.run()
+    bad = random_locus(rng, 4, 10)
+    bad.col_idx[1] = 77
+    with pytest.raises(lib.BayesError, match="ascending"):
+        ctx.submit(lib.make_desc_array([bad], [5], [50], [1]))
+    assert L.bayes_gibbs_num_loci(ctx.h) == 0                      # nothing of a failed submit is kept
+    too_wide = random_locus(rng, 5000, 3, density=0.001)
+    with pytest.raises(lib.BayesError, match="4096"):
+        ctx.submit(lib.make_desc_array([too_wide], [5], [50], [1]))
+    with pytest.raises(lib.BayesError, match="samples"):
+        ctx.submit(lib.make_desc_array([loc], [5], [0], [1]))
+    ctx._T, ctx._chains = [], []
+    ctx.submit(lib.make_desc_array([loc], [5], [50], [1]))
+    ctx.upload()
+    with pytest.raises(lib.BayesError, match="clear"):
+        ctx.submit(lib.make_desc_array([loc], [5], [50], [1]))
+    with pytest.raises(lib.BayesError, match="before"):
+        ctx.set_trace(0, 0, 5)
+    ctx._T, ctx._chains = [loc.T], [1]
+    with pytest.raises(lib.BayesError, match="download"):
+        ctx.fetch(0)
+    ctx.run(); ctx.download(); ctx.sync()
+    assert ctx.fetch(0)["final_counts"].sum() == loc.n_frag
+    assert L.bayes_gibbs_fetch(ctx.h, 5, 0, None, None, None, None) == -1
+    assert L.bayes_gibbs_fetch(ctx.h, 0, 3, None, None, None, None) == -1
+    h = C.c_void_p()
+    assert L.bayes_gibbs_create(99, C.byref(h)) == -1              # no such device
+    ctx.close()
+
+
+def test_empty_batch_and_single_candidate_only(lib):
+    ctx = lib.GibbsContext(0)
+    ctx.run_batch(lib.make_desc_array([], [], [], []))
+    assert ctx.last_launches() == 0 and ctx.num_jobs() == 0
+    from oracle.oracle_py import Locus
+    one = Locus(1, [0, 1, 2], [0, 0], [1.0, 1.0], [7, 5], [1500.0], 1000000)
+    ctx.clear()
+    ctx.run_batch(lib.make_desc_array([one], [10], [100], [3]))
+    g = ctx.fetch(0)
+    assert ctx.last_launches() == 0 and g["occ"][0] == 100 and g["m2"][0] == 0
+    assert g["mean"][0] == (12 * 1e9) / (1000000 * 1500.0)
+    ctx.close()

@@ -159,3 +159,46 @@ def test_synth_batch_is_regenerable(lib):
             assert e > s and np.all(np.diff(l.col_idx[s:e]) > 0) and abs(l.val[s:e].sum() - 1) < 1e-12
     st = a.stats()
     assert st["draws"] > 0 and st["algo_bytes"] > 0
+
+
+def _bad_locus(lib, mutate):
+    rng = np.random.default_rng(9)
+    loc = random_locus(rng, 4, 6, single_frac=0.0)
+    mutate(loc)
+    return loc
+
+
+@pytest.mark.parametrize("name,mutate", [
+    ("columns not ascending", lambda l: l.col_idx.__setitem__(slice(0, 2), l.col_idx[:2][::-1].copy())),
+    ("column out of range", lambda l: l.col_idx.__setitem__(1, 99)),
+    ("negative probability", lambda l: l.val.__setitem__(0, -0.1)),
+    ("nan probability", lambda l: l.val.__setitem__(0, float("nan"))),
+    ("row count < 1", lambda l: l.row_count.__setitem__(2, 0)),
+    ("row without support", lambda l: l.val.__setitem__(slice(int(l.row_ptr[1]), int(l.row_ptr[2])), 0.0)),
+    ("row_ptr not monotone", lambda l: l.row_ptr.__setitem__(2, 0)),
+])
+def test_malformed_loci_are_rejected(lib, name, mutate):
+    # the reference aborts on such input through asserts (assignmentGenerator.cpp:67, 284); the library returns
+    # BAYES_E_INVALID and a message instead
+    loc = _bad_locus(lib, mutate)
+    d = lib.make_desc(loc, 0, 1, 0)
+    L = lib.load_library()
+    rc = L.bayes_min_read_cover(C.byref(d), 1, None)
+    assert rc == -1, name
+    assert len(L.bayes_last_error()) > 0
+
+
+def test_degenerate_but_valid_loci(lib, oracle):
+    # one row / one candidate / every row with a single cell / wide row: the host pieces accept them
+    from oracle.oracle_py import Locus
+    one = Locus(1, [0, 1], [0], [1.0], [5], [1000.0], 1000)
+    assert lib.min_read_cover(one, 7)[0] == 1
+    single = Locus(3, [0, 1, 2, 3], [2, 0, 1], [1.0, 1.0, 1.0], [4, 1, 9], [500.0, 600.0, 700.0], 1000)
+    n, flags = lib.min_read_cover(single, 7)
+    assert n == 3 and flags.tolist() == [1, 1, 1]
+    assert lib.min_read_cover(single, 7)[0] == oracle.min_read_cover(single, SITE, 7)[0]
+    T = 4096  # the supported maximum (internal.h kMaxT)
+    wide = Locus(T, [0, T], np.arange(T), np.full(T, 1.0 / T), [100], np.full(T, 900.0), 1000)
+    assert lib.min_read_cover(wide, 3)[0] == 1
+    row_off, tab = lib.simplex_table(1.0 / T, 1.0, T, 100)
+    assert len(row_off) == T + 1 and np.all(np.diff(row_off) >= 1) and tab[row_off[1] - 1] > 1 - 1e-9
