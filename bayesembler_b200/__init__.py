@@ -21,6 +21,10 @@ EXPORTED_SYMBOLS = [
     "bayes_gibbs_set_trace", "bayes_gibbs_fetch_trace", "bayes_top_marginals", "bayes_step_generate_assignment",
     "bayes_step_init_assignment", "bayes_step_generate_expression", "bayes_step_variates", "bayes_min_read_cover",
     "bayes_simplex_table", "bayes_chain_key", "bayes_locus_cost", "bayes_partition_lpt", "bayes_philox4x32",
+    "bayes_seq_model_create_gaussian", "bayes_seq_model_destroy", "bayes_seq_model_three_prime_prob", "bayes_seq_model_length_prob",
+    "bayes_seq_model_effective_length", "bayes_fragment_model_estimate", "bayes_collapsed_map_build", "bayes_collapsed_map_destroy",
+    "bayes_collapsed_map_T", "bayes_collapsed_map_R", "bayes_collapsed_map_nnz", "bayes_collapsed_map_export",
+    "bayes_collapsed_map_stats", "bayes_fetch_fragment_lengths",
 ]
 
 
@@ -34,6 +38,14 @@ class LocusDesc(C.Structure):
                 ("row_count", C.c_void_p), ("efflen", C.c_void_p), ("total_num_fragments", C.c_double), ("gamma", C.c_double),
                 ("pi", C.c_double), ("burn_in", C.c_int32), ("samples", C.c_int32), ("seed", C.c_uint64),
                 ("n_chains", C.c_int32), ("reserved", C.c_int32)]
+
+
+class RawLocusDesc(C.Structure):
+    """bayes_raw_locus"""
+    _fields_ = [("n_cand", C.c_int32), ("exon_ptr", C.c_void_p), ("exon_start", C.c_void_p), ("exon_end", C.c_void_p),
+                ("cand_length", C.c_void_p), ("is_premrna", C.c_void_p), ("subgraph_id", C.c_void_p), ("n_subgraphs", C.c_int32),
+                ("strand_plus", C.c_int32), ("n_frag", C.c_int32), ("read_pos", C.c_void_p), ("cigar_ptr", C.c_void_p),
+                ("cigar_op", C.c_void_p), ("cigar_len", C.c_void_p), ("frag_prob", C.c_void_p)]
 
 
 class Locus(object):
@@ -109,6 +121,20 @@ def load_library(path=None):
         "bayes_locus_cost": (dbl, [C.POINTER(LocusDesc)]),
         "bayes_partition_lpt": (C.c_int, [i64, vp, i32, vp]),
         "bayes_philox4x32": (None, [u64, vp, vp]),
+        "bayes_seq_model_create_gaussian": (C.c_int, [dbl, dbl, i32, C.POINTER(vp)]),
+        "bayes_seq_model_destroy": (None, [vp]),
+        "bayes_seq_model_three_prime_prob": (dbl, [vp, i32, i32]),
+        "bayes_seq_model_length_prob": (dbl, [vp, i32, i32]),
+        "bayes_seq_model_effective_length": (dbl, [vp, i32]),
+        "bayes_fragment_model_estimate": (C.c_int, [i32, vp, vp, C.POINTER(dbl), C.POINTER(dbl)]),
+        "bayes_collapsed_map_build": (C.c_int, [C.POINTER(RawLocusDesc), vp, i32, vp, C.POINTER(vp)]),
+        "bayes_collapsed_map_destroy": (None, [vp]),
+        "bayes_collapsed_map_T": (i32, [vp]),
+        "bayes_collapsed_map_R": (i32, [vp]),
+        "bayes_collapsed_map_nnz": (i64, [vp]),
+        "bayes_collapsed_map_export": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+        "bayes_collapsed_map_stats": (C.c_int, [vp, vp]),
+        "bayes_fetch_fragment_lengths": (i64, [C.POINTER(RawLocusDesc), vp, i64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -361,4 +387,79 @@ def step_variates(kind, a, p, key, n, device=0):
     out = np.zeros(n)
     k = {"gamma": 0, "binomial": 1, "uniform_int": 2}[kind]
     _check(load_library().bayes_step_variates(device, k, float(a), float(p), int(key), n, _ptr(out)), "bayes_step_variates")
+    return out
+
+
+# ---- likelihood builder --------------------------------------------------------------------------
+def make_raw_desc(raw):
+    """bayes_raw_locus for an object with the flat arrays of the same names (e.g. oracle.f1_py.RawLocus)."""
+    d = RawLocusDesc(raw.n_cand, raw.exon_ptr.ctypes.data, raw.exon_start.ctypes.data, raw.exon_end.ctypes.data,
+                     raw.cand_length.ctypes.data, raw.is_premrna.ctypes.data, raw.subgraph_id.ctypes.data, raw.n_subgraphs,
+                     raw.strand_plus, raw.n_frag, raw.read_pos.ctypes.data, raw.cigar_ptr.ctypes.data, raw.cigar_op.ctypes.data,
+                     raw.cigar_len.ctypes.data, raw.frag_prob.ctypes.data)
+    d._keep = raw
+    return d
+
+
+class SequencingModel(object):
+    """bayes_seq_model: GaussianFragmentLengthModel + SequencingModel tables (sequencingModel.cpp:34-76)."""
+
+    def __init__(self, mean, sd, max_transcript_length):
+        self.lib = load_library()
+        h = C.c_void_p()
+        _check(self.lib.bayes_seq_model_create_gaussian(mean, sd, max_transcript_length, C.byref(h)), "bayes_seq_model_create_gaussian")
+        self.h = h
+        self.max_len = max_transcript_length
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.bayes_seq_model_destroy(self.h)
+            self.h = None
+
+    def three_prime_prob(self, pos, tran_length):
+        return self.lib.bayes_seq_model_three_prime_prob(self.h, pos, tran_length)
+
+    def length_prob(self, fragment_length, pos):
+        return self.lib.bayes_seq_model_length_prob(self.h, fragment_length, pos)
+
+    def effective_length(self, length):
+        return self.lib.bayes_seq_model_effective_length(self.h, length)
+
+
+def estimate_fragment_model(hist):
+    lengths = np.ascontiguousarray(sorted(hist), np.uint32)
+    counts = np.ascontiguousarray([hist[int(k)] for k in lengths], np.uint32)
+    med, mad = C.c_double(0), C.c_double(0)
+    _check(load_library().bayes_fragment_model_estimate(len(lengths), _ptr(lengths), _ptr(counts), C.byref(med), C.byref(mad)),
+           "bayes_fragment_model_estimate")
+    return med.value, mad.value
+
+
+def build_collapsed_map(raw, model, no_coverage_exclude=False):
+    """AlignmentParser::calculateFragTranProbabilities through the C ABI -> dict with the CSR arrays and a Locus factory."""
+    L = load_library()
+    d = make_raw_desc(raw)
+    cx = np.bincount(raw.subgraph_id, minlength=raw.n_subgraphs).astype(np.int32)
+    h = C.c_void_p()
+    rc = _check(L.bayes_collapsed_map_build(C.byref(d), model.h, int(no_coverage_exclude), _ptr(cx), C.byref(h)), "bayes_collapsed_map_build")
+    try:
+        T, R, nnz = L.bayes_collapsed_map_T(h), L.bayes_collapsed_map_R(h), L.bayes_collapsed_map_nnz(h)
+        out = dict(return_code=rc, T=T, R=R, complexity=cx, row_ptr=np.zeros(R + 1, np.int32), col_idx=np.zeros(nnz, np.int32),
+                   val=np.zeros(nnz), counts=np.zeros(R, np.int32), new_to_old=np.zeros(T, np.int32), efflen=np.zeros(T),
+                   stats=np.zeros(10, np.int64))
+        if rc == 0:
+            _check(L.bayes_collapsed_map_export(h, _ptr(out["row_ptr"]), _ptr(out["col_idx"]), _ptr(out["val"]), _ptr(out["counts"]),
+                                                _ptr(out["new_to_old"]), _ptr(out["efflen"])), "bayes_collapsed_map_export")
+        L.bayes_collapsed_map_stats(h, _ptr(out["stats"]))
+    finally:
+        L.bayes_collapsed_map_destroy(h)
+    return out
+
+
+def fetch_fragment_lengths(raw):
+    L = load_library()
+    d = make_raw_desc(raw)
+    n = _check(L.bayes_fetch_fragment_lengths(C.byref(d), None, 0), "bayes_fetch_fragment_lengths")
+    out = np.zeros(n, np.uint32)
+    _check(L.bayes_fetch_fragment_lengths(C.byref(d), _ptr(out), n), "bayes_fetch_fragment_lengths")
     return out

@@ -162,6 +162,62 @@ int bayes_partition_lpt(int64_t n, const double *cost, int32_t n_parts, int32_t 
 /* Philox4x32-10 block (known-answer tests) */
 void bayes_philox4x32(uint64_t key, const uint32_t ctr[4], uint32_t out[4]);
 
+/* ---- likelihood / compatibility builder (host, C++): produces the sampler's input ------------ */
+/* One locus at the level AlignmentParser::calculateFragTranProbabilities consumes (alignmentParser.cpp:251):
+ * candidates = vector<Candidate> (utils.h:109-117), fragments = vector<FragmentAlignment*> (utils.h:73-77). */
+typedef struct {
+    int32_t n_cand;
+    const int32_t *exon_ptr;     /* n_cand + 1: exons (Candidate::vertices) of candidate i are [exon_ptr[i], exon_ptr[i+1]) */
+    const int32_t *exon_start;   /* Vertex::start, 1-based inclusive                                                     */
+    const int32_t *exon_end;     /* Vertex::end                                                                          */
+    const int32_t *cand_length;  /* Candidate::length                                                                    */
+    const int32_t *is_premrna;   /* Candidate::isPreMrna                                                                 */
+    const int32_t *subgraph_id;  /* index of Candidate::graph_name among the locus' sub-graphs (may be NULL)             */
+    int32_t n_subgraphs;
+    int32_t strand_plus;         /* candidates.front().vertices.front().strand == "+" (alignmentParser.cpp:273)           */
+    int32_t n_frag;
+    const uint32_t *read_pos;    /* 2 n_frag: read_data.first.first, read_data.second.first (0-based leftmost position)   */
+    const int32_t *cigar_ptr;    /* 2 n_frag + 1 offsets into cigar_op / cigar_len, mates of a fragment back to back      */
+    const char *cigar_op;        /* BamTools::CigarOp::Type: M N I D                                                     */
+    const uint32_t *cigar_len;   /* BamTools::CigarOp::Length                                                            */
+    const double *frag_prob;     /* FragmentAlignment::probability                                                       */
+} bayes_raw_locus;
+
+typedef struct bayes_seq_model bayes_seq_model;
+typedef struct bayes_collapsed_map bayes_collapsed_map;
+
+/* GaussianFragmentLengthModel(mean, sd) (fragmentLengthModel.cpp:40-69) tabulated by SequencingModel's constructor
+ * (sequencingModel.cpp:34-57) for transcript lengths up to max_transcript_length */
+int bayes_seq_model_create_gaussian(double mean, double sd, int32_t max_transcript_length, bayes_seq_model **out);
+void bayes_seq_model_destroy(bayes_seq_model *model);
+/* SequencingModel::calculateThreePrimeProb / calculateLengthProb / getEffectiveLength (sequencingModel.cpp:59-76) */
+double bayes_seq_model_three_prime_prob(const bayes_seq_model *model, int32_t three_prime_pos, int32_t tran_length);
+double bayes_seq_model_length_prob(const bayes_seq_model *model, int32_t fragment_length, int32_t three_prime_pos);
+double bayes_seq_model_effective_length(const bayes_seq_model *model, int32_t transcript_length);
+/* GaussianFragmentLengthModel::estimateParameters (fragmentLengthModel.cpp:71-161): median and median absolute deviation
+ * of a fragment length histogram (mean = median, sd = 1.4826 * MAD, :56-59) */
+int bayes_fragment_model_estimate(int32_t n, const uint32_t *length, const uint32_t *count, double *median_out, double *mad_out);
+/* AlignmentParser::calculateFragTranProbabilities (alignmentParser.cpp:251-689).  Returns CollapsedMap::return_code
+ * (0, 3 = every candidate excluded, 4 = no rows) or a negative BAYES_E_*; subgraph_complexity (n_subgraphs entries or
+ * NULL) is decremented per excluded candidate (:501-502) -- its maximum sets the iteration count (assembler.cpp:1598). */
+int bayes_collapsed_map_build(const bayes_raw_locus *locus, const bayes_seq_model *model, int32_t no_coverage_exclude,
+                              int32_t *subgraph_complexity, bayes_collapsed_map **out);
+void bayes_collapsed_map_destroy(bayes_collapsed_map *cm);
+int32_t bayes_collapsed_map_T(const bayes_collapsed_map *cm);
+int32_t bayes_collapsed_map_R(const bayes_collapsed_map *cm);
+int64_t bayes_collapsed_map_nnz(const bayes_collapsed_map *cm);
+/* CollapsedMap (utils.h:129-136) as the CSR arrays bayes_locus_desc takes: row_ptr R+1, col_idx / val nnz, row_count R,
+ * new -> old candidate index and effective length T each; any pointer may be NULL */
+int bayes_collapsed_map_export(const bayes_collapsed_map *cm, int32_t *row_ptr, int32_t *col_idx, double *val, int32_t *row_count,
+                               int32_t *new_to_old, double *efflen);
+/* the numbers of the "BAM-FILE PARSING STATS" log block (alignmentParser.cpp:662-681): fragments parsed, matched,
+ * unmatched, removed by underflow, fragment-candidate matches, unique rows, candidates excluded, of which without
+ * mapped fragments / internal coverage / upstream coverage */
+int bayes_collapsed_map_stats(const bayes_collapsed_map *cm, int64_t *stats10);
+/* AlignmentParser::fetchFragmentLengths (alignmentParser.cpp:692-725): implied fragment length of every (fragment,
+ * candidate) match in fragment-major order; returns the number of matches (lengths_out may be NULL) */
+int64_t bayes_fetch_fragment_lengths(const bayes_raw_locus *locus, uint32_t *lengths_out, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif
