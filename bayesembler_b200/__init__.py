@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "bayes_simplex_table", "bayes_chain_key", "bayes_locus_cost", "bayes_partition_lpt", "bayes_philox4x32",
     "bayes_seq_model_create_gaussian", "bayes_seq_model_destroy", "bayes_seq_model_three_prime_prob", "bayes_seq_model_length_prob",
     "bayes_seq_model_effective_length", "bayes_fragment_model_estimate", "bayes_collapsed_map_build", "bayes_collapsed_map_destroy",
-    "bayes_collapsed_map_T", "bayes_collapsed_map_R", "bayes_collapsed_map_nnz", "bayes_collapsed_map_export",
+    "bayes_collapsed_map_num_candidates", "bayes_collapsed_map_num_rows", "bayes_collapsed_map_nnz", "bayes_collapsed_map_export",
     "bayes_collapsed_map_stats", "bayes_fetch_fragment_lengths",
 ]
 
@@ -129,8 +129,8 @@ def load_library(path=None):
         "bayes_fragment_model_estimate": (C.c_int, [i32, vp, vp, C.POINTER(dbl), C.POINTER(dbl)]),
         "bayes_collapsed_map_build": (C.c_int, [C.POINTER(RawLocusDesc), vp, i32, vp, C.POINTER(vp)]),
         "bayes_collapsed_map_destroy": (None, [vp]),
-        "bayes_collapsed_map_T": (i32, [vp]),
-        "bayes_collapsed_map_R": (i32, [vp]),
+        "bayes_collapsed_map_num_candidates": (i32, [vp]),
+        "bayes_collapsed_map_num_rows": (i32, [vp]),
         "bayes_collapsed_map_nnz": (i64, [vp]),
         "bayes_collapsed_map_export": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
         "bayes_collapsed_map_stats": (C.c_int, [vp, vp]),
@@ -443,7 +443,7 @@ def build_collapsed_map(raw, model, no_coverage_exclude=False):
     h = C.c_void_p()
     rc = _check(L.bayes_collapsed_map_build(C.byref(d), model.h, int(no_coverage_exclude), _ptr(cx), C.byref(h)), "bayes_collapsed_map_build")
     try:
-        T, R, nnz = L.bayes_collapsed_map_T(h), L.bayes_collapsed_map_R(h), L.bayes_collapsed_map_nnz(h)
+        T, R, nnz = L.bayes_collapsed_map_num_candidates(h), L.bayes_collapsed_map_num_rows(h), L.bayes_collapsed_map_nnz(h)
         out = dict(return_code=rc, T=T, R=R, complexity=cx, row_ptr=np.zeros(R + 1, np.int32), col_idx=np.zeros(nnz, np.int32),
                    val=np.zeros(nnz), counts=np.zeros(R, np.int32), new_to_old=np.zeros(T, np.int32), efflen=np.zeros(T),
                    stats=np.zeros(10, np.int64))

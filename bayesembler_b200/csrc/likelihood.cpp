@@ -518,8 +518,8 @@ int bayes_collapsed_map_build(const bayes_raw_locus *L, const bayes_seq_model *m
 }
 
 void bayes_collapsed_map_destroy(bayes_collapsed_map *cm) { delete cm; }
-int32_t bayes_collapsed_map_T(const bayes_collapsed_map *cm) { return cm ? cm->T : 0; }
-int32_t bayes_collapsed_map_R(const bayes_collapsed_map *cm) { return cm ? (int32_t)cm->row_count.size() : 0; }
+int32_t bayes_collapsed_map_num_candidates(const bayes_collapsed_map *cm) { return cm ? cm->T : 0; }
+int32_t bayes_collapsed_map_num_rows(const bayes_collapsed_map *cm) { return cm ? (int32_t)cm->row_count.size() : 0; }
 int64_t bayes_collapsed_map_nnz(const bayes_collapsed_map *cm) { return cm ? (int64_t)cm->val.size() : 0; }
 
 // CSR arrays (R + 1, nnz, nnz, R), new -> old candidate index and effective length (T each); any pointer may be NULL

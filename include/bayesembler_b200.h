@@ -203,8 +203,8 @@ int bayes_fragment_model_estimate(int32_t n, const uint32_t *length, const uint3
 int bayes_collapsed_map_build(const bayes_raw_locus *locus, const bayes_seq_model *model, int32_t no_coverage_exclude,
                               int32_t *subgraph_complexity, bayes_collapsed_map **out);
 void bayes_collapsed_map_destroy(bayes_collapsed_map *cm);
-int32_t bayes_collapsed_map_T(const bayes_collapsed_map *cm);
-int32_t bayes_collapsed_map_R(const bayes_collapsed_map *cm);
+int32_t bayes_collapsed_map_num_candidates(const bayes_collapsed_map *cm);
+int32_t bayes_collapsed_map_num_rows(const bayes_collapsed_map *cm);
 int64_t bayes_collapsed_map_nnz(const bayes_collapsed_map *cm);
 /* CollapsedMap (utils.h:129-136) as the CSR arrays bayes_locus_desc takes: row_ptr R+1, col_idx / val nnz, row_count R,
  * new -> old candidate index and effective length T each; any pointer may be NULL */
