@@ -28,6 +28,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <map>
 #include <sstream>
 #include <stdexcept>
@@ -385,6 +386,215 @@ class GibbsBatch {
     GibbsBatch &operator=(const GibbsBatch &);
     bayes_gibbs_ctx *ctx;
     std::vector<GibbsOutput *> outputs;
+};
+
+
+// =====================================================================================================================
+// Likelihood builder: the reference classes that produce the sampler's input, on the C ABI's host
+// functions (bayes_seq_model_*, bayes_collapsed_map_*).  Same constructor / method signatures as the reference.
+// =====================================================================================================================
+namespace BamTools {  // utils.h:63 only needs CigarOp from BamTools
+struct CigarOp {
+    char Type;
+    uint32_t Length;
+    CigarOp(char t = 0, uint32_t l = 0) : Type(t), Length(l) {}
+};
+}  // namespace BamTools
+
+typedef std::pair<unsigned, std::vector<BamTools::CigarOp> > ReadData;  // utils.h:63
+struct FragmentAlignment {                                               // utils.h:73-77
+    std::pair<ReadData, ReadData> read_data;
+    double probability;
+};
+
+// fragmentLengthModel.h:41-69
+class FragmentLengthModel {
+   public:
+    virtual double pmf(unsigned) = 0;
+    virtual ~FragmentLengthModel() {}
+};
+class GaussianFragmentLengthModel : public FragmentLengthModel {
+   public:
+    GaussianFragmentLengthModel() : mean(0), sd(1) {}
+    GaussianFragmentLengthModel(double mean_in, double sd_in) : mean(mean_in), sd(sd_in) {}   // fragmentLengthModel.cpp:40-49
+    explicit GaussianFragmentLengthModel(const std::map<unsigned, unsigned> &fragment_lengths) {  // :52-64
+        std::pair<double, double> p = estimateParameters(fragment_lengths);
+        mean = p.first;
+        sd = 1.4826 * p.second;
+    }
+    std::pair<double, double> estimateParameters(const std::map<unsigned, unsigned> &fragment_lengths) const {  // :120-161
+        std::vector<uint32_t> len, cnt;
+        for (std::map<unsigned, unsigned>::const_iterator it = fragment_lengths.begin(); it != fragment_lengths.end(); ++it) {
+            len.push_back(it->first);
+            cnt.push_back(it->second);
+        }
+        double median = 0, mad = 0;
+        check(bayes_fragment_model_estimate((int32_t)len.size(), len.data(), cnt.data(), &median, &mad), "estimateParameters");
+        return std::make_pair(median, mad);
+    }
+    double pmf(unsigned fragment_length) {  // :66-69
+        const double var = pow(sd, 2), norm_const = 1 / (sd * sqrt(2 * 3.14159265358979323846264338327950288));
+        return norm_const * exp(-(pow((double)fragment_length - mean, 2) / (2 * var)));
+    }
+    double getMean() const { return mean; }
+    double getSd() const { return sd; }
+
+   private:
+    double mean, sd;
+};
+
+// sequencingModel.h:43-59; only the Gaussian model is wired into the CLI (assembler.cpp:1984-1987)
+class SequencingModel {
+   public:
+    SequencingModel(FragmentLengthModel *fragment_length_model_pt, int max_transcript_length, std::stringstream &log_stream) : model(0) {
+        GaussianFragmentLengthModel *g = dynamic_cast<GaussianFragmentLengthModel *>(fragment_length_model_pt);
+        if (!g) throw std::invalid_argument("SequencingModel: only GaussianFragmentLengthModel is supported");
+        check(bayes_seq_model_create_gaussian(g->getMean(), g->getSd(), max_transcript_length, &model), "bayes_seq_model_create_gaussian");
+        log_stream << "[bayesembler_b200] Tabulated fragment length and 3'-position probabilities up to transcript lengths of "
+                   << max_transcript_length << std::endl;
+    }
+    ~SequencingModel() { bayes_seq_model_destroy(model); }
+    double calculateThreePrimeProb(int three_prime_pos, int tran_length) { return bayes_seq_model_three_prime_prob(model, three_prime_pos, tran_length); }
+    double calculateLengthProb(int fragment_length, int three_prime_pos) { return bayes_seq_model_length_prob(model, fragment_length, three_prime_pos); }
+    double getEffectiveLength(int transcript_length) { return bayes_seq_model_effective_length(model, transcript_length); }
+    const bayes_seq_model *handle() const { return model; }
+
+   private:
+    SequencingModel(const SequencingModel &);
+    SequencingModel &operator=(const SequencingModel &);
+    bayes_seq_model *model;
+};
+
+// utils.h:129-136 with the probability matrix in CSR form (the reference's is a dense Eigen::MatrixXd); it offers the
+// rows() / cols() / (i, j) accessors AssignmentGenerator's templated constructor reads, and AssignmentGenerator also
+// takes it directly.
+struct CollapsedMap {
+    struct Csr {
+        int T;
+        std::vector<int32_t> row_ptr, col_idx;
+        std::vector<double> val;
+        int rows() const { return (int)row_ptr.size() - 1; }
+        int cols() const { return T; }
+        double operator()(int i, int j) const {
+            const int32_t *b = col_idx.data() + row_ptr[i], *e = col_idx.data() + row_ptr[i + 1];
+            const int32_t *p = std::lower_bound(b, e, (int32_t)j);
+            return p != e && *p == j ? val[p - col_idx.data()] : 0.0;
+        }
+    } probability_matrix;
+    std::vector<int> counts;
+    IdxMap new_idx_to_old_idx_effective_length;
+    int return_code;
+};
+
+// alignmentParser.h:44-63
+class AlignmentParser {
+   public:
+    // alignmentParser.cpp:251-689; like the reference it deletes the FragmentAlignment objects it is given
+    CollapsedMap calculateFragTranProbabilities(std::vector<Candidate> &candidates, std::vector<FragmentAlignment *> *fragment_alignments,
+                                                SequencingModel *sequencing_model, bool no_coverage_exclude, std::stringstream &log_stream,
+                                                std::map<std::string, int> *subgraph_complexity) {
+        Flat f(candidates, fragment_alignments);
+        std::vector<int32_t> complexity(f.graph_names.size(), 0);
+        for (size_t g = 0; g < f.graph_names.size(); g++) complexity[g] = (*subgraph_complexity)[f.graph_names[g]];
+        bayes_collapsed_map *cm = 0;
+        const int rc = bayes_collapsed_map_build(&f.raw, sequencing_model->handle(), no_coverage_exclude ? 1 : 0, complexity.data(), &cm);
+        check(rc, "calculateFragTranProbabilities");
+        CollapsedMap out;
+        out.return_code = rc;
+        out.probability_matrix.T = bayes_collapsed_map_num_candidates(cm);
+        int64_t st[10];
+        bayes_collapsed_map_stats(cm, st);
+        if (rc == 0) {
+            const int R = bayes_collapsed_map_num_rows(cm), T = out.probability_matrix.T;
+            const int64_t nnz = bayes_collapsed_map_nnz(cm);
+            out.probability_matrix.row_ptr.resize(R + 1);
+            out.probability_matrix.col_idx.resize(nnz);
+            out.probability_matrix.val.resize(nnz);
+            std::vector<int32_t> counts(R), new_to_old(T);
+            std::vector<double> efflen(T);
+            bayes_collapsed_map_export(cm, out.probability_matrix.row_ptr.data(), out.probability_matrix.col_idx.data(), out.probability_matrix.val.data(),
+                                       counts.data(), new_to_old.data(), efflen.data());
+            out.counts.assign(counts.begin(), counts.end());
+            for (int t = 0; t < T; t++) out.new_idx_to_old_idx_effective_length[t] = std::make_pair((int)new_to_old[t], efflen[t]);
+            for (size_t g = 0; g < f.graph_names.size(); g++) (*subgraph_complexity)[f.graph_names[g]] = complexity[g];
+        } else {
+            out.probability_matrix.row_ptr.assign(1, 0);
+        }
+        bayes_collapsed_map_destroy(cm);
+        log_stream << "[bayesembler_b200] " << st[0] << " fragment(s) parsed, " << st[1] << " matched a transcript, " << st[5]
+                   << " unique rows, " << st[6] << " of " << candidates.size() << " candidates excluded" << std::endl;
+        for (size_t i = 0; i < fragment_alignments->size(); i++) delete (*fragment_alignments)[i];
+        return out;
+    }
+
+    // alignmentParser.cpp:692-725
+    void fetchFragmentLengths(std::map<unsigned, unsigned> *fragment_length_map, std::vector<Candidate> &candidates,
+                              std::vector<FragmentAlignment *> *fragment_alignments, std::stringstream &) {
+        Flat f(candidates, fragment_alignments);
+        const int64_t n = bayes_fetch_fragment_lengths(&f.raw, 0, 0);
+        check((int)n, "fetchFragmentLengths");
+        std::vector<uint32_t> lengths(n);
+        bayes_fetch_fragment_lengths(&f.raw, lengths.data(), n);
+        for (int64_t i = 0; i < n; i++) (*fragment_length_map)[lengths[i]]++;
+        for (size_t i = 0; i < fragment_alignments->size(); i++) delete (*fragment_alignments)[i];
+    }
+
+   private:
+    // vector<Candidate> + vector<FragmentAlignment*> -> the flat arrays of bayes_raw_locus
+    struct Flat {
+        bayes_raw_locus raw;
+        std::vector<int32_t> exon_ptr, exon_start, exon_end, cand_length, is_premrna, subgraph_id, cigar_ptr;
+        std::vector<uint32_t> read_pos, cigar_len;
+        std::vector<char> cigar_op;
+        std::vector<double> frag_prob;
+        std::vector<std::string> graph_names;
+        Flat(const std::vector<Candidate> &candidates, const std::vector<FragmentAlignment *> *frags) {
+            exon_ptr.push_back(0);
+            for (size_t i = 0; i < candidates.size(); i++) {
+                const Candidate &c = candidates[i];
+                for (size_t k = 0; k < c.vertices.size(); k++) {
+                    exon_start.push_back(c.vertices[k].start);
+                    exon_end.push_back(c.vertices[k].end);
+                }
+                exon_ptr.push_back((int32_t)exon_start.size());
+                cand_length.push_back(c.length);
+                is_premrna.push_back(c.isPreMrna ? 1 : 0);
+                size_t g = 0;
+                while (g < graph_names.size() && graph_names[g] != c.graph_name) g++;
+                if (g == graph_names.size()) graph_names.push_back(c.graph_name);
+                subgraph_id.push_back((int32_t)g);
+            }
+            cigar_ptr.push_back(0);
+            for (size_t i = 0; i < frags->size(); i++) {
+                const FragmentAlignment &f = *(*frags)[i];
+                for (int m = 0; m < 2; m++) {
+                    const ReadData &rd = m == 0 ? f.read_data.first : f.read_data.second;
+                    read_pos.push_back(rd.first);
+                    for (size_t k = 0; k < rd.second.size(); k++) {
+                        cigar_op.push_back(rd.second[k].Type);
+                        cigar_len.push_back(rd.second[k].Length);
+                    }
+                    cigar_ptr.push_back((int32_t)cigar_op.size());
+                }
+                frag_prob.push_back(f.probability);
+            }
+            raw.n_cand = (int32_t)candidates.size();
+            raw.exon_ptr = exon_ptr.data();
+            raw.exon_start = exon_start.data();
+            raw.exon_end = exon_end.data();
+            raw.cand_length = cand_length.data();
+            raw.is_premrna = is_premrna.data();
+            raw.subgraph_id = subgraph_id.data();
+            raw.n_subgraphs = (int32_t)graph_names.size();
+            raw.strand_plus = !candidates.empty() && !candidates.front().vertices.empty() && candidates.front().vertices.front().strand == "+" ? 1 : 0;
+            raw.n_frag = (int32_t)frags->size();
+            raw.read_pos = read_pos.data();
+            raw.cigar_ptr = cigar_ptr.data();
+            raw.cigar_op = cigar_op.data();
+            raw.cigar_len = cigar_len.data();
+            raw.frag_prob = frag_prob.data();
+        }
+    };
 };
 
 }  // namespace bayesembler_b200

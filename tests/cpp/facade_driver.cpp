@@ -131,6 +131,81 @@ int facade_run_loci(int n, const int *T_arr, const int64_t *row_off, const int64
     }
 }
 
+// Likelihood builder through the facade classes, the way assembler.cpp:1511-1514 calls them; same argument list as
+// ref_collapsed_map (oracle/ref_f1_driver.cpp).
+int facade_collapsed_map(int n_cand, const int *exon_ptr, const int *exon_start, const int *exon_end, const int *cand_length,
+                         const int *is_premrna, const int *subgraph_id, int strand_plus, int n_frag, const uint32_t *read_pos,
+                         const int *cigar_ptr, const char *cigar_op, const uint32_t *cigar_len, const double *frag_prob, double frag_mean,
+                         double frag_sd, int max_transcript_length, int no_coverage_exclude, int n_subgraphs, int *subgraph_complexity,
+                         int r_cap, int *T_out, int *R_out, double *P_out, int *counts_out, int *new_to_old, double *efflen_out) {
+    std::vector<Candidate> candidates(n_cand);
+    for (int i = 0; i < n_cand; i++) {
+        Candidate &c = candidates[i];
+        std::stringstream nm, gn;
+        nm << "cand" << i;
+        gn << "g" << subgraph_id[i];
+        c.idx = i;
+        c.name = nm.str();
+        c.graph_name = gn.str();
+        c.length = cand_length[i];
+        c.isPreMrna = is_premrna[i] != 0;
+        for (int k = exon_ptr[i]; k < exon_ptr[i + 1]; k++) {
+            Vertex v;
+            v.reference = "chr1";
+            v.strand = strand_plus ? "+" : "-";
+            v.start = exon_start[k];
+            v.end = exon_end[k];
+            c.vertices.push_back(v);
+        }
+    }
+    std::vector<FragmentAlignment *> frags(n_frag);
+    for (int i = 0; i < n_frag; i++) {
+        FragmentAlignment *f = new FragmentAlignment;
+        for (int m = 0; m < 2; m++) {
+            ReadData &rd = m == 0 ? f->read_data.first : f->read_data.second;
+            rd.first = read_pos[2 * i + m];
+            for (int k = cigar_ptr[2 * i + m]; k < cigar_ptr[2 * i + m + 1]; k++) rd.second.push_back(BamTools::CigarOp(cigar_op[k], cigar_len[k]));
+        }
+        f->probability = frag_prob[i];
+        frags[i] = f;
+    }
+    std::map<std::string, int> complexity;
+    for (int g = 0; g < n_subgraphs; g++) {
+        std::stringstream gn;
+        gn << "g" << g;
+        complexity[gn.str()] = subgraph_complexity[g];
+    }
+    std::stringstream log;
+    GaussianFragmentLengthModel flm(frag_mean, frag_sd);
+    SequencingModel sm(&flm, max_transcript_length, log);
+    AlignmentParser parser;
+    CollapsedMap cm = parser.calculateFragTranProbabilities(candidates, &frags, &sm, no_coverage_exclude != 0, log, &complexity);
+    for (int g = 0; g < n_subgraphs; g++) {
+        std::stringstream gn;
+        gn << "g" << g;
+        subgraph_complexity[g] = complexity[gn.str()];
+    }
+    *T_out = 0;
+    *R_out = 0;
+    if (cm.return_code != 0) return cm.return_code;
+    const int R = cm.probability_matrix.rows(), T = cm.probability_matrix.cols();
+    *T_out = T;
+    *R_out = R;
+    if (R > r_cap) return -1;
+    for (int i = 0; i < R; i++) {
+        counts_out[i] = cm.counts[i];
+        for (int j = 0; j < T; j++) P_out[(size_t)i * T + j] = cm.probability_matrix(i, j);
+    }
+    for (int t = 0; t < T; t++) {
+        new_to_old[t] = cm.new_idx_to_old_idx_effective_length[t].first;
+        efflen_out[t] = cm.new_idx_to_old_idx_effective_length[t].second;
+    }
+    // the CollapsedMap plugs into the sampler classes as the reference's does (assembler.cpp:1548)
+    mt_rng_t rng(1);
+    AssignmentGenerator ag(&rng, &cm.probability_matrix, &cm.counts);
+    return ag.getNumFragments() > 0 ? 0 : -2;
+}
+
 // the CDF table as the facade's FixedBinomialFixedGammaSimplexSizeGenerator exposes it (row lengths only + flat values)
 int facade_simplex_rows(double pi, double gamma, int T, int num_fragments, int *row_len, double *flat) {
     mt_rng_t rng;

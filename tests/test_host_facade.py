@@ -123,3 +123,28 @@ def test_facade_worker_matches_c_abi(facade, lib, batched):
         assert np.array_equal(got[i]["mean"], want["mean"]), (i, got[i]["mean"], want["mean"])
         assert np.array_equal(got[i]["m2"], want["m2"]), (i, got[i]["m2"], want["m2"])
     ctx.close()
+
+
+@pytest.mark.parametrize("ci", range(9))
+def test_facade_likelihood_builder_matches_reference_golden(facade, ci):
+    """AlignmentParser / SequencingModel / GaussianFragmentLengthModel of the facade (row f1) against the reference's
+    CollapsedMaps recorded in tests/golden/f1_vectors.npz."""
+    import sys
+    from oracle import f1_py
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden_f1
+    g = np.load(os.path.join(ROOT, "tests", "golden", "f1_vectors.npz"))
+    p = "case%d_" % ci
+    loc = f1_py.RawLocus(*[g[p + f] for f in make_golden_f1.FIELDS[:6]], int(g[p + "strand_plus"]),
+                         *[g[p + f] for f in make_golden_f1.FIELDS[6:]])
+    rc, T, R, nce = [int(x) for x in g[p + "rc"]]
+    fn = facade.facade_collapsed_map
+    fn.restype = C.c_int
+    fn.argtypes = f1_py._CM_ARGS
+    got = f1_py._call_collapsed_map(fn, loc, 200.0, 20.0, int(loc.cand_length.max()), bool(nce))
+    assert got["return_code"] == rc
+    if rc == 0:
+        assert got["T"] == T and got["R"] == R
+        assert np.array_equal(got["P"], g[p + "P"]) and np.array_equal(got["counts"], g[p + "counts"])
+        assert np.array_equal(got["new_to_old"], g[p + "new_to_old"]) and np.array_equal(got["efflen"], g[p + "efflen"])
+        assert np.array_equal(got["complexity"], g[p + "complexity"])
