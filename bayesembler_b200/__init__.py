@@ -105,7 +105,7 @@ def load_library(path=None):
         "bayes_gibbs_chain_info": (C.c_int, [vp, i64, i32, C.POINTER(dbl), C.POINTER(i32)]),
         "bayes_gibbs_num_loci": (i64, [vp]),
         "bayes_gibbs_num_jobs": (i64, [vp]),
-        "bayes_gibbs_unit_stats": (i64, [vp, vp, vp]),
+        "bayes_gibbs_unit_stats": (i64, [vp, vp, vp, vp]),
         "bayes_gibbs_phase_seconds": (C.c_int, [vp, vp]),
         "bayes_gibbs_last_launches": (i32, [vp]),
         "bayes_gibbs_set_trace": (C.c_int, [vp, i64, i32, i32]),
@@ -278,10 +278,12 @@ class GibbsContext(object):
 
     def unit_stats(self):
         """Per-unit shapes and (start ns, end ns, SM) of the last run."""
-        n = self.lib.bayes_gibbs_unit_stats(self.h, None, None)
+        n = self.lib.bayes_gibbs_unit_stats(self.h, None, None, None)
         shape = np.zeros((n, 8), np.int32)
         clock = np.zeros((n, 3), np.uint64)
-        _check(self.lib.bayes_gibbs_unit_stats(self.h, _ptr(shape), _ptr(clock)), "bayes_gibbs_unit_stats")
+        pred = np.zeros((n, 5))
+        _check(self.lib.bayes_gibbs_unit_stats(self.h, _ptr(shape), _ptr(clock), _ptr(pred)), "bayes_gibbs_unit_stats")
+        self.unit_predicted_s, self.unit_features = pred[:, 0].copy(), pred[:, 1:].copy()
         return shape, clock
 
     def phase_seconds(self):

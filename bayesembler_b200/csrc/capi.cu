@@ -124,6 +124,8 @@ struct bayes_gibbs_ctx {
     DevBuf<uint64_t> d_unit_clock;
 
     std::vector<Launch> launches;
+    std::vector<double> unit_pred;  // time model's estimate per unit (seconds), launch order
+    std::vector<double> unit_feat;  // 4 per unit: chain columns, uniform slabs, uniform blocks, uniform block-columns
     int32_t last_launches = 0;
     // wall-clock seconds of the host phases of the last batch: prepare (fold, cover, tables), unit formation + packing,
     // H2D enqueue, launch enqueue, D2H enqueue, final synchronise (= device time not hidden behind the host)
@@ -267,13 +269,14 @@ int build_units(bayes_gibbs_ctx *ctx) {
         }
         S.iters = (double)groups[i][0].locus->burn + groups[i][0].locus->samples;
     });
-    // Time model in microseconds per iteration, fitted on B200 to loci running alone (profiles/README.md).  A chain slab
+    // Time model in microseconds per iteration, fitted by least squares to the measured durations of the 4 183 units of
+    // config 2 on a FULL B200 (tools/schedule_report.py -> gpurun_out/unit_stats.npz, profiles/README.md): a chain slab
     // costs chain_us(h) per column (one conditional binomial of its slowest lane per step: fewer lanes, fewer divergent
-    // paths), a uniform slab a fixed part (row sum) plus, per Philox block of its busiest lane, a fixed part and a little
-    // per column; the one-warp E-step and the two block barriers cost kEstepUs.  The warps of a unit take slabs from a
-    // shared counter, heaviest first (greedy list scheduling).
-    auto chain_us = [](int h) { return h >= 32 ? 1.7 : h >= 16 ? 1.5 : h >= 8 ? 1.2 : 1.1; };
-    const double kEstepUs = 4.0, kUniformSlabUs = 0.3, kUniformBlockUs = 0.25, kUniformColumnUs = 0.05;
+    // paths), a uniform slab a fixed part (row sum) plus, per Philox block of its busiest lane, a fixed part and a
+    // little per column; the one-warp E-step, the two block barriers and the loop overhead cost kEstepUs.  The warps of
+    // a unit take slabs from a shared counter, heaviest first (greedy list scheduling).
+    auto chain_us = [](int h) { return h >= 32 ? 1.3 : h >= 16 ? 1.15 : h >= 8 ? 0.95 : 0.9; };
+    const double kEstepUs = 12.5, kUniformSlabUs = 0.8, kUniformBlockUs = 1.55, kUniformColumnUs = 0.16;
     auto slab_layout = [](const Shape &S, int h, int *chain_slabs, int *n_slabs) {
         const int n_items = (int)S.nnz.size();
         *chain_slabs = (S.n_chain + h - 1) / h;
@@ -301,6 +304,24 @@ int build_units(bayes_gibbs_ctx *ctx) {
         return worst + kEstepUs;
     };
     auto unit_time = [&](const Shape &S, int warps, int h) { return 1e-6 * S.iters * iteration_us(S, warps, h); };
+    // totals the model is made of (exposed through bayes_gibbs_unit_stats for calibration)
+    auto unit_features = [&](const Shape &S, int h, double *f4) {
+        int chain_slabs, n_slabs;
+        slab_layout(S, h, &chain_slabs, &n_slabs);
+        const int n_items = (int)S.nnz.size();
+        f4[0] = f4[1] = f4[2] = f4[3] = 0;
+        for (int s = 0; s < n_slabs; s++) {
+            const bool chain = s < chain_slabs;
+            const int first = chain ? s * h : S.n_chain + (s - chain_slabs) * h, last = chain ? S.n_chain : n_items;
+            int width = 0, blocks = 0;
+            for (int l = 0; l < h && first + l < last; l++) {
+                width = std::max(width, S.nnz[first + l]);
+                blocks = std::max(blocks, S.blocks[first + l]);
+            }
+            if (chain) f4[0] += width;
+            else { f4[1] += 1; f4[2] += blocks; f4[3] += (double)blocks * width; }
+        }
+    };
     auto smem_estimate = [&](const Shape &S, int h) {
         int chain_slabs, n_slabs;
         slab_layout(S, h, &chain_slabs, &n_slabs);
@@ -349,7 +370,7 @@ int build_units(bayes_gibbs_ctx *ctx) {
         while (!heap.empty()) {
             const Item top = heap.top();
             const int64_t i = top.second;
-            if (top.first <= 1.0 * occupied / capacity) break;  // the batch is throughput-bound from here on
+            if (top.first <= 0.75 * occupied / capacity) break;  // the batch is throughput-bound from here on
             heap.pop();
             // next rung that actually shortens the unit
             int k = step[i] + 1;
@@ -379,6 +400,7 @@ int build_units(bayes_gibbs_ctx *ctx) {
         pack_unit(groups[i], group_wide[i] != 0, unit_h[i], &packed[i]);
         packed[i].d.block = 32 * unit_warps[i];
         packed[i].cost = unit_time(shapes[i], unit_warps[i], unit_h[i]);  // estimated duration: the launch-order key
+        unit_features(shapes[i], unit_h[i], packed[i].features);
     });
 
     // One launch per class = (kernel, block size, matrix placement, shared-memory bucket) and duration band.  The bucket
@@ -406,8 +428,13 @@ int build_units(bayes_gibbs_ctx *ctx) {
         return packed[a].cost > packed[b].cost;
     });
     int rc;
-    for (int64_t i = 0; i < n_units; i++)
+    ctx->unit_pred.clear();
+    ctx->unit_feat.clear();
+    for (int64_t i = 0; i < n_units; i++) {
         if ((rc = append_unit(ctx, packed[order[i]]))) return rc;
+        ctx->unit_pred.push_back(packed[order[i]].cost);
+        for (int k = 0; k < 4; k++) ctx->unit_feat.push_back(packed[order[i]].features[k]);
+    }
     const UnitDev *units = ctx->h_units.p;
     for (int64_t i = 0; i < n_units;) {
         int64_t j = i;
@@ -811,10 +838,10 @@ int bayes_gibbs_chain_info(bayes_gibbs_ctx *ctx, int64_t locus_id, int32_t chain
 
 // Diagnostics of the last run: per unit {wide, block, n_slots, n_slabs, n_cells, iterations, T of slot 0, mat_smem} and
 // {start ns, end ns, SM id}.  Returns the number of units (call with NULL pointers to size the buffers).
-int64_t bayes_gibbs_unit_stats(bayes_gibbs_ctx *ctx, int32_t *shape8, uint64_t *clock3) {
+int64_t bayes_gibbs_unit_stats(bayes_gibbs_ctx *ctx, int32_t *shape8, uint64_t *clock3, double *predicted_s) {
     if (!ctx) return BAYES_E_INVALID;
     const int64_t n = (int64_t)ctx->h_units.n;
-    if (!shape8 && !clock3) return n;
+    if (!shape8 && !clock3 && !predicted_s) return n;
     if (!ctx->ran) {
         set_error("bayes_gibbs_unit_stats: no run yet");
         return BAYES_E_STATE;
@@ -827,6 +854,11 @@ int64_t bayes_gibbs_unit_stats(bayes_gibbs_ctx *ctx, int32_t *shape8, uint64_t *
             int32_t *o = shape8 + 8 * i;
             o[0] = u.wide; o[1] = u.block; o[2] = u.n_slots; o[3] = u.n_slabs; o[4] = u.n_cells; o[5] = u.burn + u.samples; o[6] = u.T[0];
             o[7] = u.mat_smem | (u.slab_h << 8);
+        }
+    if (predicted_s)
+        for (int64_t i = 0; i < n; i++) {
+            predicted_s[5 * i] = i < (int64_t)ctx->unit_pred.size() ? ctx->unit_pred[i] : 0.0;
+            for (int k = 0; k < 4; k++) predicted_s[5 * i + 1 + k] = 4 * i + k < (int64_t)ctx->unit_feat.size() ? ctx->unit_feat[4 * i + k] : 0.0;
         }
     if (clock3 && n && cuda_rc(cudaMemcpy(clock3, ctx->d_unit_clock.p, 3 * n * sizeof(uint64_t), cudaMemcpyDeviceToHost), "unit clock D2H"))
         return BAYES_E_CUDA;

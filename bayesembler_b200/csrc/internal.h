@@ -130,6 +130,7 @@ struct PackedUnit {
     std::vector<int32_t> slab_cell_off, row_n, row_nnz, base_counts, tab_row;
     std::vector<uint32_t> row_info;
     double cost = 0;
+    double features[4] = {0, 0, 0, 0};  // the time model's inputs (capi.cu)
 };
 
 // shape of one A-step item before packing (pack.cpp builds them, capi.cu sizes units with them)

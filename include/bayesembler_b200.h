@@ -112,8 +112,10 @@ int64_t bayes_gibbs_num_loci(bayes_gibbs_ctx *ctx);
 int64_t bayes_gibbs_num_jobs(bayes_gibbs_ctx *ctx);
 /* Scheduling diagnostics of the last run, one entry per thread-block unit: shape8 = {wide, threads, slots, row slabs,
  * padded cells, iterations, T of slot 0, matrix in shared memory | rows per slab << 8}, clock3 = {start ns, end ns, SM id} (globaltimer).
- * Returns the number of units; call with both pointers NULL to size the buffers. */
-int64_t bayes_gibbs_unit_stats(bayes_gibbs_ctx *ctx, int32_t *shape8, uint64_t *clock3);
+ * predicted_s = 5 doubles per unit: the scheduler's time-model estimate (s) and its inputs (chain slab columns,
+ * uniform slabs, uniform Philox blocks, uniform block-columns).  Returns the number of units; call with all pointers NULL
+ * to size the buffers. */
+int64_t bayes_gibbs_unit_stats(bayes_gibbs_ctx *ctx, int32_t *shape8, uint64_t *clock3, double *predicted_s);
 /* Wall-clock seconds of the host phases of the last batch: {prepare (fold rows, read cover, CDF tables), unit formation
  * and packing, H2D enqueue, launch enqueue, D2H enqueue, final synchronise}. */
 int bayes_gibbs_phase_seconds(bayes_gibbs_ctx *ctx, double *out6);

@@ -69,6 +69,14 @@ def main():
     show(np.argsort(-end)[:args.top], "last to finish")
     show(np.argsort(-dur)[:args.top], "longest")
     show(np.arange(min(args.top, len(dur))), "first in launch order")
+    pred = ctx.unit_predicted_s * 1e3
+    ratio = dur / np.maximum(pred, 1e-9)
+    print("\ntime model: measured / predicted duration, by block size (median, 10-90 %%), overall corr %.3f" % np.corrcoef(pred, dur)[0, 1])
+    for b in sorted(set(shape[:, 1].tolist())):
+        m = shape[:, 1] == b
+        print("  %4d threads  n=%5d  median %.2f  (%.2f - %.2f)" % (b, m.sum(), np.median(ratio[m]), np.percentile(ratio[m], 10), np.percentile(ratio[m], 90)))
+    np.savez(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "unit_stats.npz"), shape=shape, slab_h=slab_h,
+             start=start, end=end, pred=pred, feat=ctx.unit_features)
     # utilisation timeline: resident warps over time in 20 buckets
     edges = np.linspace(0, span, 21)
     occ = []
