@@ -347,6 +347,8 @@ int build_units(bayes_gibbs_ctx *ctx) {
         static const int ladder[][2] = {{1, 32}, {2, 32}, {4, 32}, {8, 32}, {8, 16}, {16, 16}, {16, 8}};
         const int n_ladder = (int)(sizeof(ladder) / sizeof(ladder[0]));
         const double capacity = (double)ctx->sm_count * kWarpsPerSM;  // resident warps at the kernels' register count
+        const char *spw = getenv("BAYES_SMEM_PER_WARP");  // experiment knob
+        const double smem_per_warp = spw ? atof(spw) : 8192.0;
         std::vector<int> step(n_units, 0);
         std::vector<double> t(n_units);
         double occupied = 0;  // sum of warps * time
@@ -361,7 +363,7 @@ int build_units(bayes_gibbs_ctx *ctx) {
             slab_layout(S, 32, &chain_slabs, &n_slabs);
             const double smem_est = smem_estimate(S, 32);
             int k = 0;
-            while (k + 1 < 4 && ladder[k][0] * 8192.0 < smem_est && ladder[k + 1][0] < 2 * n_slabs) k++;
+            while (k + 1 < 4 && ladder[k][0] * smem_per_warp < smem_est && ladder[k + 1][0] < 2 * n_slabs) k++;
             step[i] = k;
             t[i] = unit_time(S, ladder[k][0], ladder[k][1]);
             occupied += ladder[k][0] * t[i];
