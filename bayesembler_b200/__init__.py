@@ -25,6 +25,9 @@ EXPORTED_SYMBOLS = [
     "bayes_seq_model_effective_length", "bayes_fragment_model_estimate", "bayes_collapsed_map_build", "bayes_collapsed_map_destroy",
     "bayes_collapsed_map_num_candidates", "bayes_collapsed_map_num_rows", "bayes_collapsed_map_nnz", "bayes_collapsed_map_export",
     "bayes_collapsed_map_stats", "bayes_fetch_fragment_lengths",
+    "bayes_all_paths_build", "bayes_path_set_destroy", "bayes_path_set_num_candidates", "bayes_path_set_num_exons",
+    "bayes_path_set_export", "bayes_path_set_stats", "bayes_path_set_graph_name", "bayes_path_set_reference",
+    "bayes_path_set_strand", "bayes_path_set_candidate_name",
 ]
 
 
@@ -135,6 +138,16 @@ def load_library(path=None):
         "bayes_collapsed_map_export": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
         "bayes_collapsed_map_stats": (C.c_int, [vp, vp]),
         "bayes_fetch_fragment_lengths": (i64, [C.POINTER(RawLocusDesc), vp, i64]),
+        "bayes_all_paths_build": (C.c_int, [C.c_char_p, i32, i32, C.POINTER(vp)]),
+        "bayes_path_set_destroy": (None, [vp]),
+        "bayes_path_set_num_candidates": (i32, [vp]),
+        "bayes_path_set_num_exons": (i32, [vp]),
+        "bayes_path_set_export": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+        "bayes_path_set_stats": (C.c_int, [vp, vp]),
+        "bayes_path_set_graph_name": (C.c_char_p, [vp]),
+        "bayes_path_set_reference": (C.c_char_p, [vp]),
+        "bayes_path_set_strand": (C.c_char_p, [vp]),
+        "bayes_path_set_candidate_name": (C.c_int, [vp, i32, C.c_char_p, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -464,4 +477,31 @@ def fetch_fragment_lengths(raw):
     n = _check(L.bayes_fetch_fragment_lengths(C.byref(d), None, 0), "bayes_fetch_fragment_lengths")
     out = np.zeros(n, np.uint32)
     _check(L.bayes_fetch_fragment_lengths(C.byref(d), _ptr(out), n), "bayes_fetch_fragment_lengths")
+    return out
+
+
+def all_paths(dot, no_pre_mrna=False, max_candidate_number=100):
+    """AllPaths(dot).findFullPaths(no_pre_mrna, max_candidate_number, log) through the C ABI -> dict with the candidate
+    arrays bayes_raw_locus takes, names, graph name / reference / strand and the numbers of the log block."""
+    L = load_library()
+    h = C.c_void_p()
+    _check(L.bayes_all_paths_build(dot.encode() if isinstance(dot, str) else dot, int(bool(no_pre_mrna)), int(max_candidate_number),
+                                   C.byref(h)), "bayes_all_paths_build")
+    try:
+        n, ne = L.bayes_path_set_num_candidates(h), L.bayes_path_set_num_exons(h)
+        out = dict(n_cand=n, exon_ptr=np.zeros(n + 1, np.int32), exon_start=np.zeros(ne, np.int32), exon_end=np.zeros(ne, np.int32),
+                   cand_length=np.zeros(n, np.int32), is_premrna=np.zeros(n, np.int32), stats=np.zeros(6, np.int32),
+                   graph_name=L.bayes_path_set_graph_name(h).decode(), reference=L.bayes_path_set_reference(h).decode(),
+                   strand=L.bayes_path_set_strand(h).decode())
+        _check(L.bayes_path_set_export(h, _ptr(out["exon_ptr"]), _ptr(out["exon_start"]), _ptr(out["exon_end"]), _ptr(out["cand_length"]),
+                                       _ptr(out["is_premrna"])), "bayes_path_set_export")
+        _check(L.bayes_path_set_stats(h, _ptr(out["stats"])), "bayes_path_set_stats")
+        buf = C.create_string_buffer(len(out["graph_name"]) + 32)
+        names = []
+        for i in range(n):
+            _check(L.bayes_path_set_candidate_name(h, i, buf, len(buf)), "bayes_path_set_candidate_name")
+            names.append(buf.value.decode())
+        out["names"] = names
+    finally:
+        L.bayes_path_set_destroy(h)
     return out

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbayesembler_b200.so")
-SOURCES = ["capi.cu", "gibbs_kernel.cu", "host_steps.cpp", "pack.cpp", "likelihood.cpp"]
+SOURCES = ["capi.cu", "gibbs_kernel.cu", "host_steps.cpp", "pack.cpp", "likelihood.cpp", "allpaths.cpp"]
 HEADERS = ["internal.h", "layout.h", "rng.cuh", os.path.join("..", "..", "include", "bayesembler_b200.h")]
 
 

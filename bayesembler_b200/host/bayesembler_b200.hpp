@@ -13,6 +13,7 @@
 //                N_f, T, rng, assignment_minimum)
 //   GibbsOutput(samples, T), getTopMarginals, writeEnsembleGtf,           same (gibbsOutput.h:46-50); Ensemble holds std::vector<double>
 //   writeCandidateGtf                                                      instead of Eigen::VectorXd
+//   AllPaths(dot).findFullPaths(no_pre_mrna, max_candidates, log)         same (allPaths.h:95-98); malformed DOT throws instead of asserting
 //   void GibbsSampler::runSampler(GibbsOutput*, burn, samples, log)       same, synchronous, ONE locus on the GPU (correct, latency-bound);
 //                                                                         GibbsBatch::add(...) + run() is the batched form the GPU wants
 //
@@ -595,6 +596,60 @@ class AlignmentParser {
             raw.frag_prob = frag_prob.data();
         }
     };
+};
+
+// allPaths.h:43-98
+class AllPaths {
+   public:
+    // allPaths.cpp:42-49: the reference parses the DOT text here and aborts (assert) on a malformed one; the text is kept
+    // and parsed by findFullPaths, which throws std::runtime_error instead
+    explicit AllPaths(std::string dotfile_in) : dot(dotfile_in), junction_threshold(1) {}
+
+    // allPaths.cpp:116-304.  Same candidates, names, order and log lines (without the reference's time stamps).
+    std::vector<Candidate> findFullPaths(bool no_pre_mrna, int max_candidate_number, std::stringstream &log_stream) {
+        bayes_path_set *ps = 0;
+        check(bayes_all_paths_build(dot.c_str(), no_pre_mrna ? 1 : 0, max_candidate_number, &ps), "findFullPaths");
+        int32_t st[6];
+        bayes_path_set_stats(ps, st);
+        const int n = bayes_path_set_num_candidates(ps), ne = bayes_path_set_num_exons(ps);
+        std::vector<int32_t> exon_ptr(n + 1), exon_start(ne), exon_end(ne), length(n), pre(n);
+        bayes_path_set_export(ps, exon_ptr.data(), exon_start.data(), exon_end.data(), length.data(), pre.data());
+        const std::string graph_name = bayes_path_set_graph_name(ps), reference = bayes_path_set_reference(ps), strand = bayes_path_set_strand(ps);
+        log_stream << "\nNumber of vertices in graph: " << st[0] << std::endl;
+        log_stream << "Number of sources in graph: " << st[1] << std::endl;
+        log_stream << "Number of sinks in graph: " << st[2] << std::endl;
+        for (int t = 1; t <= st[3]; t++)
+            log_stream << "Too many candidates to continue - adjusting junction threshold from " << t << " to " << t + 1 << std::endl;
+        junction_threshold = st[5];
+        std::vector<Candidate> out(n);
+        std::vector<char> name(graph_name.size() + 32);
+        for (int i = 0; i < n; i++) {
+            Candidate &c = out[i];
+            c.idx = i;
+            bayes_path_set_candidate_name(ps, i, name.data(), (int32_t)name.size());
+            c.name = name.data();
+            c.graph_name = graph_name;
+            c.length = length[i];
+            c.isPreMrna = pre[i] != 0;
+            for (int k = exon_ptr[i]; k < exon_ptr[i + 1]; k++) {
+                Vertex v;
+                v.reference = reference;
+                v.strand = strand;
+                v.start = exon_start[k];
+                v.end = exon_end[k];
+                c.vertices.push_back(v);
+            }
+        }
+        bayes_path_set_destroy(ps);
+        log_stream << "Number of paths in splice-graph (transcripts): " << n << std::endl;
+        return out;
+    }
+
+    int junctionThreshold() const { return junction_threshold; }  // private in the reference; exposed for logs / tests
+
+   private:
+    std::string dot;
+    int junction_threshold;
 };
 
 }  // namespace bayesembler_b200

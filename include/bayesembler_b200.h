@@ -220,6 +220,32 @@ int bayes_collapsed_map_stats(const bayes_collapsed_map *cm, int64_t *stats10);
  * candidate) match in fragment-major order; returns the number of matches (lengths_out may be NULL) */
 int64_t bayes_fetch_fragment_lengths(const bayes_raw_locus *locus, uint32_t *lengths_out, int64_t cap);
 
+/* ---- candidate enumeration (host, C++): splice graph -> candidate transcripts ---------------- */
+/* AllPaths(dot).findFullPaths(no_pre_mrna, max_candidate_number, log) (allPaths.h:95-98, allPaths.cpp:42-343; call site
+ * assembler.cpp:1462-1463).  `dot` is one splice graph in the DOT mini-format the reference writes (assembler.cpp:764-861):
+ *     digraph <name> {   <id> [label="ref;strand;start;end"] ...   pre_mrna [label=...]   <id>-><id> [coverage="n"] ...   }
+ * Every source-to-sink path becomes a candidate; while there are more than max_candidate_number of them the junction
+ * threshold rises and junctions with less coverage are dropped (allPaths.cpp:173-295).  Candidates come out in the
+ * reference's order (sources in vertex order = node ids sorted as strings; depth first in edge-statement order). */
+typedef struct bayes_path_set bayes_path_set;
+int bayes_all_paths_build(const char *dot, int32_t no_pre_mrna, int32_t max_candidate_number, bayes_path_set **out);
+void bayes_path_set_destroy(bayes_path_set *ps);
+int32_t bayes_path_set_num_candidates(const bayes_path_set *ps);
+int32_t bayes_path_set_num_exons(const bayes_path_set *ps);
+/* vector<Candidate> (utils.h:109-117) as the arrays bayes_raw_locus takes: exon_ptr n_cand + 1, exon_start / exon_end (adjacent
+ * exons merged, allPaths.cpp:237-244), Candidate::length, Candidate::isPreMrna; any pointer may be NULL */
+int bayes_path_set_export(const bayes_path_set *ps, int32_t *exon_ptr, int32_t *exon_start, int32_t *exon_end, int32_t *cand_length,
+                          int32_t *is_premrna);
+/* the numbers of the log block (allPaths.cpp:132-134, :317, :301): vertices, sources, sinks of the graph as read,
+ * junction-threshold adjustments, paths, and the final junction threshold */
+int bayes_path_set_stats(const bayes_path_set *ps, int32_t *stats6);
+/* Candidate::graph_name and the Vertex::reference / Vertex::strand shared by all vertices (valid until destroy) */
+const char *bayes_path_set_graph_name(const bayes_path_set *ps);
+const char *bayes_path_set_reference(const bayes_path_set *ps);
+const char *bayes_path_set_strand(const bayes_path_set *ps);
+/* Candidate::name of candidate i ("<graph>_seq<i>" or "<graph>_pre", allPaths.cpp:254, :270); returns its length */
+int bayes_path_set_candidate_name(const bayes_path_set *ps, int32_t i, char *buf, int32_t cap);
+
 #ifdef __cplusplus
 }
 #endif

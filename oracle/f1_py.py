@@ -93,9 +93,17 @@ def random_raw_locus(rng, n_exons=6, n_cand=5, n_frag=400, strand_plus=True, pre
     if premrna:
         cands.append([(exons[0][0], exons[-1][1])])
         is_pre.append(1)
+    sub = [0] * len(cands)
+    if two_subgraphs:
+        sub = [i % 2 for i in range(len(cands))]
+    return _sample_fragments(rng, cands, is_pre, sub, n_frag, strand_plus, premrna, indel_rate, junk_rate, frag_mean, frag_sd)
+
+
+def _sample_fragments(rng, cands, is_pre, sub, n_frag, strand_plus, premrna_last, indel_rate, junk_rate, frag_mean, frag_sd):
+    """Paired-end fragments sampled from candidates (lists of (start, end) exons) with random abundances."""
     lengths = [sum(e - s + 1 for s, e in c) for c in cands]
     rho = rng.gamma(0.5, size=len(cands)) * (rng.random(len(cands)) > 0.3)
-    if premrna:
+    if premrna_last:
         rho[-1] *= 0.05
     if rho.sum() == 0:
         rho[0] = 1.0
@@ -124,10 +132,16 @@ def random_raw_locus(rng, n_exons=6, n_cand=5, n_frag=400, strand_plus=True, pre
     exon_ptr = np.cumsum([0] + [len(c) for c in cands])
     es = [s for c in cands for s, _ in c]
     ee = [e for c in cands for _, e in c]
-    sub = [0] * len(cands)
-    if two_subgraphs:
-        sub = [i % 2 for i in range(len(cands))]
     return RawLocus(exon_ptr, es, ee, lengths, is_pre, sub, strand_plus, read_pos, cigar_ptr, cigar_op, cigar_len, prob)
+
+
+def fragments_for_candidates(rng, exon_ptr, exon_start, exon_end, cand_length, is_premrna, n_frag=400, strand_plus=True, indel_rate=0.0,
+                             junk_rate=0.02, frag_mean=200.0, frag_sd=20.0):
+    """Fragments for GIVEN candidates in the flat layout of bayes_path_set_export (row f2 -> row f1)."""
+    cands = [[(int(exon_start[k]), int(exon_end[k])) for k in range(exon_ptr[i], exon_ptr[i + 1])] for i in range(len(cand_length))]
+    assert [sum(e - s + 1 for s, e in c) for c in cands] == [int(x) for x in cand_length]
+    return _sample_fragments(rng, cands, [int(x) for x in is_premrna], [0] * len(cands), n_frag, strand_plus, False, indel_rate, junk_rate,
+                             frag_mean, frag_sd)
 
 
 def _p(a):

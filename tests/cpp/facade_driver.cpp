@@ -1,6 +1,7 @@
 // C-callable test driver around the C++ host facade (bayesembler_b200/host/bayesembler_b200.hpp); built by
 // tests/test_host_facade.py with g++ and linked against libbayesembler_b200.so.  facade_run_loci() is written the way
 // Assembler::bayesemblerCallback builds and runs its sampler objects (assembler.cpp:1548-1609).
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../bayesembler_b200/host/bayesembler_b200.hpp"
@@ -217,6 +218,52 @@ int facade_simplex_rows(double pi, double gamma, int T, int num_fragments, int *
         for (size_t j = 0; j < rows[k].size(); j++) flat[at++] = rows[k][j];
     }
     return at;
+}
+
+// AllPaths of the facade driven like assembler.cpp:1462-1474, flattened with the signature of oracle/ref_f2_driver.cpp's
+// ref_all_paths so that the same Python binding reads both
+int facade_all_paths(const char *dot, int no_pre_mrna, int max_candidate_number, int cap_cand, int cap_exons, int *exon_ptr, int *exon_start,
+                     int *exon_end, int *cand_length, int *is_premrna, int *cand_idx, char *names, int names_cap, char *graph_name,
+                     int graph_name_cap, int *stats5) {
+    std::stringstream log;
+    std::vector<Candidate> cands;
+    try {
+        AllPaths paths((std::string(dot)));
+        cands = paths.findFullPaths(no_pre_mrna != 0, max_candidate_number, log);
+    } catch (const std::runtime_error &) {
+        return -2;
+    }
+    if ((int)cands.size() > cap_cand) return -1;
+    int ne = 0;
+    std::string all_names;
+    exon_ptr[0] = 0;
+    graph_name[0] = 0;
+    for (size_t i = 0; i < cands.size(); i++) {
+        if (ne + (int)cands[i].vertices.size() > cap_exons) return -1;
+        for (size_t j = 0; j < cands[i].vertices.size(); j++, ne++) {
+            exon_start[ne] = cands[i].vertices[j].start;
+            exon_end[ne] = cands[i].vertices[j].end;
+        }
+        exon_ptr[i + 1] = ne;
+        cand_length[i] = cands[i].length;
+        is_premrna[i] = cands[i].isPreMrna ? 1 : 0;
+        cand_idx[i] = cands[i].idx;
+        all_names += cands[i].name + "\n";
+        if (i == 0) strncpy(graph_name, cands[i].graph_name.c_str(), graph_name_cap - 1), graph_name[graph_name_cap - 1] = 0;
+    }
+    if ((int)all_names.size() + 1 > names_cap) return -1;
+    memcpy(names, all_names.c_str(), all_names.size() + 1);
+    // the numbers of the log block, read back from the text the facade wrote
+    const char *keys[5] = {"Number of vertices in graph: ", "Number of sources in graph: ", "Number of sinks in graph: ", 0,
+                           "Number of paths in splice-graph (transcripts): "};
+    for (int k = 0; k < 5; k++) stats5[k] = 0;
+    std::string line;
+    while (std::getline(log, line)) {
+        for (int k = 0; k < 5; k++)
+            if (keys[k] && line.find(keys[k]) != std::string::npos) stats5[k] = atoi(line.c_str() + line.find(keys[k]) + strlen(keys[k]));
+        if (line.find("Too many candidates to continue") != std::string::npos) stats5[3]++;
+    }
+    return (int)cands.size();
 }
 
 }  // extern "C"

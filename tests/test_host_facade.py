@@ -148,3 +148,23 @@ def test_facade_likelihood_builder_matches_reference_golden(facade, ci):
         assert np.array_equal(got["P"], g[p + "P"]) and np.array_equal(got["counts"], g[p + "counts"])
         assert np.array_equal(got["new_to_old"], g[p + "new_to_old"]) and np.array_equal(got["efflen"], g[p + "efflen"])
         assert np.array_equal(got["complexity"], g[p + "complexity"])
+
+
+def test_facade_all_paths_matches_reference_golden(facade):
+    """AllPaths of the facade (row f2) against the reference's candidates recorded in tests/golden/f2_vectors.json, through the
+    same flat signature as the reference driver (names, exon chains, lengths, pre-mRNA flags, log numbers)."""
+    import json
+    from oracle import f2_py
+    import test_f2_allpaths as t2
+    ref_like = f2_py.ReferenceF2.__new__(f2_py.ReferenceF2)
+    facade.facade_all_paths.restype = C.c_int
+
+    class _L(object):
+        ref_all_paths = facade.facade_all_paths
+    ref_like.lib = _L
+    golden = json.load(open(os.path.join(ROOT, "tests", "golden", "f2_vectors.json")))
+    for ci, c in enumerate(golden):
+        dot, nopre, maxc = t2._case(c)
+        t2._same(ref_like.all_paths(dot, nopre, maxc), c["want"], ci)
+    facade.facade_all_paths.argtypes = None
+    assert facade.facade_all_paths(b"digraph g {", 0, 100, 0, 0, *([None] * 6), None, 0, None, 0, None) == -2  # throws, does not abort
