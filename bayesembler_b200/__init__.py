@@ -18,7 +18,7 @@ EXPORTED_SYMBOLS = [
     "bayes_gibbs_download", "bayes_gibbs_sync", "bayes_gibbs_run_batch", "bayes_gibbs_clear", "bayes_gibbs_fetch",
     "bayes_gibbs_fetch_all",
     "bayes_gibbs_locus_info", "bayes_gibbs_chain_info", "bayes_gibbs_num_loci", "bayes_gibbs_num_jobs", "bayes_gibbs_unit_stats", "bayes_gibbs_phase_seconds", "bayes_gibbs_last_launches",
-    "bayes_gibbs_set_trace", "bayes_gibbs_fetch_trace", "bayes_top_marginals", "bayes_step_generate_assignment",
+    "bayes_gibbs_set_trace", "bayes_gibbs_fetch_trace", "bayes_gibbs_set_calibration", "bayes_top_marginals", "bayes_step_generate_assignment",
     "bayes_step_init_assignment", "bayes_step_generate_expression", "bayes_step_variates", "bayes_min_read_cover",
     "bayes_simplex_table", "bayes_chain_key", "bayes_locus_cost", "bayes_partition_lpt", "bayes_philox4x32",
     "bayes_seq_model_create_gaussian", "bayes_seq_model_destroy", "bayes_seq_model_three_prime_prob", "bayes_seq_model_length_prob",
@@ -112,6 +112,7 @@ def load_library(path=None):
         "bayes_gibbs_phase_seconds": (C.c_int, [vp, vp]),
         "bayes_gibbs_last_launches": (i32, [vp]),
         "bayes_gibbs_set_trace": (C.c_int, [vp, i64, i32, i32]),
+        "bayes_gibbs_set_calibration": (C.c_int, [vp, i32]),
         "bayes_gibbs_fetch_trace": (C.c_int, [vp, vp, vp, vp, vp]),
         "bayes_top_marginals": (C.c_int, [i32, i32, vp, vp, vp, dbl, vp, vp, vp]),
         "bayes_step_generate_assignment": (C.c_int, [C.c_int, C.POINTER(LocusDesc), vp, u64, C.c_uint32, vp]),
@@ -306,6 +307,10 @@ class GibbsContext(object):
 
     def last_launches(self):
         return self.lib.bayes_gibbs_last_launches(self.h)
+
+    def set_calibration(self, iterations):
+        """-1 = automatic, 0 = off, n = calibration pass of n iterations (bayes_gibbs_set_calibration)."""
+        _check(self.lib.bayes_gibbs_set_calibration(self.h, int(iterations)), "bayes_gibbs_set_calibration")
 
     def set_trace(self, locus_id, chain, trace_iters):
         _check(self.lib.bayes_gibbs_set_trace(self.h, locus_id, chain, trace_iters), "bayes_gibbs_set_trace")

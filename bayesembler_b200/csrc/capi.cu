@@ -96,8 +96,19 @@ struct Launch {
 
 using namespace bayes;
 
+// shape of a unit before it is packed: its A-step items in processing order (build_units)
+struct UnitShape {
+    std::vector<int32_t> nnz;     // per item
+    std::vector<int32_t> blocks;  // per item: Philox blocks of a uniform item
+    int n_chain = 0;
+    double iters = 0;
+};
+
 struct bayes_gibbs_ctx {
     int device = 0, sm_count = 148;
+    std::vector<UnitShape> shape_cache;    // build_units: kept from the first build of an upload for the calibrated rebuild
+    std::vector<PackedUnit> packed_cache;  // idem, in unit formation order
+    std::vector<int> packed_h;             // slab height each cached unit was packed with
     cudaStream_t own_stream = nullptr, stream = nullptr;
     int host_threads = 0;
     bool uploaded = false, ran = false, downloaded = false;
@@ -124,6 +135,10 @@ struct bayes_gibbs_ctx {
     DevBuf<uint64_t> d_unit_clock;
 
     std::vector<Launch> launches;
+    std::vector<int64_t> unit_group;    // launch order -> index of the unit in formation order (stable across rebuilds)
+    std::vector<double> unit_model_us;  // time model's per-iteration estimate at the unit's shape, before calibration
+    int32_t calibration = -1;           // iterations of the calibration pass: -1 = automatic, 0 = off
+    bool calibrated = false;
     std::vector<double> unit_pred;  // time model's estimate per unit (seconds), launch order
     std::vector<double> unit_feat;  // 4 per unit: chain columns, uniform slabs, uniform blocks, uniform block-columns
     int32_t last_launches = 0;
@@ -213,7 +228,7 @@ int append_unit(bayes_gibbs_ctx *ctx, PackedUnit &U) {
 // others get a wide unit each.  Units are then ordered so that each launch is one (kernel, block size, matrix
 // placement) class with its most expensive units first: the hardware block scheduler hands blocks out in index order,
 // which makes this the largest-first queue of the reference (assembler.cpp:1886-1916).
-int build_units(bayes_gibbs_ctx *ctx) {
+int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
     ctx->h_units.n = ctx->h_val.n = ctx->h_efflen.n = ctx->h_tab_val.n = ctx->h_col.n = 0;
     ctx->h_slab.n = ctx->h_row_n.n = ctx->h_row_nnz.n = ctx->h_row_info.n = ctx->h_base.n = ctx->h_tab_row.n = 0;
     ctx->launches.clear();
@@ -250,15 +265,16 @@ int build_units(bayes_gibbs_ctx *ctx) {
 
     // ---- shape of every unit before it is packed: its A-step items in processing order (chain items, then uniform
     // items, pack.cpp) -> slab widths for any slab height
-    struct Shape {
-        std::vector<int32_t> nnz;     // per item
-        std::vector<int32_t> blocks;  // per item: Philox blocks of a uniform item
-        int n_chain = 0;
-        double iters = 0;
-    };
-    std::vector<Shape> shapes(n_units);
-    parallel_for(host_thread_count(ctx, n_units), n_units, [&](int64_t i) {
-        Shape &S = shapes[i];
+    // (a rebuild after the calibration pass forms the same units: their shapes and packed matrices are kept)
+    const bool reuse = group_scale && (int64_t)ctx->shape_cache.size() == n_units && (int64_t)ctx->packed_cache.size() == n_units;
+    std::vector<UnitShape> &shapes = ctx->shape_cache;
+    if (!reuse) {
+        shapes.assign(n_units, UnitShape());
+        ctx->packed_cache.clear();
+        ctx->packed_h.clear();
+    }
+    if (!reuse) parallel_for(host_thread_count(ctx, n_units), n_units, [&](int64_t i) {
+        UnitShape &S = shapes[i];
         std::vector<ItemShape> items;
         build_items(groups[i], &items, &S.n_chain);
         S.nnz.reserve(items.size());
@@ -277,12 +293,12 @@ int build_units(bayes_gibbs_ctx *ctx) {
     // a unit take slabs from a shared counter, heaviest first (greedy list scheduling).
     auto chain_us = [](int h) { return h >= 32 ? 1.3 : h >= 16 ? 1.15 : h >= 8 ? 0.95 : 0.9; };
     const double kEstepUs = 12.5, kUniformSlabUs = 0.8, kUniformBlockUs = 1.55, kUniformColumnUs = 0.16;
-    auto slab_layout = [](const Shape &S, int h, int *chain_slabs, int *n_slabs) {
+    auto slab_layout = [](const UnitShape &S, int h, int *chain_slabs, int *n_slabs) {
         const int n_items = (int)S.nnz.size();
         *chain_slabs = (S.n_chain + h - 1) / h;
         *n_slabs = *chain_slabs + (n_items - S.n_chain + h - 1) / h;
     };
-    auto iteration_us = [&](const Shape &S, int warps, int h) {
+    auto iteration_us = [&](const UnitShape &S, int warps, int h) {
         int chain_slabs, n_slabs;
         slab_layout(S, h, &chain_slabs, &n_slabs);
         const int n_items = (int)S.nnz.size();
@@ -303,9 +319,13 @@ int build_units(bayes_gibbs_ctx *ctx) {
         }
         return worst + kEstepUs;
     };
-    auto unit_time = [&](const Shape &S, int warps, int h) { return 1e-6 * S.iters * iteration_us(S, warps, h); };
+    // group_scale (calibrate_units): measured / modelled per-iteration time of the unit at its first shape
+    auto unit_time = [&](const UnitShape &S, int warps, int h) {
+        const double scale = group_scale ? (*group_scale)[&S - shapes.data()] : 1.0;
+        return 1e-6 * S.iters * iteration_us(S, warps, h) * scale;
+    };
     // totals the model is made of (exposed through bayes_gibbs_unit_stats for calibration)
-    auto unit_features = [&](const Shape &S, int h, double *f4) {
+    auto unit_features = [&](const UnitShape &S, int h, double *f4) {
         int chain_slabs, n_slabs;
         slab_layout(S, h, &chain_slabs, &n_slabs);
         const int n_items = (int)S.nnz.size();
@@ -322,7 +342,7 @@ int build_units(bayes_gibbs_ctx *ctx) {
             else { f4[1] += 1; f4[2] += blocks; f4[3] += (double)blocks * width; }
         }
     };
-    auto smem_estimate = [&](const Shape &S, int h) {
+    auto smem_estimate = [&](const UnitShape &S, int h) {
         int chain_slabs, n_slabs;
         slab_layout(S, h, &chain_slabs, &n_slabs);
         const int n_items = (int)S.nnz.size();
@@ -358,7 +378,7 @@ int build_units(bayes_gibbs_ctx *ctx) {
             // A unit's matrix sits in shared memory whatever its block size; the SM runs out of shared memory before it
             // runs out of warp slots when units of much more than 227 KB / 32 keep one warp each, so such units start with as
             // many warps as their footprint pays for (they are parked warps otherwise nobody could use).
-            const Shape &S = shapes[i];
+            const UnitShape &S = shapes[i];
             int chain_slabs, n_slabs;
             slab_layout(S, 32, &chain_slabs, &n_slabs);
             const double smem_est = smem_estimate(S, 32);
@@ -397,9 +417,12 @@ int build_units(bayes_gibbs_ctx *ctx) {
         }
     }
 
-    std::vector<PackedUnit> packed(n_units);
+    std::vector<PackedUnit> &packed = ctx->packed_cache;
+    packed.resize(n_units);
+    ctx->packed_h.resize(n_units, 0);
     parallel_for(host_thread_count(ctx, n_units), n_units, [&](int64_t i) {
-        pack_unit(groups[i], group_wide[i] != 0, unit_h[i], &packed[i]);
+        if (!reuse || ctx->packed_h[i] != unit_h[i]) pack_unit(groups[i], group_wide[i] != 0, unit_h[i], &packed[i]);
+        ctx->packed_h[i] = unit_h[i];
         packed[i].d.block = 32 * unit_warps[i];
         packed[i].cost = unit_time(shapes[i], unit_warps[i], unit_h[i]);  // estimated duration: the launch-order key
         unit_features(shapes[i], unit_h[i], packed[i].features);
@@ -432,9 +455,12 @@ int build_units(bayes_gibbs_ctx *ctx) {
     int rc;
     ctx->unit_pred.clear();
     ctx->unit_feat.clear();
+    ctx->unit_group.assign(order.begin(), order.end());
+    ctx->unit_model_us.clear();
     for (int64_t i = 0; i < n_units; i++) {
         if ((rc = append_unit(ctx, packed[order[i]]))) return rc;
         ctx->unit_pred.push_back(packed[order[i]].cost);
+        ctx->unit_model_us.push_back(iteration_us(shapes[order[i]], unit_warps[order[i]], unit_h[order[i]]));
         for (int k = 0; k < 4; k++) ctx->unit_feat.push_back(packed[order[i]].features[k]);
     }
     const UnitDev *units = ctx->h_units.p;
@@ -628,13 +654,15 @@ int bayes_gibbs_submit(bayes_gibbs_ctx *ctx, int32_t n_loci, const bayes_locus_d
     return BAYES_OK;
 }
 
+static int calibrate_units(bayes_gibbs_ctx *ctx, int32_t iters, std::vector<double> *group_scale);
+
 int bayes_gibbs_upload(bayes_gibbs_ctx *ctx) {
     if (!ctx) return BAYES_E_INVALID;
     int rc = use_device(ctx);
     if (rc) return rc;
     const double t0 = now_s();
-    if ((rc = build_units(ctx))) return rc;
-    const double t1 = now_s();
+    if ((rc = build_units(ctx, nullptr))) return rc;
+    double t1 = now_s();
     ctx->phase_s[1] = t1 - t0;
     if (ctx->trace_locus >= 0) {
         const size_t n = (size_t)ctx->trace_iters * ctx->trace_T;
@@ -651,22 +679,36 @@ int bayes_gibbs_upload(bayes_gibbs_ctx *ctx) {
     if ((rc = ctx->h_occ.resize(n_out)) || (rc = ctx->h_counts.resize(n_out)) || (rc = ctx->h_mean.resize(n_out)) ||
         (rc = ctx->h_m2.resize(n_out)))
         return rc;
+    ctx->phase_s[2] = now_s() - t1;
+    // calibration pass (see calibrate_units): worth it once the batch is several times what the GPU holds at once
+    ctx->calibrated = false;
+    int32_t calib = ctx->calibration;
+    if (const char *e = getenv("BAYES_CALIB_ITERS")) calib = atoi(e);  // experiment knob
+    if (calib < 0) calib = (int64_t)ctx->h_units.n >= 8 * (int64_t)ctx->sm_count ? 256 : 0;
+    if (calib > 0 && ctx->h_units.n > 0 && ctx->trace_locus < 0) {
+        t1 = now_s();
+        std::vector<double> scale;
+        if ((rc = calibrate_units(ctx, calib, &scale))) return rc;
+        const double t2 = now_s();
+        if ((rc = build_units(ctx, &scale))) return rc;
+        const double t3 = now_s();
+        if ((rc = upload_units(ctx))) return rc;
+        ctx->phase_s[1] += t3 - t2;
+        ctx->phase_s[2] += (t2 - t1) + (now_s() - t3);
+        ctx->calibrated = true;
+    }
+    std::vector<UnitShape>().swap(ctx->shape_cache);
+    std::vector<PackedUnit>().swap(ctx->packed_cache);
     ctx->uploaded = true;
     ctx->ran = ctx->downloaded = false;
-    ctx->phase_s[2] = now_s() - t1;
     return BAYES_OK;
 }
 
-int bayes_gibbs_run(bayes_gibbs_ctx *ctx) {
-    if (!ctx) return BAYES_E_INVALID;
-    if (!ctx->uploaded) {
-        set_error("bayes_gibbs_run: call bayes_gibbs_upload first");
-        return BAYES_E_STATE;
-    }
-    int rc = use_device(ctx);
-    if (rc) return rc;
-    const double t0 = now_s();
-    const KernelArgs args = kernel_args(ctx);
+// Issue every class launch of the batch on its own stream, longest units first (iter_cap > 0: calibration pass).
+static int issue_launches(bayes_gibbs_ctx *ctx, int32_t iter_cap) {
+    int rc;
+    KernelArgs args = kernel_args(ctx);
+    args.iter_cap = iter_cap;
     ctx->last_launches = 0;
     const size_t n_l = ctx->launches.size();
     if (!ctx->fork_ev) CU(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
@@ -715,6 +757,56 @@ int bayes_gibbs_run(bayes_gibbs_ctx *ctx) {
         }
         ctx->last_launches++;
     }
+    return BAYES_OK;
+}
+
+// Calibration pass.  The time model only sees the SHAPE of a unit; what a conditional binomial or a CDF walk costs also
+// depends on the fragment counts and on how sparse the expression vector gets, which leaves +-30 % per unit -- enough
+// to start a long unit late and to leave the GPU half empty for the last quarter of the batch.  So every unit first runs
+// its first `iters` iterations (about 1 % of a chain) with the GPU as full as it will be, the second half is timed on the
+// device, and the units are then sized, widened and ordered again with measured / modelled as a per-unit correction.
+// Measured on config 2 (tools/calib_ab.py, profiles/README.md): measured / predicted unit duration 0.52-1.07 (5-95 %)
+// without, 0.73-1.27 with; step 1.89 s -> 1.78 s; 256 or 1024 iterations make no difference.  Tried on top and rejected:
+// widening the units that start last (they hold more warps but do not finish sooner), 32 hardware queues
+// (CUDA_DEVICE_MAX_CONNECTIONS: no change), 5.8-12 KB of shared memory per warp instead of 8 (within +-2 %).
+static int calibrate_units(bayes_gibbs_ctx *ctx, int32_t iters, std::vector<double> *group_scale) {
+    int rc;
+    const int64_t n = (int64_t)ctx->h_units.n;
+    if ((rc = issue_launches(ctx, iters))) return rc;
+    std::vector<uint64_t> clock(3 * (size_t)n);
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(clock.data(), ctx->d_unit_clock.p, clock.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    group_scale->assign((size_t)n, 1.0);
+    for (int64_t i = 0; i < n; i++) {
+        const UnitDev &u = ctx->h_units.p[i];
+        const int total = std::min(iters, u.burn + u.samples);
+        const int timed = total - (total >> 1);
+        const double us = 1e-3 * (double)(clock[3 * i + 1] - clock[3 * i]) / std::max(1, timed);
+        const double scale = us / std::max(1e-3, ctx->unit_model_us[i]);
+        (*group_scale)[ctx->unit_group[i]] = std::min(4.0, std::max(0.25, scale));
+    }
+    return BAYES_OK;
+}
+
+int bayes_gibbs_set_calibration(bayes_gibbs_ctx *ctx, int32_t iterations) {
+    if (!ctx || iterations < -1) {
+        set_error("bayes_gibbs_set_calibration: bad arguments");
+        return BAYES_E_INVALID;
+    }
+    ctx->calibration = iterations;
+    return BAYES_OK;
+}
+
+int bayes_gibbs_run(bayes_gibbs_ctx *ctx) {
+    if (!ctx) return BAYES_E_INVALID;
+    if (!ctx->uploaded) {
+        set_error("bayes_gibbs_run: call bayes_gibbs_upload first");
+        return BAYES_E_STATE;
+    }
+    int rc = use_device(ctx);
+    if (rc) return rc;
+    const double t0 = now_s();
+    if ((rc = issue_launches(ctx, 0))) return rc;
     ctx->ran = true;
     ctx->downloaded = false;
     ctx->phase_s[3] = now_s() - t0;
@@ -855,7 +947,7 @@ int64_t bayes_gibbs_unit_stats(bayes_gibbs_ctx *ctx, int32_t *shape8, uint64_t *
             const UnitDev &u = ctx->h_units.p[i];
             int32_t *o = shape8 + 8 * i;
             o[0] = u.wide; o[1] = u.block; o[2] = u.n_slots; o[3] = u.n_slabs; o[4] = u.n_cells; o[5] = u.burn + u.samples; o[6] = u.T[0];
-            o[7] = u.mat_smem | (u.slab_h << 8);
+            o[7] = u.mat_smem | (u.slab_h << 8) | (((u.smem_bytes + 1023) >> 10) << 16);  // + shared memory of the unit, KB
         }
     if (predicted_s)
         for (int64_t i = 0; i < n; i++) {

@@ -500,15 +500,21 @@ __global__ void __maxnreg__(BAYES_MAXNREG) gibbs_bundle_kernel(const __grid_cons
 
     const bool tracing = A.trace_unit == ui;
     const bool my_trace = tracing && threadIdx.x < 32 && g == A.trace_slot && L.valid;
-    const int total = U.burn + U.samples, burn = U.burn;
+    const int burn = U.burn;
+    const int total = A.iter_cap > 0 && A.iter_cap < U.burn + U.samples ? A.iter_cap : U.burn + U.samples;
+    const int stamp_at = A.iter_cap > 0 ? total >> 1 : -2;  // calibration pass: time the second half only
 
     // it == -1 is initAssignment (gibbsSampler.cpp:90): the same A-step code on theta == 1, no E-step before it
     for (int it = -1; it < total; it++) {
-        if (threadIdx.x == 0) *next_slab = 0;
+        if (threadIdx.x == 0) {
+            *next_slab = 0;
+            if (it == stamp_at) A.unit_clock[3 * ui] = global_ns();
+        }
         if (it >= 0 && threadIdx.x < 32) {
             if (my_trace && it == 0) A.tr_init[L.t] = counts[lane];
             if (my_trace && it > 0 && it - 1 < A.trace_iters) A.tr_counts[(size_t)(it - 1) * L.Tg + L.t] = counts[lane];
-            const int b = bundle_e_step(L, theta, counts, tab_val, (uint32_t)it, it >= burn);
+            // (the timed half of a calibration pass runs as sampling iterations: nine tenths of a chain are)
+            const int b = bundle_e_step(L, theta, counts, tab_val, (uint32_t)it, it >= burn || (stamp_at >= 0 && it >= stamp_at));
             if (my_trace && it < A.trace_iters) {
                 A.tr_theta[(size_t)it * L.Tg + L.t] = theta[lane];
                 if (L.t == 0) A.tr_b[it] = b;
@@ -587,18 +593,23 @@ __global__ void __maxnreg__(BAYES_MAXNREG) gibbs_wide_kernel(const __grid_consta
     const MatView M = stage_matrix<MAT_SMEM>(A, U, lay, smem);
 
     const bool tracing = A.trace_unit == ui;
-    const int total = U.burn + U.samples, burn = U.burn;
+    const int burn = U.burn;
+    const int total = A.iter_cap > 0 && A.iter_cap < U.burn + U.samples ? A.iter_cap : U.burn + U.samples;
+    const int stamp_at = A.iter_cap > 0 ? total >> 1 : -2;  // calibration pass: time the second half only
 
     // it == -1 is initAssignment (gibbsSampler.cpp:90): the same A-step code on theta == 1, no E-step before it
     for (int it = -1; it < total; it++) {
-        if (threadIdx.x == 0) *next_slab = 0;
+        if (threadIdx.x == 0) {
+            *next_slab = 0;
+            if (it == stamp_at) A.unit_clock[3 * ui] = global_ns();
+        }
         if (it >= 0 && threadIdx.x < 32) {
             const bool tr = tracing && it < A.trace_iters;
             if (tracing && it == 0)
                 for (int t = threadIdx.x; t < T; t += 32) A.tr_init[t] = E.counts[t];
             if (tracing && it > 0 && it - 1 < A.trace_iters)
                 for (int t = threadIdx.x; t < T; t += 32) A.tr_counts[(size_t)(it - 1) * T + t] = E.counts[t];
-            const int b = wide_e_step(E, key, (uint32_t)it, it >= burn, tr ? A.tr_theta + (size_t)it * T : nullptr);
+            const int b = wide_e_step(E, key, (uint32_t)it, it >= burn || (stamp_at >= 0 && it >= stamp_at), tr ? A.tr_theta + (size_t)it * T : nullptr);
             if (tr && threadIdx.x == 0) A.tr_b[it] = b;
         }
         __syncthreads();

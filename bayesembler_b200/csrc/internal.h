@@ -79,6 +79,9 @@ struct KernelArgs {
     double *out_m2;
     int32_t *out_counts;
     uint64_t *unit_clock;  // per unit: globaltimer ns at block start, at block end, SM id (3 words)
+    // calibration pass (capi.cu, calibrate_units): run only the first iter_cap iterations of every chain and put the
+    // time stamp of iteration iter_cap / 2 in the "start" word, so that end - start times the second half; 0 = off
+    int32_t iter_cap;
     // replay trace of one slot (trace_unit < 0: off)
     int64_t trace_unit;
     int32_t trace_slot;

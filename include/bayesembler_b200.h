@@ -119,6 +119,10 @@ int64_t bayes_gibbs_unit_stats(bayes_gibbs_ctx *ctx, int32_t *shape8, uint64_t *
 /* Wall-clock seconds of the host phases of the last batch: {prepare (fold rows, read cover, CDF tables), unit formation
  * and packing, H2D enqueue, launch enqueue, D2H enqueue, final synchronise}. */
 int bayes_gibbs_phase_seconds(bayes_gibbs_ctx *ctx, double *out6);
+/* Calibration pass of bayes_gibbs_upload: every unit runs its first `iterations` Gibbs iterations once, timed on the device,
+ * and the batch is then sized and ordered with the measured per-iteration times (results do not depend on it: draws are
+ * keyed by site).  -1 = automatic (256 iterations when the batch is several times what the GPU holds at once), 0 = off. */
+int bayes_gibbs_set_calibration(bayes_gibbs_ctx *ctx, int32_t iterations);
 /* kernels launched by the last bayes_gibbs_run() */
 int32_t bayes_gibbs_last_launches(bayes_gibbs_ctx *ctx);
 

@@ -57,6 +57,19 @@ def test_full_size_deterministic(full_run, lib):
         assert np.array_equal(res[k], again[k]), k
 
 
+def test_full_size_schedule_independent(full_run, lib):
+    """The default run above went through the calibration pass (bayes_gibbs_set_calibration: automatic for a batch of this
+    size); without it the units are sized and ordered differently and every result is the same."""
+    batch, descs, ctx, res = full_run
+    other = lib.GibbsContext(0)
+    other.set_calibration(0)
+    other.run_batch(descs)
+    plain = other.fetch_all()
+    other.close()
+    for k in res:
+        assert np.array_equal(res[k], plain[k]), k
+
+
 def test_full_size_spot_check_against_oracle(full_run, lib, oracle):
     batch, descs, ctx, res = full_run
     rng = np.random.default_rng(11)

@@ -125,7 +125,10 @@ def test_full_chain_replay(lib, oracle, T, R, mc, gamma):
     assert np.array_equal(g["final_counts"], o["counts_trace"][-1])
 
 
-def test_batch_mixed_loci_and_chains(lib, oracle):
+@pytest.mark.parametrize("calibration", [0, 40, 100000])
+def test_batch_mixed_loci_and_chains(lib, oracle, calibration):
+    """calibration: the pass of bayes_gibbs_upload that times the first iterations of every unit and re-forms the batch
+    (off / shorter than every chain / longer than every chain) must not change a single draw."""
     rng = np.random.default_rng(2024)
     shapes = [(1, 4, 30), (5, 50, 100), (2, 3, 10), (20, 90, 40), (1, 1, 5), (9, 33, 25), (64, 150, 60), (3, 1000, 30)]
     loci = [random_locus(rng, T, R, max_count=mc) for (T, R, mc) in shapes]
@@ -134,6 +137,7 @@ def test_batch_mixed_loci_and_chains(lib, oracle):
     samples = [10 * b for b in burn]
     chains = [1, 3, 2, 1, 2, 4, 1, 2]
     ctx = lib.GibbsContext(0)
+    ctx.set_calibration(calibration)
     descs = lib.make_desc_array(loci, burn, samples, seeds, n_chains=chains)
     ctx.run_batch(descs)
     for i, loc in enumerate(loci):

@@ -15,6 +15,6 @@ t0 = time.perf_counter(); ctx.run(); ctx.sync(); dt = time.perf_counter() - t0
 shape, clock = ctx.unit_stats()
 dur = (clock[:, 1] - clock[:, 0]) * 1e-6
 print("T=%d R=%d units=%d launches=%d shape0=%s h=%d wall %.1f ms, unit dur mean %.1f max %.1f ms, Miter/s %.1f" % (
-    batch.T[0], batch.R[0], len(shape), ctx.last_launches(), shape[0, :7].tolist(), shape[0, 7] >> 8, dt * 1e3, dur.mean(), dur.max(), iters * chains / dt / 1e6))
+    batch.T[0], batch.R[0], len(shape), ctx.last_launches(), shape[0, :7].tolist(), (shape[0, 7] >> 8) & 255, dt * 1e3, dur.mean(), dur.max(), iters * chains / dt / 1e6))
 t0 = (clock[:, 0] - clock[:, 0].min()) * 1e-6
 print("start times: max %.1f ms; resident est %.0f units" % (t0.max(), dur.sum() / (dt * 1e3)))

@@ -41,7 +41,7 @@ def main():
     wall2_ms = 1e3 * (time.perf_counter() - t0) / 2
     print("wall clock of one run() + sync: %.1f ms; two runs back to back: %.1f ms each" % (wall_ms, wall2_ms))
     shape, clock = ctx.unit_stats()
-    slab_h = shape[:, 7] >> 8
+    slab_h = (shape[:, 7] >> 8) & 255
     shape[:, 7] &= 1
     st = batch.stats(n_chains=args.chains)
     t0 = clock[:, 0].min()
