@@ -13,6 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbayesembler_b200.so")
+CLI = os.path.join(HERE, "bayesembler_b200_cli")
+CLI_SOURCES = [os.path.join(HERE, "host", f) for f in ("main.cpp", "assembler.hpp", "bayesembler_b200.hpp")]
 SOURCES = ["capi.cu", "gibbs_kernel.cu", "host_steps.cpp", "pack.cpp", "likelihood.cpp", "allpaths.cpp"]
 HEADERS = ["internal.h", "layout.h", "rng.cuh", os.path.join("..", "..", "include", "bayesembler_b200.h")]
 
@@ -56,6 +58,22 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_cli(force=False):
+    """The command line of the host driver (host/main.cpp), linked against the library next to it."""
+    build()
+    deps = CLI_SOURCES + [LIB, os.path.join(HERE, "..", "include", "bayesembler_b200.h")]
+    if not force and os.path.exists(CLI) and all(os.path.getmtime(d) <= os.path.getmtime(CLI) for d in deps):
+        return CLI
+    cmd = ["/usr/bin/g++", "-O2", "-std=gnu++17", "-Wall", "-Werror", "-o", CLI, CLI_SOURCES[0], "-L" + HERE, "-lbayesembler_b200",
+           "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout)
+        raise RuntimeError("g++ failed building %s" % CLI)
+    return CLI
+
+
 if __name__ == "__main__":
     build(force=True, verbose=True)
+    build_cli(force=True)
     print(LIB)

@@ -135,3 +135,24 @@ class SynthBatch(object):
             # algorithmic bytes, f64 values / u32 columns: 12 nnz + 8 R + 24 T per iteration, + 40 T when sampling
             algo_bytes=float((iters * (12 * nnz + 8 * R + 24 * T) + samp * 40 * T)[multi].sum()),
             rows=int(R.sum()), cells=int(nnz.sum()), candidates=int(T.sum()))
+
+
+def write_graph_file(path, graphs, unique_pairs, mapped_pairs=None):
+    """The input of the host driver (host/assembler.hpp, bayesembler_b200_cli --graph-file): what the reference's grapherCallback
+    queues per graph.  graphs = [(dot_strings, fragments, single_path)], fragments = an object with the fragment arrays of
+    bayes_raw_locus (read_pos, cigar_ptr, cigar_op, cigar_len, frag_prob)."""
+    with open(path, "w") as f:
+        f.write("# bayesembler_b200 graph file\n")
+        f.write("fragments %d %d\n" % (unique_pairs, unique_pairs if mapped_pairs is None else mapped_pairs))
+        for dots, fr, single in graphs:
+            n_frag = 0 if fr is None else len(fr.frag_prob)
+            f.write("graph %d %d %d\n" % (len(dots), n_frag, int(bool(single))))
+            for d in dots:
+                assert d.endswith("}\n")
+                f.write(d)
+            for i in range(n_frag):
+                mates = []
+                for m in (2 * i, 2 * i + 1):
+                    a, b = fr.cigar_ptr[m], fr.cigar_ptr[m + 1]
+                    mates.append("%d %s" % (fr.read_pos[m], "".join("%d%s" % (fr.cigar_len[k], chr(fr.cigar_op[k])) for k in range(a, b))))
+                f.write("%s %s %.17g\n" % (mates[0], mates[1], fr.frag_prob[i]))

@@ -37,3 +37,25 @@ def lib():
     _build.build()
     bb.load_library()
     return bb
+
+
+@pytest.fixture(scope="session")
+def facade(lib):
+    """tests/cpp/facade_driver.cpp: C-callable test driver around the C++ host facade, built with g++ against the library."""
+    import ctypes as C
+    import subprocess
+    from oracle import oracle_py
+    SRC = os.path.join(ROOT, "tests", "cpp", "facade_driver.cpp")
+    HPP = os.path.join(ROOT, "bayesembler_b200", "host", "bayesembler_b200.hpp")
+    OUT = os.path.join(ROOT, "tests", "cpp", "libfacade_test.so")
+    libdir = os.path.join(ROOT, "bayesembler_b200")
+    newest = max(os.path.getmtime(p) for p in (SRC, HPP, os.path.join(ROOT, "include", "bayesembler_b200.h")))
+    if not os.path.exists(OUT) or os.path.getmtime(OUT) < newest:
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=gnu++17", "-fPIC", "-shared", "-Wall", "-Werror", "-o", OUT, SRC,
+                               "-L" + libdir, "-lbayesembler_b200", "-Wl,-rpath," + libdir])
+    lib.load_library()
+    L = C.CDLL(OUT)
+    L.facade_gtf.restype = C.c_int
+    L.facade_gtf.argtypes = oracle_py.GTF_ARGTYPES
+    L.facade_gtf_from_accumulators.restype = C.c_int
+    return L

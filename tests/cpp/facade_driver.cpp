@@ -266,4 +266,51 @@ int facade_all_paths(const char *dot, int no_pre_mrna, int max_candidate_number,
     return (int)cands.size();
 }
 
+// GibbsOutput with GIVEN accumulators -> getTopMarginals + writeEnsembleGtf (mode 0) / writeCandidateGtf (mode 1), candidates flat
+// as in bayes_path_set_export with their names '\n'-joined.  Returns the text length, -1 when cap is too small, -5 / -7 for the
+// soft codes of assembler.cpp:1609-1625 (mode 0 only).
+int facade_gtf_from_accumulators(int T, int samples, const int *occ, const double *mean, const double *m2, int n_cand, const int *exon_ptr,
+                                 const int *starts, const int *ends, const int *premrna, const char *names, const char *graph_name,
+                                 const char *reference, const char *strand, const int *old_idx, const double *efflen, int total_num_fragments,
+                                 double count_threshold, double marginal_threshold, int mode, char *out, int cap) {
+    GibbsOutput go(samples, T);
+    for (int t = 0; t < T; t++) {
+        go.marginal_occurence[t] = occ[t];
+        go.marginal_mean_cumulant[t] = mean[t];
+        go.marginal_var_cumulant[t] = m2[t];
+    }
+    std::vector<Candidate> cands(n_cand);
+    std::stringstream nm(names);
+    for (int i = 0; i < n_cand; i++) {
+        cands[i].idx = i;
+        std::getline(nm, cands[i].name);
+        cands[i].graph_name = graph_name;
+        cands[i].isPreMrna = premrna[i] != 0;
+        cands[i].length = 0;
+        for (int k = exon_ptr[i]; k < exon_ptr[i + 1]; k++) {
+            Vertex v;
+            v.reference = reference;
+            v.strand = strand;
+            v.start = starts[k];
+            v.end = ends[k];
+            cands[i].vertices.push_back(v);
+            cands[i].length += ends[k] - starts[k] + 1;
+        }
+    }
+    IdxMap m;
+    for (int t = 0; t < T; t++) m[t] = std::make_pair(old_idx[t], efflen[t]);
+    std::string text;
+    if (mode == 0) {
+        Ensemble top = go.getTopMarginals(marginal_threshold);
+        if (top.indices.empty()) return -5;
+        text = go.writeEnsembleGtf(top, cands, m, total_num_fragments, count_threshold);
+        if (text.empty()) return -7;
+    } else {
+        text = go.writeCandidateGtf(cands, m, total_num_fragments);
+    }
+    if ((int)text.size() + 1 > cap) return -1;
+    memcpy(out, text.c_str(), text.size() + 1);
+    return (int)text.size();
+}
+
 }  // extern "C"

@@ -24,20 +24,6 @@ GTF_SHAPES = [dict(T=7, samples=40, n_cand=9), dict(T=3, samples=25, n_cand=3), 
               dict(T=1, samples=10, n_cand=2)]
 
 
-@pytest.fixture(scope="module")
-def facade(lib):
-    libdir = os.path.join(ROOT, "bayesembler_b200")
-    newest = max(os.path.getmtime(p) for p in (SRC, HPP, os.path.join(ROOT, "include", "bayesembler_b200.h")))
-    if not os.path.exists(OUT) or os.path.getmtime(OUT) < newest:
-        subprocess.check_call(["/usr/bin/g++", "-O2", "-std=gnu++17", "-fPIC", "-shared", "-Wall", "-Werror", "-o", OUT, SRC,
-                               "-L" + libdir, "-lbayesembler_b200", "-Wl,-rpath," + libdir])
-    lib.load_library()
-    L = C.CDLL(OUT)
-    L.facade_gtf.restype = C.c_int
-    L.facade_gtf.argtypes = oracle_py.GTF_ARGTYPES
-    return L
-
-
 @pytest.mark.parametrize("gi", range(4))
 def test_gtf_text_matches_reference_golden(facade, gi):
     g = np.load(GOLD)
