@@ -65,7 +65,7 @@ def build_cli(force=False):
     if not force and os.path.exists(CLI) and all(os.path.getmtime(d) <= os.path.getmtime(CLI) for d in deps):
         return CLI
     cmd = ["/usr/bin/g++", "-O2", "-std=gnu++17", "-Wall", "-Werror", "-o", CLI, CLI_SOURCES[0], "-L" + HERE, "-lbayesembler_b200",
-           "-Wl,-rpath,$ORIGIN"]
+           "-pthread", "-Wl,-rpath,$ORIGIN"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout)

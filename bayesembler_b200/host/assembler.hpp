@@ -33,6 +33,7 @@
 #include <iostream>
 #include <list>
 #include <memory>
+#include <thread>
 
 #include "bayesembler_b200.hpp"
 
@@ -63,6 +64,7 @@ struct OptionsContainer {  // utils.h:140-170
     unsigned gibbs_base_iterations = 1000;
     unsigned gibbs_scale_iterations = 60;
     int device = 0;  // CUDA device the sampler batch runs on
+    std::string devices;  // "0,1,2,3": shard the graphs over several GPUs by cost (overrides device)
 };
 
 // ---- main.cpp:52-154 ---------------------------------------------------------------------------------------------------
@@ -98,7 +100,9 @@ inline void printHelp(std::ostream &out, bool advanced) {
            "  --gibbs-iteration-scaling arg (=60)             scaling factor used to calculate number of Gibbs iterations (burn-in &\n"
            "                                                  sample-size) using: burn-in = 1000 + <gibbs-iteration-scaling> *\n"
            "                                                  number_of_candidates, sample-size = 10 * burn-in\n"
-           "  --device arg (=0)                               CUDA device of the sampler batch\n";
+           "  --device arg (=0)                               CUDA device of the sampler batch\n"
+           "  --devices arg                                   comma-separated CUDA devices: the graphs are sharded over them by cost\n"
+           "                                                  (greedy, largest first), one host thread and one batch per device\n";
 }
 
 // Returns 0 = run, 1 = help was printed (the reference returns 1 too, main.cpp:119-127), -1 = error (message on err).
@@ -119,7 +123,8 @@ inline int parseCommandLine(int argc, char *const argv[], OptionsContainer *opt,
                           {"output-mode", 0, 1, &o.output_mode}, {"library-size", 0, 2, &o.total_num_fragments},
                           {"keep-temp-files", 0, 4, &o.keep_temp_files}, {"max-candidate-number", 0, 2, &o.max_candidate_number},
                           {"dirichlet-parameter", 0, 3, &o.gamma}, {"frag-mean", 0, 3, &o.frag_mean}, {"frag-sd", 0, 3, &o.frag_sd},
-                          {"gibbs-iteration-scaling", 0, 5, &o.gibbs_scale_iterations}, {"device", 0, 2, &o.device}};
+                          {"gibbs-iteration-scaling", 0, 5, &o.gibbs_scale_iterations}, {"device", 0, 2, &o.device},
+                          {"devices", 0, 1, &o.devices}};
     const int n_specs = (int)(sizeof(specs) / sizeof(specs[0]));
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
@@ -323,10 +328,43 @@ class Assembler {
         }
         // ---- every sampler of the run as one GPU batch (gibbsSampler.cpp:55-148 for all graphs at once)
         if (n_samplers > 0) {
-            GibbsBatch batch(options_variables.device);
+            // graphs are independent (assembler.cpp:1441-1445): with several devices they are sharded by cost, largest first to
+            // the lightest device (bayes_partition_lpt -- the reference's largest-first queue, :1886-1916, turned into shards);
+            // one host thread and one batch per device, no exchange between them
+            std::vector<int> devices = deviceList();
+            std::vector<int> idx;
+            std::vector<double> cost;
             for (int g = 0; g < graph_number; g++)
-                if (prepared[g].sampler) batch.add(*prepared[g].sampler, prepared[g].gibbs_output.get(), prepared[g].burn_in, prepared[g].samples);
-            batch.run();
+                if (prepared[g].sampler) {
+                    bayes_locus_desc d = prepared[g].sampler->desc(prepared[g].burn_in, prepared[g].samples);
+                    idx.push_back(g);
+                    cost.push_back(bayes_locus_cost(&d));
+                }
+            std::vector<int32_t> part(idx.size(), 0);
+            check(bayes_partition_lpt((int64_t)idx.size(), cost.data(), (int32_t)devices.size(), part.data()), "bayes_partition_lpt");
+            std::vector<std::string> errors(devices.size());
+            std::vector<std::thread> workers;
+            for (size_t p = 0; p < devices.size(); p++)
+                workers.emplace_back([&, p]() {
+                    try {
+                        size_t mine = 0;
+                        for (size_t k = 0; k < idx.size(); k++) mine += part[k] == (int32_t)p;
+                        if (mine == 0) return;
+                        GibbsBatch batch(devices[p]);
+                        for (size_t k = 0; k < idx.size(); k++)
+                            if (part[k] == (int32_t)p) {
+                                Prepared &P = prepared[idx[k]];
+                                batch.add(*P.sampler, P.gibbs_output.get(), P.burn_in, P.samples);
+                            }
+                        batch.run();
+                    } catch (std::exception &e) {
+                        errors[p] = e.what();
+                    }
+                });
+            for (size_t p = 0; p < workers.size(); p++) workers[p].join();
+            for (size_t p = 0; p < errors.size(); p++)
+                if (!errors[p].empty()) throw std::runtime_error("device " + std::to_string(devices[p]) + ": " + errors[p]);
+            if (devices.size() > 1) cout_ << n_samplers << " sampler(s) sharded over " << devices.size() << " device(s)" << std::endl;
         }
         // ---- bayesemblerCallback, after the sampler (:1604-1631), and outputCallback (:1746-1839)
         std::ofstream ensemble_file((options_variables.output_prefix + "assembly.gtf").c_str());
@@ -491,6 +529,16 @@ class Assembler {
     }
 
    private:
+    std::vector<int> deviceList() const {
+        std::vector<int> out;
+        std::stringstream ss(options_variables.devices);
+        std::string tok;
+        while (std::getline(ss, tok, ','))
+            if (!tok.empty()) out.push_back(atoi(tok.c_str()));
+        if (out.empty()) out.push_back(options_variables.device);
+        return out;
+    }
+
     OptionsContainer options_variables;
 };
 

@@ -253,3 +253,21 @@ def test_cli_run_matches_the_chained_oracles(cli, lib, oracle, facade, tmp_path)
     med, mad = f1_py.OracleF1().estimate_fragment_model(hist)
     want_ens2, _, _ = _expected(lib, oracle, facade, single_graph, n_pairs, 11, med, 1.4826 * mad)
     assert open(prefix + "est_assembly.gtf").read() == want_ens2
+
+
+@pytest.mark.gpu
+def test_cli_devices_shards_give_identical_files(cli, tmp_path):
+    """--devices 0,1: graphs sharded over the GPUs by cost (bayes_partition_lpt), one batch per device; the files do not change."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    path, graphs, n_pairs = _make_run(tmp_path)
+    out = {}
+    for tag, extra in (("one", ("--device", "0")), ("two", ("--devices", "0,1"))):
+        prefix = os.path.join(str(tmp_path), tag + "_")
+        rc, text, err = run(cli, "-g", path, "-o", prefix, "--seed", "4", "--frag-mean", "200", "--frag-sd", "20", "--output-mode", "full", *extra)
+        assert rc == 0, err
+        out[tag] = [open(prefix + f).read() for f in ("assembly.gtf", "candidates.gtf", "graph_logs.txt")]
+        if tag == "two":
+            assert "sharded over 2 device(s)" in text
+    assert out["one"] == out["two"] and len(out["one"][0]) > 0
