@@ -40,3 +40,11 @@ ncu --set full --clock-control none --import-source on -k regex:gibbs_ -c 3 -f -
 echo "ncu full rc=$?"
 # ... and the saturated regime: 4096 chains of one mid-size locus = ONE launch class that fills every SM
 bash tools/ncu_bulk.sh ${TAG}_bulk 1220 4096 1100
+
+# the other configurations at shortened chains (rates only; bench.py measures configs[1])
+python tools/config_rate.py --config 3 --loci 444 --burn 20 --samples 200 > $OUT/${TAG}_configs.txt 2>&1
+python tools/config_rate.py --config 4 --loci 40000 --burn 100 --samples 1000 >> $OUT/${TAG}_configs.txt 2>&1
+python tools/config_rate.py --config 5 --loci 200 --chains 64 --burn 100 --samples 1000 >> $OUT/${TAG}_configs.txt 2>&1
+python tools/config_rate.py --config 1 --loci 200 --burn 100 --samples 1000 >> $OUT/${TAG}_configs.txt 2>&1
+cat $OUT/${TAG}_configs.txt
+python tools/schedule_report.py > $OUT/${TAG}_sched.txt 2>&1
