@@ -122,7 +122,7 @@ struct bayes_gibbs_ctx {
     PinBuf<double> h_val, h_efflen, h_tab_val;
     PinBuf<uint16_t> h_col;
     PinBuf<int32_t> h_slab, h_row_n, h_row_nnz, h_base, h_tab_row;
-    PinBuf<uint32_t> h_row_info;
+    PinBuf<uint32_t> h_row_info, h_row_mask;
     // results (pinned)
     PinBuf<int32_t> h_occ, h_counts;
     PinBuf<double> h_mean, h_m2;
@@ -131,7 +131,7 @@ struct bayes_gibbs_ctx {
     DevBuf<double> d_val, d_efflen, d_tab_val, d_mean, d_m2, d_tr_theta;
     DevBuf<uint16_t> d_col;
     DevBuf<int32_t> d_slab, d_row_n, d_row_nnz, d_base, d_tab_row, d_occ, d_counts, d_tr_counts, d_tr_b, d_tr_init;
-    DevBuf<uint32_t> d_row_info;
+    DevBuf<uint32_t> d_row_info, d_row_mask;
     DevBuf<uint64_t> d_unit_clock;
 
     std::vector<Launch> launches;
@@ -212,8 +212,9 @@ int append_unit(bayes_gibbs_ctx *ctx, PackedUnit &U) {
     U.d.lane_off = (int64_t)ctx->h_efflen.n;
     U.d.tab_off = (int64_t)ctx->h_tab_val.n;
     U.d.tabrow_off = (int64_t)ctx->h_tab_row.n;
+    U.d.mask_off = (int64_t)ctx->h_row_mask.n;
     if ((rc = append(ctx->h_slab, U.slab_cell_off)) || (rc = append(ctx->h_val, U.val)) || (rc = append(ctx->h_col, U.col)) ||
-        (rc = append(ctx->h_row_n, U.row_n)) || (rc = append(ctx->h_row_nnz, U.row_nnz)) || (rc = append(ctx->h_row_info, U.row_info)) ||
+        (rc = append(ctx->h_row_n, U.row_n)) || (rc = append(ctx->h_row_nnz, U.row_nnz)) || (rc = append(ctx->h_row_info, U.row_info)) || (rc = append(ctx->h_row_mask, U.row_mask)) ||
         (rc = append(ctx->h_efflen, U.efflen)) || (rc = append(ctx->h_base, U.base_counts)) ||
         (rc = append(ctx->h_tab_val, U.tab_val)) || (rc = append(ctx->h_tab_row, U.tab_row)))
         return rc;
@@ -230,7 +231,7 @@ int append_unit(bayes_gibbs_ctx *ctx, PackedUnit &U) {
 // which makes this the largest-first queue of the reference (assembler.cpp:1886-1916).
 int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
     ctx->h_units.n = ctx->h_val.n = ctx->h_efflen.n = ctx->h_tab_val.n = ctx->h_col.n = 0;
-    ctx->h_slab.n = ctx->h_row_n.n = ctx->h_row_nnz.n = ctx->h_row_info.n = ctx->h_base.n = ctx->h_tab_row.n = 0;
+    ctx->h_slab.n = ctx->h_row_n.n = ctx->h_row_nnz.n = ctx->h_row_info.n = ctx->h_row_mask.n = ctx->h_base.n = ctx->h_tab_row.n = 0;
     ctx->launches.clear();
     ctx->trace_unit = -1;
 
@@ -414,6 +415,20 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         for (int64_t i = 0; i < n_units; i++) {
             unit_warps[i] = fw ? std::max(1, std::min(atoi(fw), kMaxBlock / 32)) : ladder[step[i]][0];
             unit_h[i] = fh ? atoi(fh) : ladder[step[i]][1];
+            // A locus with hundreds of candidates (config-3 class) is one long dependent chain of iterations that each walk
+            // a thousand rows: all 16 warps, and the tallest slabs that still give every warp one -- its A-step is a scan of
+            // the rows' candidate masks (gibbs_kernel.cu, assign_rows_wide), which all lanes of a slab do in lock step, so
+            // short slabs only idle lanes (measured on the largest config-3 locus: 4.4 of 32 lanes active at h = 8).
+            if (group_wide[i] && groups[i][0].locus->T > 128 && !fw && !fh) {
+                int h = 32, chain_slabs = 0, n_slabs = 0;
+                for (; h > 8; h /= 2) {
+                    slab_layout(shapes[i], h, &chain_slabs, &n_slabs);
+                    if (n_slabs >= kMaxBlock / 32) break;
+                }
+                slab_layout(shapes[i], h, &chain_slabs, &n_slabs);
+                unit_h[i] = h;
+                unit_warps[i] = std::max(1, std::min(kMaxBlock / 32, n_slabs));
+            }
         }
     }
 
@@ -494,6 +509,7 @@ KernelArgs kernel_args(bayes_gibbs_ctx *ctx) {
     a.row_n = ctx->d_row_n.p;
     a.row_nnz = ctx->d_row_nnz.p;
     a.row_info = ctx->d_row_info.p;
+    a.row_mask = ctx->d_row_mask.p;
     a.efflen = ctx->d_efflen.p;
     a.base_counts = ctx->d_base.p;
     a.tab_val = ctx->d_tab_val.p;
@@ -519,6 +535,7 @@ int upload_units(bayes_gibbs_ctx *ctx) {
     if ((rc = h2d(ctx->d_units, ctx->h_units, st)) || (rc = h2d(ctx->d_val, ctx->h_val, st)) || (rc = h2d(ctx->d_col, ctx->h_col, st)) ||
         (rc = h2d(ctx->d_slab, ctx->h_slab, st)) || (rc = h2d(ctx->d_row_n, ctx->h_row_n, st)) ||
         (rc = h2d(ctx->d_row_nnz, ctx->h_row_nnz, st)) || (rc = h2d(ctx->d_row_info, ctx->h_row_info, st)) ||
+        (rc = h2d(ctx->d_row_mask, ctx->h_row_mask, st)) ||
         (rc = h2d(ctx->d_efflen, ctx->h_efflen, st)) || (rc = h2d(ctx->d_base, ctx->h_base, st)) ||
         (rc = h2d(ctx->d_tab_val, ctx->h_tab_val, st)) || (rc = h2d(ctx->d_tab_row, ctx->h_tab_row, st)))
         return rc;
@@ -1038,7 +1055,7 @@ static int step_assignment(int device, const bayes_locus_desc *locus, const doub
     if (!init && (rc = cuda_rc(cudaMemcpyAsync(ctx->d_mean.p, theta, T * sizeof(double), cudaMemcpyHostToDevice, st), "theta H2D")))
         return fail(rc);
     const KernelArgs args = kernel_args(ctx);
-    if ((rc = launch_step_assignment(args, init, ctx->d_mean.p, iteration, ctx->d_occ.p, 12 * (size_t)T + 32, st))) return fail(rc);
+    if ((rc = launch_step_assignment(args, init, ctx->d_mean.p, iteration, ctx->d_occ.p, 12 * (size_t)T + 8 * (((size_t)T + 31) / 32) + 48, st))) return fail(rc);
     if ((rc = cuda_rc(cudaMemcpyAsync(counts_out, ctx->d_occ.p, T * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "counts D2H")))
         return fail(rc);
     if ((rc = cuda_rc(cudaStreamSynchronize(st), "step sync"))) return fail(rc);

@@ -37,6 +37,11 @@
 #ifndef BAYES_MAXNREG
 #define BAYES_MAXNREG 72
 #endif
+// A wide unit is one locus with hundreds of candidates on 8-16 warps; a batch has few of them and they are limited by their
+// own dependent chain, not by how many fit an SM: no register cap worth spilling for.
+#ifndef BAYES_WIDE_MAXNREG
+#define BAYES_WIDE_MAXNREG 128
+#endif
 
 namespace bayes {
 
@@ -71,6 +76,10 @@ struct MatView {
     const uint32_t *row_info;  // slot << 27 | original row index
     int n_slabs;
     int h;  // rows per slab (lanes >= h idle in the A-step)
+    // wide units only: which candidates each row has a cell for, T bits per row as n_words 32-bit words, word w of the row
+    // in lane l of slab s at row_mask[(s * n_words + w) * h + l] (global memory)
+    const uint32_t *row_mask;
+    int n_words;
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -235,6 +244,188 @@ __device__ __forceinline__ void assign_rows(const MatView &M, const double *thet
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// A-step of a wide unit.  With hundreds of candidates the expression vector is almost empty (the simplex holds a few tens
+// of them), so nearly every product P_ij theta_j of a row is zero, and walking all cells of a row to find the few that
+// are not -- twice per iteration, each step a dependent load from L2 -- is what a wide unit used to spend its time on
+// (745 us per iteration on config 3).  Here every row carries a bit mask of its candidates; ANDed with the mask of the
+// current simplex (wide_e_step leaves it in shared memory) it names the cells in play directly: cell k of a row is the
+// k-th set bit of its mask.  Same arithmetic on the same cells in the same (ascending candidate) order as assign_rows,
+// so the results are identical: the cells skipped are exactly those whose product is zero.
+// ------------------------------------------------------------------------------------------------------------------
+struct ActiveCells {
+    const uint32_t *rm;     // the row's mask words, stride h
+    const uint32_t *amask;  // simplex mask: S+ words, then the picked-null words (shared memory)
+    int h, n_words, w, kbase;
+    uint32_t m_all, m;
+    __device__ __forceinline__ void start() {
+        w = -1;
+        kbase = 0;
+        m_all = 0u;
+        m = 0u;
+    }
+    // next cell of the row whose candidate is in the simplex: k = its index in the row, c = its candidate
+    __device__ __forceinline__ bool next(int &k, int &c) {
+        while (m == 0u) {
+            kbase += __popc(m_all);
+            if (++w >= n_words) return false;
+            m_all = __ldg(rm + (size_t)w * h);
+            m = m_all & (amask[w] | amask[n_words + w]);
+        }
+        const int bit = __ffs((int)m) - 1;
+        m &= m - 1u;
+        k = kbase + __popc(m_all & ((1u << bit) - 1u));
+        c = (w << 5) + bit;
+        return true;
+    }
+};
+
+// The cells of one row whose product P_ij theta_j is not zero, in ascending candidate order.  The first walk (the row sum)
+// scans the masks and remembers up to kRowCache cells with their products; every later walk of the same row (one per
+// Philox block of a uniform item, one for a binomial chain) replays that list instead of scanning and gathering again.
+// Rows with more cells in play (the first iterations of a chain, before the simplex has thinned out) are scanned each time.
+constexpr int kRowCache = 24;
+struct RowWalk {
+    ActiveCells scan;
+    const double *val, *theta;
+    uint32_t *kc;  // k << 12 | c
+    double *pv;
+    int n, i;
+    bool cached;
+    __device__ __forceinline__ void start() {
+        i = 0;
+        if (!cached) scan.start();
+    }
+    __device__ __forceinline__ bool next(int &k, int &c, double &p) {
+        if (cached) {
+            if (i >= n) return false;
+            k = (int)(kc[i] >> 12);
+            c = (int)(kc[i] & 4095u);
+            p = pv[i];
+            i++;
+            return true;
+        }
+        while (scan.next(k, c)) {
+            p = val[scan.h * k] * theta[c];
+            if (p != 0.0) return true;
+        }
+        return false;
+    }
+};
+
+__device__ __forceinline__ void assign_rows_wide(const MatView &M, const uint32_t *amask, const double *theta, int32_t *counts, uint64_t key,
+                                                 uint32_t iteration, const bool init, int *next_slab) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const uint32_t phase = init ? PH_INIT_ASSIGN : PH_ASSIGN;
+    const int H = M.h;
+    const bool dynamic = next_slab != nullptr && n_warps > 1;
+    uint32_t kc[kRowCache];
+    double pv[kRowCache];
+    for (int s = dynamic ? 0 : warp;; s += n_warps) {
+        if (dynamic) {
+            if (lane == 0) s = atomicAdd(next_slab, 1);
+            s = __shfl_sync(0xffffffffu, s, 0);
+        }
+        if (s >= M.n_slabs) break;
+        if (lane >= H) continue;
+        const int r = s * H + lane;
+        const uint32_t item = (uint32_t)M.row_nnz[r];
+        if ((item & kItemNnzMask) == 0) continue;  // padding lane
+        const bool chain = init || ((item >> kItemChainShift) & 1u);
+        const int n = M.row_n[r];
+        const uint32_t id = M.row_info[r] & ((1u << kRowSlotShift) - 1u);
+        const double *val = M.val + M.slab[s] + lane;
+        RowWalk cells;
+        cells.scan.rm = M.row_mask + (size_t)s * M.n_words * H + lane;
+        cells.scan.amask = amask;
+        cells.scan.h = H;
+        cells.scan.n_words = M.n_words;
+        cells.val = val;
+        cells.theta = theta;
+        cells.kc = kc;
+        cells.pv = pv;
+
+        // Z, the last cell in play and how many there are (assign_rows: :280-282, :304-306, :344)
+        double Z = 0.0, p;
+        int kl = -1, c_last = 0, in_play = 0, k, c;
+        cells.scan.start();
+        while (cells.scan.next(k, c)) {
+            p = val[H * k] * theta[c];
+            Z += p;
+            if (p != 0.0) {
+                kl = k;
+                c_last = c;
+                if (in_play < kRowCache) {
+                    kc[in_play] = ((uint32_t)k << 12) | (uint32_t)c;
+                    pv[in_play] = p;
+                }
+                in_play++;
+            }
+        }
+        cells.n = in_play;
+        cells.cached = in_play <= kRowCache;
+        if (init) Z = 1.0;
+        bool tiny = false;
+        if ((item >> kItemTinyShift) & 1u) {
+            tiny = !(Z >= 1e-300);
+            cells.start();
+            while (cells.next(k, c, p)) tiny |= p < 1e-300;
+            if (chain && tiny) {
+                kl = -1;
+                in_play = 0;
+                cells.start();
+                while (cells.next(k, c, p))
+                    if (p / Z >= DBL_MIN) {
+                        kl = k;
+                        c_last = c;
+                        in_play++;
+                    }
+            }
+        }
+        if (kl < 0) continue;
+        const double rZ = __drcp_rn(Z);
+        int rem = n;
+        if (!chain) {
+            if (in_play > 1) {
+                const Site site = make_site(key, phase, iteration, id, 0);
+                const int blocks = (int)((item >> kItemBlockShift) & 7u);
+                for (int j = 0; j < blocks; j++) {
+                    const u32x4 w = site.block((uint32_t)j);
+                    const int left = n - 4 * j < 4 ? n - 4 * j : 4;
+                    double cum = 0.0;
+                    int prev = 0;
+                    cells.start();
+                    while (cells.next(k, c, p) && k < kl) {
+                        cum += tiny ? p / Z : div_by(p, Z, rZ);
+                        const uint32_t t = __double2uint_ru(__fma_rn(cum, 4294967296.0, -1.0));
+                        int below = 0;
+                        if (cum > 0.0)
+                            below = (int)(w.x <= t) + ((left > 1) & (int)(w.y <= t)) + ((left > 2) & (int)(w.z <= t)) + ((left > 3) & (int)(w.w <= t));
+                        if (below > prev) atomicAdd(&counts[c], below - prev);
+                        rem -= below - prev;
+                        prev = below;
+                        if (below >= left) break;
+                    }
+                }
+            }
+        } else if (in_play > 1) {
+            double divider = 1.0;
+            cells.start();
+            while (rem > 0 && cells.next(k, c, p) && k < kl) {
+                const double np = tiny ? p / Z : div_by(p, Z, rZ);
+                if (np >= DBL_MIN) {
+                    const Site site = make_site(key, phase, iteration, id, (uint32_t)c);
+                    const int got = binomial_variate(site, rem, np / divider);
+                    if (got > 0) atomicAdd(&counts[c], got);
+                    rem -= got;
+                }
+                divider -= np;  // below double_underflow: no draw, but the divider still shrinks (:360)
+            }
+        }
+        if (rem > 0) atomicAdd(&counts[c_last], rem);
+    }
+}
+
 // FixedBinomialFixedGammaSimplexSizeGenerator::sampleSimplexSize (simplexSizeGenerator.cpp:214-224): one uniform_01,
 // std::upper_bound on the CDF row of |S+|, + |S+|
 __device__ __forceinline__ int sample_simplex(const double *tab_val, const int32_t *tab_row, int n_plus, uint64_t key, uint32_t iteration) {
@@ -328,6 +519,7 @@ struct WideState {
     int32_t *counts, *occ;
     const int32_t *base;
     uint32_t *mask;  // [0, nch): S+ of the counts; [nch, 2 nch): picked null transcripts
+    uint16_t *act;   // members of the simplex, ascending (scratch of the E-step)
     const double *tab_val;
     const int32_t *tab_row;
     int T, nch, N_f;
@@ -369,24 +561,42 @@ __device__ __forceinline__ int wide_e_step(const WideState &E, uint64_t key, uin
             __syncwarp();
         }
     }
+    // The simplex holds b of the T candidates, a few per 32-candidate chunk: the draws and the divisions below run over
+    // a compacted list of its members (b / 32 rounds with full lanes) instead of over every chunk with a few lanes each.
+    // Sums keep the order they always had (per lane over the chunks, then across the lanes).
+    int n_act = 0;
+    for (int c = 0; c < nch; c++) {
+        const int t = c * 32 + lane;
+        const uint32_t m = E.mask[c] | E.mask[nch + c];
+        if ((m >> lane) & 1u) E.act[n_act + __popc(m & ((1u << lane) - 1u))] = (uint16_t)t;
+        n_act += __popc(m);
+        if (t < T) E.theta[t] = 0.0;
+    }
+    __syncwarp();
+    for (int i0 = 0; i0 < n_act; i0 += 32) {
+        const int i = i0 + lane;
+        if (i < n_act) {
+            const int t = E.act[i];
+            E.theta[t] = gamma_variate(make_site(key, PH_GAMMA, iteration, (uint32_t)t, 0), (double)E.counts[t] + E.gamma);
+        }
+    }
+    __syncwarp();
     double part = 0.0;
     for (int c = 0; c < nch; c++) {
         const int t = c * 32 + lane;
-        const bool active = ((E.mask[c] | E.mask[nch + c]) >> lane) & 1u;
-        double g = 0.0;
-        if (active) g = gamma_variate(make_site(key, PH_GAMMA, iteration, (uint32_t)t, 0), (double)E.counts[t] + E.gamma);
-        if (t < T) E.theta[t] = g;
-        part += g;
+        if (t < T) {
+            part += E.theta[t];
+            E.counts[t] = E.base[t];
+        }
     }
     const double norm = warp_sum(part);
-    for (int c = 0; c < nch; c++) {
-        const int t = c * 32 + lane;
-        if (t < T) {
+    for (int i0 = 0; i0 < n_act; i0 += 32) {
+        const int i = i0 + lane;
+        if (i < n_act) {
+            const int t = E.act[i];
             const double g = E.theta[t];
             const double th = g != 0.0 ? g / norm : 0.0;
             E.theta[t] = th;
-            E.counts[t] = E.base[t];
-            if (tr_theta) tr_theta[t] = th;
             if (sampling && g != 0.0) {
                 const double fpkm = (th * (double)E.N_f * 1e9) / E.den[t];
                 const int o = ++E.occ[t];
@@ -401,6 +611,10 @@ __device__ __forceinline__ int wide_e_step(const WideState &E, uint64_t key, uin
             }
         }
     }
+    if (tr_theta) {
+        __syncwarp();
+        for (int t = lane; t < T; t += 32) tr_theta[t] = E.theta[t];
+    }
     return b;
 }
 
@@ -414,6 +628,8 @@ __device__ __forceinline__ MatView stage_matrix(const KernelArgs &A, const UnitD
     MatView M;
     M.n_slabs = U.n_slabs;
     M.h = U.slab_h;
+    M.row_mask = A.row_mask + U.mask_off;  // wide units only (read through L1, never staged)
+    M.n_words = (U.Tpad + 31) >> 5;
     if (MAT_SMEM) {
         double *sv = (double *)(smem + lay.val);
         uint16_t *sc = (uint16_t *)(smem + lay.col);
@@ -541,7 +757,7 @@ __global__ void __maxnreg__(BAYES_MAXNREG) gibbs_bundle_kernel(const __grid_cons
 
 // ------------------------------------------------------------------------------------------------------------------
 template <bool MAT_SMEM>
-__global__ void __maxnreg__(BAYES_MAXNREG) gibbs_wide_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
+__global__ void __maxnreg__(BAYES_WIDE_MAXNREG) gibbs_wide_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int64_t ui = unit_base + blockIdx.x;
     if (threadIdx.x == 0) A.unit_clock[3 * ui] = global_ns();
@@ -559,6 +775,7 @@ __global__ void __maxnreg__(BAYES_MAXNREG) gibbs_wide_kernel(const __grid_consta
     int32_t *base = (int32_t *)(smem + lay.base);
     E.base = base;
     E.mask = (uint32_t *)(smem + lay.mask);
+    E.act = (uint16_t *)(smem + lay.act);
     E.T = T;
     E.nch = (T + 31) >> 5;
     E.N_f = U.N_f[0];
@@ -578,6 +795,11 @@ __global__ void __maxnreg__(BAYES_MAXNREG) gibbs_wide_kernel(const __grid_consta
         E.m2[t] = 0.0;
         E.theta[t] = 1.0;  // initAssignment runs the A-step on P_ij itself
         E.den[t] = A.efflen[U.lane_off + t] * n_total;  // valueContainer.cpp:235 denominator
+    }
+    // initAssignment (theta == 1): every candidate is "in the simplex"
+    for (int c = threadIdx.x; c < E.nch; c += blockDim.x) {
+        E.mask[c] = c == E.nch - 1 && (T & 31) ? (1u << (T & 31)) - 1u : 0xffffffffu;
+        E.mask[E.nch + c] = 0u;
     }
     if (U.tab_smem) {
         double *tv = (double *)(smem + lay.tab_val);
@@ -613,7 +835,7 @@ __global__ void __maxnreg__(BAYES_MAXNREG) gibbs_wide_kernel(const __grid_consta
             if (tr && threadIdx.x == 0) A.tr_b[it] = b;
         }
         __syncthreads();
-        assign_rows(M, E.theta, E.counts, skey, 0, (uint32_t)(it < 0 ? 0 : it), it < 0, next_slab);
+        assign_rows_wide(M, E.mask, E.theta, E.counts, key, (uint32_t)(it < 0 ? 0 : it), it < 0, next_slab);
         __syncthreads();
     }
     if (tracing && total - 1 < A.trace_iters)
@@ -646,9 +868,21 @@ __global__ void step_assignment_kernel(const __grid_constant__ KernelArgs A, con
         counts[t] = A.base_counts[U.lane_off + t];
     }
     if (threadIdx.x == 0) skey[0] = U.key[0];
+    // simplex mask of the given expression vector: candidates with theta != 0 (assign_rows_wide)
+    const int n_words = (T + 31) >> 5;
+    uint32_t *amask = (uint32_t *)(counts + T);
+    __syncthreads();
+    if (threadIdx.x < 32)
+        for (int w = 0; w < n_words; w++) {
+            const int t = w * 32 + (int)threadIdx.x;
+            const uint32_t pm = __ballot_sync(0xffffffffu, t < T && theta[t] != 0.0);
+            if (threadIdx.x == 0) { amask[w] = pm; amask[n_words + w] = 0u; }
+        }
     MatView M;
     M.n_slabs = U.n_slabs;
     M.h = U.slab_h;
+    M.row_mask = A.row_mask + U.mask_off;
+    M.n_words = n_words;
     M.val = A.val + U.cell_off;
     M.col = A.col + U.cell_off;
     M.slab = A.slab_cell_off + U.slab_off;
@@ -656,7 +890,7 @@ __global__ void step_assignment_kernel(const __grid_constant__ KernelArgs A, con
     M.row_nnz = A.row_nnz + U.row_off;
     M.row_info = A.row_info + U.row_off;
     __syncthreads();
-    assign_rows(M, theta, counts, skey, 0, iteration, INIT, nullptr);
+    assign_rows_wide(M, amask, theta, counts, skey[0], iteration, INIT, nullptr);
     __syncthreads();
     for (int t = threadIdx.x; t < T; t += blockDim.x) counts_out[t] = counts[t];
 }
@@ -693,7 +927,7 @@ __global__ void step_expression_kernel(int T, const int32_t *counts_in, int b, d
     } else {
         WideState E;
         E.theta = theta; E.den = theta; E.mean = theta; E.m2 = theta;
-        E.counts = counts; E.occ = counts; E.base = base; E.mask = mask;
+        E.counts = counts; E.occ = counts; E.base = base; E.mask = mask; E.act = (uint16_t *)(mask + 2 * nch + 2);
         E.tab_val = tab; E.tab_row = tab_row;
         E.T = T; E.nch = nch; E.N_f = 0; E.gamma = gamma;
         wide_e_step(E, key, iteration, false, theta_out);
@@ -774,7 +1008,7 @@ int launch_step_assignment(const KernelArgs &args, bool init, const double *d_th
 int launch_step_expression(int T, const int32_t *d_counts, int b, double gamma, uint64_t key, uint32_t iteration, double *d_theta,
                            void *stream) {
     const size_t nT = T <= 32 ? 32 : (size_t)T;
-    const size_t smem = 8 * (nT + (size_t)T + 2) + 4 * (2 * nT + (size_t)T + 1) + 4 * (2 * ((nT + 31) / 32) + 2) + 16;
+    const size_t smem = 8 * (nT + (size_t)T + 2) + 4 * (2 * nT + (size_t)T + 1) + 4 * (2 * ((nT + 31) / 32) + 2) + 2 * nT + 16;
     step_expression_kernel<<<1, 32, smem, (cudaStream_t)stream>>>(T, d_counts, b, gamma, key, iteration, d_theta);
     return check(cudaGetLastError(), "step_expression_kernel launch");
 }

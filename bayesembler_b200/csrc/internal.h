@@ -53,6 +53,7 @@ struct UnitDev {
     int64_t lane_off;   // -> efflen / base_counts: 32 entries (bundle, by lane) or T entries (wide)
     int64_t tab_off;    // -> tab_val (tables of the slots back to back)
     int64_t tabrow_off; // -> tab_row: slot g at g * (Tpad + 1), T + 1 offsets relative to the unit's tab_off
+    int64_t mask_off;   // -> row_mask (wide units): ceil(T / 32) words per padded row, [slab][word][lane]
     // per slot
     int32_t T[kMaxSlots];
     int32_t N_f[kMaxSlots];      // fragments of the locus (folded rows included)
@@ -70,6 +71,7 @@ struct KernelArgs {
     const int32_t *row_n;
     const int32_t *row_nnz;
     const uint32_t *row_info;
+    const uint32_t *row_mask;
     const double *efflen;
     const int32_t *base_counts;
     const double *tab_val;
@@ -131,7 +133,7 @@ struct PackedUnit {
     std::vector<double> val, efflen, tab_val;
     std::vector<uint16_t> col;
     std::vector<int32_t> slab_cell_off, row_n, row_nnz, base_counts, tab_row;
-    std::vector<uint32_t> row_info;
+    std::vector<uint32_t> row_info, row_mask;
     double cost = 0;
     double features[4] = {0, 0, 0, 0};  // the time model's inputs (capi.cu)
 };

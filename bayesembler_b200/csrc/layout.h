@@ -15,7 +15,7 @@ struct SmemLayout {
     // byte offsets from the start of dynamic shared memory; 8-byte members first
     uint32_t theta, den, mean, m2, tab_val, val, key;                      // double / uint64
     uint32_t counts, base, occ, tab_row, mask, slab, row_n, row_nnz, row_info, next_slab;  // int32
-    uint32_t col;                                                          // uint16
+    uint32_t col, act;                                                     // uint16
     uint32_t total;
 };
 
@@ -45,6 +45,8 @@ BAYES_LAYOUT_HD SmemLayout unit_layout(bool wide, int nT, int n_slots, int Tpad,
     L.row_nnz = o; o += mat_smem ? 4u * Rp : 0u;
     L.row_info = o; o += mat_smem ? 4u * Rp : 0u;
     L.col = o; o += mat_smem ? 2u * (uint32_t)n_cells : 0u;
+    o = (o + 1u) & ~1u;
+    L.act = o; o += wide ? 2u * uT : 0u;
     L.total = (o + 15u) & ~15u;
     return L;
 }

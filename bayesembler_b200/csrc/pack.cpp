@@ -191,6 +191,9 @@ void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, PackedU
     const int n_cells = U.slab_cell_off[n_slabs];
     U.val.assign(n_cells, 0.0);
     U.col.assign(n_cells, 0);
+    // wide units: T bits per padded row saying which candidates the row has a cell for (gibbs_kernel.cu, assign_rows_wide)
+    const int n_words = wide ? (L0.T + 31) / 32 : 0;
+    U.row_mask.assign((size_t)n_slabs * H * n_words, 0u);
     for (int i = 0; i < n_items; i++) {
         const ItemShape &it = items[i];
         const PreLocus &L = *slots[it.slot].locus;
@@ -208,6 +211,10 @@ void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, PackedU
             const size_t at = (size_t)U.slab_cell_off[s] + H * (size_t)k + l;
             U.val[at] = L.cell_val[L.row_ptr[it.r] + k];
             U.col[at] = (uint16_t)(lane0 + L.cell_col[L.row_ptr[it.r] + k]);
+            if (wide) {
+                const int c = L.cell_col[L.row_ptr[it.r] + k];
+                U.row_mask[((size_t)s * n_words + (c >> 5)) * H + l] |= 1u << (c & 31);
+            }
         }
     }
 
