@@ -46,6 +46,9 @@ for f in ("rng.cuh", "gibbs_kernel.cu"):
         m = re.match(r"^(?:template.*>\s*)?(?:BAYES_HD(?:_NOINLINE)?|__device__|__global__|static|inline).*?\b([A-Za-z_0-9]+)\s*\(", line)
         if m and not line.startswith(" "):
             marks.append((i, m.group(1)))
+        ms = re.match(r"^struct\s+([A-Za-z_0-9]+)\s*\{", line)  # member functions count for their struct
+        if ms:
+            marks.append((i, ms.group(1)))
     bounds[f] = marks
 
 
