@@ -32,6 +32,7 @@
 #include <fstream>
 #include <iostream>
 #include <list>
+#include <atomic>
 #include <memory>
 #include <thread>
 
@@ -79,7 +80,7 @@ inline void printHelp(std::ostream &out, bool advanced) {
            "== Optional arguments ==:\n"
            "  -o [ --output-prefix ] arg                      prefix to be used on all output filenames (OBS: to use output directory <dir>\n"
            "                                                  without any prefix on the output files, use <dir/>)\n"
-           "  -p [ --num-threads ] arg (=1)                   number of host threads used for graph preparation\n"
+           "  -p [ --num-threads ] arg (=1)                   number of host threads preparing graphs (paths, likelihoods, read cover)\n"
            "  -s [ --strand-specific ] arg (=unstranded)      data is strand-specific. Use \"first\" to indicate mate orientation as in the dUTP\n"
            "                                                  protocol or \"second\" if opposite\n"
            "  -c [ --confidence-threshold ] arg (=0.5)        exclude candidates with a confidence below <confidence-threshold>\n"
@@ -319,12 +320,32 @@ class Assembler {
               << " single-path graph(s)" << std::endl;
 
         // ---- bayesemblerCallback, host part, per graph (:1420-1599); the samplers are queued, not run
+        // --num-threads host threads take graphs off one counter, like the reference's workers take them off the queue (:1424-1436)
         std::vector<Prepared> prepared(graph_number);
-        int remaining = graph_number, n_samplers = 0;
-        for (int g = 0; g < graph_number; g++) {
-            remaining--;  // the seed of a graph is --seed + graphs left in the queue after it (:1435-1437)
-            prepareGraph(*sorted[g], options_variables.seed + remaining, adjusted_fragment_count, fragment_length_model.get(), &prepared[g]);
-            n_samplers += prepared[g].sampler ? 1 : 0;
+        int n_samplers = 0;
+        {
+            std::atomic<int> next_graph(0);
+            std::vector<std::string> errors(std::max(1, options_variables.num_threads));
+            auto work = [&](int tid) {
+                try {
+                    for (;;) {
+                        const int g = next_graph.fetch_add(1);
+                        if (g >= graph_number) return;
+                        // the seed of a graph is --seed + graphs left in the queue after it (:1435-1437)
+                        prepareGraph(*sorted[g], options_variables.seed + (graph_number - 1 - g), adjusted_fragment_count, fragment_length_model.get(),
+                                     &prepared[g]);
+                    }
+                } catch (std::exception &e) {
+                    errors[tid] = e.what();
+                }
+            };
+            std::vector<std::thread> pool;
+            for (int t = 1; t < (int)errors.size(); t++) pool.emplace_back(work, t);
+            work(0);
+            for (size_t t = 0; t < pool.size(); t++) pool[t].join();
+            for (size_t t = 0; t < errors.size(); t++)
+                if (!errors[t].empty()) throw std::runtime_error(errors[t]);
+            for (int g = 0; g < graph_number; g++) n_samplers += prepared[g].sampler ? 1 : 0;
         }
         // ---- every sampler of the run as one GPU batch (gibbsSampler.cpp:55-148 for all graphs at once)
         if (n_samplers > 0) {

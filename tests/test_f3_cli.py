@@ -138,7 +138,7 @@ def test_graphs_that_never_reach_the_sampler(cli, tmp_path):
     path = os.path.join(str(tmp_path), "g.txt")
     synth.write_graph_file(path, [([lone], far, False), ([lone.replace("graph_70", "graph_72")], None, False)], 40)
     prefix = os.path.join(str(tmp_path), "out", "run1_")
-    rc, out, err = run(cli, "-g", path, "-o", prefix, "--frag-mean", "200", "--frag-sd", "20", "--output-mode", "full", "--seed", "3")
+    rc, out, err = run(cli, "-g", path, "-o", prefix, "--frag-mean", "200", "--frag-sd", "20", "--output-mode", "full", "--seed", "3", "-p", "3")
     assert rc == 0, err
     assert "2 graph(s) were parsed in total" in out and "0 graph(s) were assembled successfully" in out
     assert open(prefix + "assembly.gtf").read() == "" and open(prefix + "candidates.gtf").read() == ""
@@ -238,7 +238,7 @@ def test_cli_run_matches_the_chained_oracles(cli, lib, oracle, facade, tmp_path)
     assert "%d graph(s) were assembled successfully" % codes.count(0) in out
     assert "%d graph(s) were not assembled due to insufficient candidate coverage" % codes.count(3) in out
     # the same run with the fragment length distribution estimated from the single-path graphs (assembler.cpp:1919-1987)
-    rc, out2, err = run(cli, "-g", path, "-o", prefix + "est_", "--seed", "11", "--output-mode", "full")
+    rc, out2, err = run(cli, "-g", path, "-o", prefix + "est_", "--seed", "11", "--output-mode", "full", "--num-threads", "4")
     assert rc == 0, err
     hist = {}
     for dots, fr, single in single_graph:
