@@ -33,6 +33,7 @@
 #include <iostream>
 #include <list>
 #include <atomic>
+#include <chrono>
 #include <memory>
 #include <thread>
 
@@ -276,6 +277,9 @@ class Assembler {
 
     // assembler.cpp:1841-2030 from the point where the splice graphs exist; returns the number of graphs assembled (code 0)
     int runBayesemblerBatched(std::ostream &cout_) {
+        typedef std::chrono::steady_clock Clock;
+        auto seconds = [](Clock::time_point a, Clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+        const Clock::time_point t_start = Clock::now();
         std::ifstream in(options_variables.graph_file.c_str());
         if (!in) throw std::runtime_error("cannot open graph file " + options_variables.graph_file);
         double unique_pairs = 0, mapped_pairs = 0;
@@ -319,6 +323,7 @@ class Assembler {
         cout_ << "\nStarting Bayesembler on " << graph_number - single_graph_number << " multi-path graph(s) and " << single_graph_number
               << " single-path graph(s)" << std::endl;
 
+        const Clock::time_point t_model = Clock::now();
         // ---- bayesemblerCallback, host part, per graph (:1420-1599); the samplers are queued, not run
         // --num-threads host threads take graphs off one counter, like the reference's workers take them off the queue (:1424-1436)
         std::vector<Prepared> prepared(graph_number);
@@ -347,6 +352,7 @@ class Assembler {
                 if (!errors[t].empty()) throw std::runtime_error(errors[t]);
             for (int g = 0; g < graph_number; g++) n_samplers += prepared[g].sampler ? 1 : 0;
         }
+        const Clock::time_point t_prepared = Clock::now();
         // ---- every sampler of the run as one GPU batch (gibbsSampler.cpp:55-148 for all graphs at once)
         if (n_samplers > 0) {
             // graphs are independent (assembler.cpp:1441-1445): with several devices they are sharded by cost, largest first to
@@ -387,6 +393,7 @@ class Assembler {
                 if (!errors[p].empty()) throw std::runtime_error("device " + std::to_string(devices[p]) + ": " + errors[p]);
             if (devices.size() > 1) cout_ << n_samplers << " sampler(s) sharded over " << devices.size() << " device(s)" << std::endl;
         }
+        const Clock::time_point t_sampled = Clock::now();
         // ---- bayesemblerCallback, after the sampler (:1604-1631), and outputCallback (:1746-1839)
         std::ofstream ensemble_file((options_variables.output_prefix + "assembly.gtf").c_str());
         std::ofstream candidates_file, log_file;
@@ -418,6 +425,10 @@ class Assembler {
         cout_ << "\t" << stats_list[7] << " graph(s) were not assembled due to transcripts being pre-mRNA or having an expected count lower than "
               << options_variables.count_threshold << std::endl;
         cout_ << std::endl;
+        const Clock::time_point t_end = Clock::now();
+        cout_ << "Timing: input + fragment length model " << seconds(t_start, t_model) << " s, graph preparation on " << options_variables.num_threads
+              << " host thread(s) " << seconds(t_model, t_prepared) << " s, " << n_samplers << " sampler(s) on the GPU " << seconds(t_prepared, t_sampled)
+              << " s, output " << seconds(t_sampled, t_end) << " s" << std::endl;
         return stats_list[0];
     }
 
