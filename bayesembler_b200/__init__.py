@@ -6,6 +6,7 @@ fails loudly when the library is missing, and creating a context fails when no B
 """
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 
@@ -198,6 +199,7 @@ class GibbsContext(object):
         self.h = h
         self._T = []
         self._chains = []
+        self._lock = threading.Lock()
         if stream is not None:
             _check(self.lib.bayes_gibbs_set_stream(self.h, C.c_void_p(stream)), "bayes_gibbs_set_stream")
         if host_threads:
@@ -214,20 +216,29 @@ class GibbsContext(object):
         except Exception:
             pass
 
-    def _note(self, desc_array):
+    def _note(self, desc_array, first=None):
+        """Pointer to a bayes_locus_desc[] and, once the ids are known, the sizes the fetch calls need."""
         if isinstance(desc_array, np.ndarray):  # structured array laid out as bayes_locus_desc[] (synth.DESC_DTYPE)
-            self._T.extend(int(t) for t in desc_array["T"])
-            self._chains.extend(int(c) for c in desc_array["n_chains"])
-            return C.c_void_p(desc_array.ctypes.data)
-        for d in desc_array:
-            self._T.append(d.T)
-            self._chains.append(d.n_chains)
-        return C.cast(desc_array, C.c_void_p)
+            ptr = C.c_void_p(desc_array.ctypes.data)
+            shapes = [(int(t), int(c)) for t, c in zip(desc_array["T"], desc_array["n_chains"])]
+        else:
+            ptr = C.cast(desc_array, C.c_void_p)
+            shapes = [(d.T, d.n_chains) for d in desc_array]
+        if first is not None:
+            with self._lock:  # submit may be called from several threads; ids come from the library
+                need = first + len(shapes)
+                if len(self._T) < need:
+                    self._T.extend([0] * (need - len(self._T)))
+                    self._chains.extend([0] * (need - len(self._chains)))
+                for i, (t, c) in enumerate(shapes):
+                    self._T[first + i] = t
+                    self._chains[first + i] = c
+        return ptr
 
     def submit(self, desc_array):
         first = C.c_int64(0)
-        ptr = self._note(desc_array)
-        _check(self.lib.bayes_gibbs_submit(self.h, len(desc_array), ptr, C.byref(first)), "bayes_gibbs_submit")
+        _check(self.lib.bayes_gibbs_submit(self.h, len(desc_array), self._note(desc_array), C.byref(first)), "bayes_gibbs_submit")
+        self._note(desc_array, first.value)
         return first.value
 
     def upload(self):
@@ -244,8 +255,8 @@ class GibbsContext(object):
 
     def run_batch(self, desc_array):
         first = C.c_int64(0)
-        ptr = self._note(desc_array)
-        _check(self.lib.bayes_gibbs_run_batch(self.h, len(desc_array), ptr, C.byref(first)), "bayes_gibbs_run_batch")
+        _check(self.lib.bayes_gibbs_run_batch(self.h, len(desc_array), self._note(desc_array), C.byref(first)), "bayes_gibbs_run_batch")
+        self._note(desc_array, first.value)
         return first.value
 
     def fetch_all(self):

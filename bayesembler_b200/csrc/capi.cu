@@ -12,6 +12,7 @@
 #include <map>
 #include <numeric>
 #include <queue>
+#include <mutex>
 #include <thread>
 #include <tuple>
 
@@ -113,6 +114,7 @@ struct bayes_gibbs_ctx {
     int host_threads = 0;
     bool uploaded = false, ran = false, downloaded = false;
 
+    std::mutex submit_lock;         // bayes_gibbs_submit may be called from several host threads (one worker per graph in the reference)
     std::vector<PreLocus> loci;     // per submitted locus
     std::vector<int64_t> out_base;  // locus -> offset of chain 0 in the outputs (chains of a locus are contiguous)
     int64_t out_len = 0;            // total T over all (locus, chain)
@@ -649,7 +651,6 @@ int bayes_gibbs_submit(bayes_gibbs_ctx *ctx, int32_t n_loci, const bayes_locus_d
         set_error("bayes_gibbs_submit: batch already uploaded; call bayes_gibbs_clear first");
         return BAYES_E_STATE;
     }
-    if (first_id) *first_id = (int64_t)ctx->loci.size();
     const double t0 = now_s();
     // fold rows, read cover, CDF table: independent per locus
     std::vector<PreLocus> pre(n_loci);
@@ -661,6 +662,12 @@ int bayes_gibbs_submit(bayes_gibbs_ctx *ctx, int32_t n_loci, const bayes_locus_d
             set_error("bayes_gibbs_submit: locus " + std::to_string(i) + ": " + perr[i]);
             return prc[i];
         }
+    std::lock_guard<std::mutex> guard(ctx->submit_lock);  // the preparation above ran unlocked; ids are handed out here
+    if (ctx->uploaded) {
+        set_error("bayes_gibbs_submit: batch already uploaded; call bayes_gibbs_clear first");
+        return BAYES_E_STATE;
+    }
+    if (first_id) *first_id = (int64_t)ctx->loci.size();
     ctx->loci.reserve(ctx->loci.size() + n_loci);
     for (int32_t i = 0; i < n_loci; i++) {
         ctx->out_base.push_back(ctx->out_len);

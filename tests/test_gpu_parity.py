@@ -201,3 +201,28 @@ def test_empty_batch_and_single_candidate_only(lib):
     assert ctx.last_launches() == 0 and g["occ"][0] == 100 and g["m2"][0] == 0
     assert g["mean"][0] == (12 * 1e9) / (1000000 * 1500.0)
     ctx.close()
+
+
+def test_concurrent_submit(lib, oracle):
+    """bayes_gibbs_submit from several host threads at once (the reference's workers each own one graph, assembler.cpp:1420-1445):
+    every caller gets its own ids and every locus its own chain."""
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(77)
+    loci = [random_locus(rng, int(rng.integers(2, 14)), int(rng.integers(5, 60)), max_count=40) for _ in range(48)]
+    seeds = [int(s) for s in rng.integers(1, 2 ** 40, len(loci))]
+    burn, samples = 40, 400
+    ctx = lib.GibbsContext(0)
+    descs = [lib.make_desc_array(loci[i:i + 4], [burn] * 4, [samples] * 4, seeds[i:i + 4]) for i in range(0, len(loci), 4)]
+    with ThreadPoolExecutor(6) as ex:
+        firsts = list(ex.map(ctx.submit, descs))
+    assert sorted(firsts) == list(range(0, len(loci), 4))
+    ctx.upload()
+    ctx.run()
+    ctx.download()
+    ctx.sync()
+    for first, base in zip(firsts, range(0, len(loci), 4)):
+        for j in range(4):
+            g = ctx.fetch(first + j)
+            o = oracle.run_sampler(loci[base + j], burn, samples, SITE, lib.chain_key(seeds[base + j], 0))
+            assert np.array_equal(g["occ"], o["occ"]), (first, j)
+    ctx.close()
