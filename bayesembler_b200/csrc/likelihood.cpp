@@ -301,6 +301,13 @@ static int check_raw(const bayes_raw_locus *L, const char *who) {
             return BAYES_E_INVALID;
         }
     }
+    // FragmentAlignment::probability is a product of base-call probabilities (assembler.cpp calculateSequencingProbability):
+    // a number in [0, 1]; NaN or infinity would poison every row it is merged into
+    for (int i = 0; i < L->n_frag; i++)
+        if (!(L->frag_prob[i] >= 0.0) || !std::isfinite(L->frag_prob[i])) {
+            set_error(std::string(who) + ": fragment probability is negative or not finite");
+            return BAYES_E_INVALID;
+        }
     return BAYES_OK;
 }
 
