@@ -57,6 +57,8 @@ int prepare_locus(const bayes_locus_desc &in, PreLocus *out, std::string *err) {
     if (rc != 0) return rc;
     if (in.T > kMaxT) { *err = "T exceeds the supported maximum (4096 candidates)"; return BAYES_E_INVALID; }
     if (!in.efflen) { *err = "null efflen"; return BAYES_E_INVALID; }
+    for (int t = 0; t < in.T; t++)  // SequencingModel::getEffectiveLength is a sum of probabilities (sequencingModel.cpp:47-57): > 0
+        if (!(in.efflen[t] > 0.0) || !std::isfinite(in.efflen[t])) { *err = "effective length must be finite and > 0"; return BAYES_E_INVALID; }
     if (!(in.gamma >= DBL_MIN)) { *err = "gamma must be > 0"; return BAYES_E_INVALID; }  // assembler.cpp:1567
     if (in.burn_in < 0 || in.samples < 1) { *err = "need burn_in >= 0 and samples >= 1"; return BAYES_E_INVALID; }
     if (!(in.total_num_fragments >= 1.0) || in.total_num_fragments > 2147483647.0) { *err = "total_num_fragments out of int range"; return BAYES_E_INVALID; }

@@ -170,14 +170,16 @@ def test_error_paths_and_call_order(lib):
         ctx.submit(lib.make_desc_array([too_wide], [5], [50], [1]))
     with pytest.raises(lib.BayesError, match="samples"):
         ctx.submit(lib.make_desc_array([loc], [5], [0], [1]))
-    ctx._T, ctx._chains = [], []
+    no_length = random_locus(rng, 4, 10)
+    no_length.efflen[2] = 0.0
+    with pytest.raises(lib.BayesError, match="effective length"):
+        ctx.submit(lib.make_desc_array([no_length], [5], [50], [1]))
     ctx.submit(lib.make_desc_array([loc], [5], [50], [1]))
     ctx.upload()
     with pytest.raises(lib.BayesError, match="clear"):
         ctx.submit(lib.make_desc_array([loc], [5], [50], [1]))
     with pytest.raises(lib.BayesError, match="before"):
         ctx.set_trace(0, 0, 5)
-    ctx._T, ctx._chains = [loc.T], [1]
     with pytest.raises(lib.BayesError, match="download"):
         ctx.fetch(0)
     ctx.run(); ctx.download(); ctx.sync()
