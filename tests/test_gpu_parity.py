@@ -51,7 +51,8 @@ def test_uniform_int_variates(lib, oracle, rng_n):
     assert np.array_equal(g, o)
 
 
-SHAPES = [(2, 5, 30), (3, 40, 60), (10, 150, 300), (31, 400, 100), (33, 300, 2000), (100, 700, 50), (257, 200, 500)]
+SHAPES = [(2, 5, 30), (3, 40, 60), (10, 150, 300), (31, 400, 100), (33, 300, 2000), (100, 700, 50), (257, 200, 500), (1500, 90, 40),
+          (4096, 40, 25)]
 
 
 @pytest.mark.parametrize("T,R,mc", SHAPES)
@@ -96,7 +97,7 @@ def test_step_generate_expression(lib, oracle, T, gamma):
 
 
 @pytest.mark.parametrize("T,R,mc,gamma", [(2, 6, 40, 1.0), (3, 30, 60, 1.0), (8, 120, 400, 1.0), (12, 60, 100, 0.5),
-                                          (30, 500, 80, 1.0), (40, 200, 3000, 2.0), (100, 300, 50, 1.0)])
+                                          (30, 500, 80, 1.0), (40, 200, 3000, 2.0), (100, 300, 50, 1.0), (300, 700, 40, 1.0)])
 def test_full_chain_replay(lib, oracle, T, R, mc, gamma):
     rng = np.random.default_rng(T * 31 + R)
     loc = random_locus(rng, T, R, max_count=mc, gamma=gamma)
