@@ -214,7 +214,7 @@ int append_unit(bayes_gibbs_ctx *ctx, PackedUnit &U) {
     U.d.lane_off = (int64_t)ctx->h_efflen.n;
     U.d.tab_off = (int64_t)ctx->h_tab_val.n;
     U.d.tabrow_off = (int64_t)ctx->h_tab_row.n;
-    U.d.mask_off = (int64_t)ctx->h_row_mask.n;
+    U.d.mask_off = (int64_t)(ctx->h_row_mask.n / 2);  // in 64-bit words
     if ((rc = append(ctx->h_slab, U.slab_cell_off)) || (rc = append(ctx->h_val, U.val)) || (rc = append(ctx->h_col, U.col)) ||
         (rc = append(ctx->h_row_n, U.row_n)) || (rc = append(ctx->h_row_nnz, U.row_nnz)) || (rc = append(ctx->h_row_info, U.row_info)) || (rc = append(ctx->h_row_mask, U.row_mask)) ||
         (rc = append(ctx->h_efflen, U.efflen)) || (rc = append(ctx->h_base, U.base_counts)) ||
@@ -1062,7 +1062,7 @@ static int step_assignment(int device, const bayes_locus_desc *locus, const doub
     if (!init && (rc = cuda_rc(cudaMemcpyAsync(ctx->d_mean.p, theta, T * sizeof(double), cudaMemcpyHostToDevice, st), "theta H2D")))
         return fail(rc);
     const KernelArgs args = kernel_args(ctx);
-    if ((rc = launch_step_assignment(args, init, ctx->d_mean.p, iteration, ctx->d_occ.p, 12 * (size_t)T + 8 * (((size_t)T + 31) / 32) + 48, st))) return fail(rc);
+    if ((rc = launch_step_assignment(args, init, ctx->d_mean.p, iteration, ctx->d_occ.p, 12 * (size_t)T + 8 * (((size_t)T + 63) / 64) + 48, st))) return fail(rc);
     if ((rc = cuda_rc(cudaMemcpyAsync(counts_out, ctx->d_occ.p, T * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "counts D2H")))
         return fail(rc);
     if ((rc = cuda_rc(cudaStreamSynchronize(st), "step sync"))) return fail(rc);

@@ -76,9 +76,9 @@ struct MatView {
     const uint32_t *row_info;  // slot << 27 | original row index
     int n_slabs;
     int h;  // rows per slab (lanes >= h idle in the A-step)
-    // wide units only: which candidates each row has a cell for, T bits per row as n_words 32-bit words, word w of the row
+    // wide units only: which candidates each row has a cell for, T bits per row as n_words 64-bit words, word w of the row
     // in lane l of slab s at row_mask[(s * n_words + w) * h + l] (global memory)
-    const uint32_t *row_mask;
+    const uint64_t *row_mask;
     int n_words;
 };
 
@@ -254,28 +254,28 @@ __device__ __forceinline__ void assign_rows(const MatView &M, const double *thet
 // so the results are identical: the cells skipped are exactly those whose product is zero.
 // ------------------------------------------------------------------------------------------------------------------
 struct ActiveCells {
-    const uint32_t *rm;     // the row's mask words, stride h
-    const uint32_t *amask;  // simplex mask: S+ words, then the picked-null words (shared memory)
+    const uint64_t *rm;     // the row's mask words, stride h
+    const uint64_t *amask;  // simplex mask, 64 candidates per word (shared memory, written by the E-step)
     int h, n_words, w, kbase;
-    uint32_t m_all, m;
+    uint64_t m_all, m;
     __device__ __forceinline__ void start() {
         w = -1;
         kbase = 0;
-        m_all = 0u;
-        m = 0u;
+        m_all = 0ull;
+        m = 0ull;
     }
     // next cell of the row whose candidate is in the simplex: k = its index in the row, c = its candidate
     __device__ __forceinline__ bool next(int &k, int &c) {
-        while (m == 0u) {
-            kbase += __popc(m_all);
+        while (m == 0ull) {
+            kbase += __popcll(m_all);
             if (++w >= n_words) return false;
-            m_all = __ldg(rm + (size_t)w * h);
-            m = m_all & (amask[w] | amask[n_words + w]);
+            m_all = __ldg((const unsigned long long *)rm + (size_t)w * h);
+            m = m_all & amask[w];
         }
-        const int bit = __ffs((int)m) - 1;
-        m &= m - 1u;
-        k = kbase + __popc(m_all & ((1u << bit) - 1u));
-        c = (w << 5) + bit;
+        const int bit = __ffsll((long long)m) - 1;
+        m &= m - 1ull;
+        k = kbase + __popcll(m_all & ((1ull << bit) - 1ull));
+        c = (w << 6) + bit;
         return true;
     }
 };
@@ -313,7 +313,7 @@ struct RowWalk {
     }
 };
 
-__device__ __forceinline__ void assign_rows_wide(const MatView &M, const uint32_t *amask, const double *theta, int32_t *counts, uint64_t key,
+__device__ __forceinline__ void assign_rows_wide(const MatView &M, const uint64_t *amask, const double *theta, int32_t *counts, uint64_t key,
                                                  uint32_t iteration, const bool init, int *next_slab) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const uint32_t phase = init ? PH_INIT_ASSIGN : PH_ASSIGN;
@@ -520,6 +520,7 @@ struct WideState {
     const int32_t *base;
     uint32_t *mask;  // [0, nch): S+ of the counts; [nch, 2 nch): picked null transcripts
     uint16_t *act;   // members of the simplex, ascending (scratch of the E-step)
+    uint64_t *amask; // the simplex as a bit mask, 64 candidates per word: what the A-step ANDs the rows' masks with
     const double *tab_val;
     const int32_t *tab_row;
     int T, nch, N_f;
@@ -611,6 +612,11 @@ __device__ __forceinline__ int wide_e_step(const WideState &E, uint64_t key, uin
             }
         }
     }
+    for (int w = lane; w < (nch + 1) / 2; w += 32) {
+        const uint32_t lo = E.mask[2 * w] | E.mask[nch + 2 * w];
+        const uint32_t hi = 2 * w + 1 < nch ? E.mask[2 * w + 1] | E.mask[nch + 2 * w + 1] : 0u;
+        E.amask[w] = ((uint64_t)hi << 32) | lo;
+    }
     if (tr_theta) {
         __syncwarp();
         for (int t = lane; t < T; t += 32) tr_theta[t] = E.theta[t];
@@ -628,8 +634,8 @@ __device__ __forceinline__ MatView stage_matrix(const KernelArgs &A, const UnitD
     MatView M;
     M.n_slabs = U.n_slabs;
     M.h = U.slab_h;
-    M.row_mask = A.row_mask + U.mask_off;  // wide units only (read through L1, never staged)
-    M.n_words = (U.Tpad + 31) >> 5;
+    M.row_mask = (const uint64_t *)A.row_mask + U.mask_off;
+    M.n_words = (U.Tpad + 63) >> 6;
     if (MAT_SMEM) {
         double *sv = (double *)(smem + lay.val);
         uint16_t *sc = (uint16_t *)(smem + lay.col);
@@ -776,6 +782,7 @@ __global__ void __maxnreg__(BAYES_WIDE_MAXNREG) gibbs_wide_kernel(const __grid_c
     E.base = base;
     E.mask = (uint32_t *)(smem + lay.mask);
     E.act = (uint16_t *)(smem + lay.act);
+    E.amask = (uint64_t *)(smem + lay.amask);
     E.T = T;
     E.nch = (T + 31) >> 5;
     E.N_f = U.N_f[0];
@@ -797,10 +804,8 @@ __global__ void __maxnreg__(BAYES_WIDE_MAXNREG) gibbs_wide_kernel(const __grid_c
         E.den[t] = A.efflen[U.lane_off + t] * n_total;  // valueContainer.cpp:235 denominator
     }
     // initAssignment (theta == 1): every candidate is "in the simplex"
-    for (int c = threadIdx.x; c < E.nch; c += blockDim.x) {
-        E.mask[c] = c == E.nch - 1 && (T & 31) ? (1u << (T & 31)) - 1u : 0xffffffffu;
-        E.mask[E.nch + c] = 0u;
-    }
+    for (int w = threadIdx.x; w < (T + 63) >> 6; w += blockDim.x)
+        E.amask[w] = w == ((T + 63) >> 6) - 1 && (T & 63) ? (1ull << (T & 63)) - 1ull : ~0ull;
     if (U.tab_smem) {
         double *tv = (double *)(smem + lay.tab_val);
         int32_t *tr = (int32_t *)(smem + lay.tab_row);
@@ -835,7 +840,7 @@ __global__ void __maxnreg__(BAYES_WIDE_MAXNREG) gibbs_wide_kernel(const __grid_c
             if (tr && threadIdx.x == 0) A.tr_b[it] = b;
         }
         __syncthreads();
-        assign_rows_wide(M, E.mask, E.theta, E.counts, key, (uint32_t)(it < 0 ? 0 : it), it < 0, next_slab);
+        assign_rows_wide(M, E.amask, E.theta, E.counts, key, (uint32_t)(it < 0 ? 0 : it), it < 0, next_slab);
         __syncthreads();
     }
     if (tracing && total - 1 < A.trace_iters)
@@ -862,26 +867,27 @@ __global__ void step_assignment_kernel(const __grid_constant__ KernelArgs A, con
     const int T = U.T[0];
     double *theta = (double *)smem;
     uint64_t *skey = (uint64_t *)(theta + T);
-    int32_t *counts = (int32_t *)(skey + 1);
+    // simplex mask of the given expression vector: candidates with theta != 0 (assign_rows_wide)
+    const int n_words = (T + 63) >> 6;
+    uint64_t *amask = (uint64_t *)(skey + 1);
+    int32_t *counts = (int32_t *)(amask + n_words);
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
         theta[t] = INIT ? 1.0 : theta_in[t];
         counts[t] = A.base_counts[U.lane_off + t];
     }
     if (threadIdx.x == 0) skey[0] = U.key[0];
-    // simplex mask of the given expression vector: candidates with theta != 0 (assign_rows_wide)
-    const int n_words = (T + 31) >> 5;
-    uint32_t *amask = (uint32_t *)(counts + T);
     __syncthreads();
     if (threadIdx.x < 32)
         for (int w = 0; w < n_words; w++) {
-            const int t = w * 32 + (int)threadIdx.x;
-            const uint32_t pm = __ballot_sync(0xffffffffu, t < T && theta[t] != 0.0);
-            if (threadIdx.x == 0) { amask[w] = pm; amask[n_words + w] = 0u; }
+            const int t0 = w * 64 + (int)threadIdx.x;
+            const uint32_t lo = __ballot_sync(0xffffffffu, t0 < T && theta[t0] != 0.0);
+            const uint32_t hi = __ballot_sync(0xffffffffu, t0 + 32 < T && theta[t0 + 32] != 0.0);
+            if (threadIdx.x == 0) amask[w] = ((uint64_t)hi << 32) | lo;
         }
     MatView M;
     M.n_slabs = U.n_slabs;
     M.h = U.slab_h;
-    M.row_mask = A.row_mask + U.mask_off;
+    M.row_mask = (const uint64_t *)A.row_mask + U.mask_off;
     M.n_words = n_words;
     M.val = A.val + U.cell_off;
     M.col = A.col + U.cell_off;
@@ -928,6 +934,7 @@ __global__ void step_expression_kernel(int T, const int32_t *counts_in, int b, d
         WideState E;
         E.theta = theta; E.den = theta; E.mean = theta; E.m2 = theta;
         E.counts = counts; E.occ = counts; E.base = base; E.mask = mask; E.act = (uint16_t *)(mask + 2 * nch + 2);
+        E.amask = (uint64_t *)(smem + ((8 * (nT + (size_t)T + 2) + 4 * (2 * nT + (size_t)T + 1) + 4 * (2 * (size_t)nch + 2) + 2 * nT + 15) & ~(size_t)7));
         E.tab_val = tab; E.tab_row = tab_row;
         E.T = T; E.nch = nch; E.N_f = 0; E.gamma = gamma;
         wide_e_step(E, key, iteration, false, theta_out);
@@ -1008,7 +1015,7 @@ int launch_step_assignment(const KernelArgs &args, bool init, const double *d_th
 int launch_step_expression(int T, const int32_t *d_counts, int b, double gamma, uint64_t key, uint32_t iteration, double *d_theta,
                            void *stream) {
     const size_t nT = T <= 32 ? 32 : (size_t)T;
-    const size_t smem = 8 * (nT + (size_t)T + 2) + 4 * (2 * nT + (size_t)T + 1) + 4 * (2 * ((nT + 31) / 32) + 2) + 2 * nT + 16;
+    const size_t smem = 8 * (nT + (size_t)T + 2) + 4 * (2 * nT + (size_t)T + 1) + 4 * (2 * ((nT + 31) / 32) + 2) + 2 * nT + 32 + 8 * ((nT + 63) / 64 + 1);
     step_expression_kernel<<<1, 32, smem, (cudaStream_t)stream>>>(T, d_counts, b, gamma, key, iteration, d_theta);
     return check(cudaGetLastError(), "step_expression_kernel launch");
 }

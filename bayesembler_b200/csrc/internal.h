@@ -53,7 +53,7 @@ struct UnitDev {
     int64_t lane_off;   // -> efflen / base_counts: 32 entries (bundle, by lane) or T entries (wide)
     int64_t tab_off;    // -> tab_val (tables of the slots back to back)
     int64_t tabrow_off; // -> tab_row: slot g at g * (Tpad + 1), T + 1 offsets relative to the unit's tab_off
-    int64_t mask_off;   // -> row_mask (wide units): ceil(T / 32) words per padded row, [slab][word][lane]
+    int64_t mask_off;   // -> row_mask (wide units), in 64-bit words: ceil(T / 64) words per padded row, [slab][word][lane]
     // per slot
     int32_t T[kMaxSlots];
     int32_t N_f[kMaxSlots];      // fragments of the locus (folded rows included)

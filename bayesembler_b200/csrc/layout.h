@@ -13,7 +13,7 @@ namespace bayes {
 
 struct SmemLayout {
     // byte offsets from the start of dynamic shared memory; 8-byte members first
-    uint32_t theta, den, mean, m2, tab_val, val, key;                      // double / uint64
+    uint32_t theta, den, mean, m2, tab_val, val, key, amask;               // double / uint64
     uint32_t counts, base, occ, tab_row, mask, slab, row_n, row_nnz, row_info, next_slab;  // int32
     uint32_t col, act;                                                     // uint16
     uint32_t total;
@@ -34,6 +34,7 @@ BAYES_LAYOUT_HD SmemLayout unit_layout(bool wide, int nT, int n_slots, int Tpad,
     L.tab_val = o; o += tab_smem ? 8u * (uint32_t)tab_len : 0u;
     L.val = o; o += mat_smem ? 8u * (uint32_t)n_cells : 0u;
     L.key = o; o += 8u * (uint32_t)n_slots;
+    L.amask = o; o += wide ? 8u * ((uT + 63u) / 64u) : 0u;
     L.next_slab = o; o += 8u;
     L.counts = o; o += 4u * uT;
     L.base = o; o += wide ? 4u * uT : 0u;

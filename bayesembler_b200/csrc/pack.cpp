@@ -194,8 +194,8 @@ void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, PackedU
     U.val.assign(n_cells, 0.0);
     U.col.assign(n_cells, 0);
     // wide units: T bits per padded row saying which candidates the row has a cell for (gibbs_kernel.cu, assign_rows_wide)
-    const int n_words = wide ? (L0.T + 31) / 32 : 0;
-    U.row_mask.assign((size_t)n_slabs * H * n_words, 0u);
+    const int n_words = wide ? (L0.T + 63) / 64 : 0;  // 64-bit words, stored as pairs of uint32 (low half first)
+    U.row_mask.assign((size_t)n_slabs * H * n_words * 2, 0u);
     for (int i = 0; i < n_items; i++) {
         const ItemShape &it = items[i];
         const PreLocus &L = *slots[it.slot].locus;
@@ -215,7 +215,7 @@ void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, PackedU
             U.col[at] = (uint16_t)(lane0 + L.cell_col[L.row_ptr[it.r] + k]);
             if (wide) {
                 const int c = L.cell_col[L.row_ptr[it.r] + k];
-                U.row_mask[((size_t)s * n_words + (c >> 5)) * H + l] |= 1u << (c & 31);
+                U.row_mask[2 * (((size_t)s * n_words + (c >> 6)) * H + l) + ((c >> 5) & 1)] |= 1u << (c & 31);
             }
         }
     }
