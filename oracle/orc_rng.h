@@ -19,7 +19,7 @@
  *   - gamma: Marsaglia & Tsang 2000 (alpha>=1), alpha<1 by the U^(1/alpha)
  *     boost, alpha==1 by inversion; normal by Box-Muller (cosine branch);
  *   - binomial: inversion (BINV, Kachitvichyanukul & Schmeiser 1988) when
- *     n*min(p,1-p) < 10, else BTRD (Hoermann 1993).
+ *     n*min(p,1-p) < ORC_BINV_NQ (32), else BTRD (Hoermann 1993).
  * The same file backs (a) the Boost stand-in headers under oracle/shim/ that
  * the UNMODIFIED reference translation units are compiled against
  * (oracle/_ref) and (b) the C restatement in oracle/bayes_oracle.c, so that
