@@ -19,7 +19,8 @@ EXPORTED_SYMBOLS = [
     "bayes_gibbs_download", "bayes_gibbs_sync", "bayes_gibbs_run_batch", "bayes_gibbs_clear", "bayes_gibbs_fetch",
     "bayes_gibbs_fetch_all",
     "bayes_gibbs_locus_info", "bayes_gibbs_chain_info", "bayes_gibbs_num_loci", "bayes_gibbs_num_jobs", "bayes_gibbs_unit_stats", "bayes_gibbs_phase_seconds", "bayes_gibbs_last_launches",
-    "bayes_gibbs_set_trace", "bayes_gibbs_fetch_trace", "bayes_gibbs_set_calibration", "bayes_top_marginals", "bayes_step_generate_assignment",
+    "bayes_gibbs_set_trace", "bayes_gibbs_fetch_trace", "bayes_gibbs_set_calibration", "bayes_gibbs_set_mode", "bayes_gibbs_get_mode",
+    "bayes_top_marginals", "bayes_step_generate_assignment", "bayes_step_assignment",
     "bayes_step_init_assignment", "bayes_step_generate_expression", "bayes_step_variates", "bayes_min_read_cover",
     "bayes_simplex_table", "bayes_chain_key", "bayes_locus_cost", "bayes_partition_lpt", "bayes_philox4x32",
     "bayes_seq_model_create_gaussian", "bayes_seq_model_destroy", "bayes_seq_model_three_prime_prob", "bayes_seq_model_length_prob",
@@ -34,6 +35,11 @@ EXPORTED_SYMBOLS = [
 
 class BayesError(RuntimeError):
     pass
+
+
+# sampling modes (include/bayesembler_b200.h)
+MODE_FAST, MODE_REPLAY = 0, 1
+_MODES = {"fast": MODE_FAST, "replay": MODE_REPLAY, MODE_FAST: MODE_FAST, MODE_REPLAY: MODE_REPLAY}
 
 
 class LocusDesc(C.Structure):
@@ -114,6 +120,9 @@ def load_library(path=None):
         "bayes_gibbs_last_launches": (i32, [vp]),
         "bayes_gibbs_set_trace": (C.c_int, [vp, i64, i32, i32]),
         "bayes_gibbs_set_calibration": (C.c_int, [vp, i32]),
+        "bayes_gibbs_set_mode": (C.c_int, [vp, i32]),
+        "bayes_gibbs_get_mode": (i32, [vp]),
+        "bayes_step_assignment": (C.c_int, [C.c_int, C.POINTER(LocusDesc), vp, u64, C.c_uint32, i32, vp]),
         "bayes_gibbs_fetch_trace": (C.c_int, [vp, vp, vp, vp, vp]),
         "bayes_top_marginals": (C.c_int, [i32, i32, vp, vp, vp, dbl, vp, vp, vp]),
         "bayes_step_generate_assignment": (C.c_int, [C.c_int, C.POINTER(LocusDesc), vp, u64, C.c_uint32, vp]),
@@ -192,11 +201,13 @@ def make_desc_array(loci, burn_in, samples, seeds, pi=None, n_chains=1):
 class GibbsContext(object):
     """One GPU's sampler context (bayes_gibbs_ctx)."""
 
-    def __init__(self, device=0, stream=None, host_threads=0):
+    def __init__(self, device=0, stream=None, host_threads=0, mode=None):
         self.lib = load_library()
         h = C.c_void_p()
         _check(self.lib.bayes_gibbs_create(device, C.byref(h)), "bayes_gibbs_create")
         self.h = h
+        if mode is not None:
+            self.set_mode(mode)
         self._T = []
         self._chains = []
         self._lock = threading.Lock()
@@ -323,6 +334,13 @@ class GibbsContext(object):
         """-1 = automatic, 0 = off, n = calibration pass of n iterations (bayes_gibbs_set_calibration)."""
         _check(self.lib.bayes_gibbs_set_calibration(self.h, int(iterations)), "bayes_gibbs_set_calibration")
 
+    def set_mode(self, mode):
+        """"fast" (production, the default) or "replay" (the reference's order of draws); before upload."""
+        _check(self.lib.bayes_gibbs_set_mode(self.h, _MODES[mode]), "bayes_gibbs_set_mode")
+
+    def get_mode(self):
+        return "replay" if self.lib.bayes_gibbs_get_mode(self.h) == MODE_REPLAY else "fast"
+
     def set_trace(self, locus_id, chain, trace_iters):
         _check(self.lib.bayes_gibbs_set_trace(self.h, locus_id, chain, trace_iters), "bayes_gibbs_set_trace")
         self._trace = (self._T[locus_id], trace_iters)
@@ -403,6 +421,16 @@ def step_init_assignment(loc, key, device=0):
     d = make_desc(loc, 0, 1, 0, pi=0.5)
     counts = np.zeros(loc.T, np.int32)
     _check(load_library().bayes_step_init_assignment(device, C.byref(d), int(key), _ptr(counts)), "bayes_step_init_assignment")
+    return counts
+
+
+def step_assignment(loc, theta, key, iteration=0, mode="fast", device=0):
+    """generateAssignment (theta given) or initAssignment (theta None) in the given sampling mode."""
+    d = make_desc(loc, 0, 1, 0, pi=0.5)
+    theta = None if theta is None else np.ascontiguousarray(theta, np.float64)
+    counts = np.zeros(loc.T, np.int32)
+    _check(load_library().bayes_step_assignment(device, C.byref(d), _ptr(theta), int(key), iteration, _MODES[mode], _ptr(counts)),
+           "bayes_step_assignment")
     return counts
 
 

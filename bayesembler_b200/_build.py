@@ -15,8 +15,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbayesembler_b200.so")
 CLI = os.path.join(HERE, "bayesembler_b200_cli")
 CLI_SOURCES = [os.path.join(HERE, "host", f) for f in ("main.cpp", "assembler.hpp", "bayesembler_b200.hpp")]
-SOURCES = ["capi.cu", "gibbs_kernel.cu", "host_steps.cpp", "pack.cpp", "likelihood.cpp", "allpaths.cpp"]
-HEADERS = ["internal.h", "layout.h", "rng.cuh", os.path.join("..", "..", "include", "bayesembler_b200.h")]
+SOURCES = ["capi.cu", "gibbs_kernel.cu", "gibbs_fast.cu", "host_steps.cpp", "pack.cpp", "likelihood.cpp", "allpaths.cpp"]
+HEADERS = ["internal.h", "layout.h", "rng.cuh", "gibbs_common.cuh", os.path.join("..", "..", "include", "bayesembler_b200.h")]
 
 
 def nvcc_path():
@@ -30,7 +30,7 @@ def nvcc_command(out=LIB, extra=()):
     # -fmad=false: keep the sampler's own double arithmetic un-contracted so that it rounds like the CPU oracle
     # (the CUDA math library's log/exp/cos use explicit fma internally and are unaffected).
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
-           "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-shared", "-o", out]
+           "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-ffp-contract=off", "-shared", "-o", out]
     if os.environ.get("BAYES_NVCC_FLAGS"):  # experiment knob, e.g. -DBAYES_BINV_NQ=24.0
         cmd += os.environ["BAYES_NVCC_FLAGS"].split()
     cmd += list(extra)

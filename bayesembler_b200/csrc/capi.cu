@@ -124,17 +124,24 @@ struct bayes_gibbs_ctx {
     PinBuf<double> h_val, h_efflen, h_tab_val;
     PinBuf<uint16_t> h_col;
     PinBuf<int32_t> h_slab, h_row_n, h_row_nnz, h_base, h_tab_row;
-    PinBuf<uint32_t> h_row_info, h_row_mask;
+    PinBuf<uint32_t> h_row_info, h_row_mask, h_pool_desc;
+    PinBuf<int32_t> h_row_woff;
     // results (pinned)
-    PinBuf<int32_t> h_occ, h_counts;
+    PinBuf<int32_t> h_occ, h_counts, h_unit_err;
     PinBuf<double> h_mean, h_m2;
 
     DevBuf<UnitDev> d_units;
     DevBuf<double> d_val, d_efflen, d_tab_val, d_mean, d_m2, d_tr_theta;
     DevBuf<uint16_t> d_col;
     DevBuf<int32_t> d_slab, d_row_n, d_row_nnz, d_base, d_tab_row, d_occ, d_counts, d_tr_counts, d_tr_b, d_tr_init;
-    DevBuf<uint32_t> d_row_info, d_row_mask;
+    DevBuf<uint32_t> d_row_info, d_row_mask, d_pool_desc, d_queue;
+    DevBuf<int32_t> d_row_woff, d_unit_err;
+    DevBuf<double> d_scr_cum;
+    DevBuf<uint16_t> d_scr_col;
     DevBuf<uint64_t> d_unit_clock;
+    int mode = BAYES_MODE_FAST;      // sampling mode of the next upload (bayes_gibbs_set_mode)
+    int built_mode = BAYES_MODE_FAST;  // mode the uploaded units were packed for
+    int64_t scr_len = 0, q_len = 0;  // global scratch of the fast-mode units whose matrix is not in shared memory
 
     std::vector<Launch> launches;
     std::vector<int64_t> unit_group;    // launch order -> index of the unit in formation order (stable across rebuilds)
@@ -215,8 +222,17 @@ int append_unit(bayes_gibbs_ctx *ctx, PackedUnit &U) {
     U.d.tab_off = (int64_t)ctx->h_tab_val.n;
     U.d.tabrow_off = (int64_t)ctx->h_tab_row.n;
     U.d.mask_off = (int64_t)(ctx->h_row_mask.n / 2);  // in 64-bit words
+    U.d.woff_off = (int64_t)ctx->h_row_woff.n;
+    U.d.pooldesc_off = (int64_t)ctx->h_pool_desc.n;
+    U.d.scr_off = ctx->scr_len;
+    U.d.q_off = ctx->q_len;
+    if (!U.row_woff.empty() && !U.d.mat_smem) {  // fast mode, streaming unit
+        ctx->scr_len += U.d.n_chain_cells;
+        ctx->q_len += 6 * (int64_t)U.d.qcap;
+    }
     if ((rc = append(ctx->h_slab, U.slab_cell_off)) || (rc = append(ctx->h_val, U.val)) || (rc = append(ctx->h_col, U.col)) ||
         (rc = append(ctx->h_row_n, U.row_n)) || (rc = append(ctx->h_row_nnz, U.row_nnz)) || (rc = append(ctx->h_row_info, U.row_info)) || (rc = append(ctx->h_row_mask, U.row_mask)) ||
+        (rc = append(ctx->h_row_woff, U.row_woff)) || (rc = append(ctx->h_pool_desc, U.pool_desc)) ||
         (rc = append(ctx->h_efflen, U.efflen)) || (rc = append(ctx->h_base, U.base_counts)) ||
         (rc = append(ctx->h_tab_val, U.tab_val)) || (rc = append(ctx->h_tab_row, U.tab_row)))
         return rc;
@@ -234,6 +250,10 @@ int append_unit(bayes_gibbs_ctx *ctx, PackedUnit &U) {
 int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
     ctx->h_units.n = ctx->h_val.n = ctx->h_efflen.n = ctx->h_tab_val.n = ctx->h_col.n = 0;
     ctx->h_slab.n = ctx->h_row_n.n = ctx->h_row_nnz.n = ctx->h_row_info.n = ctx->h_row_mask.n = ctx->h_base.n = ctx->h_tab_row.n = 0;
+    ctx->h_row_woff.n = ctx->h_pool_desc.n = 0;
+    ctx->scr_len = ctx->q_len = 0;
+    const bool fast = ctx->mode == BAYES_MODE_FAST;
+    ctx->built_mode = ctx->mode;
     ctx->launches.clear();
     ctx->trace_unit = -1;
 
@@ -301,7 +321,56 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         *chain_slabs = (S.n_chain + h - 1) / h;
         *n_slabs = *chain_slabs + (n_items - S.n_chain + h - 1) / h;
     };
-    auto iteration_us = [&](const UnitShape &S, int warps, int h) {
+    // Fast mode (gibbs_fast.cu): a chain slab only compacts its rows' cells in play (cheap, per column); the binomials
+    // are the nodes of the rows' splitting trees, processed level by level by ALL threads of the unit, 32 nodes per warp
+    // pass whichever row they belong to; a uniform slab reads its words from the pool (generated during the E-step by
+    // the other warps, after it by a one-warp unit).  A row's cells in play are estimated as half its stored cells.
+    const double kFastEstepUs = 9.0, kFastChainColUs = 0.10, kFastLevelUs = 1.9, kFastBarrierUs = 0.25, kFastUniformSlabUs = 0.7,
+                 kFastUniformBlockUs = 0.35, kFastUniformColumnUs = 0.10, kFastPoolUs = 0.6;
+    auto tree_batches = [](const UnitShape &S, int lanes, int *levels) {
+        // nodes with two or more cells per tree level, summed over the chain rows; returns the warp passes they need
+        double passes = 0;
+        int lv = 0;
+        for (int d = 0; d < 13; d++) {
+            int64_t nodes = 0;
+            for (int i = 0; i < S.n_chain; i++) {
+                const int k = std::max(2, (S.nnz[i] + 1) / 2);
+                const int64_t w = (int64_t)1 << d;
+                if (w < k) nodes += std::min<int64_t>(w, k - w);
+            }
+            if (nodes == 0) break;
+            lv++;
+            passes += (double)((nodes + lanes - 1) / lanes);
+        }
+        *levels = lv;
+        return passes;
+    };
+    auto iteration_us_fast = [&](const UnitShape &S, int warps, int h) {
+        int chain_slabs, n_slabs;
+        slab_layout(S, h, &chain_slabs, &n_slabs);
+        const int n_items = (int)S.nnz.size();
+        std::vector<double> load(warps, 0.0);
+        double worst = 0, blocks_total = 0;
+        for (int s = 0; s < n_slabs; s++) {
+            const bool chain = s < chain_slabs;
+            const int first = chain ? s * h : S.n_chain + (s - chain_slabs) * h, last = chain ? S.n_chain : n_items;
+            int width = 0, blocks = 0;
+            for (int l = 0; l < h && first + l < last; l++) {
+                width = std::max(width, S.nnz[first + l]);
+                blocks = std::max(blocks, S.blocks[first + l]);
+                blocks_total += S.blocks[first + l];
+            }
+            const double us = chain ? 0.3 + width * kFastChainColUs : kFastUniformSlabUs + blocks * (kFastUniformBlockUs + width * kFastUniformColumnUs);
+            double &l0 = *std::min_element(load.begin(), load.end());
+            l0 += us;
+            worst = std::max(worst, l0);
+        }
+        int levels = 0;
+        const double passes = tree_batches(S, 32 * warps, &levels);
+        const double pool = warps > 1 ? 0.0 : kFastPoolUs * ceil(blocks_total / 32.0);
+        return kFastEstepUs + pool + worst + passes * kFastLevelUs + (levels + 2) * kFastBarrierUs * (warps > 1 ? 1.0 : 0.2);
+    };
+    auto iteration_us_replay = [&](const UnitShape &S, int warps, int h) {
         int chain_slabs, n_slabs;
         slab_layout(S, h, &chain_slabs, &n_slabs);
         const int n_items = (int)S.nnz.size();
@@ -322,6 +391,7 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         }
         return worst + kEstepUs;
     };
+    auto iteration_us = [&](const UnitShape &S, int warps, int h) { return fast ? iteration_us_fast(S, warps, h) : iteration_us_replay(S, warps, h); };
     // group_scale (calibrate_units): measured / modelled per-iteration time of the unit at its first shape
     auto unit_time = [&](const UnitShape &S, int warps, int h) {
         const double scale = group_scale ? (*group_scale)[&S - shapes.data()] : 1.0;
@@ -344,6 +414,11 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
             if (chain) f4[0] += width;
             else { f4[1] += 1; f4[2] += blocks; f4[3] += (double)blocks * width; }
         }
+        if (fast) {  // fast mode: uniform slabs and blocks share one entry, the freed one holds the tree's warp passes at one warp
+            int levels = 0;
+            f4[1] = f4[1] + 0.001 * f4[2];
+            f4[2] = tree_batches(S, 32, &levels);
+        }
     };
     auto smem_estimate = [&](const UnitShape &S, int h) {
         int chain_slabs, n_slabs;
@@ -357,7 +432,7 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
             for (int l = 0; l < h && first + l < last; l++) width = std::max(width, S.nnz[first + l]);
             cells += (double)h * width;
         }
-        return 10.0 * cells + 12.0 * h * n_slabs + 1024.0;
+        return (fast ? 12.0 : 10.0) * cells + (fast ? 16.0 : 12.0) * h * n_slabs + (fast ? 2048.0 : 1024.0);
     };
 
     // Warps and slab height per unit.  Throughput is best with ONE warp per unit walking full 32-row slabs: every extra
@@ -367,8 +442,9 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
     // (occupied warp-seconds / warps it keeps resident), move that unit one step down the ladder below.
     std::vector<int> unit_warps(n_units, 1), unit_h(n_units, 32);
     {
+        // (fast mode: the latency of a unit is in its tree levels, which all threads share whatever the slab height: more warps only)
         static const int ladder[][2] = {{1, 32}, {2, 32}, {4, 32}, {8, 32}, {8, 16}, {16, 16}, {16, 8}};
-        const int n_ladder = (int)(sizeof(ladder) / sizeof(ladder[0]));
+        const int n_ladder = fast ? 4 : (int)(sizeof(ladder) / sizeof(ladder[0]));
         const double capacity = (double)ctx->sm_count * kWarpsPerSM;  // resident warps at the kernels' register count
         const char *spw = getenv("BAYES_SMEM_PER_WARP");  // experiment knob
         const double smem_per_warp = spw ? atof(spw) : 8192.0;
@@ -403,7 +479,7 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
             for (; k < n_ladder; k++) {
                 int chain_slabs, n_slabs;
                 slab_layout(shapes[i], ladder[k][1], &chain_slabs, &n_slabs);
-                if (ladder[k][0] >= 2 * n_slabs && ladder[k][0] > ladder[step[i]][0]) continue;  // idle warps only
+                if (!fast && ladder[k][0] >= 2 * n_slabs && ladder[k][0] > ladder[step[i]][0]) continue;  // idle warps only
                 tk = unit_time(shapes[i], ladder[k][0], ladder[k][1]);
                 if (tk < 0.93 * t[i]) break;
             }
@@ -438,7 +514,7 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
     packed.resize(n_units);
     ctx->packed_h.resize(n_units, 0);
     parallel_for(host_thread_count(ctx, n_units), n_units, [&](int64_t i) {
-        if (!reuse || ctx->packed_h[i] != unit_h[i]) pack_unit(groups[i], group_wide[i] != 0, unit_h[i], &packed[i]);
+        if (!reuse || ctx->packed_h[i] != unit_h[i]) pack_unit(groups[i], group_wide[i] != 0, unit_h[i], fast, &packed[i]);
         ctx->packed_h[i] = unit_h[i];
         packed[i].d.block = 32 * unit_warps[i];
         packed[i].cost = unit_time(shapes[i], unit_warps[i], unit_h[i]);  // estimated duration: the launch-order key
@@ -451,10 +527,16 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
     // blocks out launch by launch, so the launches are issued longest units first across ALL classes -- the
     // largest-first queue of the reference (assembler.cpp:1886-1916) -- with the blocks of 8 or more warps, which only
     // fit an SM that is still nearly empty, ahead of everything else.
-    auto smem_bucket = [](int32_t bytes) -> int32_t {
+    const int32_t smem_limit = (int32_t)max_unit_smem();
+    auto smem_bucket = [smem_limit](int32_t bytes) -> int32_t {
         int32_t step = bytes <= 8 * 1024 ? 2048 : bytes <= 32 * 1024 ? 4096 : 16 * 1024;
-        return (bytes + step - 1) / step * step;
+        return std::min(smem_limit, (bytes + step - 1) / step * step);
     };
+    for (int64_t i = 0; i < n_units; i++)
+        if (packed[i].d.smem_bytes > smem_limit) {
+            set_error("a unit needs " + std::to_string(packed[i].d.smem_bytes) + " bytes of shared memory, more than the device offers");
+            return BAYES_E_INVALID;
+        }
     auto band_of = [](const PackedUnit &u) -> int {
         if (u.d.block >= 256) return 1000;                            // critical, hard to place later
         return (int)floor(log(std::max(u.cost, 1e-6)) / log(1.4));   // +-18 % of duration per band
@@ -521,6 +603,12 @@ KernelArgs kernel_args(bayes_gibbs_ctx *ctx) {
     a.out_m2 = ctx->d_m2.p;
     a.out_counts = ctx->d_counts.p;
     a.unit_clock = ctx->d_unit_clock.p;
+    a.row_woff = ctx->d_row_woff.p;
+    a.pool_desc = ctx->d_pool_desc.p;
+    a.scr_cum = ctx->d_scr_cum.p;
+    a.scr_col = ctx->d_scr_col.p;
+    a.queue = ctx->d_queue.p;
+    a.unit_err = ctx->d_unit_err.p;
     a.trace_unit = ctx->trace_unit;
     a.trace_slot = ctx->trace_slot;
     a.trace_iters = ctx->trace_iters;
@@ -537,7 +625,10 @@ int upload_units(bayes_gibbs_ctx *ctx) {
     if ((rc = h2d(ctx->d_units, ctx->h_units, st)) || (rc = h2d(ctx->d_val, ctx->h_val, st)) || (rc = h2d(ctx->d_col, ctx->h_col, st)) ||
         (rc = h2d(ctx->d_slab, ctx->h_slab, st)) || (rc = h2d(ctx->d_row_n, ctx->h_row_n, st)) ||
         (rc = h2d(ctx->d_row_nnz, ctx->h_row_nnz, st)) || (rc = h2d(ctx->d_row_info, ctx->h_row_info, st)) ||
-        (rc = h2d(ctx->d_row_mask, ctx->h_row_mask, st)) ||
+        (rc = h2d(ctx->d_row_mask, ctx->h_row_mask, st)) || (rc = h2d(ctx->d_row_woff, ctx->h_row_woff, st)) ||
+        (rc = h2d(ctx->d_pool_desc, ctx->h_pool_desc, st)) || (rc = ctx->d_scr_cum.reserve((size_t)ctx->scr_len)) ||
+        (rc = ctx->d_scr_col.reserve((size_t)ctx->scr_len)) || (rc = ctx->d_queue.reserve((size_t)ctx->q_len)) ||
+        (rc = ctx->d_unit_err.reserve(ctx->h_units.n + 1)) || (rc = ctx->h_unit_err.resize(ctx->h_units.n + 1)) ||
         (rc = h2d(ctx->d_efflen, ctx->h_efflen, st)) || (rc = h2d(ctx->d_base, ctx->h_base, st)) ||
         (rc = h2d(ctx->d_tab_val, ctx->h_tab_val, st)) || (rc = h2d(ctx->d_tab_row, ctx->h_tab_row, st)))
         return rc;
@@ -575,8 +666,10 @@ int bayes_gibbs_create(int device, bayes_gibbs_ctx **out) {
     }
     int rc = configure_kernels();
     if (rc) return rc;
+    if ((rc = configure_fast_kernels())) return rc;
     bayes_gibbs_ctx *ctx = new (std::nothrow) bayes_gibbs_ctx();
     if (!ctx) return BAYES_E_NOMEM;
+    if (const char *m = getenv("BAYES_MODE")) ctx->mode = strcmp(m, "replay") == 0 ? BAYES_MODE_REPLAY : BAYES_MODE_FAST;
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     rc = cuda_rc(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -596,6 +689,10 @@ void bayes_gibbs_destroy(bayes_gibbs_ctx *ctx) {
     ctx->h_units.release(); ctx->h_val.release(); ctx->h_efflen.release(); ctx->h_tab_val.release(); ctx->h_col.release();
     ctx->h_slab.release(); ctx->h_row_n.release(); ctx->h_row_nnz.release(); ctx->h_row_info.release(); ctx->h_base.release();
     ctx->h_tab_row.release(); ctx->h_occ.release(); ctx->h_counts.release(); ctx->h_mean.release(); ctx->h_m2.release();
+    ctx->h_row_mask.release(); ctx->d_row_mask.release();
+    ctx->h_pool_desc.release(); ctx->h_row_woff.release(); ctx->h_unit_err.release();
+    ctx->d_pool_desc.release(); ctx->d_queue.release(); ctx->d_row_woff.release(); ctx->d_unit_err.release();
+    ctx->d_scr_cum.release(); ctx->d_scr_col.release();
     ctx->d_units.release(); ctx->d_val.release(); ctx->d_efflen.release(); ctx->d_tab_val.release(); ctx->d_mean.release();
     ctx->d_m2.release(); ctx->d_tr_theta.release(); ctx->d_col.release(); ctx->d_slab.release(); ctx->d_row_n.release();
     ctx->d_row_nnz.release(); ctx->d_row_info.release(); ctx->d_base.release(); ctx->d_tab_row.release(); ctx->d_occ.release();
@@ -684,6 +781,7 @@ int bayes_gibbs_upload(bayes_gibbs_ctx *ctx) {
     if (!ctx) return BAYES_E_INVALID;
     int rc = use_device(ctx);
     if (rc) return rc;
+    if (ctx->uploaded) CU(cudaStreamSynchronize(ctx->stream));  // a second upload rewrites the pinned staging buffers
     const double t0 = now_s();
     if ((rc = build_units(ctx, nullptr))) return rc;
     double t1 = now_s();
@@ -734,6 +832,7 @@ static int issue_launches(bayes_gibbs_ctx *ctx, int32_t iter_cap) {
     KernelArgs args = kernel_args(ctx);
     args.iter_cap = iter_cap;
     ctx->last_launches = 0;
+    CU(cudaMemsetAsync(ctx->d_unit_err.p, 0, (ctx->h_units.n + 1) * sizeof(int32_t), ctx->stream));
     const size_t n_l = ctx->launches.size();
     if (!ctx->fork_ev) CU(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
     while (ctx->aux.size() < n_l) {
@@ -774,7 +873,9 @@ static int issue_launches(bayes_gibbs_ctx *ctx, int32_t iter_cap) {
             CU(cudaEventRecord(ctx->gate_ev[i], ctx->gate));
             CU(cudaStreamWaitEvent(st, ctx->gate_ev[i], 0));
         }
-        if ((rc = launch_units(args, l.unit_base, l.n_units, l.block, l.wide, l.mat_smem, l.smem, st))) return rc;
+        if (ctx->built_mode == BAYES_MODE_FAST) rc = launch_units_fast(args, l.unit_base, l.n_units, l.block, l.wide, l.mat_smem, l.smem, st);
+        else rc = launch_units(args, l.unit_base, l.n_units, l.block, l.wide, l.mat_smem, l.smem, st);
+        if (rc) return rc;
         if (n_l > 1) {
             CU(cudaEventRecord(ctx->join_ev[i], st));
             CU(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[i], 0));
@@ -821,6 +922,21 @@ int bayes_gibbs_set_calibration(bayes_gibbs_ctx *ctx, int32_t iterations) {
     return BAYES_OK;
 }
 
+int bayes_gibbs_set_mode(bayes_gibbs_ctx *ctx, int32_t mode) {
+    if (!ctx || (mode != BAYES_MODE_FAST && mode != BAYES_MODE_REPLAY)) {
+        set_error("bayes_gibbs_set_mode: bad arguments");
+        return BAYES_E_INVALID;
+    }
+    if (ctx->uploaded) {
+        set_error("bayes_gibbs_set_mode: must be called before bayes_gibbs_upload");
+        return BAYES_E_STATE;
+    }
+    ctx->mode = mode;
+    return BAYES_OK;
+}
+
+int32_t bayes_gibbs_get_mode(bayes_gibbs_ctx *ctx) { return ctx ? ctx->mode : BAYES_E_INVALID; }
+
 int bayes_gibbs_run(bayes_gibbs_ctx *ctx) {
     if (!ctx) return BAYES_E_INVALID;
     if (!ctx->uploaded) {
@@ -853,6 +969,8 @@ int bayes_gibbs_download(bayes_gibbs_ctx *ctx) {
         CU(cudaMemcpyAsync(ctx->h_m2.p, ctx->d_m2.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaMemcpyAsync(ctx->h_counts.p, ctx->d_counts.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     }
+    if (ctx->h_units.n)
+        CU(cudaMemcpyAsync(ctx->h_unit_err.p, ctx->d_unit_err.p, ctx->h_units.n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     ctx->downloaded = true;
     ctx->phase_s[4] = now_s() - t0;
     return BAYES_OK;
@@ -865,6 +983,17 @@ int bayes_gibbs_sync(bayes_gibbs_ctx *ctx) {
     const double t0 = now_s();
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->phase_s[5] = now_s() - t0;
+    if (ctx->downloaded)
+        for (size_t i = 0; i < ctx->h_units.n; i++)
+            if (ctx->h_unit_err.p[i] != 0) {
+                // the reference aborts here: assert(normalisation_constant >= double_underflow) (assignmentGenerator.cpp:284),
+                // assert(gamma_base_sample >= double_underflow) (expressionGenerator.cpp:115)
+                const int code = ctx->h_unit_err.p[i];
+                set_error(code == 1   ? "a row had no candidate with a non-zero probability under the sampled expression (unit " + std::to_string(i) + ")"
+                          : code == 2 ? "a Gamma draw underflowed (unit " + std::to_string(i) + ")"
+                                      : "internal bounds check " + std::to_string(code) + " failed (unit " + std::to_string(i) + ")");
+                return BAYES_E_NUMERIC;
+            }
     return BAYES_OK;
 }
 
@@ -1031,7 +1160,12 @@ int bayes_gibbs_fetch_trace(bayes_gibbs_ctx *ctx, double *theta_trace, int32_t *
 
 // ---- single steps --------------------------------------------------------------------------------------------------
 static int step_assignment(int device, const bayes_locus_desc *locus, const double *theta, uint64_t key, uint32_t iteration,
-                           int32_t *counts_out, bool init) {
+                           int32_t *counts_out, bool init, int mode = BAYES_MODE_REPLAY) {
+    if (mode != BAYES_MODE_FAST && mode != BAYES_MODE_REPLAY) {
+        set_error("bayes_step_assignment: bad mode");
+        return BAYES_E_INVALID;
+    }
+    const bool fast = mode == BAYES_MODE_FAST;
     if (!locus || !counts_out || (!init && !theta)) {
         set_error("bayes_step_*_assignment: null argument");
         return BAYES_E_INVALID;
@@ -1054,7 +1188,9 @@ static int step_assignment(int device, const bayes_locus_desc *locus, const doub
     }
     const int T = d.T;
     PackedUnit U;
-    pack_unit(std::vector<SlotRef>(1, SlotRef{&P, 0, 0}), true, 32, &U);  // wide layout: columns stay candidate indices
+    pack_unit(std::vector<SlotRef>(1, SlotRef{&P, 0, 0}), true, 32, fast, &U);  // wide layout: columns stay candidate indices
+    U.d.mat_smem = 0;  // the step kernels read the matrix (and the fast-mode scratch) from global memory
+    ctx->scr_len = ctx->q_len = 0;
     if ((rc = append_unit(ctx, U))) return fail(rc);
     if ((rc = upload_units(ctx))) return fail(rc);
     cudaStream_t st = ctx->stream;
@@ -1062,11 +1198,21 @@ static int step_assignment(int device, const bayes_locus_desc *locus, const doub
     if (!init && (rc = cuda_rc(cudaMemcpyAsync(ctx->d_mean.p, theta, T * sizeof(double), cudaMemcpyHostToDevice, st), "theta H2D")))
         return fail(rc);
     const KernelArgs args = kernel_args(ctx);
-    if ((rc = launch_step_assignment(args, init, ctx->d_mean.p, iteration, ctx->d_occ.p, 12 * (size_t)T + 8 * (((size_t)T + 63) / 64) + 48, st))) return fail(rc);
+    const size_t smem = 12 * (size_t)T + 8 * (((size_t)T + 63) / 64) + 48 + 4 * kFastCtlWords;
+    if ((rc = cuda_rc(cudaMemsetAsync(ctx->d_unit_err.p, 0, sizeof(int32_t), st), "memset"))) return fail(rc);
+    if (fast) rc = launch_step_assignment_fast(args, init, ctx->d_mean.p, iteration, ctx->d_occ.p, smem, st);
+    else rc = launch_step_assignment(args, init, ctx->d_mean.p, iteration, ctx->d_occ.p, smem, st);
+    if (rc) return fail(rc);
     if ((rc = cuda_rc(cudaMemcpyAsync(counts_out, ctx->d_occ.p, T * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "counts D2H")))
         return fail(rc);
+    int32_t unit_err = 0;
+    if ((rc = cuda_rc(cudaMemcpyAsync(&unit_err, ctx->d_unit_err.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st), "err D2H"))) return fail(rc);
     if ((rc = cuda_rc(cudaStreamSynchronize(st), "step sync"))) return fail(rc);
     bayes_gibbs_destroy(ctx);
+    if (unit_err != 0) {
+        set_error("bayes_step_assignment: a row had no candidate with a non-zero probability (reference: assert, assignmentGenerator.cpp:284)");
+        return BAYES_E_NUMERIC;
+    }
     return BAYES_OK;
 }
 
@@ -1077,6 +1223,11 @@ int bayes_step_generate_assignment(int device, const bayes_locus_desc *locus, co
 
 int bayes_step_init_assignment(int device, const bayes_locus_desc *locus, uint64_t key, int32_t *counts_out) {
     return step_assignment(device, locus, nullptr, key, 0, counts_out, true);
+}
+
+int bayes_step_assignment(int device, const bayes_locus_desc *locus, const double *theta, uint64_t key, uint32_t iteration, int32_t mode,
+                          int32_t *counts_out) {
+    return step_assignment(device, locus, theta, key, iteration, counts_out, theta == nullptr, mode);
 }
 
 int bayes_step_generate_expression(int device, int32_t T, const int32_t *counts, int32_t b, double gamma, uint64_t key,

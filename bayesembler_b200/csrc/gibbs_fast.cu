@@ -1,0 +1,863 @@
+// Fast (production) sampling mode of the persistent Gibbs kernels for sm_100a.
+//
+// Same model, same conditional distributions and the same E-step as the replay-mode kernels (gibbs_kernel.cu), but the
+// A-step no longer mirrors the ORDER in which the reference draws (assignmentGenerator.cpp:263-373); SURVEY.md section 7
+// allows any exact multinomial per row outside replay.  What changes, and why:
+//
+//  * rows with >= 20 fragments: the reference's chain of conditional binomials (:336-365) is k strictly dependent draws
+//    for a row with k cells in play -- it set both the critical path of config 2 and the iteration time of config 3.
+//    Here a row's cells in play are compacted into a per-iteration scratch list of running sums, and the multinomial
+//    is drawn by a balanced binary TREE of binomials over that list (node (a, len): left half gets
+//    Binomial(m, mass(left) / mass(node))).  All nodes of one tree level, over all rows of the unit, are independent:
+//    they are queued in shared memory and processed level by level with one lane per node, densely packed,
+//    whichever row they came from.  Depth log2 k instead of k, and full warps instead of lanes waiting for the
+//    deepest row of their slab.
+//  * rows with < 20 fragments (:289-334): the 32-bit words they locate in their CDF come from a per-iteration POOL of
+//    Philox blocks of the slot -- fragments of all such rows back to back, four to a block, instead of at least one
+//    block per row (the median row has ONE fragment) -- generated with full lanes, by the warps that would otherwise
+//    idle during the one-warp E-step; one reciprocal per row and un-normalised running sums instead of a division
+//    per cell.
+//  * per-candidate state of a bundle (Welford accumulators, constants) lives in shared memory instead of in registers
+//    of warp 0 that every other thread had to allocate as well.
+// The CPU oracle restates this mode draw for draw (oracle/bayes_oracle.c, assignment_fast); tests compare the two.
+// No tensor cores: nothing here is a dense contraction.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdlib.h>
+
+#include "internal.h"
+#include "layout.h"
+#include "rng.cuh"
+#include "gibbs_common.cuh"
+
+#ifndef BAYES_FAST_MAXNREG
+#define BAYES_FAST_MAXNREG 64
+#endif
+#ifndef BAYES_FAST_WIDE_MAXNREG
+#define BAYES_FAST_WIDE_MAXNREG 128
+#endif
+
+namespace bayes {
+
+namespace {
+
+constexpr uint32_t kFull = 0xffffffffu;
+// ctl words
+constexpr int kCtlSlab = 0, kCtlQ0 = 1, kCtlErr = 4;
+
+#ifdef BAYES_DEBUG_BOUNDS
+// debug build: every index derived from packed data is checked; a violation lands in the unit's error word
+#define BAYES_CHECK(cond, code) do { if (!(cond)) V.ctl[kCtlErr] = (code); } while (0)
+#else
+#define BAYES_CHECK(cond, code) do { } while (0)
+#endif
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+struct FastView {
+    // packed matrix: shared memory (MAT_SMEM) or global
+    const double *val;
+    const uint16_t *col;
+    const int32_t *slab;
+    const int32_t *row_n;
+    const int32_t *row_nnz;
+    const uint32_t *row_info;
+    const int32_t *row_woff;
+    const uint64_t *row_mask;  // wide units, global
+    int n_words;
+    int n_slabs, n_chain_slabs, h, n_cells, n_chain_cells;
+    // per-iteration scratch of the chain rows and the task queues: where the matrix is
+    double *scr_cum;
+    uint16_t *scr_col;
+    uint32_t *queue;  // two buffers of 3 * qcap words: fragments | node | padded row
+    int qcap;
+    const uint32_t *pool;  // this iteration's uniform words (shared memory) or nullptr
+    const int32_t *pool_first;  // per slot: first block of the slot in the unit's pool (UnitDev, global)
+    int *ctl;
+};
+
+// Four consecutive words of a slot's pool starting at unit-level word `w`.
+__device__ __forceinline__ u32x4 pool_words4(const FastView &V, const uint64_t *skey, uint32_t slot, uint32_t ph_pool, uint32_t iteration, int w) {
+    u32x4 o;
+    if (V.pool) {
+        o.x = V.pool[w]; o.y = V.pool[w + 1]; o.z = V.pool[w + 2]; o.w = V.pool[w + 3];
+        return o;
+    }
+    // not staged (pool larger than shared memory): the blocks are computed where they are needed -- the same words
+    const int wl = w - 4 * V.pool_first[slot];  // word of the slot's own pool
+    const uint32_t b0 = (uint32_t)wl >> 2, off = (uint32_t)wl & 3u;
+    const uint64_t key = skey[slot];
+    const u32x4 A = make_site(key, ph_pool, iteration, b0 >> 12, 0).block(b0 & 4095u);
+    if (off == 0u) return A;
+    const u32x4 B = make_site(key, ph_pool, iteration, (b0 + 1u) >> 12, 0).block((b0 + 1u) & 4095u);
+    const uint32_t a[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+    o.x = a[off]; o.y = a[off + 1]; o.z = a[off + 2]; o.w = a[off + 3];
+    return o;
+}
+
+// Pool of the iteration: block b of the unit = block (desc & 0xffffff) of the pool of slot (desc >> 24).
+__device__ __forceinline__ void fast_pool_gen(uint32_t *pool, const uint32_t *pool_desc, int pool_blocks, const uint64_t *skey, uint32_t iteration,
+                                              bool init, int first_thread, int n_threads) {
+    const uint32_t ph = init ? PH_INIT_POOL : PH_POOL;
+    for (int b = (int)threadIdx.x - first_thread; b < pool_blocks; b += n_threads) {
+        const uint32_t desc = pool_desc[b], blk = desc & 0xffffffu;
+        const u32x4 w = make_site(skey[desc >> 24], ph, iteration, blk >> 12, 0).block(blk & 4095u);
+        reinterpret_cast<uint4 *>(pool)[b] = make_uint4(w.x, w.y, w.z, w.w);
+    }
+}
+
+// Warp-aggregated append of at most one task per lane to queue buffer `buf`, counted by ctl word `cnt`.  All 32 lanes call.
+__device__ __forceinline__ void push_tasks(const FastView &V, int cnt, int buf, bool want, uint32_t n, uint32_t node, uint32_t row) {
+    const uint32_t m = __ballot_sync(kFull, want);
+    if (m == 0u) return;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&V.ctl[cnt], __popc(m));
+    base = __shfl_sync(kFull, base, leader);
+    if (want) {
+        const int idx = base + __popc(m & lanemask_lt());
+        BAYES_CHECK(idx < V.qcap, 101);
+        uint32_t *q = V.queue + (size_t)buf * 3 * V.qcap;
+        q[idx] = n;
+        q[V.qcap + idx] = node;
+        q[2 * V.qcap + idx] = row;
+    }
+}
+
+// Where the words of one Philox block (up to `left` of them) land in a row's CDF: number of words below the threshold
+__device__ __forceinline__ int words_below(const u32x4 &w, int left, uint32_t t) {
+    return (int)(w.x <= t) + ((left > 1) & (int)(w.y <= t)) + ((left > 2) & (int)(w.z <= t)) + ((left > 3) & (int)(w.w <= t));
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// A-step, first part (one lane per row, SELL-h slabs): rows of the chain slabs compact their cells in play into the
+// scratch lists and queue the root of their tree; the other rows draw from the pool right away.
+// Bundle: a row's stored cells are few (T <= 32), all of them are visited.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fast_rows_bundle(const FastView &V, const double *theta, int32_t *counts, const uint64_t *skey, uint32_t iteration,
+                                                 const bool init) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const uint32_t ph_pool = init ? PH_INIT_POOL : PH_POOL;
+    const int H = V.h;
+    const bool dynamic = n_warps > 1;
+    for (int s = warp;; s += n_warps) {
+        if (dynamic) {
+            if (lane == 0) s = atomicAdd(&V.ctl[kCtlSlab], 1);
+            s = __shfl_sync(kFull, s, 0);
+        }
+        if (s >= V.n_slabs) break;
+        const int r = s * H + lane;
+        const uint32_t item = lane < H ? (uint32_t)V.row_nnz[r] : 0u;
+        const int nnz = (int)(item & kItemNnzMask);  // 0: padding lane
+        const bool live = nnz > 0;
+        const int n = live ? V.row_n[r] : 0;
+        const int cell0 = V.slab[s] + lane;
+        BAYES_CHECK(!live || cell0 + H * (nnz - 1) < V.n_cells, 102);
+        const double *val = V.val + cell0;
+        const uint16_t *col = V.col + cell0;
+        if (s < V.n_chain_slabs) {
+            BAYES_CHECK(!live || cell0 + H * (nnz - 1) < V.n_chain_cells, 103);
+            double *sc = V.scr_cum + cell0;
+            uint16_t *scol = V.scr_col + cell0;
+            double cum = 0.0;
+            int k2 = 0, c_last = 0;
+            for (int k = 0; k < nnz; k++) {
+                const int c = col[H * k];
+                const double p = val[H * k] * theta[c];
+                if (p > 0.0) {
+                    cum += p;
+                    sc[H * k2] = cum;
+                    scol[H * k2] = (uint16_t)c;
+                    k2++;
+                    c_last = c;
+                }
+            }
+            if (live) {
+                if (k2 == 1) atomicAdd(&counts[c_last], n);
+                else if (k2 == 0) V.ctl[kCtlErr] = 1;  // reference: assert(normalisation_constant >= double_underflow) (:284)
+            }
+            push_tasks(V, kCtlQ0, 0, live && k2 >= 2, (uint32_t)n, (uint32_t)(k2 - 1) << 12, (uint32_t)r);
+        } else if (live) {
+            double Z = 0.0;
+            int kl = -1, in_play = 0;
+            for (int k = 0; k < nnz; k++) {
+                const double p = val[H * k] * theta[col[H * k]];
+                Z += p;
+                if (p > 0.0) {
+                    kl = k;
+                    in_play++;
+                }
+            }
+            if (kl < 0) {
+                V.ctl[kCtlErr] = 1;
+            } else {
+                const int c_last = col[H * kl];
+                int rem = n;
+                if (in_play > 1) {
+                    const double rZ = __drcp_rn(Z);
+                    const int w0 = V.row_woff[r];
+                    const uint32_t slot = V.row_info[r] >> kRowSlotShift;
+                    for (int j0 = 0; j0 < n; j0 += 4) {
+                        const int left = n - j0 < 4 ? n - j0 : 4;
+                        const u32x4 w = pool_words4(V, skey, slot, ph_pool, iteration, w0 + j0);
+                        double cum = 0.0;
+                        int prev = 0;
+                        for (int k = 0; k < kl; k++) {
+                            const int c = col[H * k];
+                            const double p = val[H * k] * theta[c];
+                            if (!(p > 0.0)) continue;
+                            cum += p;
+                            // word * 2^-32 < cum / Z  <=>  word <= ceil(cum (1/Z) 2^32 - 1); the conversion saturates
+                            const uint32_t t = __double2uint_ru(__fma_rn(cum * rZ, 4294967296.0, -1.0));
+                            const int below = words_below(w, left, t);
+                            if (below > prev) atomicAdd(&counts[c], below - prev);
+                            rem -= below - prev;
+                            prev = below;
+                            if (below >= left) break;
+                        }
+                    }
+                }
+                if (rem > 0) atomicAdd(&counts[c_last], rem);  // the last cell in play takes what the others left
+            }
+        }
+    }
+}
+
+// Wide unit: a row stores hundreds of cells of which a few tens are in play; the cells in play are named by the row's
+// candidate mask ANDed with the simplex mask (ActiveCells, gibbs_common.cuh), never by visiting the stored cells.
+constexpr int kFastRowCache = 24;
+
+__device__ __forceinline__ void fast_rows_wide(const FastView &V, const uint64_t *amask, const double *theta, int32_t *counts, const uint64_t *skey,
+                                               uint32_t iteration, const bool init) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const uint32_t ph_pool = init ? PH_INIT_POOL : PH_POOL;
+    const int H = V.h;
+    const bool dynamic = n_warps > 1;
+    uint32_t kc[kFastRowCache];  // candidates of the first cells in play of the row
+    double pc[kFastRowCache];    // their running sums
+    for (int s = warp;; s += n_warps) {
+        if (dynamic) {
+            if (lane == 0) s = atomicAdd(&V.ctl[kCtlSlab], 1);
+            s = __shfl_sync(kFull, s, 0);
+        }
+        if (s >= V.n_slabs) break;
+        const int r = s * H + lane;
+        const uint32_t item = lane < H ? (uint32_t)V.row_nnz[r] : 0u;
+        const int nnz = (int)(item & kItemNnzMask);
+        const bool live = nnz > 0;
+        const int n = live ? V.row_n[r] : 0;
+        const int cell0 = V.slab[s] + lane;
+        const double *val = V.val + cell0;
+        ActiveCells scan;
+        scan.rm = V.row_mask + (size_t)s * V.n_words * H + lane;
+        scan.amask = amask;
+        scan.h = H;
+        scan.n_words = V.n_words;
+        int k, c;
+        if (s < V.n_chain_slabs) {
+            double *sc = V.scr_cum + cell0;
+            uint16_t *scol = V.scr_col + cell0;
+            double cum = 0.0;
+            int k2 = 0, c_last = 0;
+            if (live) {
+                scan.start();
+                while (scan.next(k, c)) {
+                    BAYES_CHECK(k < nnz && cell0 + H * k < V.n_chain_cells, 104);
+                    const double p = val[H * k] * theta[c];
+                    if (p > 0.0) {
+                        cum += p;
+                        sc[H * k2] = cum;
+                        scol[H * k2] = (uint16_t)c;
+                        k2++;
+                        c_last = c;
+                    }
+                }
+                if (k2 == 1) atomicAdd(&counts[c_last], n);
+                else if (k2 == 0) V.ctl[kCtlErr] = 1;
+            }
+            push_tasks(V, kCtlQ0, 0, live && k2 >= 2, (uint32_t)n, (uint32_t)(k2 - 1) << 12, (uint32_t)r);
+        } else if (live) {
+            double Z = 0.0;
+            int in_play = 0, c_last = 0;
+            scan.start();
+            while (scan.next(k, c)) {
+                BAYES_CHECK(k < nnz && cell0 + H * k < V.n_cells, 105);
+                const double p = val[H * k] * theta[c];
+                if (p > 0.0) {
+                    Z += p;
+                    if (in_play < kFastRowCache) {
+                        kc[in_play] = (uint32_t)c;
+                        pc[in_play] = Z;
+                    }
+                    in_play++;
+                    c_last = c;
+                }
+            }
+            if (in_play == 0) {
+                V.ctl[kCtlErr] = 1;
+            } else {
+                int rem = n;
+                if (in_play > 1) {
+                    const double rZ = __drcp_rn(Z);
+                    const int w0 = V.row_woff[r];
+                    for (int j0 = 0; j0 < n; j0 += 4) {
+                        const int left = n - j0 < 4 ? n - j0 : 4;
+                        const u32x4 w = pool_words4(V, skey, 0, ph_pool, iteration, w0 + j0);
+                        int prev = 0;
+                        if (in_play <= kFastRowCache) {
+                            for (int i = 0; i < in_play - 1; i++) {
+                                const uint32_t t = __double2uint_ru(__fma_rn(pc[i] * rZ, 4294967296.0, -1.0));
+                                const int below = words_below(w, left, t);
+                                if (below > prev) atomicAdd(&counts[kc[i]], below - prev);
+                                rem -= below - prev;
+                                prev = below;
+                                if (below >= left) break;
+                            }
+                        } else {
+                            double cum = 0.0;
+                            int seen = 0;
+                            scan.start();
+                            while (scan.next(k, c)) {
+                                const double p = val[H * k] * theta[c];
+                                if (!(p > 0.0)) continue;
+                                if (++seen == in_play) break;  // the last cell in play takes the rest
+                                cum += p;
+                                const uint32_t t = __double2uint_ru(__fma_rn(cum * rZ, 4294967296.0, -1.0));
+                                const int below = words_below(w, left, t);
+                                if (below > prev) atomicAdd(&counts[c], below - prev);
+                                rem -= below - prev;
+                                prev = below;
+                                if (below >= left) break;
+                            }
+                        }
+                    }
+                }
+                if (rem > 0) atomicAdd(&counts[c_last], rem);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// A-step, second part: the splitting trees of the chain rows, level by level.  One lane per node of the level,
+// whichever row it belongs to; children with two or more cells are queued for the next level, single cells receive
+// their fragments.  Three rotating counters (this level, next level, the one being reset) and two queue buffers need
+// one block barrier per level.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fast_tree_levels(const FastView &V, int32_t *counts, const uint64_t *skey, uint32_t iteration, const bool init) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ph_tree = init ? PH_INIT_TREE : PH_TREE;
+    const int H = V.h, hs = __ffs(H) - 1, qcap = V.qcap;
+    int cur = kCtlQ0, nxt = kCtlQ0 + 1, old = kCtlQ0 + 2, buf = 0;
+    for (;;) {
+        const int Q = V.ctl[cur];
+        if (Q == 0) break;
+        if (threadIdx.x == 0) V.ctl[old] = 0;
+        const uint32_t *q = V.queue + (size_t)buf * 3 * qcap;
+        for (int i0 = warp * 32; i0 < Q; i0 += (int)blockDim.x) {
+            const int i = i0 + lane;
+            bool push_l = false, push_r = false;
+            uint32_t n_l = 0, n_r = 0, node_l = 0, node_r = 0, row = 0;
+            if (i < Q) {
+                const uint32_t n = q[i], node = q[qcap + i];
+                row = q[2 * qcap + i];
+                const int a = (int)(node & 4095u), len = (int)(node >> 12) + 1, half = len >> 1, len_r = len - half;
+                const int cell0 = V.slab[row >> hs] + (int)(row & (uint32_t)(H - 1));
+                BAYES_CHECK(cell0 + H * (a + len - 1) < V.n_chain_cells, 106);
+                const double *sc = V.scr_cum + cell0;
+                const double Pa = a ? sc[H * (a - 1)] : 0.0, Pm = sc[H * (a + half - 1)], Pb = sc[H * (a + len - 1)];
+                const double p_left = (Pm - Pa) / (Pb - Pa);
+                const uint32_t info = V.row_info[row];
+                const Site site = make_site(skey[info >> kRowSlotShift], ph_tree | (node << 8), iteration, info & ((1u << kRowSlotShift) - 1u), 0);
+                n_l = (uint32_t)binomial_variate(site, (int)n, p_left);
+                n_r = n - n_l;
+                if (n_l) {
+                    if (half == 1) atomicAdd(&counts[V.scr_col[cell0 + H * a]], (int)n_l);
+                    else { push_l = true; node_l = (uint32_t)a | ((uint32_t)(half - 1) << 12); }
+                }
+                if (n_r) {
+                    if (len_r == 1) atomicAdd(&counts[V.scr_col[cell0 + H * (a + half)]], (int)n_r);
+                    else { push_r = true; node_r = (uint32_t)(a + half) | ((uint32_t)(len_r - 1) << 12); }
+                }
+            }
+            push_tasks(V, nxt, buf ^ 1, push_l, n_l, node_l, row);
+            push_tasks(V, nxt, buf ^ 1, push_r, n_r, node_r, row);
+        }
+        __syncthreads();
+        const int t = old;
+        old = cur;
+        cur = nxt;
+        nxt = t;
+        buf ^= 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// E-step of a bundle (warp 0): lane = slot * Tpad + t.  ExpressionGenerator::generateExpression
+// (expressionGenerator.cpp:77-132) for every slot of the bundle at once, + getFPKM / addSample when sampling
+// (valueContainer.cpp:226-239, gibbsOutput.cpp:51-75).  Same draws as bundle_e_step of the replay kernels; the
+// per-lane state is read from / written to shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+struct FastBundleE {
+    double *theta, *den, *mean, *m2;
+    int32_t *counts, *base, *occ;
+    const uint64_t *skey;
+    const double *sgamma;
+    const int32_t *sT, *sNf;
+    const double *tab_val;
+    const int32_t *tab_row;
+    int *ctl;
+    int Tpad, sh, n_slots;
+};
+
+__device__ __forceinline__ int fast_bundle_e_step(const FastBundleE &E, uint32_t iteration, bool sampling) {
+    const int lane = threadIdx.x & 31;
+    const int Tpad = E.Tpad, g = lane >> E.sh, t = lane & (Tpad - 1);
+    const bool slot_ok = g < E.n_slots;
+    const int Tg = slot_ok ? E.sT[g] : 0;
+    const bool valid = t < Tg;
+    const uint64_t key = slot_ok ? E.skey[g] : 0ull;
+    const double gamma = slot_ok ? E.sgamma[g] : 1.0;
+    const uint32_t segmask = Tpad == 32 ? kFull : (((1u << Tpad) - 1u) << (g * Tpad));
+    const uint32_t validmask = Tg == 32 ? kFull : (((1u << Tg) - 1u) << (g * Tpad));
+    const int cnt = E.counts[lane];
+    const uint32_t pm = __ballot_sync(kFull, valid && cnt > 0) & segmask;
+    const int n_plus = __popc(pm);
+    int b = 0, n_pick = 0;
+    if (Tg > 0) {
+        b = sample_simplex(E.tab_val, E.tab_row + g * (Tpad + 1), n_plus, key, iteration);
+        n_pick = b - n_plus;
+    }
+    // expressionGenerator.cpp:104-127: the uniform_int draws are independent (site = pick ordinal): lane t of the slot makes
+    // the draw of pick t, only the selection is sequential
+    uint32_t my_pick = 0u;
+    if (valid && t < n_pick) my_pick = uniform_int(make_site(key, PH_NULLPICK, iteration, (uint32_t)t, 0), (uint32_t)(Tg - n_plus - t));
+    uint32_t sel = 0u;
+    const int max_pick = __reduce_max_sync(kFull, n_pick);
+    const int lane0 = lane - t;
+    for (int k = 0; k < max_pick; k++) {
+        const uint32_t s = __shfl_sync(kFull, my_pick, (lane0 + k) & 31);
+        if (k < n_pick) {
+            const uint32_t nullm = validmask & ~(pm | sel);
+            sel |= 1u << __fns(nullm, 0, (int)s + 1);
+        }
+    }
+    const bool active = ((pm | sel) >> lane) & 1u;
+    double gv = 0.0;
+    if (active) {
+        gv = gamma_variate(make_site(key, PH_GAMMA, iteration, (uint32_t)t, 0), (double)cnt + gamma);
+        if (!(gv >= DBL_MIN)) E.ctl[kCtlErr] = 2;  // reference: assert(gamma_base_sample >= double_underflow) (expressionGenerator.cpp:115)
+    }
+    double norm = gv;
+    for (int o = Tpad >> 1; o > 0; o >>= 1) norm += __shfl_xor_sync(kFull, norm, o);
+    const double th = active ? gv / norm : 0.0;  // valueContainer.cpp:216-224
+    E.theta[lane] = th;
+    E.counts[lane] = E.base[lane];  // fresh CountValueContainer for the next assignment (:266) + folded rows
+    if (sampling && active) {
+        const double fpkm = (th * (double)E.sNf[g] * 1e9) / E.den[lane];  // valueContainer.cpp:235
+        const int o = E.occ[lane] + 1;                                     // gibbsOutput.cpp:60
+        E.occ[lane] = o;
+        if (o == 1) {
+            E.mean[lane] = fpkm;
+        } else {
+            const double mean = E.mean[lane], delta = fpkm - mean, mu = mean + delta / o;
+            E.mean[lane] = mu;
+            E.m2[lane] += delta * (fpkm - mu);
+        }
+    }
+    return b;
+}
+
+template <bool MAT_SMEM>
+__device__ __forceinline__ FastView fast_stage(const KernelArgs &A, const UnitDev &U, const FastLayout &lay, unsigned char *smem) {
+    FastView V;
+    V.n_slabs = U.n_slabs;
+    V.n_chain_slabs = U.n_chain_slabs;
+    V.h = U.slab_h;
+    V.n_cells = U.n_cells;
+    V.n_chain_cells = U.n_chain_cells;
+    V.qcap = U.qcap;
+    V.row_mask = (const uint64_t *)A.row_mask + U.mask_off;
+    V.n_words = (U.Tpad + 63) >> 6;
+    V.ctl = (int *)(smem + lay.ctl);
+    V.pool_first = U.pool_first;
+    const int Rp = U.n_slabs * U.slab_h;
+    if (MAT_SMEM) {
+        double *sv = (double *)(smem + lay.val);
+        uint16_t *sc = (uint16_t *)(smem + lay.col);
+        int32_t *ss = (int32_t *)(smem + lay.slab);
+        int32_t *rn = (int32_t *)(smem + lay.row_n);
+        int32_t *rz = (int32_t *)(smem + lay.row_nnz);
+        uint32_t *ri = (uint32_t *)(smem + lay.row_info);
+        int32_t *rw = (int32_t *)(smem + lay.row_woff);
+        block_copy(sv, A.val + U.cell_off, U.n_cells);
+        block_copy(sc, A.col + U.cell_off, U.n_cells);
+        block_copy(ss, A.slab_cell_off + U.slab_off, U.n_slabs + 1);
+        block_copy(rn, A.row_n + U.row_off, Rp);
+        block_copy(rz, A.row_nnz + U.row_off, Rp);
+        block_copy(ri, A.row_info + U.row_off, Rp);
+        block_copy(rw, A.row_woff + U.woff_off, Rp);
+        V.val = sv; V.col = sc; V.slab = ss; V.row_n = rn; V.row_nnz = rz; V.row_info = ri; V.row_woff = rw;
+        V.scr_cum = (double *)(smem + lay.scr_cum);
+        V.scr_col = (uint16_t *)(smem + lay.scr_col);
+        V.queue = (uint32_t *)(smem + lay.queue);
+    } else {
+        V.val = A.val + U.cell_off;
+        V.col = A.col + U.cell_off;
+        V.slab = A.slab_cell_off + U.slab_off;
+        V.row_n = A.row_n + U.row_off;
+        V.row_nnz = A.row_nnz + U.row_off;
+        V.row_info = A.row_info + U.row_off;
+        V.row_woff = A.row_woff + U.woff_off;
+        V.scr_cum = A.scr_cum + U.scr_off;
+        V.scr_col = A.scr_col + U.scr_off;
+        V.queue = A.queue + U.q_off;
+    }
+    uint32_t *pool = nullptr;
+    if (U.pool_smem) {
+        pool = (uint32_t *)(smem + lay.pool);
+        block_copy((uint32_t *)(smem + lay.pool_desc), A.pool_desc + U.pooldesc_off, U.pool_blocks);
+        if (threadIdx.x < 4) pool[4 * U.pool_blocks + threadIdx.x] = 0u;  // the spare block
+    }
+    V.pool = pool;
+    return V;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+template <bool MAT_SMEM>
+__global__ void __maxnreg__(BAYES_FAST_MAXNREG) gibbs_fast_bundle_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int64_t ui = unit_base + blockIdx.x;
+    if (threadIdx.x == 0) A.unit_clock[3 * ui] = global_ns();
+    const UnitDev &U = A.units[ui];
+    const int n_slots = U.n_slots, Tpad = U.Tpad;
+    const FastLayout lay = fast_layout(false, 32, n_slots, Tpad, U.n_slabs, U.slab_h, U.n_cells, U.tab_len, U.tab_smem != 0, MAT_SMEM,
+                                       U.n_chain_cells, U.qcap, U.pool_blocks, U.pool_smem != 0);
+    uint64_t *skey = (uint64_t *)(smem + lay.key);
+    FastBundleE E;
+    E.theta = (double *)(smem + lay.theta);
+    E.den = (double *)(smem + lay.den);
+    E.mean = (double *)(smem + lay.mean);
+    E.m2 = (double *)(smem + lay.m2);
+    E.counts = (int32_t *)(smem + lay.counts);
+    E.base = (int32_t *)(smem + lay.base);
+    E.occ = (int32_t *)(smem + lay.occ);
+    E.skey = skey;
+    double *sgamma = (double *)(smem + lay.sgamma);
+    int32_t *sT = (int32_t *)(smem + lay.sT), *sNf = (int32_t *)(smem + lay.sNf);
+    E.sgamma = sgamma;
+    E.sT = sT;
+    E.sNf = sNf;
+    E.Tpad = Tpad;
+    E.n_slots = n_slots;
+    {
+        int sh = 1;
+        while ((1 << sh) < Tpad) sh++;
+        E.sh = sh;
+    }
+    if (U.tab_smem) {
+        double *tv = (double *)(smem + lay.tab_val);
+        int32_t *tr = (int32_t *)(smem + lay.tab_row);
+        block_copy(tv, A.tab_val + U.tab_off, U.tab_len);
+        block_copy(tr, A.tab_row + U.tabrow_off, n_slots * (Tpad + 1));
+        E.tab_val = tv;
+        E.tab_row = tr;
+    } else {
+        E.tab_val = A.tab_val + U.tab_off;
+        E.tab_row = A.tab_row + U.tabrow_off;
+    }
+    FastView V = fast_stage<MAT_SMEM>(A, U, lay, smem);
+    E.ctl = V.ctl;
+    uint32_t *pool = (uint32_t *)(smem + lay.pool);
+    const uint32_t *pool_desc = (const uint32_t *)(smem + lay.pool_desc);
+    const int pool_blocks = U.pool_smem ? U.pool_blocks : 0;
+    if (threadIdx.x < (unsigned)n_slots) {
+        skey[threadIdx.x] = U.key[threadIdx.x];
+        sgamma[threadIdx.x] = U.gamma[threadIdx.x];
+        sT[threadIdx.x] = U.T[threadIdx.x];
+        sNf[threadIdx.x] = U.N_f[threadIdx.x];
+    }
+    const int lane = threadIdx.x & 31;
+    const int g = lane >> E.sh, t = lane & (Tpad - 1);
+    const bool valid = g < n_slots && t < U.T[g < n_slots ? g : 0];
+    if (threadIdx.x < 32) {
+        const int32_t bc = A.base_counts[U.lane_off + lane];
+        E.theta[lane] = 1.0;  // initAssignment runs the A-step on P_ij itself
+        E.counts[lane] = bc;
+        E.base[lane] = bc;
+        E.occ[lane] = 0;
+        E.mean[lane] = 0.0;
+        E.m2[lane] = 0.0;
+        E.den[lane] = A.efflen[U.lane_off + lane] * (double)(g < n_slots ? U.N_total[g] : 1);  // valueContainer.cpp:235 denominator
+    }
+    if (threadIdx.x < kFastCtlWords) V.ctl[threadIdx.x] = 0;
+
+    const bool tracing = A.trace_unit == ui;
+    const bool my_trace = tracing && threadIdx.x < 32 && g == A.trace_slot && valid;
+    const int Tg = valid ? U.T[g] : 0;
+    const int burn = U.burn;
+    const int total = A.iter_cap > 0 && A.iter_cap < U.burn + U.samples ? A.iter_cap : U.burn + U.samples;
+    const int stamp_at = A.iter_cap > 0 ? total >> 1 : -2;  // calibration pass: time the second half only
+    const int n_threads = blockDim.x;
+    __syncthreads();
+
+    // it == -1 is initAssignment (gibbsSampler.cpp:90): the same A-step code on theta == 1, no E-step before it
+    for (int it = -1; it < total; it++) {
+        const uint32_t iter = (uint32_t)(it < 0 ? 0 : it);
+        if (threadIdx.x == 0) {
+            V.ctl[kCtlSlab] = 0;
+            V.ctl[kCtlQ0] = 0;
+            V.ctl[kCtlQ0 + 1] = 0;
+            V.ctl[kCtlQ0 + 2] = 0;
+            if (it == stamp_at) A.unit_clock[3 * ui] = global_ns();
+        }
+        if (it >= 0 && threadIdx.x < 32) {
+            if (my_trace && it == 0) A.tr_init[t] = E.counts[lane];
+            if (my_trace && it > 0 && it - 1 < A.trace_iters) A.tr_counts[(size_t)(it - 1) * Tg + t] = E.counts[lane];
+            const int b = fast_bundle_e_step(E, iter, it >= burn || (stamp_at >= 0 && it >= stamp_at));
+            if (my_trace && it < A.trace_iters) {
+                A.tr_theta[(size_t)it * Tg + t] = E.theta[lane];
+                if (t == 0) A.tr_b[it] = b;
+            }
+        }
+        // the iteration's uniform words: by the warps that have no E-step to run (all of them for initAssignment)
+        if (it < 0 || n_threads == 32) fast_pool_gen(pool, pool_desc, pool_blocks, skey, iter, it < 0, 0, n_threads);
+        else if (threadIdx.x >= 32) fast_pool_gen(pool, pool_desc, pool_blocks, skey, iter, false, 32, n_threads - 32);
+        __syncthreads();
+        fast_rows_bundle(V, E.theta, E.counts, skey, iter, it < 0);
+        __syncthreads();
+        fast_tree_levels(V, E.counts, skey, iter, it < 0);
+    }
+    if (my_trace && total - 1 < A.trace_iters) A.tr_counts[(size_t)(total - 1) * Tg + t] = E.counts[lane];
+
+    if (threadIdx.x < 32 && valid) {
+        const int64_t o = U.out_off[g] + t;
+        A.out_occ[o] = E.occ[lane];
+        A.out_mean[o] = E.mean[lane];
+        A.out_m2[o] = E.m2[lane];
+        A.out_counts[o] = E.counts[lane];
+    }
+    if (threadIdx.x == 0) {
+        A.unit_err[ui] = V.ctl[kCtlErr];
+        A.unit_clock[3 * ui + 1] = global_ns();
+        A.unit_clock[3 * ui + 2] = sm_id();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+template <bool MAT_SMEM>
+__global__ void __maxnreg__(BAYES_FAST_WIDE_MAXNREG) gibbs_fast_wide_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int64_t ui = unit_base + blockIdx.x;
+    if (threadIdx.x == 0) A.unit_clock[3 * ui] = global_ns();
+    const UnitDev &U = A.units[ui];
+    const int T = U.T[0];
+    const FastLayout lay = fast_layout(true, T, 1, U.Tpad, U.n_slabs, U.slab_h, U.n_cells, U.tab_len, U.tab_smem != 0, MAT_SMEM, U.n_chain_cells,
+                                       U.qcap, U.pool_blocks, U.pool_smem != 0);
+    WideState E;
+    E.theta = (double *)(smem + lay.theta);
+    E.den = (double *)(smem + lay.den);
+    E.mean = (double *)(smem + lay.mean);
+    E.m2 = (double *)(smem + lay.m2);
+    E.counts = (int32_t *)(smem + lay.counts);
+    E.occ = (int32_t *)(smem + lay.occ);
+    int32_t *base = (int32_t *)(smem + lay.base);
+    E.base = base;
+    E.mask = (uint32_t *)(smem + lay.mask);
+    E.act = (uint16_t *)(smem + lay.act);
+    E.amask = (uint64_t *)(smem + lay.amask);
+    E.T = T;
+    E.nch = (T + 31) >> 5;
+    E.N_f = U.N_f[0];
+    E.gamma = U.gamma[0];
+    uint64_t *skey = (uint64_t *)(smem + lay.key);
+    const uint64_t key = U.key[0];
+    if (threadIdx.x == 0) skey[0] = key;
+
+    const double n_total = (double)U.N_total[0];
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        const int32_t bc = A.base_counts[U.lane_off + t];
+        base[t] = bc;
+        E.counts[t] = bc;
+        E.occ[t] = 0;
+        E.mean[t] = 0.0;
+        E.m2[t] = 0.0;
+        E.theta[t] = 1.0;  // initAssignment runs the A-step on P_ij itself
+        E.den[t] = A.efflen[U.lane_off + t] * n_total;  // valueContainer.cpp:235 denominator
+    }
+    // initAssignment (theta == 1): every candidate is "in the simplex"
+    for (int w = threadIdx.x; w < (T + 63) >> 6; w += blockDim.x)
+        E.amask[w] = w == ((T + 63) >> 6) - 1 && (T & 63) ? (1ull << (T & 63)) - 1ull : ~0ull;
+    if (U.tab_smem) {
+        double *tv = (double *)(smem + lay.tab_val);
+        int32_t *tr = (int32_t *)(smem + lay.tab_row);
+        block_copy(tv, A.tab_val + U.tab_off, U.tab_len);
+        block_copy(tr, A.tab_row + U.tabrow_off, T + 1);
+        E.tab_val = tv;
+        E.tab_row = tr;
+    } else {
+        E.tab_val = A.tab_val + U.tab_off;
+        E.tab_row = A.tab_row + U.tabrow_off;
+    }
+    FastView V = fast_stage<MAT_SMEM>(A, U, lay, smem);
+    uint32_t *pool = (uint32_t *)(smem + lay.pool);
+    const uint32_t *pool_desc = (const uint32_t *)(smem + lay.pool_desc);
+    const int pool_blocks = U.pool_smem ? U.pool_blocks : 0;
+    if (threadIdx.x < kFastCtlWords) V.ctl[threadIdx.x] = 0;
+
+    const bool tracing = A.trace_unit == ui;
+    const int burn = U.burn;
+    const int total = A.iter_cap > 0 && A.iter_cap < U.burn + U.samples ? A.iter_cap : U.burn + U.samples;
+    const int stamp_at = A.iter_cap > 0 ? total >> 1 : -2;
+    const int n_threads = blockDim.x;
+    __syncthreads();
+
+    for (int it = -1; it < total; it++) {
+        const uint32_t iter = (uint32_t)(it < 0 ? 0 : it);
+        if (threadIdx.x == 0) {
+            V.ctl[kCtlSlab] = 0;
+            V.ctl[kCtlQ0] = 0;
+            V.ctl[kCtlQ0 + 1] = 0;
+            V.ctl[kCtlQ0 + 2] = 0;
+            if (it == stamp_at) A.unit_clock[3 * ui] = global_ns();
+        }
+        if (it >= 0 && threadIdx.x < 32) {
+            const bool tr = tracing && it < A.trace_iters;
+            if (tracing && it == 0)
+                for (int t = threadIdx.x; t < T; t += 32) A.tr_init[t] = E.counts[t];
+            if (tracing && it > 0 && it - 1 < A.trace_iters)
+                for (int t = threadIdx.x; t < T; t += 32) A.tr_counts[(size_t)(it - 1) * T + t] = E.counts[t];
+            const int b = wide_e_step(E, key, iter, it >= burn || (stamp_at >= 0 && it >= stamp_at), tr ? A.tr_theta + (size_t)it * T : nullptr);
+            if (tr && threadIdx.x == 0) A.tr_b[it] = b;
+        }
+        if (it < 0 || n_threads == 32) fast_pool_gen(pool, pool_desc, pool_blocks, skey, iter, it < 0, 0, n_threads);
+        else if (threadIdx.x >= 32) fast_pool_gen(pool, pool_desc, pool_blocks, skey, iter, false, 32, n_threads - 32);
+        __syncthreads();
+        fast_rows_wide(V, E.amask, E.theta, E.counts, skey, iter, it < 0);
+        __syncthreads();
+        fast_tree_levels(V, E.counts, skey, iter, it < 0);
+    }
+    if (tracing && total - 1 < A.trace_iters)
+        for (int t = threadIdx.x; t < T; t += blockDim.x) A.tr_counts[(size_t)(total - 1) * T + t] = E.counts[t];
+
+    const int64_t o = U.out_off[0];
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        A.out_occ[o + t] = E.occ[t];
+        A.out_mean[o + t] = E.mean[t];
+        A.out_m2[o + t] = E.m2[t];
+        A.out_counts[o + t] = E.counts[t];
+    }
+    if (threadIdx.x == 0) {
+        A.unit_err[ui] = V.ctl[kCtlErr];
+        A.unit_clock[3 * ui + 1] = global_ns();
+        A.unit_clock[3 * ui + 2] = sm_id();
+    }
+}
+
+// ---- single A-step in fast mode (same device code, one block, wide layout, everything but theta / counts in global) ----
+template <bool INIT>
+__global__ void step_assignment_fast_kernel(const __grid_constant__ KernelArgs A, const double *theta_in, uint32_t iteration, int32_t *counts_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const UnitDev &U = A.units[0];
+    const int T = U.T[0];
+    double *theta = (double *)smem;
+    uint64_t *skey = (uint64_t *)(theta + T);
+    const int n_words = (T + 63) >> 6;
+    uint64_t *amask = (uint64_t *)(skey + 1);
+    int32_t *counts = (int32_t *)(amask + n_words);
+    int *ctl = (int *)(counts + T);
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        theta[t] = INIT ? 1.0 : theta_in[t];
+        counts[t] = A.base_counts[U.lane_off + t];
+    }
+    if (threadIdx.x == 0) skey[0] = U.key[0];
+    if (threadIdx.x < kFastCtlWords) ctl[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x < 32)
+        for (int w = 0; w < n_words; w++) {
+            const int t0 = w * 64 + (int)threadIdx.x;
+            const uint32_t lo = __ballot_sync(kFull, t0 < T && theta[t0] != 0.0);
+            const uint32_t hi = __ballot_sync(kFull, t0 + 32 < T && theta[t0 + 32] != 0.0);
+            if (threadIdx.x == 0) amask[w] = ((uint64_t)hi << 32) | lo;
+        }
+    FastView V;
+    V.n_slabs = U.n_slabs;
+    V.n_chain_slabs = U.n_chain_slabs;
+    V.h = U.slab_h;
+    V.n_cells = U.n_cells;
+    V.n_chain_cells = U.n_chain_cells;
+    V.qcap = U.qcap;
+    V.row_mask = (const uint64_t *)A.row_mask + U.mask_off;
+    V.n_words = n_words;
+    V.val = A.val + U.cell_off;
+    V.col = A.col + U.cell_off;
+    V.slab = A.slab_cell_off + U.slab_off;
+    V.row_n = A.row_n + U.row_off;
+    V.row_nnz = A.row_nnz + U.row_off;
+    V.row_info = A.row_info + U.row_off;
+    V.row_woff = A.row_woff + U.woff_off;
+    V.scr_cum = A.scr_cum + U.scr_off;
+    V.scr_col = A.scr_col + U.scr_off;
+    V.queue = A.queue + U.q_off;
+    V.pool = nullptr;  // the rows compute their pool blocks themselves
+    V.pool_first = U.pool_first;
+    V.ctl = ctl;
+    __syncthreads();
+    fast_rows_wide(V, amask, theta, counts, skey, iteration, INIT);
+    __syncthreads();
+    fast_tree_levels(V, counts, skey, iteration, INIT);
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) counts_out[t] = counts[t];
+    if (threadIdx.x == 0) A.unit_err[0] = ctl[kCtlErr];
+}
+
+}  // namespace
+
+static int check_fast(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return BAYES_OK;
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return BAYES_E_CUDA;
+}
+
+int configure_fast_kernels() {
+    int rc;
+    const char *co = getenv("BAYES_CARVEOUT");  // experiment knob, percent (see configure_kernels)
+    const int carveout = co ? atoi(co) : 65;
+    const void *fns[4] = {(const void *)gibbs_fast_bundle_kernel<true>, (const void *)gibbs_fast_bundle_kernel<false>,
+                          (const void *)gibbs_fast_wide_kernel<true>, (const void *)gibbs_fast_wide_kernel<false>};
+    for (const void *f : fns) {
+        if ((rc = check_fast(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, carveout), "carveout"))) return rc;
+        if ((rc = check_fast(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_unit_smem()), "cudaFuncSetAttribute"))) return rc;
+    }
+    if ((rc = check_fast(cudaFuncSetAttribute(step_assignment_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "cudaFuncSetAttribute"))) return rc;
+    return check_fast(cudaFuncSetAttribute(step_assignment_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "cudaFuncSetAttribute");
+}
+
+int launch_units_fast(const KernelArgs &args, int64_t unit_base, int64_t n_units, int block, bool wide, bool mat_smem, size_t smem_bytes,
+                      void *stream) {
+    if (n_units <= 0) return BAYES_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)n_units;
+    if (wide) {
+        if (mat_smem) gibbs_fast_wide_kernel<true><<<grid, block, smem_bytes, st>>>(args, unit_base);
+        else gibbs_fast_wide_kernel<false><<<grid, block, smem_bytes, st>>>(args, unit_base);
+    } else {
+        if (mat_smem) gibbs_fast_bundle_kernel<true><<<grid, block, smem_bytes, st>>>(args, unit_base);
+        else gibbs_fast_bundle_kernel<false><<<grid, block, smem_bytes, st>>>(args, unit_base);
+    }
+    return check_fast(cudaGetLastError(), "gibbs fast kernel launch");
+}
+
+int launch_step_assignment_fast(const KernelArgs &args, bool init, const double *d_theta, uint32_t iteration, int32_t *d_counts_out,
+                                size_t smem_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (init) step_assignment_fast_kernel<true><<<1, 128, smem_bytes, st>>>(args, d_theta, iteration, d_counts_out);
+    else step_assignment_fast_kernel<false><<<1, 128, smem_bytes, st>>>(args, d_theta, iteration, d_counts_out);
+    return check_fast(cudaGetLastError(), "step_assignment_fast_kernel launch");
+}
+
+}  // namespace bayes

@@ -25,6 +25,7 @@
 #include "internal.h"
 #include "layout.h"
 #include "rng.cuh"
+#include "gibbs_common.cuh"
 
 // Registers per thread: 72 keeps 28 warps per SM resident (internal.h: kWarpsPerSM) and removes most of the spills that 64
 // (32 warps) forces into the inner loops.  Measured on config 2: 64 -> 2.21 s per step, 72 -> 2.01 s, 80 -> 2.09 s,
@@ -48,23 +49,6 @@ namespace bayes {
 namespace {
 
 constexpr int kZUnroll = BAYES_Z_UNROLL;
-
-__device__ __forceinline__ uint64_t global_ns() {
-    uint64_t t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ uint32_t sm_id() {
-    uint32_t s;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
-    return s;
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 // Read-only view of the packed matrix; pointers are shared-memory or global depending on the instantiation.
 struct MatView {
@@ -92,15 +76,8 @@ struct MatView {
 // this code (instruction-cache footprint) serves both.
 // ------------------------------------------------------------------------------------------------------------------
 
-// p / Z, correctly rounded, from rZ = RN(1 / Z): quotient estimate, exact residual, one fused correction (Markstein).
-// One reciprocal per row replaces a division per cell.
-__device__ __forceinline__ double div_by(double p, double Z, double rZ) {
-    const double q0 = p * rZ;
-    return __fma_rn(__fma_rn(-q0, Z, p), rZ, q0);
-}
-
 __device__ __forceinline__ void assign_rows(const MatView &M, const double *theta, int32_t *counts, const uint64_t *skey,
-                                            int lanes_per_slot, uint32_t iteration, const bool init, int *next_slab) {
+                                            int lanes_per_slot, uint32_t iteration, const bool init, int *next_slab, int32_t *err) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const uint32_t phase = init ? PH_INIT_ASSIGN : PH_ASSIGN;
     const int H = M.h;
@@ -162,7 +139,10 @@ __device__ __forceinline__ void assign_rows(const MatView &M, const double *thet
                 }
             }
         }
-        if (kl < 0) continue;  // reference: assert(normalisation_constant >= double_underflow) (:284)
+        if (kl < 0) {  // reference: assert(normalisation_constant >= double_underflow) (:284); reported as BAYES_E_NUMERIC
+            *err = 1;
+            continue;
+        }
         const int c_last = col[H * kl];
         const double rZ = __drcp_rn(Z);
 
@@ -253,33 +233,6 @@ __device__ __forceinline__ void assign_rows(const MatView &M, const double *thet
 // k-th set bit of its mask.  Same arithmetic on the same cells in the same (ascending candidate) order as assign_rows,
 // so the results are identical: the cells skipped are exactly those whose product is zero.
 // ------------------------------------------------------------------------------------------------------------------
-struct ActiveCells {
-    const uint64_t *rm;     // the row's mask words, stride h
-    const uint64_t *amask;  // simplex mask, 64 candidates per word (shared memory, written by the E-step)
-    int h, n_words, w, kbase;
-    uint64_t m_all, m;
-    __device__ __forceinline__ void start() {
-        w = -1;
-        kbase = 0;
-        m_all = 0ull;
-        m = 0ull;
-    }
-    // next cell of the row whose candidate is in the simplex: k = its index in the row, c = its candidate
-    __device__ __forceinline__ bool next(int &k, int &c) {
-        while (m == 0ull) {
-            kbase += __popcll(m_all);
-            if (++w >= n_words) return false;
-            m_all = __ldg((const unsigned long long *)rm + (size_t)w * h);
-            m = m_all & amask[w];
-        }
-        const int bit = __ffsll((long long)m) - 1;
-        m &= m - 1ull;
-        k = kbase + __popcll(m_all & ((1ull << bit) - 1ull));
-        c = (w << 6) + bit;
-        return true;
-    }
-};
-
 // The cells of one row whose product P_ij theta_j is not zero, in ascending candidate order.  The first walk (the row sum)
 // scans the masks and remembers up to kRowCache cells with their products; every later walk of the same row (one per
 // Philox block of a uniform item, one for a binomial chain) replays that list instead of scanning and gathering again.
@@ -314,7 +267,7 @@ struct RowWalk {
 };
 
 __device__ __forceinline__ void assign_rows_wide(const MatView &M, const uint64_t *amask, const double *theta, int32_t *counts, uint64_t key,
-                                                 uint32_t iteration, const bool init, int *next_slab) {
+                                                 uint32_t iteration, const bool init, int *next_slab, int32_t *err) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const uint32_t phase = init ? PH_INIT_ASSIGN : PH_ASSIGN;
     const int H = M.h;
@@ -382,7 +335,10 @@ __device__ __forceinline__ void assign_rows_wide(const MatView &M, const uint64_
                     }
             }
         }
-        if (kl < 0) continue;
+        if (kl < 0) {
+            *err = 1;
+            continue;
+        }
         const double rZ = __drcp_rn(Z);
         int rem = n;
         if (!chain) {
@@ -424,20 +380,6 @@ __device__ __forceinline__ void assign_rows_wide(const MatView &M, const uint64_
         }
         if (rem > 0) atomicAdd(&counts[c_last], rem);
     }
-}
-
-// FixedBinomialFixedGammaSimplexSizeGenerator::sampleSimplexSize (simplexSizeGenerator.cpp:214-224): one uniform_01,
-// std::upper_bound on the CDF row of |S+|, + |S+|
-__device__ __forceinline__ int sample_simplex(const double *tab_val, const int32_t *tab_row, int n_plus, uint64_t key, uint32_t iteration) {
-    const double u = u01(make_site(key, PH_SIMPLEX, iteration, 0, 0).block(0).x);
-    int lo = tab_row[n_plus - 1];
-    const int first = lo;
-    int hi = tab_row[n_plus];
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (u < tab_val[mid]) hi = mid; else lo = mid + 1;
-    }
-    return (lo - first) + n_plus;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -509,124 +451,6 @@ __device__ __forceinline__ int bundle_e_step(BundleLane &L, double *theta, int32
         }
     }
     return b;
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// E-step of a wide unit (warp 0, 32 candidates per chunk, state in shared memory)
-// ------------------------------------------------------------------------------------------------------------------
-struct WideState {
-    double *theta, *den, *mean, *m2;
-    int32_t *counts, *occ;
-    const int32_t *base;
-    uint32_t *mask;  // [0, nch): S+ of the counts; [nch, 2 nch): picked null transcripts
-    uint16_t *act;   // members of the simplex, ascending (scratch of the E-step)
-    uint64_t *amask; // the simplex as a bit mask, 64 candidates per word: what the A-step ANDs the rows' masks with
-    const double *tab_val;
-    const int32_t *tab_row;
-    int T, nch, N_f;
-    double gamma;
-};
-
-__device__ __forceinline__ int wide_e_step(const WideState &E, uint64_t key, uint32_t iteration, bool sampling, double *tr_theta) {
-    const int lane = threadIdx.x & 31;
-    const int T = E.T, nch = E.nch;
-    int n_plus = 0;
-    for (int c = 0; c < nch; c++) {
-        const int t = c * 32 + lane;
-        const uint32_t pm = __ballot_sync(0xffffffffu, t < T && E.counts[t] > 0);
-        if (lane == 0) { E.mask[c] = pm; E.mask[nch + c] = 0u; }
-        n_plus += __popc(pm);
-    }
-    __syncwarp();
-    const int b = sample_simplex(E.tab_val, E.tab_row, n_plus, key, iteration);
-    const int n_null = T - n_plus;
-    const int n_pick = b - n_plus;
-    // the draws are independent (site = pick ordinal): 32 at a time, one per lane; the selection is sequential
-    for (int k0 = 0; k0 < n_pick; k0 += 32) {
-        uint32_t my_pick = 0u;
-        if (k0 + lane < n_pick)
-            my_pick = uniform_int(make_site(key, PH_NULLPICK, iteration, (uint32_t)(k0 + lane), 0), (uint32_t)(n_null - k0 - lane));
-        const int kn = n_pick - k0 < 32 ? n_pick - k0 : 32;
-        for (int k = 0; k < kn; k++) {
-            uint32_t rem = __shfl_sync(0xffffffffu, my_pick, k);
-            int pick = -1;
-            for (int c = 0; c < nch; c++) {
-                uint32_t w = ~(E.mask[c] | E.mask[nch + c]);
-                if (c == nch - 1 && (T & 31)) w &= (1u << (T & 31)) - 1u;
-                const uint32_t pc = (uint32_t)__popc(w);
-                if (rem < pc) { pick = c * 32 + (int)__fns(w, 0, (int)rem + 1); break; }
-                rem -= pc;
-            }
-            __syncwarp();
-            if (lane == 0 && pick >= 0) E.mask[nch + (pick >> 5)] |= 1u << (pick & 31);
-            __syncwarp();
-        }
-    }
-    // The simplex holds b of the T candidates, a few per 32-candidate chunk: the draws and the divisions below run over
-    // a compacted list of its members (b / 32 rounds with full lanes) instead of over every chunk with a few lanes each.
-    // Sums keep the order they always had (per lane over the chunks, then across the lanes).
-    int n_act = 0;
-    for (int c = 0; c < nch; c++) {
-        const int t = c * 32 + lane;
-        const uint32_t m = E.mask[c] | E.mask[nch + c];
-        if ((m >> lane) & 1u) E.act[n_act + __popc(m & ((1u << lane) - 1u))] = (uint16_t)t;
-        n_act += __popc(m);
-        if (t < T) E.theta[t] = 0.0;
-    }
-    __syncwarp();
-    for (int i0 = 0; i0 < n_act; i0 += 32) {
-        const int i = i0 + lane;
-        if (i < n_act) {
-            const int t = E.act[i];
-            E.theta[t] = gamma_variate(make_site(key, PH_GAMMA, iteration, (uint32_t)t, 0), (double)E.counts[t] + E.gamma);
-        }
-    }
-    __syncwarp();
-    double part = 0.0;
-    for (int c = 0; c < nch; c++) {
-        const int t = c * 32 + lane;
-        if (t < T) {
-            part += E.theta[t];
-            E.counts[t] = E.base[t];
-        }
-    }
-    const double norm = warp_sum(part);
-    for (int i0 = 0; i0 < n_act; i0 += 32) {
-        const int i = i0 + lane;
-        if (i < n_act) {
-            const int t = E.act[i];
-            const double g = E.theta[t];
-            const double th = g != 0.0 ? g / norm : 0.0;
-            E.theta[t] = th;
-            if (sampling && g != 0.0) {
-                const double fpkm = (th * (double)E.N_f * 1e9) / E.den[t];
-                const int o = ++E.occ[t];
-                if (o == 1) {
-                    E.mean[t] = fpkm;
-                } else {
-                    const double delta = fpkm - E.mean[t];
-                    const double mu = E.mean[t] + delta / o;
-                    E.mean[t] = mu;
-                    E.m2[t] += delta * (fpkm - mu);
-                }
-            }
-        }
-    }
-    for (int w = lane; w < (nch + 1) / 2; w += 32) {
-        const uint32_t lo = E.mask[2 * w] | E.mask[nch + 2 * w];
-        const uint32_t hi = 2 * w + 1 < nch ? E.mask[2 * w + 1] | E.mask[nch + 2 * w + 1] : 0u;
-        E.amask[w] = ((uint64_t)hi << 32) | lo;
-    }
-    if (tr_theta) {
-        __syncwarp();
-        for (int t = lane; t < T; t += 32) tr_theta[t] = E.theta[t];
-    }
-    return b;
-}
-
-template <typename T>
-__device__ __forceinline__ void block_copy(T *dst, const T *src, int n) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
 template <bool MAT_SMEM>
@@ -743,7 +567,7 @@ __global__ void __maxnreg__(BAYES_MAXNREG) gibbs_bundle_kernel(const __grid_cons
             }
         }
         __syncthreads();
-        assign_rows(M, theta, counts, skey, Tpad, (uint32_t)(it < 0 ? 0 : it), it < 0, next_slab);
+        assign_rows(M, theta, counts, skey, Tpad, (uint32_t)(it < 0 ? 0 : it), it < 0, next_slab, A.unit_err + ui);
         __syncthreads();
     }
     if (my_trace && total - 1 < A.trace_iters) A.tr_counts[(size_t)(total - 1) * L.Tg + L.t] = counts[lane];
@@ -840,7 +664,7 @@ __global__ void __maxnreg__(BAYES_WIDE_MAXNREG) gibbs_wide_kernel(const __grid_c
             if (tr && threadIdx.x == 0) A.tr_b[it] = b;
         }
         __syncthreads();
-        assign_rows_wide(M, E.amask, E.theta, E.counts, key, (uint32_t)(it < 0 ? 0 : it), it < 0, next_slab);
+        assign_rows_wide(M, E.amask, E.theta, E.counts, key, (uint32_t)(it < 0 ? 0 : it), it < 0, next_slab, A.unit_err + ui);
         __syncthreads();
     }
     if (tracing && total - 1 < A.trace_iters)
@@ -896,7 +720,7 @@ __global__ void step_assignment_kernel(const __grid_constant__ KernelArgs A, con
     M.row_nnz = A.row_nnz + U.row_off;
     M.row_info = A.row_info + U.row_off;
     __syncthreads();
-    assign_rows_wide(M, amask, theta, counts, skey[0], iteration, INIT, nullptr);
+    assign_rows_wide(M, amask, theta, counts, skey[0], iteration, INIT, nullptr, A.unit_err);
     __syncthreads();
     for (int t = threadIdx.x; t < T; t += blockDim.x) counts_out[t] = counts[t];
 }

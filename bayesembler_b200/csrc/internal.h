@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/bayesembler_b200.h"
+#include "layout.h"
 
 namespace bayes {
 
@@ -54,6 +55,17 @@ struct UnitDev {
     int64_t tab_off;    // -> tab_val (tables of the slots back to back)
     int64_t tabrow_off; // -> tab_row: slot g at g * (Tpad + 1), T + 1 offsets relative to the unit's tab_off
     int64_t mask_off;   // -> row_mask (wide units), in 64-bit words: ceil(T / 64) words per padded row, [slab][word][lane]
+    // fast (production) sampling mode, gibbs_fast.cu
+    int32_t n_chain_slabs;  // the first slabs hold the rows with >= 20 fragments (tree of binomials), the others the pooled-uniform rows
+    int32_t n_chain_cells;  // padded cells of the chain slabs = entries of the per-iteration scratch (cum, col) lists
+    int32_t qcap;           // capacity of one task queue buffer (nodes of one tree level over all chain rows)
+    int32_t pool_blocks;    // Philox blocks of the unit's uniform-word pool (4 words each)
+    int32_t pool_smem;      // 1: the pool is generated into shared memory once per iteration; 0: rows compute their blocks themselves
+    int32_t fast_pad;
+    int64_t woff_off;       // -> row_woff (n_slabs * slab_h entries): first pool word of a uniform row
+    int64_t pooldesc_off;   // -> pool_desc (pool_blocks entries): slot << 24 | block of the slot's pool
+    int64_t scr_off;        // -> scr_cum / scr_col (units whose matrix is not in shared memory keep them in global memory)
+    int64_t q_off;          // -> queue words, 6 * qcap per unit (idem)
     // per slot
     int32_t T[kMaxSlots];
     int32_t N_f[kMaxSlots];      // fragments of the locus (folded rows included)
@@ -61,6 +73,7 @@ struct UnitDev {
     double gamma[kMaxSlots];
     uint64_t key[kMaxSlots];     // Philox key of the chain
     int64_t out_off[kMaxSlots];  // -> out_occ / out_mean / out_m2 / out_counts (T entries)
+    int32_t pool_first[kMaxSlots];  // fast mode: first block of the slot in the unit's uniform-word pool
 };
 
 struct KernelArgs {
@@ -81,6 +94,13 @@ struct KernelArgs {
     double *out_m2;
     int32_t *out_counts;
     uint64_t *unit_clock;  // per unit: globaltimer ns at block start, at block end, SM id (3 words)
+    // fast mode
+    const int32_t *row_woff;
+    const uint32_t *pool_desc;
+    double *scr_cum;
+    uint16_t *scr_col;
+    uint32_t *queue;
+    int32_t *unit_err;  // per unit: != 0 when a row had no candidate with a non-zero probability (reference: assert, assignmentGenerator.cpp:284)
     // calibration pass (capi.cu, calibrate_units): run only the first iter_cap iterations of every chain and put the
     // time stamp of iteration iter_cap / 2 in the "start" word, so that end - start times the second half; 0 = off
     int32_t iter_cap;
@@ -116,6 +136,10 @@ struct PreLocus {
     const SimplexPrior &prior(int chain) const { return priors[chain_prior[chain]]; }
     // multi-cell rows in processing order (binomial-chain rows first, wider first, larger counts first)
     std::vector<int32_t> row_id, row_n, row_ptr;  // row_ptr: rows + 1
+    // fast mode: first word of the row in the locus' uniform-word pool (rows with < 20 fragments, in ORIGINAL row order;
+    // -1 for the others) and the size of that pool
+    std::vector<int32_t> row_woff;
+    int64_t pool_words = 0;
     std::vector<int32_t> cell_col;
     std::vector<double> cell_val;
     double cost = 0;  // per chain
@@ -133,7 +157,8 @@ struct PackedUnit {
     std::vector<double> val, efflen, tab_val;
     std::vector<uint16_t> col;
     std::vector<int32_t> slab_cell_off, row_n, row_nnz, base_counts, tab_row;
-    std::vector<uint32_t> row_info, row_mask;
+    std::vector<uint32_t> row_info, row_mask, pool_desc;
+    std::vector<int32_t> row_woff;
     double cost = 0;
     double features[4] = {0, 0, 0, 0};  // the time model's inputs (capi.cu)
 };
@@ -149,7 +174,8 @@ void build_items(const std::vector<SlotRef> &slots, std::vector<ItemShape> *item
 int validate_locus(const bayes_locus_desc &in, std::string *err);
 int prepare_locus(const bayes_locus_desc &in, PreLocus *out, std::string *err);
 int slot_lanes(int T);  // Tpad of a bundle slot (power of two >= T), 0 when T > 32
-void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, PackedUnit *out);
+void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, bool fast, PackedUnit *out);
+size_t max_unit_smem();  // dynamic shared memory a unit may use (opt-in limit of the device, 227 KB on sm_100)
 
 // host_steps.cpp
 int min_read_cover(const bayes_locus_desc &in, uint64_t key, int32_t *in_cover);
@@ -158,6 +184,12 @@ void simplex_table(double pi, double gamma, int T, int num_fragments, std::vecto
 // gibbs_kernel.cu
 int launch_units(const KernelArgs &args, int64_t unit_base, int64_t n_units, int block, bool wide, bool mat_smem, size_t smem_bytes,
                  void *stream);
+// gibbs_fast.cu
+int launch_units_fast(const KernelArgs &args, int64_t unit_base, int64_t n_units, int block, bool wide, bool mat_smem, size_t smem_bytes,
+                      void *stream);
+int launch_step_assignment_fast(const KernelArgs &args, bool init, const double *d_theta, uint32_t iteration, int32_t *d_counts_out,
+                                size_t smem_bytes, void *stream);
+int configure_fast_kernels();
 int launch_stagger(unsigned ns, void *stream);
 int launch_step_assignment(const KernelArgs &args, bool init, const double *d_theta, uint32_t iteration, int32_t *d_counts_out,
                            size_t smem_bytes, void *stream);

@@ -52,4 +52,62 @@ BAYES_LAYOUT_HD SmemLayout unit_layout(bool wide, int nT, int n_slots, int Tpad,
     return L;
 }
 
+// ---- fast (production) sampling mode, gibbs_fast.cu ---------------------------------------------------------------
+// Every unit keeps the per-candidate state (nT entries: 32 lanes of a bundle, T of a wide unit) in shared memory, the
+// E-step loads what it needs per iteration.  Units whose matrix is staged in shared memory (mat_smem) also keep there:
+// the per-iteration scratch lists of the chain rows (running sums + candidates of the cells in play), the two task
+// queue buffers of the splitting trees, the rows' pool offsets.  The uniform-word pool is a per-iteration cache of Philox
+// blocks in shared memory; a unit whose pool does not fit computes the blocks where it needs them (same words).
+struct FastLayout {
+    uint32_t theta, den, mean, m2, tab_val, val, scr_cum, key, sgamma, amask;  // 8-byte
+    uint32_t counts, base, occ, tab_row, mask, slab, row_n, row_nnz, row_info, row_woff, pool, pool_desc, queue, sT, sNf, ctl;  // 4-byte
+    uint32_t col, scr_col, act;  // 2-byte
+    uint32_t total;
+};
+
+constexpr int kFastCtlWords = 8;  // ctl: next slab, three rotating task counters, error flag
+
+BAYES_LAYOUT_HD FastLayout fast_layout(bool wide, int nT, int n_slots, int Tpad, int n_slabs, int slab_h, int n_cells, int tab_len,
+                                       bool tab_smem, bool mat_smem, int n_chain_cells, int qcap, int pool_blocks, bool pool_smem) {
+    FastLayout L;
+    const uint32_t uT = (uint32_t)nT, Rp = (uint32_t)n_slabs * (uint32_t)slab_h, nch = (uT + 31u) / 32u;
+    const uint32_t n_tabrow = (uint32_t)n_slots * ((uint32_t)Tpad + 1u);
+    const uint32_t cells = mat_smem ? (uint32_t)n_cells : 0u, ccells = mat_smem ? (uint32_t)n_chain_cells : 0u;
+    const uint32_t rows = mat_smem ? Rp : 0u, qwords = mat_smem ? 6u * (uint32_t)qcap : 0u;
+    uint32_t o = 0;
+    L.theta = o; o += 8u * uT;
+    L.den = o; o += 8u * uT;
+    L.mean = o; o += 8u * uT;
+    L.m2 = o; o += 8u * uT;
+    L.tab_val = o; o += tab_smem ? 8u * (uint32_t)tab_len : 0u;
+    L.val = o; o += 8u * cells;
+    L.scr_cum = o; o += 8u * ccells;
+    L.key = o; o += 8u * (uint32_t)n_slots;
+    L.sgamma = o; o += 8u * (uint32_t)n_slots;
+    L.amask = o; o += wide ? 8u * ((uT + 63u) / 64u) : 0u;
+    o = (o + 15u) & ~15u;
+    L.pool = o; o += pool_smem ? 16u * ((uint32_t)pool_blocks + 1u) : 0u;  // one spare block: a row reads its words four at a time
+    L.counts = o; o += 4u * uT;
+    L.base = o; o += 4u * uT;
+    L.occ = o; o += 4u * uT;
+    L.tab_row = o; o += tab_smem ? 4u * n_tabrow : 0u;
+    L.mask = o; o += wide ? 4u * (2u * nch + 2u) : 0u;
+    L.slab = o; o += mat_smem ? 4u * ((uint32_t)n_slabs + 1u) : 0u;
+    L.row_n = o; o += 4u * rows;
+    L.row_nnz = o; o += 4u * rows;
+    L.row_info = o; o += 4u * rows;
+    L.row_woff = o; o += 4u * rows;
+    L.pool_desc = o; o += pool_smem ? 4u * (uint32_t)pool_blocks : 0u;
+    L.queue = o; o += 4u * qwords;
+    L.sT = o; o += 4u * (uint32_t)n_slots;
+    L.sNf = o; o += 4u * (uint32_t)n_slots;
+    L.ctl = o; o += 4u * (uint32_t)kFastCtlWords;
+    L.col = o; o += 2u * cells;
+    L.scr_col = o; o += 2u * ccells;
+    o = (o + 1u) & ~1u;
+    L.act = o; o += wide ? 2u * uT : 0u;
+    L.total = (o + 15u) & ~15u;
+    return L;
+}
+
 }  // namespace bayes

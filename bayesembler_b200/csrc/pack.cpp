@@ -45,6 +45,8 @@ int validate_locus(const bayes_locus_desc &in, std::string *err) {
     return BAYES_OK;
 }
 
+size_t max_unit_smem() { return 227 * 1024; }
+
 int slot_lanes(int T) {
     if (T > 32) return 0;
     int p = 2;
@@ -78,18 +80,26 @@ int prepare_locus(const bayes_locus_desc &in, PreLocus *out, std::string *err) {
     P.efflen.assign(in.efflen, in.efflen + T);
     P.base_counts.assign(T, 0);
 
-    struct Row { int32_t id, n, nnz; };
+    struct Row { int32_t id, n, nnz, woff; };
     std::vector<Row> rows;
     rows.reserve(R);
-    int64_t n_frag = 0;
+    int64_t n_frag = 0, pool_words = 0;
     for (int i = 0; i < R; i++) {
         int nz = 0, last = -1;
         for (int k = in.row_ptr[i]; k < in.row_ptr[i + 1]; k++)
             if (in.val[k] != 0.0) { nz++; last = in.col_idx[k]; }
         n_frag += in.row_count[i];
-        if (nz == 1) { P.base_counts[last] += in.row_count[i]; P.folded++; }
-        else rows.push_back(Row{i, in.row_count[i], nz});
+        if (nz == 1) { P.base_counts[last] += in.row_count[i]; P.folded++; continue; }
+        // fast mode: a row with fewer than kSmallCount fragments owns that many consecutive words of the locus' pool
+        int32_t woff = -1;
+        if (in.row_count[i] < kSmallCount) {
+            if (pool_words > 2000000000) { *err = "too many fragments in rows with < 20 fragments"; return BAYES_E_INVALID; }
+            woff = (int32_t)pool_words;
+            pool_words += in.row_count[i];
+        }
+        rows.push_back(Row{i, in.row_count[i], nz, woff});
     }
+    P.pool_words = pool_words;
     if (n_frag > 2147483647) { *err = "more than 2^31-1 fragments in one locus"; return BAYES_E_INVALID; }
     P.n_frag = (int32_t)n_frag;
     std::stable_sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) {
@@ -102,6 +112,7 @@ int prepare_locus(const bayes_locus_desc &in, PreLocus *out, std::string *err) {
     for (const Row &row : rows) {
         P.row_id.push_back(row.id);
         P.row_n.push_back(row.n);
+        P.row_woff.push_back(row.woff);
         for (int k = in.row_ptr[row.id]; k < in.row_ptr[row.id + 1]; k++) {
             if (in.val[k] == 0.0) continue;
             P.cell_col.push_back(in.col_idx[k]);
@@ -166,7 +177,7 @@ void build_items(const std::vector<SlotRef> &slots, std::vector<ItemShape> *item
     *n_chain = nc;
 }
 
-void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, PackedUnit *out) {
+void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, bool fast, PackedUnit *out) {
     const int H = slab_h;
     PackedUnit &U = *out;
     U = PackedUnit();
@@ -196,11 +207,27 @@ void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, PackedU
     // wide units: T bits per padded row saying which candidates the row has a cell for (gibbs_kernel.cu, assign_rows_wide)
     const int n_words = wide ? (L0.T + 63) / 64 : 0;  // 64-bit words, stored as pairs of uint32 (low half first)
     U.row_mask.assign((size_t)n_slabs * H * n_words * 2, 0u);
+    // fast mode: the uniform-word pools of the slots back to back, whole Philox blocks per slot
+    std::vector<int64_t> pool_base(n_slots, 0);  // first block of the slot
+    int64_t pool_blocks = 0, qcap = 0;
+    if (fast) {
+        U.row_woff.assign((size_t)n_slabs * H, 0);
+        for (int g = 0; g < n_slots; g++) {
+            pool_base[g] = pool_blocks;
+            const int64_t nb = (slots[g].locus->pool_words + 3) / 4;
+            for (int64_t b = 0; b < nb; b++) U.pool_desc.push_back(((uint32_t)g << 24) | (uint32_t)b);
+            pool_blocks += nb;
+        }
+    }
     for (int i = 0; i < n_items; i++) {
         const ItemShape &it = items[i];
         const PreLocus &L = *slots[it.slot].locus;
         const int r = position(i), s = r / H, l = r % H;
         U.row_n[r] = it.n;
+        if (fast) {
+            if (it.chain) qcap += std::max(1, it.nnz / 2);  // nodes of the deepest tree level with two or more cells
+            else U.row_woff[r] = (int32_t)(4 * pool_base[it.slot] + L.row_woff[it.r]);
+        }
         // a product P_ij theta_j can only reach the denormal range from a tiny P_ij, or from a tiny theta_j, which needs a
         // Gamma(< 1) draw: flag those rows for the exact (slow) in-play rule of the A-step
         bool may_be_tiny = L.gamma < 1.0;
@@ -242,6 +269,7 @@ void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, PackedU
         d.gamma[g] = L.gamma;
         d.key[g] = bayes_chain_key(L.seed, slots[g].chain);
         d.out_off[g] = slots[g].out_off;
+        d.pool_first[g] = (int32_t)pool_base[g];
         U.cost = std::max(U.cost, L.cost);
     }
     U.cost *= 1.0 + 0.25 * (n_slots - 1);
@@ -254,10 +282,28 @@ void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, PackedU
     d.burn = L0.burn;
     d.samples = L0.samples;
     d.tab_len = (int32_t)U.tab_val.size();
-    d.tab_smem = d.tab_len <= kTableSmemEntries;
+    d.n_chain_slabs = chain_slabs;
+    d.n_chain_cells = U.slab_cell_off[chain_slabs];
+    d.qcap = (int32_t)std::max<int64_t>(qcap, 1);
+    d.pool_blocks = (int32_t)pool_blocks;
+    // What goes to shared memory is decided on the unit's WHOLE footprint against the opt-in limit of the device: first
+    // the matrix (with, in fast mode, the scratch lists and task queues that go where the matrix goes), then the CDF
+    // tables; whatever does not fit is read from global memory (L2) instead.
+    const size_t limit = max_unit_smem();
+    auto total = [&](bool tab, bool mat, bool pool) -> size_t {
+        return fast ? fast_layout(wide, nT, n_slots, Tpad, n_slabs, H, n_cells, d.tab_len, tab, mat, d.n_chain_cells, d.qcap, d.pool_blocks, pool).total
+                    : unit_layout(wide, nT, n_slots, Tpad, n_slabs, H, n_cells, d.tab_len, tab, mat).total;
+    };
     const size_t mat_bytes = (size_t)n_cells * 10 + (size_t)n_slabs * H * 12 + 4 * ((size_t)n_slabs + 1);
-    d.mat_smem = mat_bytes <= (size_t)kMatrixSmemBytes;
-    d.smem_bytes = (int32_t)unit_layout(wide, nT, n_slots, Tpad, n_slabs, H, n_cells, d.tab_len, d.tab_smem != 0, d.mat_smem != 0).total;
+    bool tab = d.tab_len <= kTableSmemEntries, mat = mat_bytes <= (size_t)kMatrixSmemBytes, pool = fast && pool_blocks <= 8192;
+    if (total(tab, mat, pool) > limit && tab && total(false, mat, pool) <= limit) tab = false;
+    if (total(tab, mat, pool) > limit) mat = false;
+    if (total(tab, mat, pool) > limit) tab = false;
+    if (total(tab, mat, pool) > limit) pool = false;
+    d.tab_smem = tab;
+    d.mat_smem = mat;
+    d.pool_smem = pool;
+    d.smem_bytes = (int32_t)total(tab, mat, pool);  // per-candidate state alone is < 200 KB at T = 4096: always fits
     d.block = 32;  // build_units decides
 }
 

@@ -14,7 +14,7 @@
 
 #if defined(__CUDACC__)
 #define BAYES_HD __host__ __device__ __forceinline__
-#define BAYES_HD_NOINLINE __host__ __device__ __noinline__
+#define BAYES_HD_NOINLINE inline __host__ __device__ __noinline__
 #else
 #define BAYES_HD inline
 #define BAYES_HD_NOINLINE inline
@@ -28,7 +28,12 @@ enum Phase : uint32_t {
     PH_SIMPLEX = 3,      // simplex-size uniform of the iteration that uses b
     PH_GAMMA = 4,        // expression gamma draw, index = transcript
     PH_NULLPICK = 5,     // null-transcript pick, index = pick ordinal
-    PH_ASSIGN = 6        // generateAssignment, index = row, sub = column (chain) or 0 (uniforms)
+    PH_ASSIGN = 6,       // generateAssignment, index = row, sub = column (chain) or 0 (uniforms)
+    // fast (production) sampling mode, gibbs_fast.cu
+    PH_POOL = 7,         // generateAssignment, words of the rows with < 20 fragments: block b of the iteration = block (b & 4095) of index (b >> 12)
+    PH_INIT_POOL = 8,    // the same for initAssignment
+    PH_TREE = 9,         // generateAssignment, one binomial per node of a row's splitting tree: index = row, phase word = PH_TREE | node << 8
+    PH_INIT_TREE = 10    // the same for initAssignment
 };
 
 struct u32x4 {
@@ -240,7 +245,7 @@ BAYES_HD int binomial_btrd(const Site &s, int n, double q) {
 
 // 1/k for the inversion recurrence: the correctly rounded reciprocal, so a table entry is the same double as 1.0 / k
 #if defined(__CUDACC__)
-__constant__ double kInvTable[64] = {
+static __constant__ double kInvTable[64] = {
     0.0,      1.0 / 1,  1.0 / 2,  1.0 / 3,  1.0 / 4,  1.0 / 5,  1.0 / 6,  1.0 / 7,  1.0 / 8,  1.0 / 9,  1.0 / 10, 1.0 / 11, 1.0 / 12,
     1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22, 1.0 / 23, 1.0 / 24, 1.0 / 25,
     1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31, 1.0 / 32, 1.0 / 33, 1.0 / 34, 1.0 / 35, 1.0 / 36, 1.0 / 37, 1.0 / 38,

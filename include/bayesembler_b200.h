@@ -35,6 +35,22 @@ extern "C" {
 #define BAYES_E_STATE (-3)    /* call out of order                   */
 #define BAYES_E_NOMEM (-4)
 #define BAYES_E_NODEVICE (-5) /* no CUDA device: there is no CPU path */
+#define BAYES_E_NUMERIC (-6)  /* a state the reference asserts against (a row without any candidate of non-zero
+                                 probability, assignmentGenerator.cpp:284; a Gamma draw below DBL_MIN,
+                                 expressionGenerator.cpp:115): reported by bayes_gibbs_sync after a download */
+
+/* Sampling modes (bayes_gibbs_set_mode).  Both draw every iteration from exactly the conditional distributions of the
+ * reference (gibbsSampler.cpp:103-141); they differ in WHICH random numbers feed which draw.
+ *   BAYES_MODE_FAST    production mode, the default: rows with >= 20 fragments split their fragments over the cells in
+ *                      play by a balanced binary tree of binomials (depth log2 k instead of the reference's chain of k
+ *                      dependent conditional binomials, assignmentGenerator.cpp:336-365; all nodes of a tree level of
+ *                      all rows are drawn at once), rows with fewer fragments locate words of a per-iteration pool of
+ *                      Philox blocks in their CDF (:289-334).
+ *   BAYES_MODE_REPLAY  draw for draw the reference's order of draws (one site per (row, column) of the chain), the
+ *                      mode the replay parity tests pin against the reference's own code.
+ * The CPU oracle restates both (oracle/bayes_oracle.c: ORC_WS_FAST, ORC_WS_SITE). */
+#define BAYES_MODE_FAST 0
+#define BAYES_MODE_REPLAY 1
 
 typedef struct bayes_gibbs_ctx bayes_gibbs_ctx;
 
@@ -123,6 +139,10 @@ int bayes_gibbs_phase_seconds(bayes_gibbs_ctx *ctx, double *out6);
  * and the batch is then sized and ordered with the measured per-iteration times (results do not depend on it: draws are
  * keyed by site).  -1 = automatic (256 iterations when the batch is several times what the GPU holds at once), 0 = off. */
 int bayes_gibbs_set_calibration(bayes_gibbs_ctx *ctx, int32_t iterations);
+/* Sampling mode of the batches uploaded from now on (before bayes_gibbs_upload); the environment variable BAYES_MODE
+ * (fast | replay) sets the default of new contexts. */
+int bayes_gibbs_set_mode(bayes_gibbs_ctx *ctx, int32_t mode);
+int32_t bayes_gibbs_get_mode(bayes_gibbs_ctx *ctx);
 /* kernels launched by the last bayes_gibbs_run() */
 int32_t bayes_gibbs_last_launches(bayes_gibbs_ctx *ctx);
 
@@ -144,6 +164,10 @@ int bayes_step_generate_assignment(int device, const bayes_locus_desc *locus, co
                                    uint32_t iteration, int32_t *counts_out);
 /* AssignmentGenerator::initAssignment (assignmentGenerator.cpp:213-260) */
 int bayes_step_init_assignment(int device, const bayes_locus_desc *locus, uint64_t key, int32_t *counts_out);
+/* generateAssignment (theta != NULL) or initAssignment (theta == NULL) in the given sampling mode; BAYES_MODE_REPLAY is
+ * what the two functions above run */
+int bayes_step_assignment(int device, const bayes_locus_desc *locus, const double *theta, uint64_t key, uint32_t iteration,
+                          int32_t mode, int32_t *counts_out);
 /* ExpressionGenerator::generateExpression(b, gamma, map_counts) (expressionGenerator.cpp:77-132) */
 int bayes_step_generate_expression(int device, int32_t T, const int32_t *counts, int32_t b, double gamma, uint64_t key,
                                    uint32_t iteration, double *theta_out);

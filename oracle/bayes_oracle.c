@@ -34,6 +34,15 @@ typedef struct {
     orc_mt mt;
 } rng_t;
 
+/*
+ * Modes.  ORC_WS_SEQ (the reference's one sequential MT19937) and ORC_WS_SITE (the same draws from site-keyed Philox
+ * streams) MUST share every line of the sampler below: the only place that tells them apart is the word source in
+ * orc_rng.h.  That is what makes the chain  reference (SEQ) == oracle (SEQ),  oracle (SITE) == GPU replay mode  sound.
+ * Never add a branch on SEQ vs SITE to this file.
+ * ORC_WS_FAST is the product's production sampling mode: the same conditional distributions drawn in an order that
+ * suits the GPU.  It replaces exactly two functions (init_assignment / generate_assignment -> assignment_fast) and
+ * draws from sites like ORC_WS_SITE; everything else is shared.
+ */
 static void rng_init(rng_t *r, int mode, uint64_t seed) {
     if (mode == ORC_WS_SEQ) {
         orc_mt_seed(&r->mt, (uint32_t)seed);
@@ -146,6 +155,8 @@ int orc_sample_simplex(const double *table, const int *row_len, int T, int count
     return sample_simplex(table, row_len, T, count_plus_size, &r.ws, iteration);
 }
 
+static int assignment_fast(const orc_locus *L, const double *theta, orc_ws *ws, uint32_t iteration, int init, int *counts);
+
 static int plus_size(const int *counts, int T) {
     int n = 0;
     for (int t = 0; t < T; t++) n += counts[t] > 0;
@@ -186,9 +197,94 @@ static void init_assignment(const orc_locus *L, orc_ws *ws, int *counts) {
 int orc_init_assignment(const orc_locus *loc, int rng_mode, uint64_t seed, int *counts_out, uint64_t *words) {
     rng_t r;
     rng_init(&r, rng_mode, seed);
-    init_assignment(loc, &r.ws, counts_out);
+    if (rng_mode == ORC_WS_FAST) assignment_fast(loc, 0, &r.ws, 0, 1, counts_out);
+    else init_assignment(loc, &r.ws, counts_out);
     if (words) *words = r.ws.words;
     return plus_size(counts_out, loc->T);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Production ("fast") mode of the product, ORC_WS_FAST: an exact draw from the same per-row multinomials
+ * as initAssignment / generateAssignment (assignmentGenerator.cpp:213-260, 263-373) that is not tied to the
+ * reference's sequential order of draws (outside replay the sampler may pick any exact
+ * multinomial per row).  Per row i with n fragments, over its stored non-zero cells in ascending column order:
+ *   p_j = P_ij * theta_j (init: theta == 1); the cells IN PLAY are those with p_j > 0, their running sums
+ *   cum_1 < ... < cum_k, Z = cum_k;
+ *   rows with a single stored non-zero cell give it everything (whatever theta is: they are folded by the packer);
+ *   k == 1: everything goes to that cell;
+ *   n < 20 (the reference's threshold, :289): the row owns n consecutive 32-bit words of the iteration's word
+ *     POOL (rows with n < 20 in row order, words of block b = Philox block (b & 4095) of site
+ *     (POOL, iteration, b >> 12)); word w lands in the first cell j < k with
+ *     w * 2^-32 < cum_j * (1/Z), i.e. w <= ceil(cum_j (1/Z) 2^32 - 1), else in cell k (:302-334 with unsorted
+ *     uniforms and one reciprocal per row);
+ *   n >= 20: a balanced binary TREE over the cells in play instead of the chain of conditional binomials
+ *     (:336-365): node (a, len) holds m fragments for cells [a, a + len); its left half [a, a + len/2) receives
+ *     Binomial(m, (cum(a + len/2) - cum(a)) / (cum(a + len) - cum(a))), the right half the rest; one site per node
+ *     (TREE | node << 8, iteration, row), node = a | (len - 1) << 12.  Depth log2 k instead of k dependent draws.
+ * ---------------------------------------------------------------------------------------------- */
+static uint32_t sat_u32_ceil(double x) { /* __double2uint_ru */
+    if (!(x > 0.0)) return 0u;
+    if (x >= 4294967295.0) return 0xffffffffu;
+    return (uint32_t)ceil(x);
+}
+
+static void tree_split(orc_ws *ws, uint32_t phase, uint32_t iteration, uint32_t row, const double *cum, const int *cell_col,
+                       int a, int len, int m, int *counts) {
+    if (m <= 0) return;
+    if (len == 1) { counts[cell_col[a]] += m; return; }
+    const int half = len >> 1;
+    const double Pa = a > 0 ? cum[a - 1] : 0.0, Pm = cum[a + half - 1], Pb = cum[a + len - 1];
+    const double p_left = (Pm - Pa) / (Pb - Pa);
+    orc_ws_site(ws, phase | ((uint32_t)a | ((uint32_t)(len - 1) << 12)) << 8, iteration, row, 0);
+    const int left = orc_binomial(ws, m, p_left);
+    tree_split(ws, phase, iteration, row, cum, cell_col, a, half, left, counts);
+    tree_split(ws, phase, iteration, row, cum, cell_col, a + half, len - half, m - left, counts);
+}
+
+static int assignment_fast(const orc_locus *L, const double *theta, orc_ws *ws, uint32_t iteration, int init, int *counts) {
+    const uint32_t ph_pool = init ? ORC_PH_INIT_POOL : ORC_PH_POOL, ph_tree = init ? ORC_PH_INIT_TREE : ORC_PH_TREE;
+    double *cum = (double *)malloc(sizeof(double) * (size_t)(L->T > 0 ? L->T : 1));
+    int *cell_col = (int *)malloc(sizeof(int) * (size_t)(L->T > 0 ? L->T : 1));
+    uint64_t pool_at = 0; /* next word of the pool */
+    int bad = 0;
+    for (int t = 0; t < L->T; t++) counts[t] = 0;
+    for (int i = 0; i < L->R; i++) {
+        const int beg = L->row_ptr[i], end = L->row_ptr[i + 1];
+        const int n = L->row_count[i];
+        int stored = 0, only = -1;
+        for (int k = beg; k < end; k++) if (L->val[k] != 0.0) { stored++; only = L->col_idx[k]; }
+        if (stored == 1) { counts[only] += n; continue; }
+        int kk = 0;
+        double run = 0;
+        for (int k = beg; k < end; k++) {
+            if (L->val[k] == 0.0) continue;
+            const double p = L->val[k] * (init ? 1.0 : theta[L->col_idx[k]]);
+            if (p > 0.0) { run += p; cum[kk] = run; cell_col[kk] = L->col_idx[k]; kk++; }
+        }
+        const uint64_t my_words = pool_at;
+        if (n < 20) pool_at += (uint64_t)n; /* the row's words are its own whether it needs them or not */
+        if (kk == 0) { bad = 1; continue; } /* reference: assert(normalisation_constant >= double_underflow) (:284) */
+        if (kk == 1) { counts[cell_col[0]] += n; continue; }
+        if (n < 20) {
+            const double rZ = 1.0 / run;
+            for (int f = 0; f < n; f++) {
+                const uint64_t word = my_words + (uint64_t)f, blk = word >> 2;
+                orc_ws_site(ws, ph_pool, iteration, (uint32_t)(blk >> 12), 0);
+                ws->k = (uint32_t)((blk & 4095u) << 2); /* block (blk & 4095) of the site */
+                uint32_t b[4];
+                orc_ws_block(ws, b);
+                const uint32_t w = b[word & 3u];
+                int j = 0;
+                for (; j < kk - 1; j++)
+                    if (w <= sat_u32_ceil(fma(cum[j] * rZ, 4294967296.0, -1.0))) break;
+                counts[cell_col[j]] += 1;
+            }
+        } else {
+            tree_split(ws, ph_tree, iteration, (uint32_t)i, cum, cell_col, 0, kk, n, counts);
+        }
+    }
+    free(cum); free(cell_col);
+    return bad;
 }
 
 static int cmp_double(const void *a, const void *b) {
@@ -250,7 +346,8 @@ int orc_generate_assignment(const orc_locus *loc, const double *theta, int rng_m
                             int *counts_out, uint64_t *words) {
     rng_t r;
     rng_init(&r, rng_mode, seed);
-    generate_assignment(loc, theta, &r.ws, iteration, counts_out);
+    if (rng_mode == ORC_WS_FAST) assignment_fast(loc, theta, &r.ws, iteration, 0, counts_out);
+    else generate_assignment(loc, theta, &r.ws, iteration, counts_out);
     if (words) *words = r.ws.words;
     return plus_size(counts_out, loc->T);
 }
@@ -363,7 +460,8 @@ int orc_run_sampler(const orc_locus *L, double pi, int burn_in, int samples, int
         double *theta = (double *)malloc(sizeof(double) * T);
         double *fpkm = (double *)malloc(sizeof(double) * T);
 
-        init_assignment(L, &r.ws, counts);                                                  /* gibbsSampler.cpp:90 */
+        if (rng_mode == ORC_WS_FAST) assignment_fast(L, 0, &r.ws, 0, 1, counts);
+        else init_assignment(L, &r.ws, counts);                                             /* gibbsSampler.cpp:90 */
         if (init_counts) for (int t = 0; t < T; t++) init_counts[t] = counts[t];
         int b = sample_simplex(table, row_len, T, plus_size(counts, T), &r.ws, 0);          /* :96 */
 
@@ -371,7 +469,8 @@ int orc_run_sampler(const orc_locus *L, double pi, int burn_in, int samples, int
         for (int it = 0; it < total; it++) {
             if (it < trace_iters && b_trace) b_trace[it] = b;
             generate_expression(T, counts, b, L->gamma, &r.ws, (uint32_t)it, theta, 0, scratch); /* :105 / :126 */
-            generate_assignment(L, theta, &r.ws, (uint32_t)it, counts);                           /* :106 / :127 */
+            if (rng_mode == ORC_WS_FAST) assignment_fast(L, theta, &r.ws, (uint32_t)it, 0, counts);
+            else generate_assignment(L, theta, &r.ws, (uint32_t)it, counts);                      /* :106 / :127 */
             b = sample_simplex(table, row_len, T, plus_size(counts, T), &r.ws, (uint32_t)it + 1); /* :107 / :128 */
             if (it < trace_iters) {
                 if (theta_trace) for (int t = 0; t < T; t++) theta_trace[(size_t)it * T + t] = theta[t];

@@ -15,7 +15,7 @@ ORACLE_SO = os.path.join(HERE, "_build", "libbayesoracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libbayesref.so")
 REF_SRC = os.environ.get("BAYES_REF_SRC", "/root/reference/src")
 
-SEQ, SITE = 0, 1
+SEQ, SITE, FAST = 0, 1, 2  # FAST: the production sampling mode of the product (bayes_oracle.c, assignment_fast)
 
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 _f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")

@@ -105,11 +105,18 @@ enum {
     ORC_PH_SIMPLEX = 3,     /* simplex size uniform, iteration = iteration that USES b */
     ORC_PH_GAMMA = 4,       /* expression gamma draw, index = transcript               */
     ORC_PH_NULLPICK = 5,    /* null-transcript pick, index = pick ordinal              */
-    ORC_PH_ASSIGN = 6       /* generateAssignment, index = row, sub = col (chain) or 0 */
+    ORC_PH_ASSIGN = 6,      /* generateAssignment, index = row, sub = col (chain) or 0 */
+    /* production ("fast") sampling mode, ORC_WS_FAST: same distributions, different draw sites (bayes_oracle.c) */
+    ORC_PH_POOL = 7,        /* generateAssignment, words of all rows with < 20 fragments: block b of the iteration is
+                               block (b & 4095) of site index (b >> 12)                                          */
+    ORC_PH_INIT_POOL = 8,   /* the same for initAssignment                                                    */
+    ORC_PH_TREE = 9,        /* generateAssignment, one binomial per node of a row's splitting tree: index = row,
+                               phase word = ORC_PH_TREE | node << 8, node = first cell | (cells - 1) << 12       */
+    ORC_PH_INIT_TREE = 10   /* the same for initAssignment                                                    */
 };
 
 /* --------------------------------------------------------------- word source */
-enum { ORC_WS_SEQ = 0, ORC_WS_SITE = 1 };
+enum { ORC_WS_SEQ = 0, ORC_WS_SITE = 1, ORC_WS_FAST = 2 /* sites like ORC_WS_SITE; only bayes_oracle.c tells them apart */ };
 
 typedef struct {
     int mode;
@@ -129,7 +136,7 @@ static inline void orc_ws_init_seq(orc_ws *w, orc_mt *mt) {
 
 static inline void orc_ws_init_site(orc_ws *w, uint64_t key) {
     memset(w, 0, sizeof(*w));
-    w->mode = ORC_WS_SITE;
+    w->mode = ORC_WS_SITE; /* ORC_WS_FAST draws from sites in exactly the same way */
     w->key[0] = (uint32_t)key;
     w->key[1] = (uint32_t)(key >> 32);
 }

@@ -5,7 +5,7 @@ front of Assembler::runBayesemblerBatched (host/assembler.hpp) = bayesemblerCall
 CPU: option parsing (names, defaults, checks, help), the graph-file reader, the graphs that never reach the sampler (return
 codes 2 / 3 / 4) and the refusal to sample without a GPU.  GPU: a full run whose assembly.gtf / candidates.gtf /
 fragment_lengths.txt are compared, byte for byte, with the oracles chained the same way (oracle/f2_py -> oracle/f1_oracle.c ->
-oracle/bayes_oracle.c in site mode -> the GTF writer that tests/test_host_facade.py pins against the reference's)."""
+oracle/bayes_oracle.c in the sampling mode the driver ran in (fast by default, BAYES_MODE=replay for the other) -> the GTF writer that tests/test_host_facade.py pins against the reference's)."""
 import ctypes as C
 import os
 import subprocess
@@ -24,8 +24,9 @@ def cli(lib):
     return _build.build_cli()
 
 
-def run(cli, *args, cwd=None):
-    p = subprocess.run([cli] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=cwd, timeout=600)
+def run(cli, *args, cwd=None, env=None):
+    p = subprocess.run([cli] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=cwd, timeout=600,
+                       env=None if env is None else dict(os.environ, **env))
     return p.returncode, p.stdout, p.stderr
 
 
@@ -158,9 +159,9 @@ def test_no_cpu_sampler_behind_the_cli(cli, tmp_path):
 
 # ------------------------------------------------------------------------------------------------------------ full run (GPU)
 def _expected(lib, oracle, facade, graphs, n_pairs, seed, frag_mean, frag_sd, no_pre=False, max_cand=100, base=1000, scale=60,
-              count_threshold=12.0, marginal_threshold=0.5):
+              count_threshold=12.0, marginal_threshold=0.5, replay=False):
     """The reference's control flow (assembler.cpp:1420-1631) on the oracles."""
-    from oracle.oracle_py import SITE, Locus
+    from oracle.oracle_py import FAST, SITE, Locus
     orc_f1 = f1_py.OracleF1()
     order = [g for g in graphs if not g[2]] + [g for g in graphs if g[2]]
     ens, cand, codes = [], [], []
@@ -199,7 +200,7 @@ def _expected(lib, oracle, facade, graphs, n_pairs, seed, frag_mean, frag_sd, no
             rp.append(len(ci))
         loc = Locus(cm["T"], rp, ci, va, cm["counts"], cm["efflen"], int(n_pairs))
         burn = base + scale * int(cm["complexity"].max())
-        o = oracle.run_sampler(loc, burn, 10 * burn, SITE, lib.chain_key(graph_seed & 0xFFFFFFFF, 0))
+        o = oracle.run_sampler(loc, burn, 10 * burn, SITE if replay else FAST, lib.chain_key(graph_seed & 0xFFFFFFFF, 0))
         texts = []
         for mode in (0, 1):
             buf = C.create_string_buffer(1 << 22)
@@ -237,6 +238,10 @@ def test_cli_run_matches_the_chained_oracles(cli, lib, oracle, facade, tmp_path)
     assert open(prefix + "candidates.gtf").read() == want_cand
     assert "%d graph(s) were assembled successfully" % codes.count(0) in out
     assert "%d graph(s) were not assembled due to insufficient candidate coverage" % codes.count(3) in out
+    # the same run in the replay sampling mode (the reference's order of draws)
+    rc, _, err = run(cli, "-g", path, "-o", prefix + "replay_", "--seed", "11", "--frag-mean", "200", "--frag-sd", "20", env={"BAYES_MODE": "replay"})
+    assert rc == 0, err
+    assert open(prefix + "replay_assembly.gtf").read() == _expected(lib, oracle, facade, single_graph, n_pairs, 11, 200.0, 20.0, replay=True)[0]
     # the same run with the fragment length distribution estimated from the single-path graphs (assembler.cpp:1919-1987)
     rc, out2, err = run(cli, "-g", path, "-o", prefix + "est_", "--seed", "11", "--output-mode", "full", "--num-threads", "4")
     assert rc == 0, err

@@ -5,22 +5,24 @@ iteration counts and are compared draw for draw with the CPU oracle."""
 import numpy as np
 import pytest
 
-from oracle.oracle_py import SITE
+from oracle.oracle_py import FAST, SITE
+
+ORACLE_MODE = {"replay": SITE, "fast": FAST}
 
 pytestmark = pytest.mark.gpu
 
 
-def _check(lib, oracle, batch, idx, burn, samples, n_chains=1):
+def _check(lib, oracle, batch, idx, burn, samples, n_chains=1, mode="fast"):
     descs = batch.desc_array(subset=idx, n_chains=n_chains)
     descs["burn_in"] = burn
     descs["samples"] = samples
-    ctx = lib.GibbsContext(0)
+    ctx = lib.GibbsContext(0, mode=mode)
     ctx.run_batch(descs)
     shape, _ = ctx.unit_stats()
     for j, i in enumerate(idx):
         loc = batch.locus(int(i))
         for c in range(n_chains):
-            o = oracle.run_sampler(loc, burn, samples, SITE, lib.chain_key(int(batch.seeds[i]), c))
+            o = oracle.run_sampler(loc, burn, samples, ORACLE_MODE[mode], lib.chain_key(int(batch.seeds[i]), c))
             g = ctx.fetch(j, c)
             assert np.array_equal(g["occ"], o["occ"]), (int(i), c)
             np.testing.assert_allclose(g["mean"], o["mean"], rtol=1e-9)
@@ -29,22 +31,54 @@ def _check(lib, oracle, batch, idx, burn, samples, n_chains=1):
     return shape
 
 
-def test_config1_loci(lib, oracle):
+@pytest.mark.parametrize("mode", ["fast", "replay"])
+def test_config1_loci(lib, oracle, mode):
     from bayesembler_b200 import synth
     batch = synth.SynthBatch(1)
     multi = np.nonzero(batch.T > 1)[0]
     idx = multi[np.argsort(-batch.R[multi])[[0, 3, 20, 60]]]  # includes the largest locus of the configuration
-    _check(lib, oracle, batch, idx, 40, 400)
+    _check(lib, oracle, batch, idx, 40, 400, mode=mode)
 
 
-def test_config3_wide_streaming_loci(lib, oracle):
+@pytest.mark.parametrize("mode", ["fast", "replay"])
+def test_config3_wide_streaming_loci(lib, oracle, mode):
     from bayesembler_b200 import synth
     batch = synth.SynthBatch(3, n_loci=6)
     assert batch.T.min() >= 200 and batch.T.max() <= 1000
     idx = np.array([int(np.argmin(batch.T)), int(np.argmax(batch.T))])
-    shape = _check(lib, oracle, batch, idx, 10, 60)
+    shape = _check(lib, oracle, batch, idx, 10, 60, mode=mode)
     assert np.all(shape[:, 0] == 1)              # wide units
     assert np.any((shape[:, 7] & 1) == 0)        # at least one streams its matrix instead of staging it in shared memory
+
+
+@pytest.mark.parametrize("mode,pick", [("fast", [0, 9, 19, 29, 39]), ("replay", [0, 39])])
+def test_config3_long_traces(lib, oracle, mode, pick):
+    """Real config-3 loci, from the narrowest to the widest (T ~ 1000), for 2 200 iterations each with the full theta /
+    counts / simplex-size traces: long enough for the simplex to thin out, so the per-row caches of the cells in play and
+    the splitting trees run in the regime the full-length chains spend their time in."""
+    from bayesembler_b200 import synth
+    batch = synth.SynthBatch(3, n_loci=40)
+    order = np.argsort(batch.T)
+    burn, samples = 200, 2000
+    for i in order[pick]:
+        i = int(i)
+        loc = batch.locus(i)
+        descs = batch.desc_array(subset=[i])
+        descs["burn_in"] = burn
+        descs["samples"] = samples
+        ctx = lib.GibbsContext(0, mode=mode)
+        ctx.submit(descs)
+        ctx.set_trace(0, 0, burn + samples)
+        ctx.upload(); ctx.run(); ctx.download(); ctx.sync()
+        g, tr = ctx.fetch(0), ctx.fetch_trace()
+        ctx.close()
+        o = oracle.run_sampler(loc, burn, samples, ORACLE_MODE[mode], lib.chain_key(int(batch.seeds[i]), 0), trace_iters=burn + samples)
+        assert np.array_equal(tr["init_counts"], o["init_counts"]), i
+        assert np.array_equal(tr["b_trace"], o["b_trace"]), i
+        assert np.array_equal(tr["counts_trace"], o["counts_trace"]), i
+        np.testing.assert_allclose(tr["theta_trace"], o["theta_trace"], rtol=1e-9, atol=0)
+        assert np.array_equal(g["occ"], o["occ"]), i
+        np.testing.assert_allclose(g["mean"], o["mean"], rtol=1e-9)
 
 
 def test_config4_heavy_tail_loci(lib, oracle):

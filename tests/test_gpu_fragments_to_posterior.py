@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import f1_py
-from oracle.oracle_py import SITE, Locus
+from oracle.oracle_py import FAST, Locus
 
 pytestmark = pytest.mark.gpu
 
@@ -39,7 +39,7 @@ def test_fragments_to_posterior(lib, oracle):
     ctx.run_batch(lib.make_desc_array(loci, burns, samples, seeds))
     for i in range(len(loci)):
         got = ctx.fetch(i)
-        want = oracle.run_sampler(ref_loci[i], burns[i], samples[i], SITE, lib.chain_key(seeds[i], 0))
+        want = oracle.run_sampler(ref_loci[i], burns[i], samples[i], FAST, lib.chain_key(seeds[i], 0))
         assert np.array_equal(got["occ"], want["occ"]), i
         np.testing.assert_allclose(got["mean"], want["mean"], rtol=1e-9)
     ctx.close()

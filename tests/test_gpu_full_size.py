@@ -4,7 +4,7 @@ few loci against the CPU oracle (which needs seconds per locus, so it cannot che
 import numpy as np
 import pytest
 
-from oracle.oracle_py import SITE
+from oracle.oracle_py import FAST
 
 pytestmark = pytest.mark.gpu
 
@@ -73,10 +73,17 @@ def test_full_size_schedule_independent(full_run, lib):
 def test_full_size_spot_check_against_oracle(full_run, lib, oracle):
     batch, descs, ctx, res = full_run
     rng = np.random.default_rng(11)
-    multi = np.nonzero((batch.T > 1) & (batch.T <= 12))[0]
-    for i in rng.choice(multi, 5, replace=False):
-        i = int(i)
-        o = oracle.run_sampler(batch.locus(i), int(batch.burn[i]), int(batch.samples[i]), SITE, lib.chain_key(int(batch.seeds[i]), 0))
+    small = np.nonzero((batch.T > 1) & (batch.T <= 12))[0]
+    large = np.nonzero(batch.T > 12)[0]
+    # the units that are special in the full batch: the longest chains (T >= 28: several warps, critical-path sizing,
+    # calibrated re-shaping), by their cost cells x iterations
+    cells = (batch.cell_off[1:] - batch.cell_off[:-1]).astype(np.float64)
+    cost = cells * (batch.burn.astype(np.float64) + batch.samples)
+    longest = [int(i) for i in np.argsort(-cost)[:3]]
+    assert all(batch.T[i] >= 20 for i in longest)
+    picks = longest + [int(i) for i in rng.choice(large, 3, replace=False)] + [int(i) for i in rng.choice(small, 4, replace=False)]
+    for i in picks:
+        o = oracle.run_sampler(batch.locus(i), int(batch.burn[i]), int(batch.samples[i]), FAST, lib.chain_key(int(batch.seeds[i]), 0))
         g = ctx.fetch(i)
         assert np.array_equal(g["occ"], o["occ"]), i
         np.testing.assert_allclose(g["mean"], o["mean"], rtol=1e-9)

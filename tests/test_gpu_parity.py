@@ -1,12 +1,17 @@
 """GPU parity: the CUDA path (through the C ABI) against the CPU oracle, draw for draw.
 
 Both sides draw from the same site-keyed Philox streams (DESIGN.md "Replay"); integer results must be identical and
-floating point must agree to 1e-9 relative (north_star asks for 1e-6).
+floating point must agree to 1e-9 relative (north_star asks for 1e-6).  Both sampling modes of the product are held
+to this bar: "replay" (the reference's order of draws; oracle mode SITE, itself pinned against the reference's code
+in SEQ mode) and "fast" (the production mode: splitting trees + pooled uniform words; oracle mode FAST).
 """
 import numpy as np
 import pytest
 
-from oracle.oracle_py import SITE, random_locus
+from oracle.oracle_py import FAST, SITE, random_locus
+
+ORACLE_MODE = {"replay": SITE, "fast": FAST}
+MODES = ["replay", "fast"]
 
 pytestmark = pytest.mark.gpu
 
@@ -79,6 +84,42 @@ def test_step_generate_assignment(lib, oracle, T, R, mc):
         assert np.array_equal(g, o)
 
 
+@pytest.mark.parametrize("T,R,mc", SHAPES)
+def test_step_assignment_fast_mode(lib, oracle, T, R, mc):
+    """initAssignment and generateAssignment of the production mode (wide layout, candidate masks, splitting trees in
+    global memory, pool blocks computed by the rows): the same counts as the oracle's restatement of that mode."""
+    rng = np.random.default_rng(T * 13 + R)
+    loc = random_locus(rng, T, R, max_count=mc)
+    key = int(rng.integers(1, 2 ** 62))
+    g = lib.step_assignment(loc, None, key, mode="fast")
+    o, _ = oracle.init_assignment(loc, FAST, key)
+    assert g.sum() == loc.n_frag
+    assert np.array_equal(g, o)
+    for it in (0, 7, 654321):
+        th = _theta_for(rng, loc)
+        g = lib.step_assignment(loc, th, key, it, mode="fast")
+        o, _ = oracle.generate_assignment(loc, th, FAST, key, it)
+        assert g.sum() == loc.n_frag
+        assert np.array_equal(g, o)
+    # and the replay mode through the same entry point
+    th = _theta_for(rng, loc)
+    assert np.array_equal(lib.step_assignment(loc, th, key, 3, mode="replay"), oracle.generate_assignment(loc, th, SITE, key, 3)[0])
+
+
+def test_step_assignment_reports_a_row_without_candidates(lib):
+    """theta == 0 on every candidate of a row: the reference asserts (assignmentGenerator.cpp:284), the library reports."""
+    rng = np.random.default_rng(4)
+    loc = random_locus(rng, 6, 20, max_count=30, single_frac=0.0)
+    th = np.zeros(6)
+    th[0] = 1.0
+    dense = loc.dense()
+    if not ((dense[:, 0] == 0).any()):
+        pytest.skip("every row has a cell in column 0")
+    for mode in MODES:
+        with pytest.raises(lib.BayesError, match="non-zero probability"):
+            lib.step_assignment(loc, th, 5, 0, mode=mode)
+
+
 @pytest.mark.parametrize("T,gamma", [(2, 1.0), (7, 1.0), (32, 0.5), (33, 1.0), (100, 2.5), (1000, 1.0)])
 def test_step_generate_expression(lib, oracle, T, gamma):
     rng = np.random.default_rng(T)
@@ -96,15 +137,16 @@ def test_step_generate_expression(lib, oracle, T, gamma):
             assert abs(g.sum() - 1) < 1e-12
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("T,R,mc,gamma", [(2, 6, 40, 1.0), (3, 30, 60, 1.0), (8, 120, 400, 1.0), (12, 60, 100, 0.5),
                                           (30, 500, 80, 1.0), (40, 200, 3000, 2.0), (100, 300, 50, 1.0), (300, 700, 40, 1.0)])
-def test_full_chain_replay(lib, oracle, T, R, mc, gamma):
+def test_full_chain_replay(lib, oracle, T, R, mc, gamma, mode):
     rng = np.random.default_rng(T * 31 + R)
     loc = random_locus(rng, T, R, max_count=mc, gamma=gamma)
     seed = int(rng.integers(1, 2 ** 62))
     burn, samples = 60 + 3 * T, 600 + 30 * T
     total = burn + samples
-    ctx = lib.GibbsContext(0)
+    ctx = lib.GibbsContext(0, mode=mode)
     descs = lib.make_desc_array([loc], [burn], [samples], [seed])
     ctx.submit(descs)
     ctx.set_trace(0, 0, total)
@@ -113,7 +155,7 @@ def test_full_chain_replay(lib, oracle, T, R, mc, gamma):
     tr = ctx.fetch_trace()
     info = ctx.locus_info(0)
     ctx.close()
-    o = oracle.run_sampler(loc, burn, samples, SITE, lib.chain_key(seed, 0), trace_iters=total)
+    o = oracle.run_sampler(loc, burn, samples, ORACLE_MODE[mode], lib.chain_key(seed, 0), trace_iters=total)
     assert info["pi"] == o["pi"]
     assert np.array_equal(tr["init_counts"], o["init_counts"])
     assert np.array_equal(tr["b_trace"], o["b_trace"])
@@ -126,8 +168,9 @@ def test_full_chain_replay(lib, oracle, T, R, mc, gamma):
     assert np.array_equal(g["final_counts"], o["counts_trace"][-1])
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("calibration", [0, 40, 100000])
-def test_batch_mixed_loci_and_chains(lib, oracle, calibration):
+def test_batch_mixed_loci_and_chains(lib, oracle, calibration, mode):
     """calibration: the pass of bayes_gibbs_upload that times the first iterations of every unit and re-forms the batch
     (off / shorter than every chain / longer than every chain) must not change a single draw."""
     rng = np.random.default_rng(2024)
@@ -137,14 +180,15 @@ def test_batch_mixed_loci_and_chains(lib, oracle, calibration):
     burn = [50 + 5 * l.T for l in loci]
     samples = [10 * b for b in burn]
     chains = [1, 3, 2, 1, 2, 4, 1, 2]
-    ctx = lib.GibbsContext(0)
+    ctx = lib.GibbsContext(0, mode=mode)
+    assert ctx.get_mode() == mode
     ctx.set_calibration(calibration)
     descs = lib.make_desc_array(loci, burn, samples, seeds, n_chains=chains)
     ctx.run_batch(descs)
     for i, loc in enumerate(loci):
         for c in range(chains[i]):
             g = ctx.fetch(i, c)
-            o = oracle.run_sampler(loc, burn[i], samples[i], SITE, lib.chain_key(seeds[i], c))  # own read cover per chain
+            o = oracle.run_sampler(loc, burn[i], samples[i], ORACLE_MODE[mode], lib.chain_key(seeds[i], c))  # own read cover per chain
             assert o["pi"] == ctx.chain_info(i, c)["pi"]
             assert np.array_equal(g["occ"], o["occ"]), (i, c)
             np.testing.assert_allclose(g["mean"], o["mean"], rtol=RTOL)
@@ -226,6 +270,6 @@ def test_concurrent_submit(lib, oracle):
     for first, base in zip(firsts, range(0, len(loci), 4)):
         for j in range(4):
             g = ctx.fetch(first + j)
-            o = oracle.run_sampler(loci[base + j], burn, samples, SITE, lib.chain_key(seeds[base + j], 0))
+            o = oracle.run_sampler(loci[base + j], burn, samples, FAST, lib.chain_key(seeds[base + j], 0))  # default mode
             assert np.array_equal(g["occ"], o["occ"]), (first, j)
     ctx.close()
