@@ -88,7 +88,7 @@ struct PinBuf {
 struct Launch {
     int64_t unit_base, n_units;
     int block;
-    bool wide, mat_smem;
+    bool wide, mat_smem, scr_smem;
     size_t smem;
 };
 
@@ -103,6 +103,7 @@ struct UnitShape {
     std::vector<int32_t> blocks;  // per item: Philox blocks of a uniform item
     int n_chain = 0;
     double iters = 0;
+    bool wide = false;
 };
 
 struct bayes_gibbs_ctx {
@@ -124,7 +125,7 @@ struct bayes_gibbs_ctx {
     PinBuf<double> h_val, h_efflen, h_tab_val;
     PinBuf<uint16_t> h_col;
     PinBuf<int32_t> h_slab, h_row_n, h_row_nnz, h_base, h_tab_row;
-    PinBuf<uint32_t> h_row_info, h_row_mask, h_pool_desc;
+    PinBuf<uint32_t> h_row_info, h_row_mask, h_pool_desc, h_cell_meta, h_chain_tab;
     PinBuf<int32_t> h_row_woff;
     // results (pinned)
     PinBuf<int32_t> h_occ, h_counts, h_unit_err;
@@ -134,7 +135,7 @@ struct bayes_gibbs_ctx {
     DevBuf<double> d_val, d_efflen, d_tab_val, d_mean, d_m2, d_tr_theta;
     DevBuf<uint16_t> d_col;
     DevBuf<int32_t> d_slab, d_row_n, d_row_nnz, d_base, d_tab_row, d_occ, d_counts, d_tr_counts, d_tr_b, d_tr_init;
-    DevBuf<uint32_t> d_row_info, d_row_mask, d_pool_desc, d_queue;
+    DevBuf<uint32_t> d_row_info, d_row_mask, d_pool_desc, d_queue, d_cell_meta, d_chain_tab;
     DevBuf<int32_t> d_row_woff, d_unit_err;
     DevBuf<double> d_scr_cum;
     DevBuf<uint16_t> d_scr_col;
@@ -224,15 +225,18 @@ int append_unit(bayes_gibbs_ctx *ctx, PackedUnit &U) {
     U.d.mask_off = (int64_t)(ctx->h_row_mask.n / 2);  // in 64-bit words
     U.d.woff_off = (int64_t)ctx->h_row_woff.n;
     U.d.pooldesc_off = (int64_t)ctx->h_pool_desc.n;
+    U.d.meta_off = (int64_t)ctx->h_cell_meta.n;
+    U.d.ctab_off = (int64_t)ctx->h_chain_tab.n;
     U.d.scr_off = ctx->scr_len;
     U.d.q_off = ctx->q_len;
-    if (!U.row_woff.empty() && !U.d.mat_smem) {  // fast mode, streaming unit
+    if ((!U.row_woff.empty() || !U.cell_meta.empty()) && !U.d.scr_smem) {  // fast mode, scratch in global memory
         ctx->scr_len += U.d.n_chain_cells;
         ctx->q_len += 6 * (int64_t)U.d.qcap;
     }
     if ((rc = append(ctx->h_slab, U.slab_cell_off)) || (rc = append(ctx->h_val, U.val)) || (rc = append(ctx->h_col, U.col)) ||
         (rc = append(ctx->h_row_n, U.row_n)) || (rc = append(ctx->h_row_nnz, U.row_nnz)) || (rc = append(ctx->h_row_info, U.row_info)) || (rc = append(ctx->h_row_mask, U.row_mask)) ||
         (rc = append(ctx->h_row_woff, U.row_woff)) || (rc = append(ctx->h_pool_desc, U.pool_desc)) ||
+        (rc = append(ctx->h_cell_meta, U.cell_meta)) || (rc = append(ctx->h_chain_tab, U.chain_tab)) ||
         (rc = append(ctx->h_efflen, U.efflen)) || (rc = append(ctx->h_base, U.base_counts)) ||
         (rc = append(ctx->h_tab_val, U.tab_val)) || (rc = append(ctx->h_tab_row, U.tab_row)))
         return rc;
@@ -250,7 +254,7 @@ int append_unit(bayes_gibbs_ctx *ctx, PackedUnit &U) {
 int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
     ctx->h_units.n = ctx->h_val.n = ctx->h_efflen.n = ctx->h_tab_val.n = ctx->h_col.n = 0;
     ctx->h_slab.n = ctx->h_row_n.n = ctx->h_row_nnz.n = ctx->h_row_info.n = ctx->h_row_mask.n = ctx->h_base.n = ctx->h_tab_row.n = 0;
-    ctx->h_row_woff.n = ctx->h_pool_desc.n = 0;
+    ctx->h_row_woff.n = ctx->h_pool_desc.n = ctx->h_cell_meta.n = ctx->h_chain_tab.n = 0;
     ctx->scr_len = ctx->q_len = 0;
     const bool fast = ctx->mode == BAYES_MODE_FAST;
     ctx->built_mode = ctx->mode;
@@ -279,9 +283,36 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         std::vector<SlotRef> &v = kv.second;
         const int per = 32 / std::get<0>(kv.first);
         std::stable_sort(v.begin(), v.end(), [](const SlotRef &a, const SlotRef &b) { return a.locus->cost > b.locus->cost; });
-        for (size_t i = 0; i < v.size(); i += per) {
-            groups.push_back(std::vector<SlotRef>(v.begin() + i, v.begin() + std::min(v.size(), i + per)));
+        // A bundle takes slots until the lanes of warp 0 are used up or (fast mode) its shared-memory footprint reaches the
+        // budget of one warp: the SM holds 227 KB and 32 warps, and a unit that needs more than its share per warp either idles
+        // warps (when it gets them) or keeps warp slots empty (when it does not).
+        const char *ub = getenv("BAYES_UNIT_SMEM");  // experiment knob, bytes
+        const double budget = ub ? atof(ub) : (fast ? 12288.0 : 1e12);
+        for (size_t i = 0; i < v.size();) {
+            size_t j = i;
+            double bytes = 2048.0;  // per-candidate state of the 32 lanes, keys, control words
+            int64_t pool_words = 0, chain_rows = 0;
+            while (j < v.size() && (int)(j - i) < per) {
+                const PreLocus &L = *v[j].locus;
+                int64_t chain = 0, chain_cells = 0;
+                for (size_t r = 0; r < L.row_n.size(); r++)
+                    if (L.row_n[r] >= kSmallCount) { chain++; chain_cells += L.row_ptr[r + 1] - L.row_ptr[r]; }
+                // tiles: 12 bytes per cell (+ a few padding lanes), 10 per scratch entry, 16 per queued node, 5 per pool word, the CDF table
+                const double b = (g_tile_stream ? 0.0 : 13.0 * L.cell_val.size()) + 18.0 * chain_cells + 12.0 * chain + 5.0 * L.pool_words + 8.0 * L.prior(v[j].chain).tab_val.size() + 64.0;
+                const int64_t pw = 4 * ((L.pool_words + 3) / 4);
+                if (j > i && (bytes + b > budget || (fast && (pool_words + pw >= kMaxTilePoolWords || chain_rows + chain >= (1 << 15))))) break;
+                bytes += b;
+                pool_words += pw;
+                chain_rows += chain;
+                j++;
+            }
+            if (fast && (pool_words >= kMaxTilePoolWords || chain_rows >= (1 << 15))) {
+                set_error("a locus with at most 32 candidates has more rows than the fast sampling mode addresses (use BAYES_MODE_REPLAY)");
+                return BAYES_E_INVALID;
+            }
+            groups.push_back(std::vector<SlotRef>(v.begin() + i, v.begin() + j));
             group_wide.push_back(0);
+            i = j;
         }
     }
     const int64_t n_units = (int64_t)groups.size();
@@ -307,6 +338,7 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
             S.blocks.push_back(it.blocks);
         }
         S.iters = (double)groups[i][0].locus->burn + groups[i][0].locus->samples;
+        S.wide = group_wide[i] != 0;
     });
     // Time model in microseconds per iteration, fitted by least squares to the measured durations of the 4 183 units of
     // config 2 on a FULL B200 (tools/schedule_report.py -> gpurun_out/unit_stats.npz, profiles/README.md): a chain slab
@@ -345,7 +377,31 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         *levels = lv;
         return passes;
     };
+    // Bundles in fast mode are lane-per-cell tiles: a tile costs the same whatever its rows look like (one scan), a tile of
+    // pooled-uniform rows a little more per extra Philox block of its busiest row; tiles are handed out to the warps.
+    // (least squares over the 4 977 units of config 2 on a full B200: ~18 us fixed, ~1.1 us per tile and warp, ~3 us per tree pass)
+    const double kTileEstepUs = 18.0, kTileChainUs = 1.0, kTileUniformUs = 1.1, kTileBlockUs = 0.3, kTileLevelUs = 3.0;
+    auto iteration_us_tiles = [&](const UnitShape &S, int warps) {
+        const int n_items = (int)S.nnz.size();
+        double chain_cells = 0, unif_cells = 0, extra = 0, blocks_total = 0;
+        for (int i = 0; i < n_items; i++) {
+            if (i < S.n_chain) chain_cells += S.nnz[i];
+            else {
+                unif_cells += S.nnz[i];
+                blocks_total += S.blocks[i];
+                extra += (S.blocks[i] - 1) * (double)S.nnz[i];
+            }
+        }
+        const double chain_tiles = ceil(chain_cells / 30.0), unif_tiles = ceil(unif_cells / 30.0);
+        const double rows = chain_tiles * kTileChainUs + unif_tiles * kTileUniformUs + extra / 30.0 * kTileBlockUs;
+        int levels = 0;
+        const double passes = tree_batches(S, 32 * warps, &levels);
+        const double pool = warps > 1 ? 0.0 : kFastPoolUs * ceil(blocks_total / 32.0);
+        return kTileEstepUs + pool + std::max(rows / warps, std::min(rows, kTileUniformUs)) + passes * kTileLevelUs +
+               (levels + 2) * kFastBarrierUs * (warps > 1 ? 1.0 : 0.2);
+    };
     auto iteration_us_fast = [&](const UnitShape &S, int warps, int h) {
+        if (!S.wide) return iteration_us_tiles(S, warps);
         int chain_slabs, n_slabs;
         slab_layout(S, h, &chain_slabs, &n_slabs);
         const int n_items = (int)S.nnz.size();
@@ -447,7 +503,9 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         const int n_ladder = fast ? 4 : (int)(sizeof(ladder) / sizeof(ladder[0]));
         const double capacity = (double)ctx->sm_count * kWarpsPerSM;  // resident warps at the kernels' register count
         const char *spw = getenv("BAYES_SMEM_PER_WARP");  // experiment knob
-        const double smem_per_warp = spw ? atof(spw) : 8192.0;
+        const double smem_per_warp = spw ? atof(spw) : (fast ? 16384.0 : 8192.0);
+        const char *ce = getenv("BAYES_CRIT");  // experiment knob
+        const double crit = ce ? atof(ce) : (fast ? 0.5 : 0.75);
         std::vector<int> step(n_units, 0);
         std::vector<double> t(n_units);
         double occupied = 0;  // sum of warps * time
@@ -462,7 +520,9 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
             slab_layout(S, 32, &chain_slabs, &n_slabs);
             const double smem_est = smem_estimate(S, 32);
             int k = 0;
-            while (k + 1 < 4 && ladder[k][0] * smem_per_warp < smem_est && ladder[k + 1][0] < 2 * n_slabs) k++;
+            // (tiled units stream their matrix: their footprint does not grow with it, one warp unless they are critical)
+            const bool tiled = fast && !S.wide;
+            while (!tiled && k + 1 < 4 && ladder[k][0] * smem_per_warp < smem_est && ladder[k + 1][0] < 2 * n_slabs) k++;
             step[i] = k;
             t[i] = unit_time(S, ladder[k][0], ladder[k][1]);
             occupied += ladder[k][0] * t[i];
@@ -471,7 +531,8 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         while (!heap.empty()) {
             const Item top = heap.top();
             const int64_t i = top.second;
-            if (top.first <= 0.75 * occupied / capacity) break;  // the batch is throughput-bound from here on
+            // (fast mode: a unit that starts first runs its whole life on a full GPU, up to twice its calibrated time: a tighter bound)
+            if (top.first <= crit * occupied / capacity) break;  // the batch is throughput-bound from here on
             heap.pop();
             // next rung that actually shortens the unit
             int k = step[i] + 1;
@@ -541,8 +602,10 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         if (u.d.block >= 256) return 1000;                            // critical, hard to place later
         return (int)floor(log(std::max(u.cost, 1e-6)) / log(1.4));   // +-18 % of duration per band
     };
-    typedef std::tuple<int, int, int, int, int> ClassKey;  // (-band, wide, mat_smem, block, smem bucket)
-    auto class_of = [&](const PackedUnit &u) { return ClassKey(-band_of(u), u.d.wide, u.d.mat_smem, u.d.block, smem_bucket(u.d.smem_bytes)); };
+    typedef std::tuple<int, int, int, int, int> ClassKey;  // (-band, wide, mat_smem | scr_smem << 1, block, smem bucket)
+    auto class_of = [&](const PackedUnit &u) {
+        return ClassKey(-band_of(u), u.d.wide, u.d.mat_smem | (u.d.scr_smem << 1), u.d.block, smem_bucket(u.d.smem_bytes));
+    };
     std::vector<ClassKey> key(n_units);
     for (int64_t i = 0; i < n_units; i++) key[i] = class_of(packed[i]);
     std::vector<int64_t> order(n_units);
@@ -567,7 +630,7 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         int64_t j = i;
         const ClassKey &k = key[order[i]];
         while (j < n_units && key[order[j]] == k) j++;
-        ctx->launches.push_back(Launch{i, j - i, units[i].block, units[i].wide != 0, units[i].mat_smem != 0, (size_t)std::get<4>(k)});
+        ctx->launches.push_back(Launch{i, j - i, units[i].block, units[i].wide != 0, units[i].mat_smem != 0, units[i].scr_smem != 0, (size_t)std::get<4>(k)});
         i = j;
     }
     if (ctx->trace_locus >= 0) {
@@ -605,6 +668,8 @@ KernelArgs kernel_args(bayes_gibbs_ctx *ctx) {
     a.unit_clock = ctx->d_unit_clock.p;
     a.row_woff = ctx->d_row_woff.p;
     a.pool_desc = ctx->d_pool_desc.p;
+    a.cell_meta = ctx->d_cell_meta.p;
+    a.chain_tab = ctx->d_chain_tab.p;
     a.scr_cum = ctx->d_scr_cum.p;
     a.scr_col = ctx->d_scr_col.p;
     a.queue = ctx->d_queue.p;
@@ -626,7 +691,8 @@ int upload_units(bayes_gibbs_ctx *ctx) {
         (rc = h2d(ctx->d_slab, ctx->h_slab, st)) || (rc = h2d(ctx->d_row_n, ctx->h_row_n, st)) ||
         (rc = h2d(ctx->d_row_nnz, ctx->h_row_nnz, st)) || (rc = h2d(ctx->d_row_info, ctx->h_row_info, st)) ||
         (rc = h2d(ctx->d_row_mask, ctx->h_row_mask, st)) || (rc = h2d(ctx->d_row_woff, ctx->h_row_woff, st)) ||
-        (rc = h2d(ctx->d_pool_desc, ctx->h_pool_desc, st)) || (rc = ctx->d_scr_cum.reserve((size_t)ctx->scr_len)) ||
+        (rc = h2d(ctx->d_pool_desc, ctx->h_pool_desc, st)) || (rc = h2d(ctx->d_cell_meta, ctx->h_cell_meta, st)) ||
+        (rc = h2d(ctx->d_chain_tab, ctx->h_chain_tab, st)) || (rc = ctx->d_scr_cum.reserve((size_t)ctx->scr_len)) ||
         (rc = ctx->d_scr_col.reserve((size_t)ctx->scr_len)) || (rc = ctx->d_queue.reserve((size_t)ctx->q_len)) ||
         (rc = ctx->d_unit_err.reserve(ctx->h_units.n + 1)) || (rc = ctx->h_unit_err.resize(ctx->h_units.n + 1)) ||
         (rc = h2d(ctx->d_efflen, ctx->h_efflen, st)) || (rc = h2d(ctx->d_base, ctx->h_base, st)) ||
@@ -670,6 +736,7 @@ int bayes_gibbs_create(int device, bayes_gibbs_ctx **out) {
     bayes_gibbs_ctx *ctx = new (std::nothrow) bayes_gibbs_ctx();
     if (!ctx) return BAYES_E_NOMEM;
     if (const char *m = getenv("BAYES_MODE")) ctx->mode = strcmp(m, "replay") == 0 ? BAYES_MODE_REPLAY : BAYES_MODE_FAST;
+    if (const char *m = getenv("BAYES_TILE_STREAM")) g_tile_stream = atoi(m) != 0;  // experiment knob
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     rc = cuda_rc(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -690,7 +757,8 @@ void bayes_gibbs_destroy(bayes_gibbs_ctx *ctx) {
     ctx->h_slab.release(); ctx->h_row_n.release(); ctx->h_row_nnz.release(); ctx->h_row_info.release(); ctx->h_base.release();
     ctx->h_tab_row.release(); ctx->h_occ.release(); ctx->h_counts.release(); ctx->h_mean.release(); ctx->h_m2.release();
     ctx->h_row_mask.release(); ctx->d_row_mask.release();
-    ctx->h_pool_desc.release(); ctx->h_row_woff.release(); ctx->h_unit_err.release();
+    ctx->h_pool_desc.release(); ctx->h_row_woff.release(); ctx->h_unit_err.release(); ctx->h_cell_meta.release(); ctx->h_chain_tab.release();
+    ctx->d_cell_meta.release(); ctx->d_chain_tab.release();
     ctx->d_pool_desc.release(); ctx->d_queue.release(); ctx->d_row_woff.release(); ctx->d_unit_err.release();
     ctx->d_scr_cum.release(); ctx->d_scr_col.release();
     ctx->d_units.release(); ctx->d_val.release(); ctx->d_efflen.release(); ctx->d_tab_val.release(); ctx->d_mean.release();
@@ -873,7 +941,7 @@ static int issue_launches(bayes_gibbs_ctx *ctx, int32_t iter_cap) {
             CU(cudaEventRecord(ctx->gate_ev[i], ctx->gate));
             CU(cudaStreamWaitEvent(st, ctx->gate_ev[i], 0));
         }
-        if (ctx->built_mode == BAYES_MODE_FAST) rc = launch_units_fast(args, l.unit_base, l.n_units, l.block, l.wide, l.mat_smem, l.smem, st);
+        if (ctx->built_mode == BAYES_MODE_FAST) rc = launch_units_fast(args, l.unit_base, l.n_units, l.block, l.wide, l.mat_smem, l.scr_smem, l.smem, st);
         else rc = launch_units(args, l.unit_base, l.n_units, l.block, l.wide, l.mat_smem, l.smem, st);
         if (rc) return rc;
         if (n_l > 1) {
@@ -1188,8 +1256,12 @@ static int step_assignment(int device, const bayes_locus_desc *locus, const doub
     }
     const int T = d.T;
     PackedUnit U;
-    pack_unit(std::vector<SlotRef>(1, SlotRef{&P, 0, 0}), true, 32, fast, &U);  // wide layout: columns stay candidate indices
+    // replay mode and wide loci: wide layout (columns stay candidate indices); fast mode with T <= 32: the tiles of a bundle
+    const bool tiles = fast && T <= 32;
+    pack_unit(std::vector<SlotRef>(1, SlotRef{&P, 0, 0}), !tiles, 32, fast, &U);
     U.d.mat_smem = 0;  // the step kernels read the matrix (and the fast-mode scratch) from global memory
+    U.d.scr_smem = 0;
+    U.d.pool_smem = 0;
     ctx->scr_len = ctx->q_len = 0;
     if ((rc = append_unit(ctx, U))) return fail(rc);
     if ((rc = upload_units(ctx))) return fail(rc);
@@ -1200,7 +1272,7 @@ static int step_assignment(int device, const bayes_locus_desc *locus, const doub
     const KernelArgs args = kernel_args(ctx);
     const size_t smem = 12 * (size_t)T + 8 * (((size_t)T + 63) / 64) + 48 + 4 * kFastCtlWords;
     if ((rc = cuda_rc(cudaMemsetAsync(ctx->d_unit_err.p, 0, sizeof(int32_t), st), "memset"))) return fail(rc);
-    if (fast) rc = launch_step_assignment_fast(args, init, ctx->d_mean.p, iteration, ctx->d_occ.p, smem, st);
+    if (fast) rc = launch_step_assignment_fast(args, init, tiles, ctx->d_mean.p, iteration, ctx->d_occ.p, smem, st);
     else rc = launch_step_assignment(args, init, ctx->d_mean.p, iteration, ctx->d_occ.p, smem, st);
     if (rc) return fail(rc);
     if ((rc = cuda_rc(cudaMemcpyAsync(counts_out, ctx->d_occ.p, T * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "counts D2H")))
@@ -1270,6 +1342,22 @@ int bayes_step_variates(int device, int kind, double a, double p, uint64_t key, 
     if ((rc = cuda_rc(cudaMemcpyAsync(out, ctx->d_mean.p, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream), "variates D2H"))) return fail(rc);
     if ((rc = cuda_rc(cudaStreamSynchronize(ctx->stream), "step sync"))) return fail(rc);
     bayes_gibbs_destroy(ctx);
+    return BAYES_OK;
+}
+
+// Development aid (host only): pack the given loci (all with the same number of candidate lanes) as ONE bundle and report
+// the shared-memory layout of the unit: out[0..] = total, matrix cells, padded rows, chain cells, qcap, pool blocks, table entries
+int bayes_debug_unit_layout(int32_t n_loci, const bayes_locus_desc *loci, int32_t fast, int32_t *out8) {
+    std::vector<PreLocus> pre(n_loci);
+    std::string err;
+    for (int i = 0; i < n_loci; i++)
+        if (int rc = prepare_locus(loci[i], &pre[i], &err)) { set_error(err); return rc; }
+    std::vector<SlotRef> slots;
+    for (int i = 0; i < n_loci; i++) slots.push_back(SlotRef{&pre[i], 0, 0});
+    PackedUnit U;
+    pack_unit(slots, pre[0].T > 32, 32, fast != 0, &U);
+    out8[0] = U.d.smem_bytes; out8[1] = U.d.n_cells; out8[2] = U.d.n_slabs * U.d.slab_h; out8[3] = U.d.n_chain_cells;
+    out8[4] = U.d.qcap; out8[5] = U.d.pool_blocks; out8[6] = U.d.tab_len; out8[7] = U.d.mat_smem | (U.d.tab_smem << 1) | (U.d.pool_smem << 2);
     return BAYES_OK;
 }
 

@@ -17,6 +17,13 @@
 //    block per row (the median row has ONE fragment) -- generated with full lanes, by the warps that would otherwise
 //    idle during the one-warp E-step; one reciprocal per row and un-normalised running sums instead of a division
 //    per cell.
+//  * bundles (loci with up to 32 candidates) drop the lane-per-row SELL slabs for lane-per-cell TILES: 32 consecutive cells,
+//    rows contiguous and never straddling a tile.  One pass per tile with all lanes busy whatever the row lengths:
+//    p = P_ij theta_j, a segmented warp-shuffle inclusive scan gives every cell its running sum and every row its
+//    total, ballots name the cells in play, and each cell takes the pool words that fall between its neighbour's
+//    threshold and its own.  No padding to the widest row of a slab (SELL-32 doubled the footprint of small units),
+//    no lanes waiting for the longest row.  The scan fixes the order of the floating-point additions of a row sum;
+//    the oracle sums in the same order.
 //  * per-candidate state of a bundle (Welford accumulators, constants) lives in shared memory instead of in registers
 //    of warp 0 that every other thread had to allocate as well.
 // The CPU oracle restates this mode draw for draw (oracle/bayes_oracle.c, assignment_fast); tests compare the two.
@@ -134,96 +141,205 @@ __device__ __forceinline__ int words_below(const u32x4 &w, int left, uint32_t t)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// A-step, first part (one lane per row, SELL-h slabs): rows of the chain slabs compact their cells in play into the
-// scratch lists and queue the root of their tree; the other rows draw from the pool right away.
-// Bundle: a row's stored cells are few (T <= 32), all of them are visited.
+// Bundles: lane-per-cell tiles.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fast_rows_bundle(const FastView &V, const double *theta, int32_t *counts, const uint64_t *skey, uint32_t iteration,
-                                                 const bool init) {
+__device__ __forceinline__ uint32_t lanemask_le() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_le;" : "=r"(m));
+    return m;
+}
+
+constexpr uint32_t kPadOrd = 0x3FFFFFFu;  // chain tiles: ordinal of a padding lane
+
+struct TileView {
+    const double *val;       // n_tiles * 32
+    const uint32_t *meta;    // idem: candidate lane | head << 5 | (fragments << 6 | pool word << 11  or  chain ordinal << 6)
+    const uint32_t *ctab;    // 3 words per chain row: fragments, slot << 27 | row, first cell
+    int n_tiles, n_chain_tiles;
+    double *scr_cum;         // n_chain_tiles * 32: running sums of the cells in play of every chain row, compacted to the row's first cells
+    uint16_t *scr_col;       // their candidate lanes
+    uint32_t *queue;         // two buffers of 2 * qcap words: fragments | ordinal | first cell << 20 | (cells - 1) << 25
+    int qcap;
+    const uint32_t *pool;    // this iteration's uniform words (shared memory) or nullptr
+    const int32_t *pool_first;
+    int sh;                  // log2 of the lanes per slot
+    int max_row;             // lanes per slot = most cells a row can have
+    int *ctl;
+};
+
+__device__ __forceinline__ void tile_push(const TileView &V, int cnt, int buf, bool want, uint32_t n, uint32_t w1) {
+    const uint32_t m = __ballot_sync(kFull, want);
+    if (m == 0u) return;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&V.ctl[cnt], __popc(m));
+    base = __shfl_sync(kFull, base, leader);
+    if (want) {
+        const int idx = base + __popc(m & lanemask_lt());
+        BAYES_CHECK(idx < V.qcap, 111);
+        uint32_t *q = V.queue + (size_t)buf * 2 * V.qcap;
+        q[idx] = n;
+        q[V.qcap + idx] = w1;
+    }
+}
+
+__device__ __forceinline__ u32x4 tile_pool_words4(const TileView &V, const uint64_t *skey, uint32_t slot, uint32_t ph_pool, uint32_t iteration, int w) {
+    u32x4 o;
+    if (V.pool) {
+        o.x = V.pool[w]; o.y = V.pool[w + 1]; o.z = V.pool[w + 2]; o.w = V.pool[w + 3];
+        return o;
+    }
+    const int wl = w - 4 * V.pool_first[slot];
+    const uint32_t b0 = (uint32_t)wl >> 2, off = (uint32_t)wl & 3u;
+    const uint64_t key = skey[slot];
+    const u32x4 A = make_site(key, ph_pool, iteration, b0 >> 12, 0).block(b0 & 4095u);
+    if (off == 0u) return A;
+    const u32x4 B = make_site(key, ph_pool, iteration, (b0 + 1u) >> 12, 0).block((b0 + 1u) & 4095u);
+    const uint32_t a[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+    o.x = a[off]; o.y = a[off + 1]; o.z = a[off + 2]; o.w = a[off + 3];
+    return o;
+}
+
+// A-step, first part: every tile in one pass.  Chain tiles compact the cells in play of their rows into the scratch
+// lists and queue the roots of the splitting trees; the other tiles locate their rows' pool words right away.
+__device__ __forceinline__ void tile_rows(const TileView &V, const double *theta, int32_t *counts, const uint64_t *skey, uint32_t iteration,
+                                          const bool init) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const uint32_t ph_pool = init ? PH_INIT_POOL : PH_POOL;
-    const int H = V.h;
-    const bool dynamic = n_warps > 1;
-    for (int s = warp;; s += n_warps) {
-        if (dynamic) {
-            if (lane == 0) s = atomicAdd(&V.ctl[kCtlSlab], 1);
-            s = __shfl_sync(kFull, s, 0);
+    const uint32_t le = lanemask_le(), lt = lanemask_lt();
+    // Tiles cost about the same, so the warps take them round robin; the next tile of the warp is loaded while this one is
+    // processed (the tiles of a streaming unit come from L2).
+    int ti = warp;
+    double v_next = 0.0;
+    uint32_t m_next = 0u;
+    if (ti < V.n_tiles) {
+        v_next = V.val[ti * 32 + lane];
+        m_next = V.meta[ti * 32 + lane];
+    }
+    for (; ti < V.n_tiles; ti += n_warps) {
+        const uint32_t meta = m_next;
+        const double v = v_next;
+        if (ti + n_warps < V.n_tiles) {
+            v_next = V.val[(ti + n_warps) * 32 + lane];
+            m_next = V.meta[(ti + n_warps) * 32 + lane];
         }
-        if (s >= V.n_slabs) break;
-        const int r = s * H + lane;
-        const uint32_t item = lane < H ? (uint32_t)V.row_nnz[r] : 0u;
-        const int nnz = (int)(item & kItemNnzMask);  // 0: padding lane
-        const bool live = nnz > 0;
-        const int n = live ? V.row_n[r] : 0;
-        const int cell0 = V.slab[s] + lane;
-        BAYES_CHECK(!live || cell0 + H * (nnz - 1) < V.n_cells, 102);
-        const double *val = V.val + cell0;
-        const uint16_t *col = V.col + cell0;
-        if (s < V.n_chain_slabs) {
-            BAYES_CHECK(!live || cell0 + H * (nnz - 1) < V.n_chain_cells, 103);
-            double *sc = V.scr_cum + cell0;
-            uint16_t *scol = V.scr_col + cell0;
-            double cum = 0.0;
-            int k2 = 0, c_last = 0;
-            for (int k = 0; k < nnz; k++) {
-                const int c = col[H * k];
-                const double p = val[H * k] * theta[c];
-                if (p > 0.0) {
-                    cum += p;
-                    sc[H * k2] = cum;
-                    scol[H * k2] = (uint16_t)c;
-                    k2++;
-                    c_last = c;
-                }
+        const int c = (int)(meta & 31u);
+        const double p = v * theta[c];
+        // segments = rows: first lane of mine, last lane of mine
+        const uint32_t hm = __ballot_sync(kFull, (meta >> kMetaHeadShift) & 1u);
+        const int seg_start = 31 - __clz(hm & le);
+        const uint32_t above = hm & ~le;
+        const int seg_end = above ? __ffs(above) - 2 : 31;
+        const uint32_t segmask = (seg_end == 31 ? kFull : ((2u << seg_end) - 1u)) & ~((1u << seg_start) - 1u);
+        // inclusive scan within the row (the order of these additions is part of the mode's definition: the oracle sums alike)
+        // (a row has at most as many cells as its slot has candidate lanes: the steps beyond that add nothing)
+        double cum = p;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            if (d >= V.max_row) break;
+            const double up = __shfl_up_sync(kFull, cum, d);
+            if (lane - d >= seg_start) cum += up;
+        }
+        const bool inplay = p > 0.0;
+        const uint32_t ip = __ballot_sync(kFull, inplay) & segmask;  // the cells in play of my row
+        if (ti < V.n_chain_tiles) {
+            const uint32_t ord = meta >> kMetaOrdShift;
+            const int k = __popc(ip), k2 = __popc(ip & lt);
+            const int base = ti * 32 + seg_start;
+            if (inplay) {
+                V.scr_cum[base + k2] = cum;
+                V.scr_col[base + k2] = (uint16_t)c;
             }
-            if (live) {
-                if (k2 == 1) atomicAdd(&counts[c_last], n);
-                else if (k2 == 0) V.ctl[kCtlErr] = 1;  // reference: assert(normalisation_constant >= double_underflow) (:284)
-            }
-            push_tasks(V, kCtlQ0, 0, live && k2 >= 2, (uint32_t)n, (uint32_t)(k2 - 1) << 12, (uint32_t)r);
-        } else if (live) {
-            double Z = 0.0;
-            int kl = -1, in_play = 0;
-            for (int k = 0; k < nnz; k++) {
-                const double p = val[H * k] * theta[col[H * k]];
-                Z += p;
-                if (p > 0.0) {
-                    kl = k;
-                    in_play++;
-                }
-            }
-            if (kl < 0) {
-                V.ctl[kCtlErr] = 1;
-            } else {
-                const int c_last = col[H * kl];
-                int rem = n;
-                if (in_play > 1) {
-                    const double rZ = __drcp_rn(Z);
-                    const int w0 = V.row_woff[r];
-                    const uint32_t slot = V.row_info[r] >> kRowSlotShift;
-                    for (int j0 = 0; j0 < n; j0 += 4) {
-                        const int left = n - j0 < 4 ? n - j0 : 4;
-                        const u32x4 w = pool_words4(V, skey, slot, ph_pool, iteration, w0 + j0);
-                        double cum = 0.0;
-                        int prev = 0;
-                        for (int k = 0; k < kl; k++) {
-                            const int c = col[H * k];
-                            const double p = val[H * k] * theta[c];
-                            if (!(p > 0.0)) continue;
-                            cum += p;
-                            // word * 2^-32 < cum / Z  <=>  word <= ceil(cum (1/Z) 2^32 - 1); the conversion saturates
-                            const uint32_t t = __double2uint_ru(__fma_rn(cum * rZ, 4294967296.0, -1.0));
-                            const int below = words_below(w, left, t);
-                            if (below > prev) atomicAdd(&counts[c], below - prev);
-                            rem -= below - prev;
-                            prev = below;
-                            if (below >= left) break;
-                        }
+            const bool head = lane == seg_start && ord != kPadOrd;
+            uint32_t n = 0;
+            if ((head || (inplay && k == 1)) && ord != kPadOrd) n = V.ctab[3 * ord];
+            if (inplay && k == 1) atomicAdd(&counts[c], (int)n);
+            if (head && k == 0) V.ctl[kCtlErr] = 1;  // reference: assert(normalisation_constant >= double_underflow) (:284)
+            // the row's fragments enter the tree as independent chunks of at most 64 (at most 32 chunks): every binomial stays small
+            const int m = head && k >= 2 ? min(32, ((int)n + 63) >> 6) : 0;
+            const int m_max = __reduce_max_sync(kFull, m);
+            for (int ch = 0; ch < m_max; ch++)
+                tile_push(V, kCtlQ0, 0, ch < m, n / (uint32_t)max(m, 1) + (uint32_t)(ch < (int)(n % (uint32_t)max(m, 1))),
+                          ord | ((uint32_t)ch << 15) | ((uint32_t)(k - 1) << 25));
+        } else {
+            const int n = (int)((meta >> kMetaNShift) & 31u);  // 0: padding lane
+            const int w0 = (int)(meta >> kMetaWoffShift);
+            const double Z = __shfl_sync(kFull, cum, seg_end);
+            if (n > 0 && ip == 0u && lane == seg_start) V.ctl[kCtlErr] = 1;
+            const bool is_last = inplay && (ip & ~le) == 0u;  // the last cell in play takes what the others left
+            const uint32_t lower = ip & lt;                   // cells in play before mine
+            const int src = lower ? 31 - __clz(lower) : lane;
+            const double rZ = __drcp_rn(Z);
+            // word * 2^-32 < cum / Z  <=>  word <= ceil(cum (1/Z) 2^32 - 1); the conversion saturates
+            const uint32_t t = __double2uint_ru(__fma_rn(cum * rZ, 4294967296.0, -1.0));
+            const int n_max = __reduce_max_sync(kFull, n);
+            for (int j0 = 0; j0 < n_max; j0 += 4) {
+                const int left = n - j0 < 4 ? n - j0 : 4;
+                int below = 0;
+                if (inplay && left > 0) {
+                    if (is_last) {
+                        below = left;
+                    } else {
+                        const u32x4 w = tile_pool_words4(V, skey, (uint32_t)c >> V.sh, ph_pool, iteration, w0 + j0);
+                        below = words_below(w, left, t);
                     }
                 }
-                if (rem > 0) atomicAdd(&counts[c_last], rem);  // the last cell in play takes what the others left
+                const int prev = __shfl_sync(kFull, below, src);
+                const int delta = lower ? below - prev : below;
+                if (delta > 0) atomicAdd(&counts[c], delta);
             }
         }
+    }
+}
+
+// A-step, second part: the splitting trees, level by level (see fast_tree_levels below for the scheme)
+__device__ __forceinline__ void tile_tree_levels(const TileView &V, int32_t *counts, const uint64_t *skey, uint32_t iteration, const bool init) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ph_tree = init ? PH_INIT_TREE : PH_TREE;
+    const int qcap = V.qcap;
+    int cur = kCtlQ0, nxt = kCtlQ0 + 1, old = kCtlQ0 + 2, buf = 0;
+    for (;;) {
+        const int Q = V.ctl[cur];
+        if (Q == 0) break;
+        if (threadIdx.x == 0) V.ctl[old] = 0;
+        const uint32_t *q = V.queue + (size_t)buf * 2 * qcap;
+        for (int i0 = warp * 32; i0 < Q; i0 += (int)blockDim.x) {
+            const int i = i0 + lane;
+            bool push_l = false, push_r = false;
+            uint32_t n_l = 0, n_r = 0, w_l = 0, w_r = 0;
+            if (i < Q) {
+                const uint32_t n = q[i], w1 = q[qcap + i];
+                const uint32_t ord = w1 & 0x7FFFu, och = w1 & 0xFFFFFu;  // och: ordinal and chunk, inherited by the children
+                const int a = (int)((w1 >> 20) & 31u), len = (int)(w1 >> 25) + 1, half = len >> 1, len_r = len - half;
+                const int base = (int)V.ctab[3 * ord + 2];
+                BAYES_CHECK(base + a + len - 1 < 32 * V.n_chain_tiles, 116);
+                const double *sc = V.scr_cum + base;
+                const double Pa = a ? sc[a - 1] : 0.0, Pm = sc[a + half - 1], Pb = sc[a + len - 1];
+                const double p_left = (Pm - Pa) / (Pb - Pa);
+                const uint32_t info = V.ctab[3 * ord + 1];
+                const uint32_t node = (uint32_t)a | ((uint32_t)(len - 1) << 12);
+                const Site site = make_site(skey[info >> kRowSlotShift], ph_tree | (node << 8), iteration, info & ((1u << kRowSlotShift) - 1u),
+                                            (w1 >> 15) & 31u);
+                n_l = (uint32_t)binomial_variate(site, (int)n, p_left);
+                n_r = n - n_l;
+                if (n_l) {
+                    if (half == 1) atomicAdd(&counts[V.scr_col[base + a]], (int)n_l);
+                    else { push_l = true; w_l = och | ((uint32_t)a << 20) | ((uint32_t)(half - 1) << 25); }
+                }
+                if (n_r) {
+                    if (len_r == 1) atomicAdd(&counts[V.scr_col[base + a + half]], (int)n_r);
+                    else { push_r = true; w_r = och | ((uint32_t)(a + half) << 20) | ((uint32_t)(len_r - 1) << 25); }
+                }
+            }
+            tile_push(V, nxt, buf ^ 1, push_l, n_l, w_l);
+            tile_push(V, nxt, buf ^ 1, push_r, n_r, w_r);
+        }
+        __syncthreads();
+        const int t = old;
+        old = cur;
+        cur = nxt;
+        nxt = t;
+        buf ^= 1;
     }
 }
 
@@ -279,7 +395,13 @@ __device__ __forceinline__ void fast_rows_wide(const FastView &V, const uint64_t
                 if (k2 == 1) atomicAdd(&counts[c_last], n);
                 else if (k2 == 0) V.ctl[kCtlErr] = 1;
             }
-            push_tasks(V, kCtlQ0, 0, live && k2 >= 2, (uint32_t)n, (uint32_t)(k2 - 1) << 12, (uint32_t)r);
+            {
+                const int m = live && k2 >= 2 ? min(32, (n + 63) >> 6) : 0;
+                const int m_max = __reduce_max_sync(kFull, m);
+                for (int ch = 0; ch < m_max; ch++)
+                    push_tasks(V, kCtlQ0, 0, ch < m, (uint32_t)(n / max(m, 1) + (ch < n % max(m, 1))),
+                               ((uint32_t)(k2 - 1) << 12) | ((uint32_t)ch << 24), (uint32_t)r);
+            }
         } else if (live) {
             double Z = 0.0;
             int in_play = 0, c_last = 0;
@@ -365,23 +487,25 @@ __device__ __forceinline__ void fast_tree_levels(const FastView &V, int32_t *cou
             if (i < Q) {
                 const uint32_t n = q[i], node = q[qcap + i];
                 row = q[2 * qcap + i];
-                const int a = (int)(node & 4095u), len = (int)(node >> 12) + 1, half = len >> 1, len_r = len - half;
+                const uint32_t chunk = node >> 24;
+                const int a = (int)(node & 4095u), len = (int)((node >> 12) & 4095u) + 1, half = len >> 1, len_r = len - half;
                 const int cell0 = V.slab[row >> hs] + (int)(row & (uint32_t)(H - 1));
                 BAYES_CHECK(cell0 + H * (a + len - 1) < V.n_chain_cells, 106);
                 const double *sc = V.scr_cum + cell0;
                 const double Pa = a ? sc[H * (a - 1)] : 0.0, Pm = sc[H * (a + half - 1)], Pb = sc[H * (a + len - 1)];
                 const double p_left = (Pm - Pa) / (Pb - Pa);
                 const uint32_t info = V.row_info[row];
-                const Site site = make_site(skey[info >> kRowSlotShift], ph_tree | (node << 8), iteration, info & ((1u << kRowSlotShift) - 1u), 0);
+                const Site site = make_site(skey[info >> kRowSlotShift], ph_tree | ((node & 0xFFFFFFu) << 8), iteration,
+                                            info & ((1u << kRowSlotShift) - 1u), chunk);
                 n_l = (uint32_t)binomial_variate(site, (int)n, p_left);
                 n_r = n - n_l;
                 if (n_l) {
                     if (half == 1) atomicAdd(&counts[V.scr_col[cell0 + H * a]], (int)n_l);
-                    else { push_l = true; node_l = (uint32_t)a | ((uint32_t)(half - 1) << 12); }
+                    else { push_l = true; node_l = (uint32_t)a | ((uint32_t)(half - 1) << 12) | (chunk << 24); }
                 }
                 if (n_r) {
                     if (len_r == 1) atomicAdd(&counts[V.scr_col[cell0 + H * (a + half)]], (int)n_r);
-                    else { push_r = true; node_r = (uint32_t)(a + half) | ((uint32_t)(len_r - 1) << 12); }
+                    else { push_r = true; node_r = (uint32_t)(a + half) | ((uint32_t)(len_r - 1) << 12) | (chunk << 24); }
                 }
             }
             push_tasks(V, nxt, buf ^ 1, push_l, n_l, node_l, row);
@@ -472,6 +596,53 @@ __device__ __forceinline__ int fast_bundle_e_step(const FastBundleE &E, uint32_t
     return b;
 }
 
+template <bool MAT_SMEM, bool SCR_SMEM>
+__device__ __forceinline__ TileView tile_stage(const KernelArgs &A, const UnitDev &U, const TileLayout &lay, unsigned char *smem) {
+    TileView V;
+    V.n_tiles = U.n_tiles;
+    V.n_chain_tiles = U.n_chain_tiles;
+    V.qcap = U.qcap;
+    V.ctl = (int *)(smem + lay.ctl);
+    V.pool_first = U.pool_first;
+    {
+        int sh = 1;
+        while ((1 << sh) < U.Tpad) sh++;
+        V.sh = sh;
+        V.max_row = U.Tpad;
+    }
+    if (MAT_SMEM) {
+        double *sv = (double *)(smem + lay.val);
+        uint32_t *sm = (uint32_t *)(smem + lay.meta);
+        block_copy(sv, A.val + U.cell_off, U.n_cells);
+        block_copy(sm, A.cell_meta + U.meta_off, U.n_cells);
+        V.val = sv; V.meta = sm;
+    } else {
+        V.val = A.val + U.cell_off;
+        V.meta = A.cell_meta + U.meta_off;
+    }
+    if (SCR_SMEM) {
+        uint32_t *st = (uint32_t *)(smem + lay.ctab);
+        block_copy(st, A.chain_tab + U.ctab_off, 3 * U.n_chain_rows);
+        V.ctab = st;
+        V.scr_cum = (double *)(smem + lay.scr_cum);
+        V.scr_col = (uint16_t *)(smem + lay.scr_col);
+        V.queue = (uint32_t *)(smem + lay.queue);
+    } else {
+        V.ctab = A.chain_tab + U.ctab_off;
+        V.scr_cum = A.scr_cum + U.scr_off;
+        V.scr_col = A.scr_col + U.scr_off;
+        V.queue = A.queue + U.q_off;
+    }
+    uint32_t *pool = nullptr;
+    if (U.pool_smem) {
+        pool = (uint32_t *)(smem + lay.pool);
+        block_copy((uint32_t *)(smem + lay.pool_desc), A.pool_desc + U.pooldesc_off, U.pool_blocks);
+        if (threadIdx.x < 4) pool[4 * U.pool_blocks + threadIdx.x] = 0u;  // the spare block
+    }
+    V.pool = pool;
+    return V;
+}
+
 template <bool MAT_SMEM>
 __device__ __forceinline__ FastView fast_stage(const KernelArgs &A, const UnitDev &U, const FastLayout &lay, unsigned char *smem) {
     FastView V;
@@ -528,15 +699,15 @@ __device__ __forceinline__ FastView fast_stage(const KernelArgs &A, const UnitDe
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-template <bool MAT_SMEM>
+template <bool MAT_SMEM, bool SCR_SMEM>
 __global__ void __maxnreg__(BAYES_FAST_MAXNREG) gibbs_fast_bundle_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int64_t ui = unit_base + blockIdx.x;
     if (threadIdx.x == 0) A.unit_clock[3 * ui] = global_ns();
     const UnitDev &U = A.units[ui];
     const int n_slots = U.n_slots, Tpad = U.Tpad;
-    const FastLayout lay = fast_layout(false, 32, n_slots, Tpad, U.n_slabs, U.slab_h, U.n_cells, U.tab_len, U.tab_smem != 0, MAT_SMEM,
-                                       U.n_chain_cells, U.qcap, U.pool_blocks, U.pool_smem != 0);
+    const TileLayout lay = tile_layout(n_slots, Tpad, U.n_tiles, U.n_chain_tiles, U.n_chain_rows, U.tab_len, U.tab_smem != 0, MAT_SMEM, SCR_SMEM,
+                                       U.qcap, U.pool_blocks, U.pool_smem != 0);
     uint64_t *skey = (uint64_t *)(smem + lay.key);
     FastBundleE E;
     E.theta = (double *)(smem + lay.theta);
@@ -570,7 +741,7 @@ __global__ void __maxnreg__(BAYES_FAST_MAXNREG) gibbs_fast_bundle_kernel(const _
         E.tab_val = A.tab_val + U.tab_off;
         E.tab_row = A.tab_row + U.tabrow_off;
     }
-    FastView V = fast_stage<MAT_SMEM>(A, U, lay, smem);
+    TileView V = tile_stage<MAT_SMEM, SCR_SMEM>(A, U, lay, smem);
     E.ctl = V.ctl;
     uint32_t *pool = (uint32_t *)(smem + lay.pool);
     const uint32_t *pool_desc = (const uint32_t *)(smem + lay.pool_desc);
@@ -628,9 +799,9 @@ __global__ void __maxnreg__(BAYES_FAST_MAXNREG) gibbs_fast_bundle_kernel(const _
         if (it < 0 || n_threads == 32) fast_pool_gen(pool, pool_desc, pool_blocks, skey, iter, it < 0, 0, n_threads);
         else if (threadIdx.x >= 32) fast_pool_gen(pool, pool_desc, pool_blocks, skey, iter, false, 32, n_threads - 32);
         __syncthreads();
-        fast_rows_bundle(V, E.theta, E.counts, skey, iter, it < 0);
+        tile_rows(V, E.theta, E.counts, skey, iter, it < 0);
         __syncthreads();
-        fast_tree_levels(V, E.counts, skey, iter, it < 0);
+        tile_tree_levels(V, E.counts, skey, iter, it < 0);
     }
     if (my_trace && total - 1 < A.trace_iters) A.tr_counts[(size_t)(total - 1) * Tg + t] = E.counts[lane];
 
@@ -815,6 +986,45 @@ __global__ void step_assignment_fast_kernel(const __grid_constant__ KernelArgs A
     if (threadIdx.x == 0) A.unit_err[0] = ctl[kCtlErr];
 }
 
+// ---- single A-step in fast mode of a locus with up to 32 candidates: the tiles of a one-slot bundle, two warps ----------------
+template <bool INIT>
+__global__ void step_assignment_tiles_kernel(const __grid_constant__ KernelArgs A, const double *theta_in, uint32_t iteration, int32_t *counts_out) {
+    __shared__ double theta[32];
+    __shared__ int32_t counts[32];
+    __shared__ uint64_t skey[1];
+    __shared__ int ctl[kFastCtlWords];
+    const UnitDev &U = A.units[0];
+    const int T = U.T[0];
+    if (threadIdx.x < 32) {
+        theta[threadIdx.x] = (int)threadIdx.x < T ? (INIT ? 1.0 : theta_in[threadIdx.x]) : 0.0;
+        counts[threadIdx.x] = A.base_counts[U.lane_off + threadIdx.x];
+    }
+    if (threadIdx.x == 0) skey[0] = U.key[0];
+    if (threadIdx.x < kFastCtlWords) ctl[threadIdx.x] = 0;
+    TileView V;
+    V.n_tiles = U.n_tiles;
+    V.n_chain_tiles = U.n_chain_tiles;
+    V.qcap = U.qcap;
+    V.ctl = ctl;
+    V.pool_first = U.pool_first;
+    V.sh = 5;  // one slot: every candidate lane belongs to slot 0
+    V.max_row = 32;
+    V.val = A.val + U.cell_off;
+    V.meta = A.cell_meta + U.meta_off;
+    V.ctab = A.chain_tab + U.ctab_off;
+    V.scr_cum = A.scr_cum + U.scr_off;
+    V.scr_col = A.scr_col + U.scr_off;
+    V.queue = A.queue + U.q_off;
+    V.pool = nullptr;
+    __syncthreads();
+    tile_rows(V, theta, counts, skey, iteration, INIT);
+    __syncthreads();
+    tile_tree_levels(V, counts, skey, iteration, INIT);
+    __syncthreads();
+    if ((int)threadIdx.x < T) counts_out[threadIdx.x] = counts[threadIdx.x];
+    if (threadIdx.x == 0) A.unit_err[0] = ctl[kCtlErr];
+}
+
 }  // namespace
 
 static int check_fast(cudaError_t e, const char *what) {
@@ -827,8 +1037,9 @@ int configure_fast_kernels() {
     int rc;
     const char *co = getenv("BAYES_CARVEOUT");  // experiment knob, percent (see configure_kernels)
     const int carveout = co ? atoi(co) : 65;
-    const void *fns[4] = {(const void *)gibbs_fast_bundle_kernel<true>, (const void *)gibbs_fast_bundle_kernel<false>,
-                          (const void *)gibbs_fast_wide_kernel<true>, (const void *)gibbs_fast_wide_kernel<false>};
+    const void *fns[5] = {(const void *)gibbs_fast_bundle_kernel<true, true>, (const void *)gibbs_fast_bundle_kernel<false, true>,
+                          (const void *)gibbs_fast_bundle_kernel<false, false>, (const void *)gibbs_fast_wide_kernel<true>,
+                          (const void *)gibbs_fast_wide_kernel<false>};
     for (const void *f : fns) {
         if ((rc = check_fast(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, carveout), "carveout"))) return rc;
         if ((rc = check_fast(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_unit_smem()), "cudaFuncSetAttribute"))) return rc;
@@ -837,8 +1048,8 @@ int configure_fast_kernels() {
     return check_fast(cudaFuncSetAttribute(step_assignment_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "cudaFuncSetAttribute");
 }
 
-int launch_units_fast(const KernelArgs &args, int64_t unit_base, int64_t n_units, int block, bool wide, bool mat_smem, size_t smem_bytes,
-                      void *stream) {
+int launch_units_fast(const KernelArgs &args, int64_t unit_base, int64_t n_units, int block, bool wide, bool mat_smem, bool scr_smem,
+                      size_t smem_bytes, void *stream) {
     if (n_units <= 0) return BAYES_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)n_units;
@@ -846,15 +1057,21 @@ int launch_units_fast(const KernelArgs &args, int64_t unit_base, int64_t n_units
         if (mat_smem) gibbs_fast_wide_kernel<true><<<grid, block, smem_bytes, st>>>(args, unit_base);
         else gibbs_fast_wide_kernel<false><<<grid, block, smem_bytes, st>>>(args, unit_base);
     } else {
-        if (mat_smem) gibbs_fast_bundle_kernel<true><<<grid, block, smem_bytes, st>>>(args, unit_base);
-        else gibbs_fast_bundle_kernel<false><<<grid, block, smem_bytes, st>>>(args, unit_base);
+        if (mat_smem) gibbs_fast_bundle_kernel<true, true><<<grid, block, smem_bytes, st>>>(args, unit_base);
+        else if (scr_smem) gibbs_fast_bundle_kernel<false, true><<<grid, block, smem_bytes, st>>>(args, unit_base);
+        else gibbs_fast_bundle_kernel<false, false><<<grid, block, smem_bytes, st>>>(args, unit_base);
     }
     return check_fast(cudaGetLastError(), "gibbs fast kernel launch");
 }
 
-int launch_step_assignment_fast(const KernelArgs &args, bool init, const double *d_theta, uint32_t iteration, int32_t *d_counts_out,
+int launch_step_assignment_fast(const KernelArgs &args, bool init, bool tiles, const double *d_theta, uint32_t iteration, int32_t *d_counts_out,
                                 size_t smem_bytes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    if (tiles) {
+        if (init) step_assignment_tiles_kernel<true><<<1, 64, 0, st>>>(args, d_theta, iteration, d_counts_out);
+        else step_assignment_tiles_kernel<false><<<1, 64, 0, st>>>(args, d_theta, iteration, d_counts_out);
+        return check_fast(cudaGetLastError(), "step_assignment_tiles_kernel launch");
+    }
     if (init) step_assignment_fast_kernel<true><<<1, 128, smem_bytes, st>>>(args, d_theta, iteration, d_counts_out);
     else step_assignment_fast_kernel<false><<<1, 128, smem_bytes, st>>>(args, d_theta, iteration, d_counts_out);
     return check_fast(cudaGetLastError(), "step_assignment_fast_kernel launch");

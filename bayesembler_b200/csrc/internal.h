@@ -32,6 +32,9 @@ constexpr uint32_t kRowSlotShift = 27;  // row_info = slot << 27 | original row 
 // may-have-denormal-range-cells << 25
 constexpr uint32_t kItemNnzMask = 0xFFFFu;
 constexpr uint32_t kItemBlockShift = 16, kItemChainShift = 24, kItemTinyShift = 25;
+// fast mode, bundle tiles: cell meta word
+constexpr uint32_t kMetaHeadShift = 5, kMetaNShift = 6, kMetaWoffShift = 11, kMetaOrdShift = 6;
+constexpr int64_t kMaxTilePoolWords = (int64_t)1 << 21;  // pool words a tiled unit can address
 
 // Device-side descriptor of one unit.  All *_off fields index the context-wide concatenated arrays.
 struct UnitDev {
@@ -61,11 +64,18 @@ struct UnitDev {
     int32_t qcap;           // capacity of one task queue buffer (nodes of one tree level over all chain rows)
     int32_t pool_blocks;    // Philox blocks of the unit's uniform-word pool (4 words each)
     int32_t pool_smem;      // 1: the pool is generated into shared memory once per iteration; 0: rows compute their blocks themselves
-    int32_t fast_pad;
+    int32_t scr_smem;       // tiled units: 1: scratch lists, chain-row table and task queues in shared memory
     int64_t woff_off;       // -> row_woff (n_slabs * slab_h entries): first pool word of a uniform row
     int64_t pooldesc_off;   // -> pool_desc (pool_blocks entries): slot << 24 | block of the slot's pool
     int64_t scr_off;        // -> scr_cum / scr_col (units whose matrix is not in shared memory keep them in global memory)
     int64_t q_off;          // -> queue words, 6 * qcap per unit (idem)
+    // fast mode, bundles: lane-per-cell TILES instead of SELL slabs (gibbs_fast.cu).  A tile is 32 consecutive cells; the cells
+    // of a row are contiguous and never straddle a tile; the first n_chain_tiles tiles hold the rows with >= 20 fragments.
+    // n_cells = 32 * n_tiles, n_chain_cells = 32 * n_chain_tiles for such a unit; val is indexed like meta.
+    int32_t n_tiles, n_chain_tiles, n_chain_rows, tile_pad;
+    int64_t meta_off;       // -> cell_meta (n_cells): candidate lane | head << 5 | (uniform rows: fragments << 6 | pool word << 11;
+                            //    chain rows: chain-row ordinal << 6)
+    int64_t ctab_off;       // -> chain_tab (3 words per chain row: fragments, slot << 27 | row, first cell of the row)
     // per slot
     int32_t T[kMaxSlots];
     int32_t N_f[kMaxSlots];      // fragments of the locus (folded rows included)
@@ -96,6 +106,8 @@ struct KernelArgs {
     uint64_t *unit_clock;  // per unit: globaltimer ns at block start, at block end, SM id (3 words)
     // fast mode
     const int32_t *row_woff;
+    const uint32_t *cell_meta;
+    const uint32_t *chain_tab;
     const uint32_t *pool_desc;
     double *scr_cum;
     uint16_t *scr_col;
@@ -157,7 +169,7 @@ struct PackedUnit {
     std::vector<double> val, efflen, tab_val;
     std::vector<uint16_t> col;
     std::vector<int32_t> slab_cell_off, row_n, row_nnz, base_counts, tab_row;
-    std::vector<uint32_t> row_info, row_mask, pool_desc;
+    std::vector<uint32_t> row_info, row_mask, pool_desc, cell_meta, chain_tab;
     std::vector<int32_t> row_woff;
     double cost = 0;
     double features[4] = {0, 0, 0, 0};  // the time model's inputs (capi.cu)
@@ -175,6 +187,8 @@ int validate_locus(const bayes_locus_desc &in, std::string *err);
 int prepare_locus(const bayes_locus_desc &in, PreLocus *out, std::string *err);
 int slot_lanes(int T);  // Tpad of a bundle slot (power of two >= T), 0 when T > 32
 void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, bool fast, PackedUnit *out);
+extern bool g_tile_stream;  // fast mode: bundles stream their tiles from global memory (L2) instead of staging them in shared memory
+int tree_chunks(int n);   // fast mode: independent chunks a row with n >= 20 fragments enters its splitting tree in (<= 64 fragments each, at most 32)
 size_t max_unit_smem();  // dynamic shared memory a unit may use (opt-in limit of the device, 227 KB on sm_100)
 
 // host_steps.cpp
@@ -185,9 +199,9 @@ void simplex_table(double pi, double gamma, int T, int num_fragments, std::vecto
 int launch_units(const KernelArgs &args, int64_t unit_base, int64_t n_units, int block, bool wide, bool mat_smem, size_t smem_bytes,
                  void *stream);
 // gibbs_fast.cu
-int launch_units_fast(const KernelArgs &args, int64_t unit_base, int64_t n_units, int block, bool wide, bool mat_smem, size_t smem_bytes,
-                      void *stream);
-int launch_step_assignment_fast(const KernelArgs &args, bool init, const double *d_theta, uint32_t iteration, int32_t *d_counts_out,
+int launch_units_fast(const KernelArgs &args, int64_t unit_base, int64_t n_units, int block, bool wide, bool mat_smem, bool scr_smem,
+                      size_t smem_bytes, void *stream);
+int launch_step_assignment_fast(const KernelArgs &args, bool init, bool tiles, const double *d_theta, uint32_t iteration, int32_t *d_counts_out,
                                 size_t smem_bytes, void *stream);
 int configure_fast_kernels();
 int launch_stagger(unsigned ns, void *stream);

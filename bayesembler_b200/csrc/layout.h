@@ -110,4 +110,47 @@ BAYES_LAYOUT_HD FastLayout fast_layout(bool wide, int nT, int n_slots, int Tpad,
     return L;
 }
 
+// ---- fast mode, bundles: lane-per-cell tiles --------------------------------------------------------------------------
+struct TileLayout {
+    uint32_t theta, den, mean, m2, tab_val, val, scr_cum, key, sgamma, pool;  // 8-byte (pool: 16)
+    uint32_t counts, base, occ, tab_row, meta, ctab, pool_desc, queue, sT, sNf, ctl;  // 4-byte
+    uint32_t scr_col;  // 2-byte
+    uint32_t total;
+};
+
+// mat_smem: the tiles (val, meta) are staged in shared memory, else streamed from global memory (L2) with a one-tile
+// prefetch; scr_smem: the chain rows' scratch lists, their table and the task queues are in shared memory (else global).
+BAYES_LAYOUT_HD TileLayout tile_layout(int n_slots, int Tpad, int n_tiles, int n_chain_tiles, int n_chain_rows, int tab_len, bool tab_smem,
+                                       bool mat_smem, bool scr_smem, int qcap, int pool_blocks, bool pool_smem) {
+    TileLayout L;
+    const uint32_t n_tabrow = (uint32_t)n_slots * ((uint32_t)Tpad + 1u);
+    const uint32_t cells = mat_smem ? 32u * (uint32_t)n_tiles : 0u, ccells = scr_smem ? 32u * (uint32_t)n_chain_tiles : 0u;
+    uint32_t o = 0;
+    L.theta = o; o += 8u * 32u;
+    L.den = o; o += 8u * 32u;
+    L.mean = o; o += 8u * 32u;
+    L.m2 = o; o += 8u * 32u;
+    L.tab_val = o; o += tab_smem ? 8u * (uint32_t)tab_len : 0u;
+    L.val = o; o += 8u * cells;
+    L.scr_cum = o; o += 8u * ccells;
+    L.key = o; o += 8u * (uint32_t)n_slots;
+    L.sgamma = o; o += 8u * (uint32_t)n_slots;
+    o = (o + 15u) & ~15u;
+    L.pool = o; o += pool_smem ? 16u * ((uint32_t)pool_blocks + 1u) : 0u;
+    L.counts = o; o += 4u * 32u;
+    L.base = o; o += 4u * 32u;
+    L.occ = o; o += 4u * 32u;
+    L.tab_row = o; o += tab_smem ? 4u * n_tabrow : 0u;
+    L.meta = o; o += 4u * cells;
+    L.ctab = o; o += scr_smem ? 12u * (uint32_t)n_chain_rows : 0u;
+    L.pool_desc = o; o += pool_smem ? 4u * (uint32_t)pool_blocks : 0u;
+    L.queue = o; o += scr_smem ? 16u * (uint32_t)qcap : 0u;  // two buffers of two words per task
+    L.sT = o; o += 4u * (uint32_t)n_slots;
+    L.sNf = o; o += 4u * (uint32_t)n_slots;
+    L.ctl = o; o += 4u * (uint32_t)kFastCtlWords;
+    L.scr_col = o; o += 2u * ccells;
+    L.total = (o + 15u) & ~15u;
+    return L;
+}
+
 }  // namespace bayes

@@ -46,6 +46,8 @@ int validate_locus(const bayes_locus_desc &in, std::string *err) {
 }
 
 size_t max_unit_smem() { return 227 * 1024; }
+int tree_chunks(int n) { return std::min(32, (n + 63) / 64); }
+bool g_tile_stream = true;
 
 int slot_lanes(int T) {
     if (T > 32) return 0;
@@ -177,7 +179,159 @@ void build_items(const std::vector<SlotRef> &slots, std::vector<ItemShape> *item
     *n_chain = nc;
 }
 
+// Per-slot tail of a packed unit: per-candidate constants, CDF tables, keys.
+static void pack_slots(const std::vector<SlotRef> &slots, bool wide, int Tpad, int nT, PackedUnit &U) {
+    const int n_slots = (int)slots.size();
+    U.efflen.assign(nT, 1.0);
+    U.base_counts.assign(nT, 0);
+    U.tab_row.assign((size_t)n_slots * (Tpad + 1), 0);
+    UnitDev &d = U.d;
+    for (int g = 0; g < n_slots; g++) {
+        const PreLocus &L = *slots[g].locus;
+        const int lane0 = wide ? 0 : g * Tpad;
+        for (int t = 0; t < L.T; t++) {
+            U.efflen[lane0 + t] = L.efflen[t];
+            U.base_counts[lane0 + t] = L.base_counts[t];
+        }
+        const SimplexPrior &sp = L.prior(slots[g].chain);
+        const int32_t tab_base = (int32_t)U.tab_val.size();
+        for (int t = 0; t <= L.T; t++) U.tab_row[(size_t)g * (Tpad + 1) + t] = tab_base + sp.tab_row[t];
+        U.tab_val.insert(U.tab_val.end(), sp.tab_val.begin(), sp.tab_val.end());
+        d.T[g] = L.T;
+        d.N_f[g] = L.n_frag;
+        d.N_total[g] = L.N_total;
+        d.gamma[g] = L.gamma;
+        d.key[g] = bayes_chain_key(L.seed, slots[g].chain);
+        d.out_off[g] = slots[g].out_off;
+        U.cost = std::max(U.cost, L.cost);
+    }
+    U.cost *= 1.0 + 0.25 * (n_slots - 1);
+    d.n_slots = n_slots;
+    d.Tpad = Tpad;
+    d.wide = wide ? 1 : 0;
+    d.burn = slots[0].locus->burn;
+    d.samples = slots[0].locus->samples;
+    d.tab_len = (int32_t)U.tab_val.size();
+}
+
+// Fast mode, bundle: lane-per-cell tiles (gibbs_fast.cu).  The rows of all slots are pooled, chain rows (>= 20 fragments)
+// first, then the others with the rows that need most Philox blocks first; every row goes to the first tile of its kind
+// that still has room for all its cells (first fit over rows in decreasing order): the rows with several Philox blocks
+// fill the first tiles among themselves, the one-block rows that follow fill the gaps, so a tile wastes few lanes and
+// few tiles loop over more than one block.
+static void pack_unit_tiles(const std::vector<SlotRef> &slots, PackedUnit *out) {
+    PackedUnit &U = *out;
+    U = PackedUnit();
+    const int n_slots = (int)slots.size();
+    const int Tpad = slot_lanes(slots[0].locus->T);
+    std::vector<ItemShape> items;
+    int n_chain = 0;
+    build_items(slots, &items, &n_chain);
+    const int n_items = (int)items.size();
+
+    std::vector<int64_t> pool_base(n_slots, 0);
+    int64_t pool_blocks = 0, qcap = 0;
+    for (int g = 0; g < n_slots; g++) {
+        pool_base[g] = pool_blocks;
+        const int64_t nb = (slots[g].locus->pool_words + 3) / 4;
+        for (int64_t b = 0; b < nb; b++) U.pool_desc.push_back(((uint32_t)g << 24) | (uint32_t)b);
+        pool_blocks += nb;
+    }
+    // tiles
+    std::vector<int> fill;         // lanes used per tile
+    std::vector<int> item_tile(n_items), item_lane(n_items);
+    int n_chain_tiles = 0;
+    auto place = [&](int first, int last, int tile0) {
+        int open0 = tile0;  // tiles before this one are full
+        for (int i = first; i < last; i++) {
+            const int need = items[i].nnz;
+            int t = -1;
+            while (open0 < (int)fill.size() && fill[open0] >= 31) open0++;  // a row has at least two cells
+            for (int k = open0; k < (int)fill.size(); k++)
+                if (fill[k] + need <= 32) { t = k; break; }
+            if (t < 0) { fill.push_back(0); t = (int)fill.size() - 1; }
+            item_tile[i] = t;
+            item_lane[i] = fill[t];
+            fill[t] += need;
+        }
+    };
+    place(0, n_chain, 0);
+    n_chain_tiles = (int)fill.size();
+    place(n_chain, n_items, n_chain_tiles);
+    const int n_tiles = (int)fill.size();
+    const size_t n_cells = (size_t)n_tiles * 32;
+    U.val.assign(n_cells, 0.0);
+    // padding lane: its own one-cell segment (head), no fragments, probability 0
+    U.cell_meta.assign(n_cells, 1u << kMetaHeadShift);
+    for (size_t i = 0; i < (size_t)n_chain_tiles * 32; i++) U.cell_meta[i] |= 0x3FFFFFFu << kMetaOrdShift;  // chain tiles: padding ordinal
+    U.chain_tab.assign((size_t)3 * n_chain, 0u);
+    for (int i = 0; i < n_items; i++) {
+        const ItemShape &it = items[i];
+        const PreLocus &L = *slots[it.slot].locus;
+        const size_t cell0 = (size_t)item_tile[i] * 32 + item_lane[i];
+        const int lane0 = it.slot * Tpad;
+        uint32_t hi;
+        if (it.chain) {
+            hi = (uint32_t)i << kMetaOrdShift;  // chain items come first: i is the chain-row ordinal
+            U.chain_tab[3 * i] = (uint32_t)it.n;
+            U.chain_tab[3 * i + 1] = ((uint32_t)it.slot << kRowSlotShift) | (uint32_t)L.row_id[it.r];
+            U.chain_tab[3 * i + 2] = (uint32_t)cell0;
+            qcap += (int64_t)tree_chunks(it.n) * std::max(1, it.nnz / 2);
+        } else {
+            const int64_t woff = 4 * pool_base[it.slot] + L.row_woff[it.r];
+            hi = ((uint32_t)it.n << kMetaNShift) | ((uint32_t)woff << kMetaWoffShift);
+        }
+        for (int k = 0; k < it.nnz; k++) {
+            U.val[cell0 + k] = L.cell_val[L.row_ptr[it.r] + k];
+            U.cell_meta[cell0 + k] = (uint32_t)(lane0 + L.cell_col[L.row_ptr[it.r] + k]) | ((k == 0 ? 1u : 0u) << kMetaHeadShift) | hi;
+        }
+    }
+    pack_slots(slots, false, Tpad, 32, U);
+    UnitDev &d = U.d;
+    for (int g = 0; g < n_slots; g++) d.pool_first[g] = (int32_t)pool_base[g];
+    d.n_slabs = 0;
+    d.slab_h = 32;
+    d.n_cells = (int32_t)n_cells;
+    d.n_tiles = n_tiles;
+    d.n_chain_tiles = n_chain_tiles;
+    d.n_chain_cells = 32 * n_chain_tiles;
+    d.n_chain_rows = n_chain;
+    d.n_chain_slabs = 0;
+    d.qcap = (int32_t)std::max<int64_t>(qcap, 1);
+    d.pool_blocks = (int32_t)pool_blocks;
+    const size_t limit = max_unit_smem();
+    // The tiles are read once per iteration, front to back, coalesced: streamed from global memory (they stay in L2) behind a
+    // one-tile prefetch they cost no shared memory, and a unit can pool as many slots as its 32 candidate lanes hold.  What is
+    // accessed at random -- scratch lists, chain-row table, task queues, the word pool, the CDF tables -- stays in shared memory.
+    auto total = [&](bool tab, bool mat, bool scr, bool pool) -> size_t {
+        return tile_layout(n_slots, Tpad, n_tiles, n_chain_tiles, n_chain, d.tab_len, tab, mat, scr, d.qcap, d.pool_blocks, pool).total;
+    };
+    bool tab = d.tab_len <= kTableSmemEntries, mat = !g_tile_stream && n_cells * 12 <= (size_t)kMatrixSmemBytes, scr = true, pool = pool_blocks <= 8192;
+    if (total(tab, mat, scr, pool) > limit && tab && total(false, mat, scr, pool) <= limit) tab = false;
+    if (total(tab, mat, scr, pool) > limit) mat = false;
+    if (total(tab, mat, scr, pool) > limit) tab = false;
+    if (total(tab, mat, scr, pool) > limit) pool = false;
+    if (total(tab, mat, scr, pool) > limit) scr = false;
+    d.tab_smem = tab;
+    d.mat_smem = mat;
+    d.scr_smem = scr;
+    d.pool_smem = pool;
+    d.smem_bytes = (int32_t)total(tab, mat, scr, pool);
+    d.block = 32;
+}
+
+// pool words a bundle of these slots addresses (fast mode): must stay below kMaxTilePoolWords
+int64_t bundle_pool_words(const std::vector<SlotRef> &slots) {
+    int64_t w = 0;
+    for (const SlotRef &s : slots) w += 4 * ((s.locus->pool_words + 3) / 4);
+    return w;
+}
+
 void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, bool fast, PackedUnit *out) {
+    if (fast && !wide) {
+        pack_unit_tiles(slots, out);
+        return;
+    }
     const int H = slab_h;
     PackedUnit &U = *out;
     U = PackedUnit();
@@ -225,7 +379,7 @@ void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, bool fa
         const int r = position(i), s = r / H, l = r % H;
         U.row_n[r] = it.n;
         if (fast) {
-            if (it.chain) qcap += std::max(1, it.nnz / 2);  // nodes of the deepest tree level with two or more cells
+            if (it.chain) qcap += (int64_t)tree_chunks(it.n) * std::max(1, it.nnz / 2);  // nodes of the deepest tree level with two or more cells, per chunk
             else U.row_woff[r] = (int32_t)(4 * pool_base[it.slot] + L.row_woff[it.r]);
         }
         // a product P_ij theta_j can only reach the denormal range from a tiny P_ij, or from a tiny theta_j, which needs a
@@ -247,41 +401,12 @@ void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, bool fa
         }
     }
 
-    U.efflen.assign(nT, 1.0);
-    U.base_counts.assign(nT, 0);
-    U.tab_row.assign((size_t)n_slots * (Tpad + 1), 0);
+    pack_slots(slots, wide, Tpad, nT, U);
     UnitDev &d = U.d;
-    d = UnitDev();
-    for (int g = 0; g < n_slots; g++) {
-        const PreLocus &L = *slots[g].locus;
-        const int lane0 = wide ? 0 : g * Tpad;
-        for (int t = 0; t < L.T; t++) {
-            U.efflen[lane0 + t] = L.efflen[t];
-            U.base_counts[lane0 + t] = L.base_counts[t];
-        }
-        const SimplexPrior &sp = L.prior(slots[g].chain);
-        const int32_t tab_base = (int32_t)U.tab_val.size();
-        for (int t = 0; t <= L.T; t++) U.tab_row[(size_t)g * (Tpad + 1) + t] = tab_base + sp.tab_row[t];
-        U.tab_val.insert(U.tab_val.end(), sp.tab_val.begin(), sp.tab_val.end());
-        d.T[g] = L.T;
-        d.N_f[g] = L.n_frag;
-        d.N_total[g] = L.N_total;
-        d.gamma[g] = L.gamma;
-        d.key[g] = bayes_chain_key(L.seed, slots[g].chain);
-        d.out_off[g] = slots[g].out_off;
-        d.pool_first[g] = (int32_t)pool_base[g];
-        U.cost = std::max(U.cost, L.cost);
-    }
-    U.cost *= 1.0 + 0.25 * (n_slots - 1);
-    d.n_slots = n_slots;
-    d.Tpad = Tpad;
-    d.wide = wide ? 1 : 0;
+    for (int g = 0; g < n_slots; g++) d.pool_first[g] = (int32_t)pool_base[g];
     d.n_slabs = n_slabs;
     d.slab_h = H;
     d.n_cells = n_cells;
-    d.burn = L0.burn;
-    d.samples = L0.samples;
-    d.tab_len = (int32_t)U.tab_val.size();
     d.n_chain_slabs = chain_slabs;
     d.n_chain_cells = U.slab_cell_off[chain_slabs];
     d.qcap = (int32_t)std::max<int64_t>(qcap, 1);
@@ -302,6 +427,7 @@ void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, bool fa
     if (total(tab, mat, pool) > limit) pool = false;
     d.tab_smem = tab;
     d.mat_smem = mat;
+    d.scr_smem = mat;
     d.pool_smem = pool;
     d.smem_bytes = (int32_t)total(tab, mat, pool);  // per-candidate state alone is < 200 KB at T = 4096: always fits
     d.block = 32;  // build_units decides

@@ -178,7 +178,9 @@ BAYES_HD double ipow(double base, int n) {
 }
 
 // BTRD (Hoermann 1993), q <= 0.5, n*q >= 10; one block per attempt.  Same operation order as oracle/orc_rng.h.
-BAYES_HD int binomial_btrd(const Site &s, int n, double q) {
+// Out of line: about 900 instructions that the fast sampling mode almost never runs (its binomials have n <= 64) and that
+// must not sit in the instruction stream of the hot loop (the executed footprint has to fit the 32 KB instruction cache).
+BAYES_HD_NOINLINE int binomial_btrd(const Site &s, int n, double q) {
     const double npq = n * q * (1.0 - q);
     const double spq = sqrt(npq);
     const double bb = 1.15 + 2.53 * spq;

@@ -209,7 +209,8 @@ int orc_init_assignment(const orc_locus *loc, int rng_mode, uint64_t seed, int *
  * reference's sequential order of draws (outside replay the sampler may pick any exact
  * multinomial per row).  Per row i with n fragments, over its stored non-zero cells in ascending column order:
  *   p_j = P_ij * theta_j (init: theta == 1); the cells IN PLAY are those with p_j > 0, their running sums
- *   cum_1 < ... < cum_k, Z = cum_k;
+ *   cum_1 < ... < cum_k, Z = the sum of the row (T > 32: summed left to right; T <= 32: in the order of a warp scan,
+ *   see below);
  *   rows with a single stored non-zero cell give it everything (whatever theta is: they are folded by the packer);
  *   k == 1: everything goes to that cell;
  *   n < 20 (the reference's threshold, :289): the row owns n consecutive 32-bit words of the iteration's word
@@ -220,7 +221,8 @@ int orc_init_assignment(const orc_locus *loc, int rng_mode, uint64_t seed, int *
  *   n >= 20: a balanced binary TREE over the cells in play instead of the chain of conditional binomials
  *     (:336-365): node (a, len) holds m fragments for cells [a, a + len); its left half [a, a + len/2) receives
  *     Binomial(m, (cum(a + len/2) - cum(a)) / (cum(a + len) - cum(a))), the right half the rest; one site per node
- *     (TREE | node << 8, iteration, row), node = a | (len - 1) << 12.  Depth log2 k instead of k dependent draws.
+ *     (TREE | node << 8, iteration, row, chunk), node = a | (len - 1) << 12.  Depth log2 k instead of k dependent
+ *     draws.  The row's fragments enter the tree in ceil(n / 64) (at most 32) independent chunks of equal size +- 1.
  * ---------------------------------------------------------------------------------------------- */
 static uint32_t sat_u32_ceil(double x) { /* __double2uint_ru */
     if (!(x > 0.0)) return 0u;
@@ -228,17 +230,23 @@ static uint32_t sat_u32_ceil(double x) { /* __double2uint_ru */
     return (uint32_t)ceil(x);
 }
 
-static void tree_split(orc_ws *ws, uint32_t phase, uint32_t iteration, uint32_t row, const double *cum, const int *cell_col,
-                       int a, int len, int m, int *counts) {
+static void tree_split(orc_ws *ws, uint32_t phase, uint32_t iteration, uint32_t row, uint32_t chunk, const double *cum,
+                       const int *cell_col, int a, int len, int m, int *counts) {
     if (m <= 0) return;
     if (len == 1) { counts[cell_col[a]] += m; return; }
     const int half = len >> 1;
     const double Pa = a > 0 ? cum[a - 1] : 0.0, Pm = cum[a + half - 1], Pb = cum[a + len - 1];
     const double p_left = (Pm - Pa) / (Pb - Pa);
-    orc_ws_site(ws, phase | ((uint32_t)a | ((uint32_t)(len - 1) << 12)) << 8, iteration, row, 0);
+    orc_ws_site(ws, phase | ((uint32_t)a | ((uint32_t)(len - 1) << 12)) << 8, iteration, row, chunk);
     const int left = orc_binomial(ws, m, p_left);
-    tree_split(ws, phase, iteration, row, cum, cell_col, a, half, left, counts);
-    tree_split(ws, phase, iteration, row, cum, cell_col, a + half, len - half, m - left, counts);
+    tree_split(ws, phase, iteration, row, chunk, cum, cell_col, a, half, left, counts);
+    tree_split(ws, phase, iteration, row, chunk, cum, cell_col, a + half, len - half, m - left, counts);
+}
+
+/* chunks a row with n >= 20 fragments is drawn in: ceil(n / 64), at most 32 */
+static int tree_chunks(int n) {
+    const int m = (n + 63) / 64;
+    return m < 32 ? m : 32;
 }
 
 static int assignment_fast(const orc_locus *L, const double *theta, orc_ws *ws, uint32_t iteration, int init, int *counts) {
@@ -256,10 +264,30 @@ static int assignment_fast(const orc_locus *L, const double *theta, orc_ws *ws, 
         if (stored == 1) { counts[only] += n; continue; }
         int kk = 0;
         double run = 0;
-        for (int k = beg; k < end; k++) {
-            if (L->val[k] == 0.0) continue;
-            const double p = L->val[k] * (init ? 1.0 : theta[L->col_idx[k]]);
-            if (p > 0.0) { run += p; cum[kk] = run; cell_col[kk] = L->col_idx[k]; kk++; }
+        if (L->T <= 32) {
+            /* Loci with up to 32 candidates: the product sums the row with a warp-shuffle inclusive scan over the row's
+             * stored cells (distances 1, 2, 4, 8, 16; a cell with theta == 0 contributes an exact zero), i.e. in a fixed
+             * tree order instead of left to right.  Same real-number sums, a different but fully specified rounding. */
+            double x[32];
+            int cc[32], m = 0;
+            for (int k = beg; k < end; k++) {
+                if (L->val[k] == 0.0) continue;
+                cc[m] = L->col_idx[k];
+                x[m++] = L->val[k] * (init ? 1.0 : theta[L->col_idx[k]]);
+            }
+            int live[32];
+            for (int j = 0; j < m; j++) live[j] = x[j] > 0.0;
+            for (int d = 1; d < 32; d <<= 1)
+                for (int j = m - 1; j >= d; j--) x[j] += x[j - d];
+            for (int j = 0; j < m; j++)
+                if (live[j]) { cum[kk] = x[j]; cell_col[kk] = cc[j]; kk++; }
+            run = m > 0 ? x[m - 1] : 0.0; /* the row sum is the scan's value at the row's last stored cell */
+        } else {
+            for (int k = beg; k < end; k++) {
+                if (L->val[k] == 0.0) continue;
+                const double p = L->val[k] * (init ? 1.0 : theta[L->col_idx[k]]);
+                if (p > 0.0) { run += p; cum[kk] = run; cell_col[kk] = L->col_idx[k]; kk++; }
+            }
         }
         const uint64_t my_words = pool_at;
         if (n < 20) pool_at += (uint64_t)n; /* the row's words are its own whether it needs them or not */
@@ -280,7 +308,11 @@ static int assignment_fast(const orc_locus *L, const double *theta, orc_ws *ws, 
                 counts[cell_col[j]] += 1;
             }
         } else {
-            tree_split(ws, ph_tree, iteration, (uint32_t)i, cum, cell_col, 0, kk, n, counts);
+            /* the n fragments are drawn as independent chunks of at most 64 (the sum of independent multinomials with the
+             * same probabilities is the multinomial of the sum): every binomial then stays in the small-n inversion regime */
+            const int m = tree_chunks(n);
+            for (int c = 0; c < m; c++)
+                tree_split(ws, ph_tree, iteration, (uint32_t)i, (uint32_t)c, cum, cell_col, 0, kk, n / m + (c < n % m), counts);
         }
     }
     free(cum); free(cell_col);
