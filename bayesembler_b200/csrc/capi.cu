@@ -499,8 +499,11 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
     std::vector<int> unit_warps(n_units, 1), unit_h(n_units, 32);
     {
         // (fast mode: the latency of a unit is in its tree levels, which all threads share whatever the slab height: more warps only)
-        static const int ladder[][2] = {{1, 32}, {2, 32}, {4, 32}, {8, 32}, {8, 16}, {16, 16}, {16, 8}};
-        const int n_ladder = fast ? 4 : (int)(sizeof(ladder) / sizeof(ladder[0]));
+        static const int ladder_replay[][2] = {{1, 32}, {2, 32}, {4, 32}, {8, 32}, {8, 16}, {16, 16}, {16, 8}};
+        // (the tiled kernel runs at 64 registers per thread: a monster locus may take a whole SM's 32 warps)
+        static const int ladder_fast[][2] = {{1, 32}, {2, 32}, {4, 32}, {8, 32}, {16, 32}, {32, 32}};
+        const int (*ladder)[2] = fast ? ladder_fast : ladder_replay;
+        const int n_ladder_all = fast ? 6 : 7;
         const double capacity = (double)ctx->sm_count * kWarpsPerSM;  // resident warps at the kernels' register count
         const char *spw = getenv("BAYES_SMEM_PER_WARP");  // experiment knob
         const double smem_per_warp = spw ? atof(spw) : (fast ? 16384.0 : 8192.0);
@@ -537,14 +540,16 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
             // next rung that actually shortens the unit
             int k = step[i] + 1;
             double tk = 0;
+            const int n_ladder = n_ladder_all;
             for (; k < n_ladder; k++) {
                 int chain_slabs, n_slabs;
                 slab_layout(shapes[i], ladder[k][1], &chain_slabs, &n_slabs);
                 if (!fast && ladder[k][0] >= 2 * n_slabs && ladder[k][0] > ladder[step[i]][0]) continue;  // idle warps only
+                if (fast && shapes[i].wide && ladder[k][0] > kMaxBlock / 32) break;                       // the wide kernel: 128 registers
                 tk = unit_time(shapes[i], ladder[k][0], ladder[k][1]);
                 if (tk < 0.93 * t[i]) break;
             }
-            if (k >= n_ladder) continue;  // cannot be shortened further: it stays out of the heap
+            if (k >= n_ladder_all || (fast && shapes[i].wide && ladder[k][0] > kMaxBlock / 32)) continue;  // cannot be shortened further: it stays out of the heap
             occupied += ladder[k][0] * tk - ladder[step[i]][0] * t[i];
             step[i] = k;
             t[i] = tk;
@@ -552,7 +557,7 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         }
         const char *fw = getenv("BAYES_FORCE_WARPS"), *fh = getenv("BAYES_FORCE_H");  // experiment knobs
         for (int64_t i = 0; i < n_units; i++) {
-            unit_warps[i] = fw ? std::max(1, std::min(atoi(fw), kMaxBlock / 32)) : ladder[step[i]][0];
+            unit_warps[i] = fw ? std::max(1, std::min(atoi(fw), (fast && !shapes[i].wide ? 1024 : kMaxBlock) / 32)) : ladder[step[i]][0];
             unit_h[i] = fh ? atoi(fh) : ladder[step[i]][1];
             // A locus with hundreds of candidates (config-3 class) is one long dependent chain of iterations that each walk
             // a thousand rows: all 16 warps, and the tallest slabs that still give every warp one -- its A-step is a scan of
@@ -604,7 +609,9 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
     };
     typedef std::tuple<int, int, int, int, int> ClassKey;  // (-band, wide, mat_smem | scr_smem << 1, block, smem bucket)
     auto class_of = [&](const PackedUnit &u) {
-        return ClassKey(-band_of(u), u.d.wide, u.d.mat_smem | (u.d.scr_smem << 1), u.d.block, smem_bucket(u.d.smem_bytes));
+        // (critical band: the largest blocks first -- a 1024-thread block needs a whole SM's registers and would wait, with
+        // everything queued behind it, for an SM to drain completely if smaller blocks were spread over all SMs before it)
+        return ClassKey(-band_of(u), u.d.wide, u.d.mat_smem | (u.d.scr_smem << 1), u.d.block >= 256 ? -u.d.block : u.d.block, smem_bucket(u.d.smem_bytes));
     };
     std::vector<ClassKey> key(n_units);
     for (int64_t i = 0; i < n_units; i++) key[i] = class_of(packed[i]);

@@ -255,8 +255,9 @@ __device__ __forceinline__ void tile_rows(const TileView &V, const double *theta
             if ((head || (inplay && k == 1)) && ord != kPadOrd) n = V.ctab[3 * ord];
             if (inplay && k == 1) atomicAdd(&counts[c], (int)n);
             if (head && k == 0) V.ctl[kCtlErr] = 1;  // reference: assert(normalisation_constant >= double_underflow) (:284)
-            // the row's fragments enter the tree as independent chunks of at most 64 (at most 32 chunks): every binomial stays small
-            const int m = head && k >= 2 ? min(32, ((int)n + 63) >> 6) : 0;
+            // the row's fragments enter the tree as independent chunks of at most 64: every binomial stays in the inversion regime
+            // (rows with more than 2048 fragments enter whole: their binomials are BTRD's either way)
+            const int m = head && k >= 2 ? (n <= 2048u ? ((int)n + 63) >> 6 : 1) : 0;
             const int m_max = __reduce_max_sync(kFull, m);
             for (int ch = 0; ch < m_max; ch++)
                 tile_push(V, kCtlQ0, 0, ch < m, n / (uint32_t)max(m, 1) + (uint32_t)(ch < (int)(n % (uint32_t)max(m, 1))),
@@ -396,7 +397,7 @@ __device__ __forceinline__ void fast_rows_wide(const FastView &V, const uint64_t
                 else if (k2 == 0) V.ctl[kCtlErr] = 1;
             }
             {
-                const int m = live && k2 >= 2 ? min(32, (n + 63) >> 6) : 0;
+                const int m = live && k2 >= 2 ? (n <= 2048 ? (n + 63) >> 6 : 1) : 0;
                 const int m_max = __reduce_max_sync(kFull, m);
                 for (int ch = 0; ch < m_max; ch++)
                     push_tasks(V, kCtlQ0, 0, ch < m, (uint32_t)(n / max(m, 1) + (ch < n % max(m, 1))),

@@ -188,7 +188,7 @@ int prepare_locus(const bayes_locus_desc &in, PreLocus *out, std::string *err);
 int slot_lanes(int T);  // Tpad of a bundle slot (power of two >= T), 0 when T > 32
 void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, bool fast, PackedUnit *out);
 extern bool g_tile_stream;  // fast mode: bundles stream their tiles from global memory (L2) instead of staging them in shared memory
-int tree_chunks(int n);   // fast mode: independent chunks a row with n >= 20 fragments enters its splitting tree in (<= 64 fragments each, at most 32)
+int tree_chunks(int n);   // fast mode: independent chunks a row with n >= 20 fragments enters its splitting tree in (<= 64 fragments each while that takes at most 32 chunks, else the row enters whole)
 size_t max_unit_smem();  // dynamic shared memory a unit may use (opt-in limit of the device, 227 KB on sm_100)
 
 // host_steps.cpp

@@ -410,6 +410,18 @@ def main():
                     "ms_per_step": ms / k, "steps": k, "warmup": w, "value": ost["draws"] / s, "unit": UNIT,
                     "loci_per_sec": ost["loci"] / s, "cell_visits_per_sec": ost["cell_visits"] / s,
                     "roofline_frac": ost["algo_bytes"] / s / 1e9 / peak}
+                if oc == 2 and not args.no_cpu_baseline:
+                    # configs[1] was the N = 1 headline of round 1: its own CPU reference rate, for comparison across rounds
+                    try:
+                        from oracle import oracle_py
+                        oracle_py.build(ref=True)
+                        n_threads = os.cpu_count() or 1
+                        smp = sized_sample(ob, locus_costs(ob), n_threads, 8.0)
+                        rate, kind, secs_cpu = cpu_reference_rate(ob, smp, n_threads)
+                        others["config2"]["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": n_threads, "kind": kind,
+                                                             "sample": sample_note(smp, ob, 2, n_threads, secs_cpu)}
+                    except Exception as e:
+                        others["config2"]["cpu_baseline"] = {"failed": repr(e)}
             except Exception as e:  # reported, never allowed to take the headline down
                 others["config%d" % oc] = {"failed": repr(e)}
         line["other_configs"] = others
