@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbayesembler_b200.so")
 CLI = os.path.join(HERE, "bayesembler_b200_cli")
 CLI_SOURCES = [os.path.join(HERE, "host", f) for f in ("main.cpp", "assembler.hpp", "bayesembler_b200.hpp")]
-SOURCES = ["capi.cu", "gibbs_kernel.cu", "gibbs_fast.cu", "host_steps.cpp", "pack.cpp", "likelihood.cpp", "allpaths.cpp"]
+SOURCES = ["capi.cu", "gibbs_kernel.cu", "gibbs_fast.cu", "gibbs_rows.cu", "host_steps.cpp", "pack.cpp", "likelihood.cpp", "allpaths.cpp"]
 HEADERS = ["internal.h", "layout.h", "rng.cuh", "gibbs_common.cuh", os.path.join("..", "..", "include", "bayesembler_b200.h")]
 
 

@@ -90,6 +90,7 @@ struct Launch {
     int block;
     bool wide, mat_smem, scr_smem;
     size_t smem;
+    int n_cta;  // > 0: cooperative-rows units (gibbs_rows.cu), CTAs per cluster
 };
 
 }  // namespace
@@ -139,6 +140,8 @@ struct bayes_gibbs_ctx {
     DevBuf<int32_t> d_row_woff, d_unit_err;
     DevBuf<double> d_scr_cum;
     DevBuf<uint16_t> d_scr_col;
+    DevBuf<uint32_t> d_gpool;        // uniform-word pools of the cooperative-rows units that do not keep them in shared memory
+    int64_t gpool_len = 0;           // in 16-byte blocks
     DevBuf<uint64_t> d_unit_clock;
     int mode = BAYES_MODE_FAST;      // sampling mode of the next upload (bayes_gibbs_set_mode)
     int built_mode = BAYES_MODE_FAST;  // mode the uploaded units were packed for
@@ -229,10 +232,12 @@ int append_unit(bayes_gibbs_ctx *ctx, PackedUnit &U) {
     U.d.ctab_off = (int64_t)ctx->h_chain_tab.n;
     U.d.scr_off = ctx->scr_len;
     U.d.q_off = ctx->q_len;
+    U.d.gpool_off = ctx->gpool_len;
     if ((!U.row_woff.empty() || !U.cell_meta.empty()) && !U.d.scr_smem) {  // fast mode, scratch in global memory
         ctx->scr_len += U.d.n_chain_cells;
-        ctx->q_len += 6 * (int64_t)U.d.qcap;
+        ctx->q_len += 6 * (int64_t)U.d.qcap * std::max(1, U.d.n_cta);
     }
+    if (U.d.n_cta > 0 && !U.d.pool_smem) ctx->gpool_len += (int64_t)U.d.n_cta * (U.d.pool_max + 1);
     if ((rc = append(ctx->h_slab, U.slab_cell_off)) || (rc = append(ctx->h_val, U.val)) || (rc = append(ctx->h_col, U.col)) ||
         (rc = append(ctx->h_row_n, U.row_n)) || (rc = append(ctx->h_row_nnz, U.row_nnz)) || (rc = append(ctx->h_row_info, U.row_info)) || (rc = append(ctx->h_row_mask, U.row_mask)) ||
         (rc = append(ctx->h_row_woff, U.row_woff)) || (rc = append(ctx->h_pool_desc, U.pool_desc)) ||
@@ -255,7 +260,7 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
     ctx->h_units.n = ctx->h_val.n = ctx->h_efflen.n = ctx->h_tab_val.n = ctx->h_col.n = 0;
     ctx->h_slab.n = ctx->h_row_n.n = ctx->h_row_nnz.n = ctx->h_row_info.n = ctx->h_row_mask.n = ctx->h_base.n = ctx->h_tab_row.n = 0;
     ctx->h_row_woff.n = ctx->h_pool_desc.n = ctx->h_cell_meta.n = ctx->h_chain_tab.n = 0;
-    ctx->scr_len = ctx->q_len = 0;
+    ctx->scr_len = ctx->q_len = ctx->gpool_len = 0;
     const bool fast = ctx->mode == BAYES_MODE_FAST;
     ctx->built_mode = ctx->mode;
     ctx->launches.clear();
@@ -316,6 +321,7 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         }
     }
     const int64_t n_units = (int64_t)groups.size();
+    std::vector<int> unit_cta(n_units, 0);  // > 0: cooperative-rows unit (fast mode, T > 32), CTAs of its cluster
 
     // ---- shape of every unit before it is packed: its A-step items in processing order (chain items, then uniform
     // items, pack.cpp) -> slab widths for any slab height
@@ -400,8 +406,20 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         return kTileEstepUs + pool + std::max(rows / warps, std::min(rows, kTileUniformUs)) + passes * kTileLevelUs +
                (levels + 2) * kFastBarrierUs * (warps > 1 ? 1.0 : 0.2);
     };
+    // Cooperative rows (gibbs_rows.cu): the replicated E-step and the cluster barrier, one warp per row (the rows are dealt over
+    // all warps of all CTAs of the cluster), the tree levels of the CTA with most of them.
+    const double kRowsEstepUs = 14.0, kRowsRowUs = 0.6;
+    auto iteration_us_rows = [&](const UnitShape &S, int warps, int n_cta) {
+        const int n_items = (int)S.nnz.size();
+        double wide_rows = 0;  // rows whose cells in play may not fit one round are walked twice
+        for (int i = S.n_chain; i < n_items; i++) wide_rows += S.nnz[i] > 64 ? 1.0 : 0.0;
+        int levels = 0;
+        const double passes = tree_batches(S, 32 * warps * n_cta, &levels);
+        return kRowsEstepUs + ceil((n_items + wide_rows) / ((double)warps * n_cta)) * kRowsRowUs + passes * kFastLevelUs + (levels + 2) * kFastBarrierUs;
+    };
     auto iteration_us_fast = [&](const UnitShape &S, int warps, int h) {
         if (!S.wide) return iteration_us_tiles(S, warps);
+        if (unit_cta[&S - shapes.data()] > 0) return iteration_us_rows(S, warps, unit_cta[&S - shapes.data()]);
         int chain_slabs, n_slabs;
         slab_layout(S, h, &chain_slabs, &n_slabs);
         const int n_items = (int)S.nnz.size();
@@ -497,6 +515,19 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
     // Greedy critical-path reduction: while the longest unit exceeds what the GPU needs for the whole batch anyway
     // (occupied warp-seconds / warps it keeps resident), move that unit one step down the ladder below.
     std::vector<int> unit_warps(n_units, 1), unit_h(n_units, 32);
+    // Fast mode, loci with more than 32 candidates: cooperative rows over a thread-block cluster (gibbs_rows.cu).  Such a locus
+    // is one long chain of dependent iterations, and what an iteration costs is latency: the more CTAs share its rows, the
+    // shorter the iteration -- and the more SMs it keeps from the other loci.  So the cluster is as large as the SMs allow when
+    // all such loci of the batch are to run at once (8 loci: 16 CTAs each; 500 loci: one CTA each, matrix streamed from L2).
+    int64_t n_rows_units = 0;
+    for (int64_t i = 0; i < n_units; i++) n_rows_units += fast && group_wide[i];
+    int rows_cta = 1;
+    if (n_rows_units > 0) {
+        const char *fc = getenv("BAYES_FORCE_CTAS");  // experiment knob
+        const int cap = rows_max_cluster(kMaxBlock, max_unit_smem());
+        int want = fc ? atoi(fc) : (int)std::min<int64_t>(kMaxCluster, ctx->sm_count / n_rows_units);
+        while (rows_cta * 2 <= want && rows_cta * 2 <= cap) rows_cta *= 2;
+    }
     {
         // (fast mode: the latency of a unit is in its tree levels, which all threads share whatever the slab height: more warps only)
         static const int ladder_replay[][2] = {{1, 32}, {2, 32}, {4, 32}, {8, 32}, {8, 16}, {16, 16}, {16, 8}};
@@ -563,7 +594,15 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
             // a thousand rows: all 16 warps, and the tallest slabs that still give every warp one -- its A-step is a scan of
             // the rows' candidate masks (gibbs_kernel.cu, assign_rows_wide), which all lanes of a slab do in lock step, so
             // short slabs only idle lanes (measured on the largest config-3 locus: 4.4 of 32 lanes active at h = 8).
-            if (group_wide[i] && groups[i][0].locus->T > 128 && !fw && !fh) {
+            if (fast && group_wide[i]) {
+                // cooperative rows: one warp per row, 16 warps unless the locus has few rows
+                unit_cta[i] = rows_cta;
+                unit_h[i] = 1;
+                const int rows = (int)shapes[i].nnz.size();
+                int w = fw ? atoi(fw) : 16;
+                while (w > 1 && (int64_t)(w / 2) * rows_cta * 2 > rows) w /= 2;
+                unit_warps[i] = std::max(1, std::min(w, kMaxBlock / 32));
+            } else if (group_wide[i] && groups[i][0].locus->T > 128 && !fw && !fh) {
                 int h = 32, chain_slabs = 0, n_slabs = 0;
                 for (; h > 8; h /= 2) {
                     slab_layout(shapes[i], h, &chain_slabs, &n_slabs);
@@ -580,8 +619,17 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
     packed.resize(n_units);
     ctx->packed_h.resize(n_units, 0);
     parallel_for(host_thread_count(ctx, n_units), n_units, [&](int64_t i) {
-        if (!reuse || ctx->packed_h[i] != unit_h[i]) pack_unit(groups[i], group_wide[i] != 0, unit_h[i], fast, &packed[i]);
-        ctx->packed_h[i] = unit_h[i];
+        if (unit_cta[i] > 0) {
+            if (!reuse || ctx->packed_h[i] != -unit_cta[i]) {
+                pack_unit_rows(groups[i], unit_cta[i], &packed[i]);
+                // (a cluster whose replicated per-candidate state leaves no room: one CTA, state only)
+                if (packed[i].d.smem_bytes > (int32_t)max_unit_smem() && unit_cta[i] > 1) pack_unit_rows(groups[i], 1, &packed[i]);
+            }
+            ctx->packed_h[i] = -unit_cta[i];
+        } else {
+            if (!reuse || ctx->packed_h[i] != unit_h[i]) pack_unit(groups[i], group_wide[i] != 0, unit_h[i], fast, &packed[i]);
+            ctx->packed_h[i] = unit_h[i];
+        }
         packed[i].d.block = 32 * unit_warps[i];
         packed[i].cost = unit_time(shapes[i], unit_warps[i], unit_h[i]);  // estimated duration: the launch-order key
         unit_features(shapes[i], unit_h[i], packed[i].features);
@@ -607,11 +655,11 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         if (u.d.block >= 256) return 1000;                            // critical, hard to place later
         return (int)floor(log(std::max(u.cost, 1e-6)) / log(1.4));   // +-18 % of duration per band
     };
-    typedef std::tuple<int, int, int, int, int> ClassKey;  // (-band, wide, mat_smem | scr_smem << 1, block, smem bucket)
+    typedef std::tuple<int, int, int, int, int> ClassKey;  // (-band, wide | CTAs per cluster << 1, mat_smem | scr_smem << 1, block, smem bucket)
     auto class_of = [&](const PackedUnit &u) {
         // (critical band: the largest blocks first -- a 1024-thread block needs a whole SM's registers and would wait, with
         // everything queued behind it, for an SM to drain completely if smaller blocks were spread over all SMs before it)
-        return ClassKey(-band_of(u), u.d.wide, u.d.mat_smem | (u.d.scr_smem << 1), u.d.block >= 256 ? -u.d.block : u.d.block, smem_bucket(u.d.smem_bytes));
+        return ClassKey(-band_of(u), u.d.wide | (u.d.n_cta << 1), u.d.mat_smem | (u.d.scr_smem << 1), u.d.block >= 256 ? -u.d.block : u.d.block, smem_bucket(u.d.smem_bytes));
     };
     std::vector<ClassKey> key(n_units);
     for (int64_t i = 0; i < n_units; i++) key[i] = class_of(packed[i]);
@@ -637,7 +685,7 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         int64_t j = i;
         const ClassKey &k = key[order[i]];
         while (j < n_units && key[order[j]] == k) j++;
-        ctx->launches.push_back(Launch{i, j - i, units[i].block, units[i].wide != 0, units[i].mat_smem != 0, units[i].scr_smem != 0, (size_t)std::get<4>(k)});
+        ctx->launches.push_back(Launch{i, j - i, units[i].block, units[i].wide != 0, units[i].mat_smem != 0, units[i].scr_smem != 0, (size_t)std::get<4>(k), units[i].n_cta});
         i = j;
     }
     if (ctx->trace_locus >= 0) {
@@ -680,6 +728,7 @@ KernelArgs kernel_args(bayes_gibbs_ctx *ctx) {
     a.scr_cum = ctx->d_scr_cum.p;
     a.scr_col = ctx->d_scr_col.p;
     a.queue = ctx->d_queue.p;
+    a.gpool = ctx->d_gpool.p;
     a.unit_err = ctx->d_unit_err.p;
     a.trace_unit = ctx->trace_unit;
     a.trace_slot = ctx->trace_slot;
@@ -700,7 +749,7 @@ int upload_units(bayes_gibbs_ctx *ctx) {
         (rc = h2d(ctx->d_row_mask, ctx->h_row_mask, st)) || (rc = h2d(ctx->d_row_woff, ctx->h_row_woff, st)) ||
         (rc = h2d(ctx->d_pool_desc, ctx->h_pool_desc, st)) || (rc = h2d(ctx->d_cell_meta, ctx->h_cell_meta, st)) ||
         (rc = h2d(ctx->d_chain_tab, ctx->h_chain_tab, st)) || (rc = ctx->d_scr_cum.reserve((size_t)ctx->scr_len)) ||
-        (rc = ctx->d_scr_col.reserve((size_t)ctx->scr_len)) || (rc = ctx->d_queue.reserve((size_t)ctx->q_len)) ||
+        (rc = ctx->d_scr_col.reserve((size_t)ctx->scr_len)) || (rc = ctx->d_queue.reserve((size_t)ctx->q_len)) || (rc = ctx->d_gpool.reserve(4 * (size_t)ctx->gpool_len)) ||
         (rc = ctx->d_unit_err.reserve(ctx->h_units.n + 1)) || (rc = ctx->h_unit_err.resize(ctx->h_units.n + 1)) ||
         (rc = h2d(ctx->d_efflen, ctx->h_efflen, st)) || (rc = h2d(ctx->d_base, ctx->h_base, st)) ||
         (rc = h2d(ctx->d_tab_val, ctx->h_tab_val, st)) || (rc = h2d(ctx->d_tab_row, ctx->h_tab_row, st)))
@@ -740,6 +789,7 @@ int bayes_gibbs_create(int device, bayes_gibbs_ctx **out) {
     int rc = configure_kernels();
     if (rc) return rc;
     if ((rc = configure_fast_kernels())) return rc;
+    if ((rc = configure_rows_kernels())) return rc;
     bayes_gibbs_ctx *ctx = new (std::nothrow) bayes_gibbs_ctx();
     if (!ctx) return BAYES_E_NOMEM;
     if (const char *m = getenv("BAYES_MODE")) ctx->mode = strcmp(m, "replay") == 0 ? BAYES_MODE_REPLAY : BAYES_MODE_FAST;
@@ -767,7 +817,7 @@ void bayes_gibbs_destroy(bayes_gibbs_ctx *ctx) {
     ctx->h_pool_desc.release(); ctx->h_row_woff.release(); ctx->h_unit_err.release(); ctx->h_cell_meta.release(); ctx->h_chain_tab.release();
     ctx->d_cell_meta.release(); ctx->d_chain_tab.release();
     ctx->d_pool_desc.release(); ctx->d_queue.release(); ctx->d_row_woff.release(); ctx->d_unit_err.release();
-    ctx->d_scr_cum.release(); ctx->d_scr_col.release();
+    ctx->d_scr_cum.release(); ctx->d_scr_col.release(); ctx->d_gpool.release();
     ctx->d_units.release(); ctx->d_val.release(); ctx->d_efflen.release(); ctx->d_tab_val.release(); ctx->d_mean.release();
     ctx->d_m2.release(); ctx->d_tr_theta.release(); ctx->d_col.release(); ctx->d_slab.release(); ctx->d_row_n.release();
     ctx->d_row_nnz.release(); ctx->d_row_info.release(); ctx->d_base.release(); ctx->d_tab_row.release(); ctx->d_occ.release();
@@ -948,7 +998,8 @@ static int issue_launches(bayes_gibbs_ctx *ctx, int32_t iter_cap) {
             CU(cudaEventRecord(ctx->gate_ev[i], ctx->gate));
             CU(cudaStreamWaitEvent(st, ctx->gate_ev[i], 0));
         }
-        if (ctx->built_mode == BAYES_MODE_FAST) rc = launch_units_fast(args, l.unit_base, l.n_units, l.block, l.wide, l.mat_smem, l.scr_smem, l.smem, st);
+        if (l.n_cta > 0) rc = launch_units_rows(args, l.unit_base, l.n_units, l.block, l.n_cta, l.smem, st);
+        else if (ctx->built_mode == BAYES_MODE_FAST) rc = launch_units_fast(args, l.unit_base, l.n_units, l.block, l.wide, l.mat_smem, l.scr_smem, l.smem, st);
         else rc = launch_units(args, l.unit_base, l.n_units, l.block, l.wide, l.mat_smem, l.smem, st);
         if (rc) return rc;
         if (n_l > 1) {
@@ -1264,12 +1315,13 @@ static int step_assignment(int device, const bayes_locus_desc *locus, const doub
     const int T = d.T;
     PackedUnit U;
     // replay mode and wide loci: wide layout (columns stay candidate indices); fast mode with T <= 32: the tiles of a bundle
-    const bool tiles = fast && T <= 32;
-    pack_unit(std::vector<SlotRef>(1, SlotRef{&P, 0, 0}), !tiles, 32, fast, &U);
+    const bool tiles = fast && T <= 32, rows = fast && T > 32;
+    if (rows) pack_unit_rows(std::vector<SlotRef>(1, SlotRef{&P, 0, 0}), 1, &U);
+    else pack_unit(std::vector<SlotRef>(1, SlotRef{&P, 0, 0}), !tiles, 32, fast, &U);
     U.d.mat_smem = 0;  // the step kernels read the matrix (and the fast-mode scratch) from global memory
     U.d.scr_smem = 0;
     U.d.pool_smem = 0;
-    ctx->scr_len = ctx->q_len = 0;
+    ctx->scr_len = ctx->q_len = ctx->gpool_len = 0;
     if ((rc = append_unit(ctx, U))) return fail(rc);
     if ((rc = upload_units(ctx))) return fail(rc);
     cudaStream_t st = ctx->stream;
@@ -1279,7 +1331,8 @@ static int step_assignment(int device, const bayes_locus_desc *locus, const doub
     const KernelArgs args = kernel_args(ctx);
     const size_t smem = 12 * (size_t)T + 8 * (((size_t)T + 63) / 64) + 48 + 4 * kFastCtlWords;
     if ((rc = cuda_rc(cudaMemsetAsync(ctx->d_unit_err.p, 0, sizeof(int32_t), st), "memset"))) return fail(rc);
-    if (fast) rc = launch_step_assignment_fast(args, init, tiles, ctx->d_mean.p, iteration, ctx->d_occ.p, smem, st);
+    if (rows) rc = launch_step_assignment_rows(args, init, ctx->d_mean.p, iteration, ctx->d_occ.p, 12 * (size_t)T + 8 * (((size_t)T + 63) / 64) + 4 * kRowsCtlWords, st);
+    else if (fast) rc = launch_step_assignment_fast(args, init, tiles, ctx->d_mean.p, iteration, ctx->d_occ.p, smem, st);
     else rc = launch_step_assignment(args, init, ctx->d_mean.p, iteration, ctx->d_occ.p, smem, st);
     if (rc) return fail(rc);
     if ((rc = cuda_rc(cudaMemcpyAsync(counts_out, ctx->d_occ.p, T * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "counts D2H")))
@@ -1362,7 +1415,8 @@ int bayes_debug_unit_layout(int32_t n_loci, const bayes_locus_desc *loci, int32_
     std::vector<SlotRef> slots;
     for (int i = 0; i < n_loci; i++) slots.push_back(SlotRef{&pre[i], 0, 0});
     PackedUnit U;
-    pack_unit(slots, pre[0].T > 32, 32, fast != 0, &U);
+    if (fast && pre[0].T > 32) pack_unit_rows(slots, 1, &U);
+    else pack_unit(slots, pre[0].T > 32, 32, fast != 0, &U);
     out8[0] = U.d.smem_bytes; out8[1] = U.d.n_cells; out8[2] = U.d.n_slabs * U.d.slab_h; out8[3] = U.d.n_chain_cells;
     out8[4] = U.d.qcap; out8[5] = U.d.pool_blocks; out8[6] = U.d.tab_len; out8[7] = U.d.mat_smem | (U.d.tab_smem << 1) | (U.d.pool_smem << 2);
     return BAYES_OK;

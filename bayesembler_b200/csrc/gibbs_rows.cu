@@ -1,0 +1,811 @@
+// Fast (production) sampling mode for loci with MORE than 32 candidates (config-3 class: 200-1000 candidate paths, a
+// thousand collapsed rows, 0.4-2.5 MB of likelihood matrix, 10^5-10^6 strictly sequential Gibbs iterations).
+//
+// What bounds such a locus is the latency of ONE iteration, so the kernel is organised around that:
+//
+//  * One locus = one thread-block CLUSTER (1, 2, 4, 8 or 16 CTAs, chosen by the host from how many such loci compete for
+//    the SMs).  The rows are dealt over the CTAs; each CTA keeps its share of the matrix (values, candidate masks, row
+//    table) resident in its own shared memory, so an iteration reads nothing from L2 / HBM.
+//  * The E-step (ExpressionGenerator::generateExpression, expressionGenerator.cpp:77-132; simplex size,
+//    simplexSizeGenerator.cpp:209-224; getFPKM + GibbsOutput::addSample) is REPLICATED: every CTA computes the same theta
+//    from the same counts with the same Philox sites, so theta and the simplex mask are never exchanged.  Inside a CTA it
+//    runs on all warps (one Gamma draw per thread); only the null-candidate selection is sequential, and that is a
+//    warp-wide rank select (prefix counts in the lanes, one ballot per pick) instead of a walk over the chunks.
+//  * The A-step (AssignmentGenerator::generateAssignment, assignmentGenerator.cpp:263-373) is WARP PER ROW: the lanes first
+//    hold the row's candidate-mask words (ANDed with the simplex mask: the cells in play, a few tens of the row's
+//    hundreds of stored cells), a shuffle prefix sum ranks them, then the lanes hold the cells in play themselves, 32 at
+//    a time: p = P_ij theta_j, warp-shuffle inclusive scan, thresholds against the row's pool words (rows with < 20
+//    fragments) or compaction into the scratch list the splitting trees work on (rows with >= 20 fragments; same trees as
+//    gibbs_fast.cu).  Stored cells that are not in play are never touched.
+//  * Counts: every CTA accumulates the fragments of ITS rows into a partial vector in its own shared memory; after one
+//    cluster barrier every CTA adds up the partial vectors of all CTAs through distributed shared memory (integer sums:
+//    the order does not matter).  The partial vectors are double-buffered, so one cluster barrier per iteration suffices.
+//
+// The order of the floating-point additions of a row sum is fixed by the scan (chunks of 32 cells in play, Hillis-Steele
+// inside a chunk, chunks chained left to right); the CPU oracle sums in the same order (oracle/bayes_oracle.c,
+// assignment_fast) and the parity tests compare the two draw for draw.  No tensor cores: nothing here is a dense contraction.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdlib.h>
+
+#include "internal.h"
+#include "layout.h"
+#include "rng.cuh"
+#include "gibbs_common.cuh"
+
+namespace cg = cooperative_groups;
+
+#ifndef BAYES_ROWS_MAXNREG
+#define BAYES_ROWS_MAXNREG 128
+#endif
+
+namespace bayes {
+
+namespace {
+
+constexpr uint32_t kFull = 0xffffffffu;
+// ctl words
+constexpr int kCtlQ0 = 1, kCtlErr = 4, kCtlNAct = 5, kCtlB = 6;
+
+#ifdef BAYES_DEBUG_BOUNDS
+#define ROWS_CHECK(cond, code) do { if (!(cond)) V.ctl[kCtlErr] = (code); } while (0)
+#else
+#define ROWS_CHECK(cond, code) do { } while (0)
+#endif
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// index of the i-th (0-based) set bit of m
+__device__ __forceinline__ int nth_set_bit64(uint64_t m, int i) {
+    const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+    const int pl = __popc(lo);
+    const bool up = i >= pl;
+    return (int)__fns(up ? hi : lo, 0, (up ? i - pl : i) + 1) + (up ? 32 : 0);
+}
+
+__device__ __forceinline__ int words_below(const u32x4 &w, int left, uint32_t t) {
+    return (int)(w.x <= t) + ((left > 1) & (int)(w.y <= t)) + ((left > 2) & (int)(w.z <= t)) + ((left > 3) & (int)(w.w <= t));
+}
+
+// What one CTA works on.  Row / cell indices are those of the unit; the staged copies start at row_base / cell_base.
+struct RowsView {
+    const double *val;         // cell - cell_base
+    const uint64_t *rmask;     // (row - row_base) * n_words + word
+    const int32_t *rcell;      // row - row_base -> first cell of the row (one more entry than rows)
+    const int32_t *row_n;      // fragments of the row
+    const uint32_t *row_info;  // slot << 27 | original row index
+    const int32_t *row_woff;   // rows with < 20 fragments: first word of the row in the CTA's pool
+    int row_base, cell_base;
+    int row_begin, row_end, chain_end;  // this CTA's rows; [row_begin, chain_end) have >= 20 fragments
+    int n_words;
+    double *scr_cum;           // rows with >= 20 fragments: running sums of the cells in play, entry (first cell - scr_base + i)
+    uint16_t *scr_col;         // their candidates
+    int scr_base, scr_len;
+    uint32_t *queue;           // two buffers of 3 * qcap words: fragments | node | row
+    int qcap;
+    const uint32_t *pool;      // this iteration's uniform words of the CTA's rows
+    int *ctl;
+};
+
+// Warp-aggregated append of at most one task per lane to queue buffer `buf`, counted by ctl word `cnt`.  All 32 lanes call.
+__device__ __forceinline__ void push_tasks(const RowsView &V, int cnt, int buf, bool want, uint32_t n, uint32_t node, uint32_t row) {
+    const uint32_t m = __ballot_sync(kFull, want);
+    if (m == 0u) return;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&V.ctl[cnt], __popc(m));
+    base = __shfl_sync(kFull, base, leader);
+    if (want) {
+        const int idx = base + __popc(m & lanemask_lt());
+        ROWS_CHECK(idx < V.qcap, 201);
+        uint32_t *q = V.queue + (size_t)buf * 3 * V.qcap;
+        q[idx] = n;
+        q[V.qcap + idx] = node;
+        q[2 * V.qcap + idx] = row;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// A-step, first part: one warp per row.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rows_assign(const RowsView &V, const uint64_t *amask, const double *theta, int32_t *acc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const uint32_t lt = lanemask_lt();
+    const int n_words = V.n_words;
+    for (int r = V.row_begin + warp; r < V.row_end; r += n_warps) {
+        const int ri = r - V.row_base;
+        const int n = V.row_n[ri];
+        const int cell0 = V.rcell[ri];
+        const bool chain = r < V.chain_end;
+        const double *val = V.val + (cell0 - V.cell_base);
+        const uint64_t *rm = V.rmask + (size_t)ri * n_words;
+        const int sb = cell0 - V.scr_base;
+        const int w_row = chain ? 0 : V.row_woff[ri];
+        double rZ = 0.0;
+        int kk_total = 0;
+        bool second = false;
+        // A row with < 20 fragments whose cells in play do not fit one round of 32 is walked twice: once for its sum, once
+        // (the same arithmetic again) for the thresholds.
+        for (;;) {
+            double carry = 0.0;
+            int kk = 0, kbase_grp = 0, below_carry = 0, c_only = 0;
+            bool done = false;
+            for (int w0 = 0; w0 < n_words; w0 += 32) {
+                const int w = w0 + lane;
+                uint64_t m_all = 0ull, m = 0ull;
+                if (w < n_words) {
+                    m_all = rm[w];
+                    m = m_all & amask[w];
+                }
+                // ranks: stored cells before my word (high half), cells in play before my word (low half)
+                const uint32_t pk = ((uint32_t)__popcll(m_all) << 16) | (uint32_t)__popcll(m);
+                uint32_t incl = pk;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t up = __shfl_up_sync(kFull, incl, d);
+                    if (lane >= d) incl += up;
+                }
+                const uint32_t tot = __shfl_sync(kFull, incl, 31), excl = incl - pk;
+                const int Kg = (int)(tot & 0xffffu);
+                const int my_kbase = kbase_grp + (int)(excl >> 16), my_jbase = (int)(excl & 0xffffu);
+                const bool single = !chain && !second && n_words <= 32 && Kg <= 32;
+                for (int j0 = 0; j0 < Kg; j0 += 32) {
+                    const int j = j0 + lane;
+                    const bool valid = j < Kg;
+                    // the word my cell sits in: the last lane whose first cell in play is not after mine
+                    int l = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const int jb = __shfl_sync(kFull, my_jbase, l + step);
+                        if (jb <= j) l += step;
+                    }
+                    const uint64_t ms = __shfl_sync(kFull, m, l), mas = __shfl_sync(kFull, m_all, l);
+                    const int kb = __shfl_sync(kFull, my_kbase, l), jb = __shfl_sync(kFull, my_jbase, l);
+                    int c = 0;
+                    double p = 0.0;
+                    if (valid) {
+                        const int bit = nth_set_bit64(ms, j - jb);
+                        const int k = kb + __popcll(mas & ((1ull << bit) - 1ull));
+                        c = ((w0 + l) << 6) + bit;
+                        ROWS_CHECK(cell0 + k < V.rcell[ri + 1], 202);
+                        p = val[k] * theta[c];
+                    }
+                    // inclusive scan of the chunk; chunks are chained left to right (the oracle sums in this order)
+                    double x = p;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const double up = __shfl_up_sync(kFull, x, d);
+                        if (lane >= d) x += up;
+                    }
+                    const double cum = carry + x;
+                    const int last = Kg - 1 - j0 < 31 ? Kg - 1 - j0 : 31;
+                    carry = __shfl_sync(kFull, cum, last);
+                    const bool inplay = p > 0.0;
+                    const uint32_t bal = __ballot_sync(kFull, inplay);
+                    const int pos = kk + __popc(bal & lt);
+                    if (chain) {
+                        if (inplay) {
+                            ROWS_CHECK(sb + pos >= 0 && sb + pos < V.scr_len, 203);
+                            V.scr_cum[sb + pos] = cum;
+                            V.scr_col[sb + pos] = (uint16_t)c;
+                        }
+                        if (bal) c_only = __shfl_sync(kFull, c, 31 - __clz(bal));
+                    } else if (second || single) {
+                        if (single) {
+                            rZ = __drcp_rn(carry);
+                            kk_total = __popc(bal);
+                        }
+                        int below = 0;
+                        if (inplay) {
+                            if (pos == kk_total - 1) {
+                                below = n;  // the last cell in play takes what the others left
+                            } else {
+                                // word * 2^-32 < cum / Z  <=>  word <= ceil(cum (1/Z) 2^32 - 1); the conversion saturates
+                                const uint32_t t = __double2uint_ru(__fma_rn(cum * rZ, 4294967296.0, -1.0));
+                                for (int b = 0; b < n; b += 4) {
+                                    const uint32_t *pw = V.pool + w_row + b;
+                                    const u32x4 wv = {pw[0], pw[1], pw[2], pw[3]};
+                                    below += words_below(wv, n - b < 4 ? n - b : 4, t);
+                                }
+                            }
+                        }
+                        const uint32_t lower = bal & lt;
+                        int prev = __shfl_sync(kFull, below, lower ? 31 - __clz(lower) : 0);
+                        if (!lower) prev = below_carry;
+                        if (inplay && below > prev) atomicAdd(&acc[c], below - prev);
+                        if (bal) below_carry = __shfl_sync(kFull, below, 31 - __clz(bal));
+                        done = true;
+                    }
+                    kk += __popc(bal);
+                }
+                kbase_grp += (int)(tot >> 16);
+            }
+            if (kk == 0) {  // reference: assert(normalisation_constant >= double_underflow) (assignmentGenerator.cpp:284)
+                if (lane == 0) V.ctl[kCtlErr] = 1;
+                break;
+            }
+            if (chain) {
+                if (kk == 1) {
+                    if (lane == 0) atomicAdd(&acc[c_only], n);
+                } else {
+                    // the row's fragments enter the tree as independent chunks of at most 64 (rows above 2048 fragments whole)
+                    const int mch = n <= 2048 ? (n + 63) >> 6 : 1;
+                    push_tasks(V, kCtlQ0, 0, lane < mch, (uint32_t)(n / mch + (lane < n % mch)), ((uint32_t)(kk - 1) << 12) | ((uint32_t)lane << 24),
+                               (uint32_t)r);
+                }
+                break;
+            }
+            if (done) break;
+            rZ = __drcp_rn(carry);
+            kk_total = kk;
+            second = true;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// A-step, second part: the splitting trees of the rows with >= 20 fragments, level by level (the scheme of
+// fast_tree_levels in gibbs_fast.cu: one lane per node of the level whichever row it belongs to, three rotating
+// counters, two queue buffers, one block barrier per level).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rows_tree_levels(const RowsView &V, int32_t *acc, const uint64_t key, uint32_t iteration, const bool init) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ph_tree = init ? PH_INIT_TREE : PH_TREE;
+    const int qcap = V.qcap;
+    int cur = kCtlQ0, nxt = kCtlQ0 + 1, old = kCtlQ0 + 2, buf = 0;
+    for (;;) {
+        const int Q = V.ctl[cur];
+        if (Q == 0) break;
+        if (threadIdx.x == 0) V.ctl[old] = 0;
+        const uint32_t *q = V.queue + (size_t)buf * 3 * qcap;
+        for (int i0 = warp * 32; i0 < Q; i0 += (int)blockDim.x) {
+            const int i = i0 + lane;
+            bool push_l = false, push_r = false;
+            uint32_t n_l = 0, n_r = 0, node_l = 0, node_r = 0, row = 0;
+            if (i < Q) {
+                const uint32_t n = q[i], node = q[qcap + i];
+                row = q[2 * qcap + i];
+                const uint32_t chunk = node >> 24;
+                const int a = (int)(node & 4095u), len = (int)((node >> 12) & 4095u) + 1, half = len >> 1, len_r = len - half;
+                const int ri = (int)row - V.row_base;
+                const int sb = V.rcell[ri] - V.scr_base;
+                ROWS_CHECK(sb >= 0 && sb + a + len - 1 < V.scr_len, 204);
+                const double *sc = V.scr_cum + sb;
+                const double Pa = a ? sc[a - 1] : 0.0, Pm = sc[a + half - 1], Pb = sc[a + len - 1];
+                const double p_left = (Pm - Pa) / (Pb - Pa);
+                const uint32_t info = V.row_info[ri];
+                const Site site = make_site(key, ph_tree | ((node & 0xFFFFFFu) << 8), iteration, info & ((1u << kRowSlotShift) - 1u), chunk);
+                n_l = (uint32_t)binomial_variate(site, (int)n, p_left);
+                n_r = n - n_l;
+                if (n_l) {
+                    if (half == 1) atomicAdd(&acc[V.scr_col[sb + a]], (int)n_l);
+                    else { push_l = true; node_l = (uint32_t)a | ((uint32_t)(half - 1) << 12) | (chunk << 24); }
+                }
+                if (n_r) {
+                    if (len_r == 1) atomicAdd(&acc[V.scr_col[sb + a + half]], (int)n_r);
+                    else { push_r = true; node_r = (uint32_t)(a + half) | ((uint32_t)(len_r - 1) << 12) | (chunk << 24); }
+                }
+            }
+            push_tasks(V, nxt, buf ^ 1, push_l, n_l, node_l, row);
+            push_tasks(V, nxt, buf ^ 1, push_r, n_r, node_r, row);
+        }
+        __syncthreads();
+        const int t = old;
+        old = cur;
+        cur = nxt;
+        nxt = t;
+        buf ^= 1;
+    }
+}
+
+// the iteration's uniform words of this CTA's rows: block b of the CTA's pool = Philox block (desc & 0xffffff) of the locus' pool
+__device__ __forceinline__ void rows_pool_gen(uint32_t *pool, const uint32_t *pool_desc, int pool_blocks, const uint64_t key, uint32_t iteration,
+                                              bool init, int first_thread, int n_threads) {
+    const uint32_t ph = init ? PH_INIT_POOL : PH_POOL;
+    for (int b = (int)threadIdx.x - first_thread; b < pool_blocks; b += n_threads) {
+        if (b < 0) continue;
+        const uint32_t blk = pool_desc[b];
+        const u32x4 w = make_site(key, ph, iteration, blk >> 12, 0).block(blk & 4095u);
+        reinterpret_cast<uint4 *>(pool)[b] = make_uint4(w.x, w.y, w.z, w.w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// E-step on all warps of the CTA (every CTA of the cluster runs it on the same counts and gets the same theta).
+// Same draws, the same sites and the same order of the floating-point sums as wide_e_step (gibbs_common.cuh).
+// Welford accumulators of candidate t are kept by CTA (t mod n_cta).  Ends with a block barrier.
+// ------------------------------------------------------------------------------------------------------------------
+struct RowsState {
+    double *theta, *den, *mean, *m2, *norm;
+    int32_t *counts, *occ;
+    const int32_t *base;
+    uint32_t *mask;    // [0, nch): S+ of the counts; [nch, 2 nch): picked null candidates
+    int32_t *actoff;   // first entry of every 32-candidate chunk in act
+    uint16_t *act;     // members of the simplex, ascending
+    uint64_t *amask;   // the simplex as a bit mask, 64 candidates per word
+    const double *tab_val;
+    const int32_t *tab_row;
+    int *ctl;
+    int T, nch, N_f;
+    double gamma;
+};
+
+__device__ __forceinline__ int rows_e_step(const RowsState &E, const uint64_t key, uint32_t iteration, bool sampling, int rank, int n_cta,
+                                           uint32_t *pool, const uint32_t *pool_desc, int pool_blocks) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5, n_threads = blockDim.x;
+    const int T = E.T, nch = E.nch;
+    const uint32_t lt = lanemask_lt();
+    // 1. S+ of the counts, theta cleared
+    for (int c = warp; c < nch; c += n_warps) {
+        const int t = c * 32 + lane;
+        const uint32_t pm = __ballot_sync(kFull, t < T && E.counts[t] > 0);
+        if (lane == 0) {
+            E.mask[c] = pm;
+            E.mask[nch + c] = 0u;
+        }
+        if (t < T) E.theta[t] = 0.0;
+    }
+    __syncthreads();
+    // 2. warp 0: simplex size and the null candidates that join S+; the other warps: this iteration's uniform words
+    if (warp == 0) {
+        const int G = (nch + 31) >> 5;  // chunks per lane (<= 4: T <= 4096), lane l holds chunks [l G, (l + 1) G)
+        uint32_t nullw[4], pmw[4], picked[4];
+        int cnt = 0, plus = 0;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const int c = lane * G + g;
+            uint32_t pm = 0u, vmask = 0u;
+            if (g < G && c < nch) {
+                pm = E.mask[c];
+                vmask = (c == nch - 1 && (T & 31)) ? (1u << (T & 31)) - 1u : kFull;
+            }
+            pmw[g] = pm;
+            nullw[g] = ~pm & vmask;
+            picked[g] = 0u;
+            cnt += __popc(nullw[g]);
+            plus += __popc(pm);
+        }
+        for (int o = 16; o > 0; o >>= 1) plus += __shfl_xor_sync(kFull, plus, o);
+        const int n_plus = plus;
+        const int b = sample_simplex(E.tab_val, E.tab_row, n_plus, key, iteration);
+        const int n_null = T - n_plus, n_pick = b - n_plus;
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(kFull, incl, d);
+            if (lane >= d) incl += up;
+        }
+        // expressionGenerator.cpp:104-127: pick k takes the (draw k)-th of the null candidates still left, in ascending order.
+        // The draws are independent (site = pick ordinal): 32 at a time, one per lane; the selection is sequential.
+        for (int k0 = 0; k0 < n_pick; k0 += 32) {
+            uint32_t my_pick = 0u;
+            if (k0 + lane < n_pick)
+                my_pick = uniform_int(make_site(key, PH_NULLPICK, iteration, (uint32_t)(k0 + lane), 0), (uint32_t)(n_null - k0 - lane));
+            const int kn = n_pick - k0 < 32 ? n_pick - k0 : 32;
+            for (int k = 0; k < kn; k++) {
+                const int rem = (int)__shfl_sync(kFull, my_pick, k);
+                const uint32_t ge = __ballot_sync(kFull, incl > rem);
+                if (ge == 0u) continue;  // cannot happen: rem < null candidates left
+                const int owner = __ffs(ge) - 1;
+                if (lane == owner) {
+                    int r2 = rem - (incl - cnt);
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const int pc = __popc(nullw[g]);
+                        if (r2 >= 0 && r2 < pc) {
+                            const uint32_t bit = __fns(nullw[g], 0, r2 + 1);
+                            nullw[g] &= ~(1u << bit);
+                            picked[g] |= 1u << bit;
+                            r2 = -1;
+                        } else if (r2 >= 0) {
+                            r2 -= pc;
+                        }
+                    }
+                    cnt--;
+                }
+                if (lane >= owner) incl--;
+            }
+        }
+        int members = 0;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const int c = lane * G + g;
+            if (g < G && c < nch) E.mask[nch + c] = picked[g];
+            members += __popc(pmw[g] | picked[g]);
+        }
+        int mi = members;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(kFull, mi, d);
+            if (lane >= d) mi += up;
+        }
+        int at = mi - members;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const int c = lane * G + g;
+            if (g < G && c < nch) {
+                E.actoff[c] = at;
+                at += __popc(pmw[g] | picked[g]);
+            }
+        }
+        if (lane == 31) E.ctl[kCtlNAct] = mi;
+        if (lane == 0) E.ctl[kCtlB] = b;
+        if (n_threads == 32) rows_pool_gen(pool, pool_desc, pool_blocks, key, iteration, false, 0, 32);
+    } else {
+        rows_pool_gen(pool, pool_desc, pool_blocks, key, iteration, false, 32, n_threads - 32);
+    }
+    __syncthreads();
+    // 3. the members of the simplex, ascending, and the simplex mask the A-step ANDs the rows' masks with
+    for (int c = warp; c < nch; c += n_warps) {
+        const uint32_t m = E.mask[c] | E.mask[nch + c];
+        if ((m >> lane) & 1u) E.act[E.actoff[c] + __popc(m & lt)] = (uint16_t)(c * 32 + lane);
+    }
+    for (int w = threadIdx.x; w < (nch + 1) / 2; w += n_threads) {
+        const uint32_t lo = E.mask[2 * w] | E.mask[nch + 2 * w];
+        const uint32_t hi = 2 * w + 1 < nch ? E.mask[2 * w + 1] | E.mask[nch + 2 * w + 1] : 0u;
+        E.amask[w] = ((uint64_t)hi << 32) | lo;
+    }
+    __syncthreads();
+    // 4. one Gamma(count + gamma) draw per member
+    const int n_act = E.ctl[kCtlNAct];
+    for (int i = threadIdx.x; i < n_act; i += n_threads) {
+        const int t = E.act[i];
+        const double gv = gamma_variate(make_site(key, PH_GAMMA, iteration, (uint32_t)t, 0), (double)E.counts[t] + E.gamma);
+        if (!(gv >= DBL_MIN)) E.ctl[kCtlErr] = 2;  // reference: assert(gamma_base_sample >= double_underflow) (expressionGenerator.cpp:115)
+        E.theta[t] = gv;
+    }
+    __syncthreads();
+    // 5. the normalising sum, in the order it always had (per lane over the chunks, then across the lanes); fresh counts
+    if (warp == 0) {
+        double part = 0.0;
+        for (int c = 0; c < nch; c++) {
+            const int t = c * 32 + lane;
+            if (t < T) part += E.theta[t];
+        }
+        const double norm = warp_sum(part);
+        if (lane == 0) *E.norm = norm;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += n_threads) E.counts[t] = E.base[t];  // fresh CountValueContainer (+ the folded rows)
+    const double norm = *E.norm;
+    for (int i = threadIdx.x; i < n_act; i += n_threads) {
+        const int t = E.act[i];
+        const double g = E.theta[t];
+        const double th = g != 0.0 ? g / norm : 0.0;  // valueContainer.cpp:216-224
+        E.theta[t] = th;
+        if (sampling && g != 0.0 && t % n_cta == rank) {
+            const double fpkm = (th * (double)E.N_f * 1e9) / E.den[t];  // valueContainer.cpp:235
+            const int o = ++E.occ[t];                                    // gibbsOutput.cpp:60
+            if (o == 1) {
+                E.mean[t] = fpkm;
+            } else {
+                const double delta = fpkm - E.mean[t];
+                const double mu = E.mean[t] + delta / o;
+                E.mean[t] = mu;
+                E.m2[t] += delta * (fpkm - mu);
+            }
+        }
+    }
+    __syncthreads();
+    return E.ctl[kCtlB];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __maxnreg__(BAYES_ROWS_MAXNREG) gibbs_rows_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int n_cta = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int64_t ui = unit_base + blockIdx.x / n_cta;
+    const bool lead = rank == 0;
+    if (lead && threadIdx.x == 0) A.unit_clock[3 * ui] = global_ns();
+    const UnitDev &U = A.units[ui];
+    const int T = U.T[0];
+    const int n_threads = blockDim.x;
+    const RowsLayout lay = rows_layout(T, n_cta, U.rows_max, U.cells_max, U.ccells_max, U.qcap, U.pool_max, U.mat_smem != 0, U.scr_smem != 0, U.pool_smem != 0);
+    RowsState E;
+    E.theta = (double *)(smem + lay.theta);
+    E.den = (double *)(smem + lay.den);
+    E.mean = (double *)(smem + lay.mean);
+    E.m2 = (double *)(smem + lay.m2);
+    E.norm = (double *)(smem + lay.norm);
+    E.counts = (int32_t *)(smem + lay.counts);
+    E.occ = (int32_t *)(smem + lay.occ);
+    int32_t *base = (int32_t *)(smem + lay.base);
+    E.base = base;
+    E.mask = (uint32_t *)(smem + lay.mask);
+    E.actoff = (int32_t *)(smem + lay.actoff);
+    E.act = (uint16_t *)(smem + lay.act);
+    E.amask = (uint64_t *)(smem + lay.amask);
+    E.tab_val = A.tab_val + U.tab_off;
+    E.tab_row = A.tab_row + U.tabrow_off;
+    E.T = T;
+    E.nch = (T + 31) >> 5;
+    E.N_f = U.N_f[0];
+    E.gamma = U.gamma[0];
+    int *ctl = (int *)(smem + lay.ctl);
+    E.ctl = ctl;
+    int32_t *part = (int32_t *)(smem + lay.part);  // two buffers of T partial counts (clusters of more than one CTA)
+    const uint64_t key = U.key[0];
+
+    const double n_total = (double)U.N_total[0];
+    for (int t = threadIdx.x; t < T; t += n_threads) {
+        const int32_t bc = A.base_counts[U.lane_off + t];
+        base[t] = bc;
+        E.counts[t] = bc;
+        E.occ[t] = 0;
+        E.mean[t] = 0.0;
+        E.m2[t] = 0.0;
+        E.theta[t] = 1.0;  // initAssignment runs the A-step on P_ij itself
+        E.den[t] = A.efflen[U.lane_off + t] * n_total;  // valueContainer.cpp:235 denominator
+        E.act[t] = (uint16_t)t;  // initAssignment: every candidate is "in the simplex"
+        if (n_cta > 1) {
+            part[t] = 0;
+            part[T + t] = 0;
+        }
+    }
+    for (int w = threadIdx.x; w < (T + 63) >> 6; w += n_threads)
+        E.amask[w] = w == ((T + 63) >> 6) - 1 && (T & 63) ? (1ull << (T & 63)) - 1ull : ~0ull;
+    if (threadIdx.x < kRowsCtlWords) ctl[threadIdx.x] = 0;
+
+    // ---- this CTA's rows ----
+    RowsView V;
+    V.row_begin = U.cta_row0[rank];
+    V.row_end = U.cta_row0[rank + 1];
+    V.chain_end = V.row_begin + U.cta_chain[rank];
+    V.n_words = (T + 63) >> 6;
+    V.qcap = U.qcap;
+    V.ctl = ctl;
+    const int32_t *g_rcell = A.slab_cell_off + U.slab_off;
+    const int cell_begin = g_rcell[V.row_begin], cell_end = g_rcell[V.row_end];
+    if (U.mat_smem) {
+        const int rows = V.row_end - V.row_begin;
+        double *sv = (double *)(smem + lay.val);
+        uint64_t *sm = (uint64_t *)(smem + lay.rmask);
+        int32_t *rc = (int32_t *)(smem + lay.rcell), *rn = (int32_t *)(smem + lay.row_n), *rw = (int32_t *)(smem + lay.row_woff);
+        uint32_t *rinfo = (uint32_t *)(smem + lay.row_info);
+        block_copy(sv, A.val + U.cell_off + cell_begin, cell_end - cell_begin);
+        block_copy(sm, (const uint64_t *)A.row_mask + U.mask_off + (size_t)V.row_begin * V.n_words, rows * V.n_words);
+        block_copy(rc, g_rcell + V.row_begin, rows + 1);
+        block_copy(rn, A.row_n + U.row_off + V.row_begin, rows);
+        block_copy(rinfo, A.row_info + U.row_off + V.row_begin, rows);
+        block_copy(rw, A.row_woff + U.woff_off + V.row_begin, rows);
+        V.val = sv; V.rmask = sm; V.rcell = rc; V.row_n = rn; V.row_info = rinfo; V.row_woff = rw;
+        V.row_base = V.row_begin;
+        V.cell_base = cell_begin;
+    } else {
+        V.val = A.val + U.cell_off;
+        V.rmask = (const uint64_t *)A.row_mask + U.mask_off;
+        V.rcell = g_rcell;
+        V.row_n = A.row_n + U.row_off;
+        V.row_info = A.row_info + U.row_off;
+        V.row_woff = A.row_woff + U.woff_off;
+        V.row_base = 0;
+        V.cell_base = 0;
+    }
+    if (U.scr_smem) {
+        V.scr_cum = (double *)(smem + lay.scr_cum);
+        V.scr_col = (uint16_t *)(smem + lay.scr_col);
+        V.scr_base = cell_begin;
+        V.scr_len = U.ccells_max;
+        V.queue = (uint32_t *)(smem + lay.queue);
+    } else {
+        V.scr_cum = A.scr_cum + U.scr_off;
+        V.scr_col = A.scr_col + U.scr_off;
+        V.scr_base = 0;
+        V.scr_len = U.n_cells;
+        V.queue = A.queue + U.q_off + (size_t)rank * 6 * U.qcap;
+    }
+    uint32_t *pool = U.pool_smem ? (uint32_t *)(smem + lay.pool) : A.gpool + 4 * ((size_t)U.gpool_off + (size_t)rank * (U.pool_max + 1));
+    const uint32_t *pool_desc = A.pool_desc + U.pooldesc_off + U.cta_pool0[rank];
+    const int pool_blocks = U.cta_pool0[rank + 1] - U.cta_pool0[rank];
+    if (threadIdx.x < 4) pool[4 * pool_blocks + threadIdx.x] = 0u;  // the spare block
+    V.pool = pool;
+
+    const bool tracing = lead && A.trace_unit == ui;
+    const int burn = U.burn;
+    const int total = A.iter_cap > 0 && A.iter_cap < U.burn + U.samples ? A.iter_cap : U.burn + U.samples;
+    const int stamp_at = A.iter_cap > 0 ? total >> 1 : -2;  // calibration pass: time the second half only
+    int cur = 0;
+    int32_t *acc = n_cta > 1 ? part : E.counts;
+    __syncthreads();
+
+    // it == -1 is initAssignment (gibbsSampler.cpp:90): the same A-step code on theta == 1, no E-step before it
+    for (int it = -1; it < total; it++) {
+        const uint32_t iter = (uint32_t)(it < 0 ? 0 : it);
+        if (threadIdx.x == 0) {
+            ctl[kCtlQ0] = 0;
+            ctl[kCtlQ0 + 1] = 0;
+            ctl[kCtlQ0 + 2] = 0;
+            if (lead && it == stamp_at) A.unit_clock[3 * ui] = global_ns();
+        }
+        if (it >= 0) {
+            if (tracing && it == 0)
+                for (int t = threadIdx.x; t < T; t += n_threads) A.tr_init[t] = E.counts[t];
+            if (tracing && it > 0 && it - 1 < A.trace_iters)
+                for (int t = threadIdx.x; t < T; t += n_threads) A.tr_counts[(size_t)(it - 1) * T + t] = E.counts[t];
+            const int b = rows_e_step(E, key, iter, it >= burn || (stamp_at >= 0 && it >= stamp_at), rank, n_cta, pool, pool_desc, pool_blocks);
+            if (tracing && it < A.trace_iters) {
+                for (int t = threadIdx.x; t < T; t += n_threads) A.tr_theta[(size_t)it * T + t] = E.theta[t];
+                if (threadIdx.x == 0) A.tr_b[it] = b;
+            }
+        } else {
+            ctl[kCtlNAct] = T;
+            rows_pool_gen(pool, pool_desc, pool_blocks, key, iter, true, 0, n_threads);
+            __syncthreads();
+        }
+        rows_assign(V, E.amask, E.theta, acc);
+        __syncthreads();
+        rows_tree_levels(V, acc, key, iter, it < 0);
+        if (n_cta > 1) {
+            // every CTA adds up the partial counts of all CTAs (distributed shared memory); only members of the simplex got any
+            cluster.sync();
+            const int n_act = ctl[kCtlNAct];
+            for (int i = threadIdx.x; i < n_act; i += n_threads) {
+                const int t = E.act[i];
+                int s = 0;
+                for (int j = 0; j < n_cta; j++) s += cluster.map_shared_rank(part, j)[cur * T + t];
+                E.counts[t] += s;
+            }
+            // the other buffer was read by the other CTAs one iteration ago (before the barrier above): clear it for the next one
+            cur ^= 1;
+            for (int t = threadIdx.x; t < T; t += n_threads) part[cur * T + t] = 0;
+            acc = part + cur * T;
+            __syncthreads();
+        }
+    }
+    if (tracing && total - 1 < A.trace_iters)
+        for (int t = threadIdx.x; t < T; t += n_threads) A.tr_counts[(size_t)(total - 1) * T + t] = E.counts[t];
+
+    const int64_t o = U.out_off[0];
+    for (int t = threadIdx.x; t < T; t += n_threads) {
+        if (t % n_cta == rank) {
+            A.out_occ[o + t] = E.occ[t];
+            A.out_mean[o + t] = E.mean[t];
+            A.out_m2[o + t] = E.m2[t];
+        }
+        if (lead) A.out_counts[o + t] = E.counts[t];
+    }
+    int err = ctl[kCtlErr];
+    if (n_cta > 1) {
+        cluster.sync();
+        if (lead && threadIdx.x == 0)
+            for (int j = 1; j < n_cta; j++) {
+                const int e = cluster.map_shared_rank(ctl, j)[kCtlErr];
+                if (e) err = e;
+            }
+        cluster.sync();  // nobody leaves while its shared memory may still be read
+    }
+    if (lead && threadIdx.x == 0) {
+        A.unit_err[ui] = err;
+        A.unit_clock[3 * ui + 1] = global_ns();
+        A.unit_clock[3 * ui + 2] = sm_id();
+    }
+}
+
+// ---- single A-step in fast mode of a locus with more than 32 candidates: the same device code, one CTA, matrix, scratch and
+// pool in global memory ----
+template <bool INIT>
+__global__ void step_assignment_rows_kernel(const __grid_constant__ KernelArgs A, const double *theta_in, uint32_t iteration, int32_t *counts_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const UnitDev &U = A.units[0];
+    const int T = U.T[0];
+    const int n_words = (T + 63) >> 6;
+    double *theta = (double *)smem;
+    uint64_t *amask = (uint64_t *)(theta + T);
+    int32_t *counts = (int32_t *)(amask + n_words);
+    int *ctl = (int *)(counts + T);
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+        theta[t] = INIT ? 1.0 : theta_in[t];
+        counts[t] = A.base_counts[U.lane_off + t];
+    }
+    if (threadIdx.x < kRowsCtlWords) ctl[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x < 32)
+        for (int w = 0; w < n_words; w++) {
+            const int t0 = w * 64 + (int)threadIdx.x;
+            const uint32_t lo = __ballot_sync(kFull, t0 < T && theta[t0] != 0.0);
+            const uint32_t hi = __ballot_sync(kFull, t0 + 32 < T && theta[t0 + 32] != 0.0);
+            if (threadIdx.x == 0) amask[w] = ((uint64_t)hi << 32) | lo;
+        }
+    const uint64_t key = U.key[0];
+    RowsView V;
+    V.row_begin = U.cta_row0[0];
+    V.row_end = U.cta_row0[1];
+    V.chain_end = V.row_begin + U.cta_chain[0];
+    V.n_words = n_words;
+    V.qcap = U.qcap;
+    V.ctl = ctl;
+    V.val = A.val + U.cell_off;
+    V.rmask = (const uint64_t *)A.row_mask + U.mask_off;
+    V.rcell = A.slab_cell_off + U.slab_off;
+    V.row_n = A.row_n + U.row_off;
+    V.row_info = A.row_info + U.row_off;
+    V.row_woff = A.row_woff + U.woff_off;
+    V.row_base = 0;
+    V.cell_base = 0;
+    V.scr_cum = A.scr_cum + U.scr_off;
+    V.scr_col = A.scr_col + U.scr_off;
+    V.scr_base = 0;
+    V.scr_len = U.n_cells;
+    V.queue = A.queue + U.q_off;
+    uint32_t *pool = A.gpool + 4 * (size_t)U.gpool_off;
+    const int pool_blocks = U.cta_pool0[1] - U.cta_pool0[0];
+    rows_pool_gen(pool, A.pool_desc + U.pooldesc_off + U.cta_pool0[0], pool_blocks, key, iteration, INIT, 0, blockDim.x);
+    if (threadIdx.x < 4) pool[4 * pool_blocks + threadIdx.x] = 0u;
+    V.pool = pool;
+    __syncthreads();
+    rows_assign(V, amask, theta, counts);
+    __syncthreads();
+    rows_tree_levels(V, counts, key, iteration, INIT);
+    __syncthreads();
+    for (int t = threadIdx.x; t < T; t += blockDim.x) counts_out[t] = counts[t];
+    if (threadIdx.x == 0) A.unit_err[0] = ctl[kCtlErr];
+}
+
+int check_rows(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return BAYES_OK;
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return BAYES_E_CUDA;
+}
+
+}  // namespace
+
+int configure_rows_kernels() {
+    int rc;
+    if ((rc = check_rows(cudaFuncSetAttribute(gibbs_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_unit_smem()), "cudaFuncSetAttribute")))
+        return rc;
+    if ((rc = check_rows(cudaFuncSetAttribute(gibbs_rows_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), "non-portable cluster size"))) return rc;
+    if ((rc = check_rows(cudaFuncSetAttribute(step_assignment_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "cudaFuncSetAttribute")))
+        return rc;
+    return check_rows(cudaFuncSetAttribute(step_assignment_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024), "cudaFuncSetAttribute");
+}
+
+// Largest cluster the device can co-schedule for the rows kernel at `block` threads and `smem_bytes` of shared memory per CTA.
+int rows_max_cluster(int block, size_t smem_bytes) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(kMaxCluster, 1, 1);
+    cfg.blockDim = dim3((unsigned)block, 1, 1);
+    cfg.dynamicSmemBytes = smem_bytes;
+    int size = 0;
+    if (cudaOccupancyMaxPotentialClusterSize(&size, gibbs_rows_kernel, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    int p = 1;
+    while (2 * p <= size && 2 * p <= kMaxCluster) p *= 2;
+    return p;
+}
+
+int launch_units_rows(const KernelArgs &args, int64_t unit_base, int64_t n_units, int block, int n_cta, size_t smem_bytes, void *stream) {
+    if (n_units <= 0) return BAYES_OK;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(n_units * n_cta), 1, 1);
+    cfg.blockDim = dim3((unsigned)block, 1, 1);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)n_cta;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return check_rows(cudaLaunchKernelEx(&cfg, gibbs_rows_kernel, args, unit_base), "gibbs rows kernel launch");
+}
+
+int launch_step_assignment_rows(const KernelArgs &args, bool init, const double *d_theta, uint32_t iteration, int32_t *d_counts_out,
+                                size_t smem_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (init) step_assignment_rows_kernel<true><<<1, 128, smem_bytes, st>>>(args, d_theta, iteration, d_counts_out);
+    else step_assignment_rows_kernel<false><<<1, 128, smem_bytes, st>>>(args, d_theta, iteration, d_counts_out);
+    return check_rows(cudaGetLastError(), "step_assignment_rows_kernel launch");
+}
+
+}  // namespace bayes

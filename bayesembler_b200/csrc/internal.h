@@ -22,6 +22,7 @@ constexpr int kMaxT = 4096;             // candidates per locus (per-candidate s
 constexpr int kMaxBlock = 512;          // threads per unit
 constexpr int kWarpsPerSM = 28;         // resident warps per SM at the kernels' 72 registers per thread
 constexpr int kMaxSlots = 16;           // slots per bundle (T = 2 -> Tpad = 2 -> 16 slots)
+constexpr int kMaxCluster = 16;         // CTAs of the thread-block cluster a wide locus may be spread over (fast mode)
 constexpr int kSmallCount = 20;         // assignmentGenerator.cpp:289: rows with fewer fragments draw uniforms
 constexpr int kTableSmemEntries = 2048; // simplex CDF tables up to this many entries are staged in shared memory
 constexpr int kMatrixSmemBytes = 96 * 1024;  // units whose packed matrix exceeds this stream it from L2/HBM
@@ -76,6 +77,13 @@ struct UnitDev {
     int64_t meta_off;       // -> cell_meta (n_cells): candidate lane | head << 5 | (uniform rows: fragments << 6 | pool word << 11;
                             //    chain rows: chain-row ordinal << 6)
     int64_t ctab_off;       // -> chain_tab (3 words per chain row: fragments, slot << 27 | row, first cell of the row)
+    // fast mode, loci with more than 32 candidates: cooperative rows over a thread-block cluster (gibbs_rows.cu).  n_cta > 0
+    // marks such a unit: n_slabs = rows, slab_h = 1 (slab_cell_off = first cell of every row), masks row-major; CTA j of the
+    // cluster owns rows [cta_row0[j], cta_row0[j + 1]), the first cta_chain[j] of them with >= 20 fragments, and the Philox
+    // blocks pool_desc[cta_pool0[j] .. cta_pool0[j + 1]) (row_woff = word within that pool).
+    int32_t n_cta, rows_max, cells_max, ccells_max, pool_max, gpool_pad;
+    int32_t cta_row0[kMaxCluster + 1], cta_chain[kMaxCluster], cta_pool0[kMaxCluster + 1];
+    int64_t gpool_off;      // -> gpool (16-byte blocks), n_cta * (pool_max + 1) per unit whose pool is not in shared memory
     // per slot
     int32_t T[kMaxSlots];
     int32_t N_f[kMaxSlots];      // fragments of the locus (folded rows included)
@@ -112,6 +120,7 @@ struct KernelArgs {
     double *scr_cum;
     uint16_t *scr_col;
     uint32_t *queue;
+    uint32_t *gpool;    // uniform-word pools of the cluster units that do not keep them in shared memory
     int32_t *unit_err;  // per unit: != 0 when a row had no candidate with a non-zero probability (reference: assert, assignmentGenerator.cpp:284)
     // calibration pass (capi.cu, calibrate_units): run only the first iter_cap iterations of every chain and put the
     // time stamp of iteration iter_cap / 2 in the "start" word, so that end - start times the second half; 0 = off
@@ -187,6 +196,7 @@ int validate_locus(const bayes_locus_desc &in, std::string *err);
 int prepare_locus(const bayes_locus_desc &in, PreLocus *out, std::string *err);
 int slot_lanes(int T);  // Tpad of a bundle slot (power of two >= T), 0 when T > 32
 void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, bool fast, PackedUnit *out);
+void pack_unit_rows(const std::vector<SlotRef> &slots, int n_cta, PackedUnit *out);  // fast mode, T > 32 (gibbs_rows.cu)
 extern bool g_tile_stream;  // fast mode: bundles stream their tiles from global memory (L2) instead of staging them in shared memory
 int tree_chunks(int n);   // fast mode: independent chunks a row with n >= 20 fragments enters its splitting tree in (<= 64 fragments each while that takes at most 32 chunks, else the row enters whole)
 size_t max_unit_smem();  // dynamic shared memory a unit may use (opt-in limit of the device, 227 KB on sm_100)
@@ -204,6 +214,12 @@ int launch_units_fast(const KernelArgs &args, int64_t unit_base, int64_t n_units
 int launch_step_assignment_fast(const KernelArgs &args, bool init, bool tiles, const double *d_theta, uint32_t iteration, int32_t *d_counts_out,
                                 size_t smem_bytes, void *stream);
 int configure_fast_kernels();
+// gibbs_rows.cu
+int launch_units_rows(const KernelArgs &args, int64_t unit_base, int64_t n_units, int block, int n_cta, size_t smem_bytes, void *stream);
+int launch_step_assignment_rows(const KernelArgs &args, bool init, const double *d_theta, uint32_t iteration, int32_t *d_counts_out,
+                                size_t smem_bytes, void *stream);
+int configure_rows_kernels();
+int rows_max_cluster(int block, size_t smem_bytes);  // largest power-of-two cluster the device co-schedules for the rows kernel at this footprint (1 when clusters are unavailable)
 int launch_stagger(unsigned ns, void *stream);
 int launch_step_assignment(const KernelArgs &args, bool init, const double *d_theta, uint32_t iteration, int32_t *d_counts_out,
                            size_t smem_bytes, void *stream);

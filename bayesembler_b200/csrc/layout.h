@@ -153,4 +153,56 @@ BAYES_LAYOUT_HD TileLayout tile_layout(int n_slots, int Tpad, int n_tiles, int n
     return L;
 }
 
+// ---- fast mode, loci with more than 32 candidates: cooperative rows over a thread-block cluster (gibbs_rows.cu) ----------
+// Every CTA of the cluster keeps the per-candidate state (the E-step is replicated), its own share of the rows (matrix
+// values, candidate masks, row table: `mat`), the scratch lists / task queues of its rows with >= 20 fragments (`scr`),
+// its pool of uniform words (`pool`) and, in a cluster of more than one CTA, two buffers of partial counts that the
+// other CTAs read through distributed shared memory.
+struct RowsLayout {
+    uint32_t theta, den, mean, m2, val, rmask, scr_cum, amask, norm;          // 8-byte
+    uint32_t pool;                                                           // 16-byte
+    uint32_t counts, base, occ, part, mask, actoff, rcell, row_n, row_info, row_woff, pool_desc, queue, ctl;  // 4-byte
+    uint32_t scr_col, act;                                                   // 2-byte
+    uint32_t total;
+};
+
+constexpr int kRowsCtlWords = 16;
+
+BAYES_LAYOUT_HD RowsLayout rows_layout(int T, int n_cta, int rows_max, int cells_max, int ccells_max, int qcap, int pool_blocks,
+                                       bool mat, bool scr, bool pool) {
+    RowsLayout L;
+    const uint32_t uT = (uint32_t)T, nch = (uT + 31u) / 32u, nw = (uT + 63u) / 64u;
+    const uint32_t rows = mat ? (uint32_t)rows_max : 0u, cells = mat ? (uint32_t)cells_max : 0u, cc = scr ? (uint32_t)ccells_max : 0u;
+    uint32_t o = 0;
+    L.theta = o; o += 8u * uT;
+    L.den = o; o += 8u * uT;
+    L.mean = o; o += 8u * uT;
+    L.m2 = o; o += 8u * uT;
+    L.val = o; o += 8u * cells;
+    L.rmask = o; o += 8u * rows * nw;
+    L.scr_cum = o; o += 8u * cc;
+    L.amask = o; o += 8u * nw;
+    L.norm = o; o += 8u;
+    o = (o + 15u) & ~15u;
+    L.pool = o; o += pool ? 16u * ((uint32_t)pool_blocks + 1u) : 0u;  // one spare block: a row reads its words four at a time
+    L.counts = o; o += 4u * uT;
+    L.base = o; o += 4u * uT;
+    L.occ = o; o += 4u * uT;
+    L.part = o; o += n_cta > 1 ? 8u * uT : 0u;
+    L.mask = o; o += 4u * (2u * nch + 2u);
+    L.actoff = o; o += 4u * (nch + 2u);
+    L.rcell = o; o += mat ? 4u * (rows + 1u) : 0u;
+    L.row_n = o; o += 4u * rows;
+    L.row_info = o; o += 4u * rows;
+    L.row_woff = o; o += 4u * rows;
+    L.pool_desc = o;  // (read from global memory: once per iteration, behind the null-candidate selection)
+    L.queue = o; o += scr ? 24u * (uint32_t)qcap : 0u;  // two buffers of three words per task
+    L.ctl = o; o += 4u * (uint32_t)kRowsCtlWords;
+    L.scr_col = o; o += 2u * cc;
+    o = (o + 1u) & ~1u;
+    L.act = o; o += 2u * uT;
+    L.total = (o + 15u) & ~15u;
+    return L;
+}
+
 }  // namespace bayes

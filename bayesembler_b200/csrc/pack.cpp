@@ -433,4 +433,100 @@ void pack_unit(const std::vector<SlotRef> &slots, bool wide, int slab_h, bool fa
     d.block = 32;  // build_units decides
 }
 
+// Fast mode, locus with more than 32 candidates: cooperative rows over a thread-block cluster (gibbs_rows.cu).  Row-major
+// matrix (values only: the candidate of a cell is the position of its bit in the row's candidate mask), row-major masks.
+// The rows are dealt over the n_cta CTAs of the cluster (rows with >= 20 fragments first, wider rows first, round robin:
+// every CTA gets the same mix), and stored CTA by CTA so that a CTA's share is one contiguous block it can keep resident in
+// its shared memory.  Every CTA has its own pool of uniform words: the Philox blocks its rows with < 20 fragments touch, row
+// after row (a block shared by two rows is generated twice, which is cheaper than sharing it across CTAs).
+void pack_unit_rows(const std::vector<SlotRef> &slots, int n_cta, PackedUnit *out) {
+    PackedUnit &U = *out;
+    U = PackedUnit();
+    const PreLocus &L = *slots[0].locus;
+    const int T = L.T;
+    std::vector<ItemShape> items;
+    int n_chain = 0;
+    build_items(slots, &items, &n_chain);
+    const int n_items = (int)items.size();
+    n_cta = std::max(1, std::min(n_cta, kMaxCluster));
+    std::vector<std::vector<int> > mine(n_cta);
+    std::vector<int> chain_of(n_cta, 0);
+    for (int i = 0; i < n_chain; i++) { mine[i % n_cta].push_back(i); chain_of[i % n_cta]++; }
+    for (int i = n_chain; i < n_items; i++) mine[(i - n_chain) % n_cta].push_back(i);
+    const int n_words = (T + 63) / 64;
+    UnitDev &d = U.d;
+    U.slab_cell_off.assign(1, 0);
+    U.row_mask.assign((size_t)n_items * n_words * 2, 0u);
+    int rows_max = 0, cells_max = 0, ccells_max = 0, pool_max = 0;
+    int64_t qcap_max = 1;
+    int row = 0;
+    for (int j = 0; j < n_cta; j++) {
+        d.cta_row0[j] = row;
+        d.cta_chain[j] = chain_of[j];
+        d.cta_pool0[j] = (int32_t)U.pool_desc.size();
+        const int cell_first = U.slab_cell_off.back();
+        int ccells = 0;
+        int64_t qcap = 0;
+        for (size_t q = 0; q < mine[j].size(); q++, row++) {
+            const ItemShape &it = items[mine[j][q]];
+            U.row_n.push_back(it.n);
+            U.row_nnz.push_back((int32_t)((uint32_t)it.nnz | ((uint32_t)it.blocks << kItemBlockShift) | ((uint32_t)(it.chain ? 1 : 0) << kItemChainShift)));
+            U.row_info.push_back((uint32_t)L.row_id[it.r]);
+            int32_t woff = 0;
+            if (it.chain) {
+                qcap += (int64_t)tree_chunks(it.n) * std::max(1, it.nnz / 2);  // nodes of the deepest tree level with two or more cells, per chunk
+                ccells += it.nnz;
+            } else {
+                const int64_t w0 = L.row_woff[it.r], b0 = w0 / 4, b1 = (w0 + it.n - 1) / 4;
+                woff = (int32_t)(4 * ((int64_t)U.pool_desc.size() - d.cta_pool0[j]) + (w0 & 3));
+                for (int64_t b = b0; b <= b1; b++) U.pool_desc.push_back((uint32_t)b);
+            }
+            U.row_woff.push_back(woff);
+            for (int k = 0; k < it.nnz; k++) {
+                const int c = L.cell_col[L.row_ptr[it.r] + k];
+                U.val.push_back(L.cell_val[L.row_ptr[it.r] + k]);
+                U.row_mask[2 * ((size_t)row * n_words + (c >> 6)) + ((c >> 5) & 1)] |= 1u << (c & 31);
+            }
+            U.slab_cell_off.push_back((int32_t)U.val.size());
+        }
+        rows_max = std::max(rows_max, (int)mine[j].size());
+        cells_max = std::max(cells_max, U.slab_cell_off.back() - cell_first);
+        ccells_max = std::max(ccells_max, ccells);
+        pool_max = std::max(pool_max, (int)U.pool_desc.size() - d.cta_pool0[j]);
+        qcap_max = std::max(qcap_max, qcap);
+    }
+    for (int j = n_cta; j <= kMaxCluster; j++) d.cta_row0[j] = row;
+    for (int j = n_cta; j < kMaxCluster; j++) d.cta_chain[j] = 0;
+    for (int j = n_cta; j <= kMaxCluster; j++) d.cta_pool0[j] = (int32_t)U.pool_desc.size();
+    pack_slots(slots, true, T, T, U);
+    d.pool_first[0] = 0;
+    d.n_cta = n_cta;
+    d.n_slabs = n_items;
+    d.slab_h = 1;
+    d.n_cells = (int32_t)U.val.size();
+    d.n_chain_slabs = 0;
+    d.n_chain_cells = d.n_cells;  // entries of the global scratch lists of a unit that does not keep them in shared memory
+    d.qcap = (int32_t)qcap_max;
+    d.pool_blocks = (int32_t)U.pool_desc.size();
+    d.rows_max = rows_max;
+    d.cells_max = cells_max;
+    d.ccells_max = ccells_max;
+    d.pool_max = pool_max;
+    // Shared memory, in the order it pays: the scratch lists and task queues of the splitting trees (random access on the
+    // critical path), the pool of uniform words, then the matrix itself (streamed reads; L2 serves them otherwise).
+    const size_t limit = max_unit_smem();
+    auto total = [&](bool mat, bool scr, bool pool) -> size_t {
+        return rows_layout(T, n_cta, rows_max, cells_max, ccells_max, d.qcap, pool_max, mat, scr, pool).total;
+    };
+    bool scr = total(false, true, false) <= limit;
+    bool pool = total(false, scr, true) <= limit;
+    bool mat = total(true, scr, pool) <= limit;
+    d.tab_smem = 0;
+    d.mat_smem = mat;
+    d.scr_smem = scr;
+    d.pool_smem = pool;
+    d.smem_bytes = (int32_t)total(mat, scr, pool);
+    d.block = 32;  // build_units decides
+}
+
 }  // namespace bayes

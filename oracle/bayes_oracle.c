@@ -209,8 +209,7 @@ int orc_init_assignment(const orc_locus *loc, int rng_mode, uint64_t seed, int *
  * reference's sequential order of draws (outside replay the sampler may pick any exact
  * multinomial per row).  Per row i with n fragments, over its stored non-zero cells in ascending column order:
  *   p_j = P_ij * theta_j (init: theta == 1); the cells IN PLAY are those with p_j > 0, their running sums
- *   cum_1 < ... < cum_k, Z = the sum of the row (T > 32: summed left to right; T <= 32: in the order of a warp scan,
- *   see below);
+ *   cum_1 < ... < cum_k, Z = the sum of the row (in the order of the product's warp scans, see below);
  *   rows with a single stored non-zero cell give it everything (whatever theta is: they are folded by the packer);
  *   k == 1: everything goes to that cell;
  *   n < 20 (the reference's threshold, :289): the row owns n consecutive 32-bit words of the iteration's word
@@ -286,10 +285,28 @@ static int assignment_fast(const orc_locus *L, const double *theta, orc_ws *ws, 
                 if (live[j]) { cum[kk] = x[j]; cell_col[kk] = cc[j]; kk++; }
             run = m > 0 ? x[m - 1] : 0.0; /* the row sum is the scan's value at the row's last stored cell */
         } else {
-            for (int k = beg; k < end; k++) {
-                if (L->val[k] == 0.0) continue;
-                const double p = L->val[k] * (init ? 1.0 : theta[L->col_idx[k]]);
-                if (p > 0.0) { run += p; cum[kk] = run; cell_col[kk] = L->col_idx[k]; kk++; }
+            /* Loci with more than 32 candidates (gibbs_rows.cu, one warp per row): the lanes hold the row's stored cells whose
+             * candidate is in the simplex (theta != 0), 32 at a time, in ascending candidate order within every block of 2048
+             * candidates; a chunk of 32 is summed by a warp-shuffle inclusive scan (distances 1, 2, 4, 8, 16), the chunks are
+             * chained left to right: cum = (sum of the chunks before) + (scan value inside the chunk). */
+            int k = beg;
+            while (k < end) {
+                double x[32];
+                int cc[32], live[32], m = 0;
+                const int block = L->col_idx[k] >> 11;
+                for (; k < end && m < 32 && (L->col_idx[k] >> 11) == block; k++) {
+                    if (L->val[k] == 0.0) continue;
+                    if (!init && theta[L->col_idx[k]] == 0.0) continue;
+                    cc[m] = L->col_idx[k];
+                    x[m++] = L->val[k] * (init ? 1.0 : theta[L->col_idx[k]]);
+                }
+                if (m == 0) continue;
+                for (int j = 0; j < m; j++) live[j] = x[j] > 0.0;
+                for (int d = 1; d < 32; d <<= 1)
+                    for (int j = m - 1; j >= d; j--) x[j] += x[j - d];
+                for (int j = 0; j < m; j++)
+                    if (live[j]) { cum[kk] = run + x[j]; cell_col[kk] = cc[j]; kk++; }
+                run = run + x[m - 1];
             }
         }
         const uint64_t my_words = pool_at;

@@ -273,3 +273,33 @@ def test_concurrent_submit(lib, oracle):
             o = oracle.run_sampler(loci[base + j], burn, samples, FAST, lib.chain_key(seeds[base + j], 0))  # default mode
             assert np.array_equal(g["occ"], o["occ"]), (first, j)
     ctx.close()
+
+
+@pytest.mark.parametrize("n_cta", [1, 2, 4, 8, 16])
+@pytest.mark.parametrize("T,R,mc", [(70, 90, 300), (300, 700, 40), (1000, 400, 120), (2500, 150, 60)])
+def test_cluster_rows_full_chain(lib, oracle, monkeypatch, T, R, mc, n_cta):
+    """Loci with more than 32 candidates in the production mode (gibbs_rows.cu): rows dealt over the CTAs of a thread-block
+    cluster, replicated E-step, partial counts summed through distributed shared memory.  Whatever the cluster size, every
+    draw, every count and every theta of the whole chain equal the oracle's."""
+    monkeypatch.setenv("BAYES_FORCE_CTAS", str(n_cta))
+    rng = np.random.default_rng(T * 7 + R)
+    loc = random_locus(rng, T, R, max_count=mc)
+    seed = int(rng.integers(1, 2 ** 62))
+    burn, samples = 40, 360
+    total = burn + samples
+    ctx = lib.GibbsContext(0, mode="fast")
+    ctx.submit(lib.make_desc_array([loc], [burn], [samples], [seed]))
+    ctx.set_trace(0, 0, total)
+    ctx.upload(); ctx.run(); ctx.download(); ctx.sync()
+    g = ctx.fetch(0)
+    tr = ctx.fetch_trace()
+    ctx.close()
+    o = oracle.run_sampler(loc, burn, samples, FAST, lib.chain_key(seed, 0), trace_iters=total)
+    assert np.array_equal(tr["init_counts"], o["init_counts"])
+    assert np.array_equal(tr["b_trace"], o["b_trace"])
+    assert np.array_equal(tr["counts_trace"], o["counts_trace"])
+    np.testing.assert_allclose(tr["theta_trace"], o["theta_trace"], rtol=RTOL, atol=0)
+    assert np.array_equal(g["occ"], o["occ"])
+    np.testing.assert_allclose(g["mean"], o["mean"], rtol=RTOL)
+    np.testing.assert_allclose(g["m2"], o["m2"], rtol=1e-7, atol=1e-9 * np.abs(o["mean"]).max() ** 2)
+    assert np.array_equal(g["final_counts"], o["counts_trace"][-1])
