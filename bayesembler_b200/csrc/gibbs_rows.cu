@@ -113,137 +113,233 @@ __device__ __forceinline__ void push_tasks(const RowsView &V, int cnt, int buf, 
 // ------------------------------------------------------------------------------------------------------------------
 // A-step, first part: one warp per row.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void rows_assign(const RowsView &V, const uint64_t *amask, const double *theta, int32_t *acc) {
+// One group of 32 mask words (32 bits each: 1024 candidates) of a row, one word per lane.
+struct MaskGroup {
+    uint32_t m_all, m;  // my word: the candidates the row has a cell for; those of them in the simplex (= the cells in play)
+    uint32_t excl;      // stored cells before my word << 16 | cells in play before my word, within the group
+    int kbase;          // stored cells of the row before this group
+    int w0;             // first word of the group
+    int Kg, stored;     // cells in play / stored cells of the group
+};
+
+__device__ __forceinline__ MaskGroup mask_group(uint32_t m_all, uint32_t m, int w0, int kbase, int lane) {
+    MaskGroup G;
+    G.m_all = m_all;
+    G.m = m;
+    const uint32_t pk = ((uint32_t)__popc(m_all) << 16) | (uint32_t)__popc(m);
+    uint32_t incl = pk;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(kFull, incl, d);
+        if (lane >= d) incl += up;
+    }
+    const uint32_t tot = __shfl_sync(kFull, incl, 31);
+    G.excl = incl - pk;
+    G.kbase = kbase;
+    G.w0 = w0;
+    G.Kg = (int)(tot & 0xffffu);
+    G.stored = (int)(tot >> 16);
+    return G;
+}
+
+// Round j0 of a group: lane l takes the (j0 + l)-th cell in play of the group; returns p = P_ij theta_j and the candidate.
+__device__ __forceinline__ double round_p(const MaskGroup &G, int j0, int lane, const double *val, const double *theta, int &c) {
+    const int j = j0 + lane;
+    // the word my cell sits in: the last lane whose first cell in play is not after mine
+    const int my_jb = (int)(G.excl & 0xffffu);
+    int l = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+        const int jb = __shfl_sync(kFull, my_jb, l + step);
+        if (jb <= j) l += step;
+    }
+    const uint32_t ms = __shfl_sync(kFull, G.m, l), mas = __shfl_sync(kFull, G.m_all, l), ex = __shfl_sync(kFull, G.excl, l);
+    double p = 0.0;
+    c = 0;
+    if (j < G.Kg) {
+        const int bit = (int)__fns(ms, 0, j - (int)(ex & 0xffffu) + 1);
+        const int k = G.kbase + (int)(ex >> 16) + __popc(mas & ((1u << bit) - 1u));
+        c = ((G.w0 + l) << 5) + bit;
+        p = val[k] * theta[c];
+    }
+    return p;
+}
+
+// inclusive scan over the lanes (the order of these additions is part of the mode's definition: the oracle sums alike)
+__device__ __forceinline__ double warp_scan(double x, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double up = __shfl_up_sync(kFull, x, d);
+        if (lane >= d) x += up;
+    }
+    return x;
+}
+
+// Rows with < 20 fragments: where the row's n pool words land among the cells in play of one round (bal != 0).  Cell i of
+// the row takes the words w with cum_(i-1) / Z <= w 2^-32 < cum_i / Z, the last cell in play what the others left.
+__device__ __forceinline__ void round_thresholds(double cum, int c, uint32_t bal, int kk, int kk_total, double rZ, int n, const uint32_t *pw, int32_t *acc,
+                                                 int &below_carry, int lane, uint32_t lt) {
+    const bool inplay = (bal >> lane) & 1u;
+    const int pos = kk + __popc(bal & lt);
+    int below = 0;
+    if (inplay) {
+        if (pos == kk_total - 1) {
+            below = n;
+        } else {
+            // word * 2^-32 < cum / Z  <=>  word <= ceil(cum (1/Z) 2^32 - 1); the conversion saturates
+            const uint32_t t = __double2uint_ru(__fma_rn(cum * rZ, 4294967296.0, -1.0));
+            for (int b = 0; b < n; b += 4) {
+                const u32x4 wv = {pw[b], pw[b + 1], pw[b + 2], pw[b + 3]};
+                below += words_below(wv, n - b < 4 ? n - b : 4, t);
+            }
+        }
+    }
+    const uint32_t lower = bal & lt;
+    int prev = __shfl_sync(kFull, below, lower ? 31 - __clz(lower) : 0);
+    if (!lower) prev = below_carry;
+    if (inplay && below > prev) atomicAdd(&acc[c], below - prev);
+    below_carry = __shfl_sync(kFull, below, 31 - __clz(bal));
+}
+
+constexpr int kRowsCachedRounds = 3;  // rows with < 20 fragments and up to 96 cells in play keep their running sums in registers
+
+__device__ __forceinline__ void rows_assign(const RowsView &V, const uint64_t *amask64, const double *theta, int32_t *acc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     const uint32_t lt = lanemask_lt();
-    const int n_words = V.n_words;
-    for (int r = V.row_begin + warp; r < V.row_end; r += n_warps) {
+    const int n_w32 = 2 * V.n_words;
+    const uint32_t *amask = (const uint32_t *)amask64;
+    // the row after this one: its table entries and first mask words are on their way while this one is worked on
+    int r = V.row_begin + warp;
+    int nx_n = 0, nx_cell0 = 0, nx_woff = 0;
+    uint32_t nx_mall = 0u;
+    if (r < V.row_end) {
         const int ri = r - V.row_base;
-        const int n = V.row_n[ri];
-        const int cell0 = V.rcell[ri];
+        nx_n = V.row_n[ri];
+        nx_cell0 = V.rcell[ri];
+        nx_woff = V.row_woff[ri];
+        if (lane < n_w32) nx_mall = ((const uint32_t *)(V.rmask + (size_t)ri * V.n_words))[lane];
+    }
+    for (; r < V.row_end; r += n_warps) {
+        const int ri = r - V.row_base;
+        const int n = nx_n, cell0 = nx_cell0;
+        const uint32_t *pw = V.pool + nx_woff;
+        const uint32_t mall0 = nx_mall;
+        if (r + n_warps < V.row_end) {
+            const int rj = ri + n_warps;
+            nx_n = V.row_n[rj];
+            nx_cell0 = V.rcell[rj];
+            nx_woff = V.row_woff[rj];
+            if (lane < n_w32) nx_mall = ((const uint32_t *)(V.rmask + (size_t)rj * V.n_words))[lane];
+        }
         const bool chain = r < V.chain_end;
         const double *val = V.val + (cell0 - V.cell_base);
-        const uint64_t *rm = V.rmask + (size_t)ri * n_words;
-        const int sb = cell0 - V.scr_base;
-        const int w_row = chain ? 0 : V.row_woff[ri];
-        double rZ = 0.0;
-        int kk_total = 0;
-        bool second = false;
-        // A row with < 20 fragments whose cells in play do not fit one round of 32 is walked twice: once for its sum, once
-        // (the same arithmetic again) for the thresholds.
-        for (;;) {
+        const uint32_t *rm = (const uint32_t *)(V.rmask + (size_t)ri * V.n_words);
+        MaskGroup G = mask_group(mall0, lane < n_w32 ? mall0 & amask[lane] : 0u, 0, 0, lane);
+        if (chain) {
+            // rows with >= 20 fragments: the running sums of the cells in play go to the row's scratch list, the splitting tree
+            // (rows_tree_levels) works on that list
+            const int sb = cell0 - V.scr_base;
             double carry = 0.0;
-            int kk = 0, kbase_grp = 0, below_carry = 0, c_only = 0;
-            bool done = false;
-            for (int w0 = 0; w0 < n_words; w0 += 32) {
-                const int w = w0 + lane;
-                uint64_t m_all = 0ull, m = 0ull;
-                if (w < n_words) {
-                    m_all = rm[w];
-                    m = m_all & amask[w];
-                }
-                // ranks: stored cells before my word (high half), cells in play before my word (low half)
-                const uint32_t pk = ((uint32_t)__popcll(m_all) << 16) | (uint32_t)__popcll(m);
-                uint32_t incl = pk;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t up = __shfl_up_sync(kFull, incl, d);
-                    if (lane >= d) incl += up;
-                }
-                const uint32_t tot = __shfl_sync(kFull, incl, 31), excl = incl - pk;
-                const int Kg = (int)(tot & 0xffffu);
-                const int my_kbase = kbase_grp + (int)(excl >> 16), my_jbase = (int)(excl & 0xffffu);
-                const bool single = !chain && !second && n_words <= 32 && Kg <= 32;
-                for (int j0 = 0; j0 < Kg; j0 += 32) {
-                    const int j = j0 + lane;
-                    const bool valid = j < Kg;
-                    // the word my cell sits in: the last lane whose first cell in play is not after mine
-                    int l = 0;
-#pragma unroll
-                    for (int step = 16; step > 0; step >>= 1) {
-                        const int jb = __shfl_sync(kFull, my_jbase, l + step);
-                        if (jb <= j) l += step;
-                    }
-                    const uint64_t ms = __shfl_sync(kFull, m, l), mas = __shfl_sync(kFull, m_all, l);
-                    const int kb = __shfl_sync(kFull, my_kbase, l), jb = __shfl_sync(kFull, my_jbase, l);
-                    int c = 0;
-                    double p = 0.0;
-                    if (valid) {
-                        const int bit = nth_set_bit64(ms, j - jb);
-                        const int k = kb + __popcll(mas & ((1ull << bit) - 1ull));
-                        c = ((w0 + l) << 6) + bit;
-                        ROWS_CHECK(cell0 + k < V.rcell[ri + 1], 202);
-                        p = val[k] * theta[c];
-                    }
-                    // inclusive scan of the chunk; chunks are chained left to right (the oracle sums in this order)
-                    double x = p;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const double up = __shfl_up_sync(kFull, x, d);
-                        if (lane >= d) x += up;
-                    }
-                    const double cum = carry + x;
-                    const int last = Kg - 1 - j0 < 31 ? Kg - 1 - j0 : 31;
-                    carry = __shfl_sync(kFull, cum, last);
+            int kk = 0, c_only = 0;
+            for (int w0 = 0;;) {
+                for (int j0 = 0; j0 < G.Kg; j0 += 32) {
+                    int c;
+                    const double p = round_p(G, j0, lane, val, theta, c);
+                    const double cum = carry + warp_scan(p, lane);
+                    carry = __shfl_sync(kFull, cum, G.Kg - 1 - j0 < 31 ? G.Kg - 1 - j0 : 31);
                     const bool inplay = p > 0.0;
                     const uint32_t bal = __ballot_sync(kFull, inplay);
-                    const int pos = kk + __popc(bal & lt);
-                    if (chain) {
-                        if (inplay) {
-                            ROWS_CHECK(sb + pos >= 0 && sb + pos < V.scr_len, 203);
-                            V.scr_cum[sb + pos] = cum;
-                            V.scr_col[sb + pos] = (uint16_t)c;
-                        }
-                        if (bal) c_only = __shfl_sync(kFull, c, 31 - __clz(bal));
-                    } else if (second || single) {
-                        if (single) {
-                            rZ = __drcp_rn(carry);
-                            kk_total = __popc(bal);
-                        }
-                        int below = 0;
-                        if (inplay) {
-                            if (pos == kk_total - 1) {
-                                below = n;  // the last cell in play takes what the others left
-                            } else {
-                                // word * 2^-32 < cum / Z  <=>  word <= ceil(cum (1/Z) 2^32 - 1); the conversion saturates
-                                const uint32_t t = __double2uint_ru(__fma_rn(cum * rZ, 4294967296.0, -1.0));
-                                for (int b = 0; b < n; b += 4) {
-                                    const uint32_t *pw = V.pool + w_row + b;
-                                    const u32x4 wv = {pw[0], pw[1], pw[2], pw[3]};
-                                    below += words_below(wv, n - b < 4 ? n - b : 4, t);
-                                }
-                            }
-                        }
-                        const uint32_t lower = bal & lt;
-                        int prev = __shfl_sync(kFull, below, lower ? 31 - __clz(lower) : 0);
-                        if (!lower) prev = below_carry;
-                        if (inplay && below > prev) atomicAdd(&acc[c], below - prev);
-                        if (bal) below_carry = __shfl_sync(kFull, below, 31 - __clz(bal));
-                        done = true;
+                    if (inplay) {
+                        const int at = sb + kk + __popc(bal & lt);
+                        ROWS_CHECK(at >= 0 && at < V.scr_len, 203);
+                        V.scr_cum[at] = cum;
+                        V.scr_col[at] = (uint16_t)c;
                     }
+                    if (bal) c_only = __shfl_sync(kFull, c, 31 - __clz(bal));
                     kk += __popc(bal);
                 }
-                kbase_grp += (int)(tot >> 16);
+                w0 += 32;
+                if (w0 >= n_w32) break;
+                const int w = w0 + lane;
+                const uint32_t ma = w < n_w32 ? rm[w] : 0u;
+                G = mask_group(ma, w < n_w32 ? ma & amask[w] : 0u, w0, G.kbase + G.stored, lane);
             }
             if (kk == 0) {  // reference: assert(normalisation_constant >= double_underflow) (assignmentGenerator.cpp:284)
                 if (lane == 0) V.ctl[kCtlErr] = 1;
-                break;
+            } else if (kk == 1) {
+                if (lane == 0) atomicAdd(&acc[c_only], n);
+            } else {
+                // the row's fragments enter the tree as independent chunks of at most 64 (rows above 2048 fragments whole)
+                const int mch = n <= 2048 ? (n + 63) >> 6 : 1;
+                push_tasks(V, kCtlQ0, 0, lane < mch, (uint32_t)(n / mch + (lane < n % mch)), ((uint32_t)(kk - 1) << 12) | ((uint32_t)lane << 24),
+                           (uint32_t)r);
             }
-            if (chain) {
-                if (kk == 1) {
-                    if (lane == 0) atomicAdd(&acc[c_only], n);
-                } else {
-                    // the row's fragments enter the tree as independent chunks of at most 64 (rows above 2048 fragments whole)
-                    const int mch = n <= 2048 ? (n + 63) >> 6 : 1;
-                    push_tasks(V, kCtlQ0, 0, lane < mch, (uint32_t)(n / mch + (lane < n % mch)), ((uint32_t)(kk - 1) << 12) | ((uint32_t)lane << 24),
-                               (uint32_t)r);
+            continue;
+        }
+        if (n_w32 <= 32 && G.Kg <= 32 * kRowsCachedRounds) {
+            // the usual row: a few tens of cells in play; their running sums stay in registers until the row sum is known
+            double cum[kRowsCachedRounds];
+            int cc[kRowsCachedRounds];
+            uint32_t bal[kRowsCachedRounds];
+            double carry = 0.0;
+            int kk_total = 0;
+#pragma unroll
+            for (int rd = 0; rd < kRowsCachedRounds; rd++) {
+                cum[rd] = 0.0;
+                cc[rd] = 0;
+                bal[rd] = 0u;
+                if (rd * 32 < G.Kg) {
+                    const double p = round_p(G, rd * 32, lane, val, theta, cc[rd]);
+                    cum[rd] = carry + warp_scan(p, lane);
+                    carry = __shfl_sync(kFull, cum[rd], G.Kg - 1 - rd * 32 < 31 ? G.Kg - 1 - rd * 32 : 31);
+                    bal[rd] = __ballot_sync(kFull, p > 0.0);
+                    kk_total += __popc(bal[rd]);
                 }
+            }
+            if (kk_total == 0) {
+                if (lane == 0) V.ctl[kCtlErr] = 1;
+                continue;
+            }
+            const double rZ = __drcp_rn(carry);
+            int kk = 0, below_carry = 0;
+#pragma unroll
+            for (int rd = 0; rd < kRowsCachedRounds; rd++)
+                if (bal[rd]) {
+                    round_thresholds(cum[rd], cc[rd], bal[rd], kk, kk_total, rZ, n, pw, acc, below_carry, lane, lt);
+                    kk += __popc(bal[rd]);
+                }
+            continue;
+        }
+        // a row with more cells in play than that (the first iterations, when the simplex still holds most candidates) is walked
+        // twice: once for its sum, once -- the same arithmetic again -- for the thresholds
+        double rZ = 0.0;
+        int kk_total = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            double carry = 0.0;
+            int kk = 0, below_carry = 0;
+            if (pass == 1) G = mask_group(mall0, lane < n_w32 ? mall0 & amask[lane] : 0u, 0, 0, lane);
+            for (int w0 = 0;;) {
+                for (int j0 = 0; j0 < G.Kg; j0 += 32) {
+                    int c;
+                    const double p = round_p(G, j0, lane, val, theta, c);
+                    const double cum = carry + warp_scan(p, lane);
+                    carry = __shfl_sync(kFull, cum, G.Kg - 1 - j0 < 31 ? G.Kg - 1 - j0 : 31);
+                    const uint32_t bal = __ballot_sync(kFull, p > 0.0);
+                    if (pass == 1 && bal) round_thresholds(cum, c, bal, kk, kk_total, rZ, n, pw, acc, below_carry, lane, lt);
+                    kk += __popc(bal);
+                }
+                w0 += 32;
+                if (w0 >= n_w32) break;
+                const int w = w0 + lane;
+                const uint32_t ma = w < n_w32 ? rm[w] : 0u;
+                G = mask_group(ma, w < n_w32 ? ma & amask[w] : 0u, w0, G.kbase + G.stored, lane);
+            }
+            if (kk == 0) {
+                if (lane == 0) V.ctl[kCtlErr] = 1;
                 break;
             }
-            if (done) break;
             rZ = __drcp_rn(carry);
             kk_total = kk;
-            second = true;
         }
     }
 }
@@ -301,6 +397,30 @@ __device__ __forceinline__ void rows_tree_levels(const RowsView &V, int32_t *acc
         nxt = t;
         buf ^= 1;
     }
+}
+
+// FixedBinomialFixedGammaSimplexSizeGenerator::sampleSimplexSize (simplexSizeGenerator.cpp:214-224) by a whole warp: the
+// table lives in global memory (L2), so instead of ten dependent probes the 32 lanes probe 32 evenly spaced entries at once.
+// Same result as sample_simplex (gibbs_common.cuh): first entry of the CDF row of |S+| that exceeds the uniform.
+__device__ __forceinline__ int sample_simplex_warp(const double *tab_val, const int32_t *tab_row, int n_plus, uint64_t key, uint32_t iteration, int lane) {
+    const double u = u01(make_site(key, PH_SIMPLEX, iteration, 0, 0).block(0).x);
+    if (n_plus < 1) n_plus = 1;  // only after fragments were lost to a flagged error (BAYES_E_NUMERIC): stay inside the table
+    int lo = tab_row[n_plus - 1], hi = tab_row[n_plus];
+    const int first = lo;
+    while (lo < hi) {
+        const int step = (hi - lo + 31) >> 5;
+        const int idx = lo + (lane + 1) * step - 1;
+        const bool above = idx < hi ? u < tab_val[idx] : true;
+        const int f = __ffs(__ballot_sync(kFull, above)) - 1;  // lane 31 probes at or beyond the end: some lane always answers
+        const int idx_f = lo + (f + 1) * step - 1;
+        lo += f * step;
+        hi = idx_f < hi ? idx_f : hi;
+        if (step == 1) {
+            lo = hi;
+            break;
+        }
+    }
+    return (lo - first) + n_plus;
 }
 
 // the iteration's uniform words of this CTA's rows: block b of the CTA's pool = Philox block (desc & 0xffffff) of the locus' pool
@@ -372,7 +492,7 @@ __device__ __forceinline__ int rows_e_step(const RowsState &E, const uint64_t ke
         }
         for (int o = 16; o > 0; o >>= 1) plus += __shfl_xor_sync(kFull, plus, o);
         const int n_plus = plus;
-        const int b = sample_simplex(E.tab_val, E.tab_row, n_plus, key, iteration);
+        const int b = sample_simplex_warp(E.tab_val, E.tab_row, n_plus, key, iteration, lane);
         const int n_null = T - n_plus, n_pick = b - n_plus;
         int incl = cnt;
 #pragma unroll

@@ -286,15 +286,15 @@ static int assignment_fast(const orc_locus *L, const double *theta, orc_ws *ws, 
             run = m > 0 ? x[m - 1] : 0.0; /* the row sum is the scan's value at the row's last stored cell */
         } else {
             /* Loci with more than 32 candidates (gibbs_rows.cu, one warp per row): the lanes hold the row's stored cells whose
-             * candidate is in the simplex (theta != 0), 32 at a time, in ascending candidate order within every block of 2048
+             * candidate is in the simplex (theta != 0), 32 at a time, in ascending candidate order within every block of 1024
              * candidates; a chunk of 32 is summed by a warp-shuffle inclusive scan (distances 1, 2, 4, 8, 16), the chunks are
              * chained left to right: cum = (sum of the chunks before) + (scan value inside the chunk). */
             int k = beg;
             while (k < end) {
                 double x[32];
                 int cc[32], live[32], m = 0;
-                const int block = L->col_idx[k] >> 11;
-                for (; k < end && m < 32 && (L->col_idx[k] >> 11) == block; k++) {
+                const int block = L->col_idx[k] >> 10;
+                for (; k < end && m < 32 && (L->col_idx[k] >> 10) == block; k++) {
                     if (L->val[k] == 0.0) continue;
                     if (!init && theta[L->col_idx[k]] == 0.0) continue;
                     cc[m] = L->col_idx[k];

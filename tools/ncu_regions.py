@@ -39,7 +39,7 @@ for r in rows:
 import os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 bounds = {}
-for f in ("rng.cuh", "gibbs_kernel.cu", "gibbs_fast.cu", "gibbs_common.cuh"):
+for f in ("rng.cuh", "gibbs_kernel.cu", "gibbs_fast.cu", "gibbs_rows.cu", "gibbs_common.cuh"):
     src = open(os.path.join(ROOT, "bayesembler_b200", "csrc", f)).read().splitlines()
     marks = []
     for i, line in enumerate(src, 1):

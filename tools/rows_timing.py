@@ -21,11 +21,14 @@ ap.add_argument("--loci", type=int, default=3)
 ap.add_argument("--iters", type=int, default=3000)
 ap.add_argument("--ctas", default="1,2,4,8,16")
 ap.add_argument("--mode", default="fast")
+ap.add_argument("--pick", type=int, default=-1, help="one locus id instead of the spread")
 ap.add_argument("--together", action="store_true", help="also run the picked loci as one batch per cluster size")
 args = ap.parse_args()
 batch = synth.SynthBatch(3)
 order = np.argsort(batch.T)
 picks = [int(order[-1])] + [int(order[(2 * k + 1) * len(order) // (2 * max(1, args.loci - 1))]) for k in range(args.loci - 1)]
+if args.pick >= 0:
+    picks = [args.pick]
 nnz = batch.cell_off[1:] - batch.cell_off[:-1]
 print("%6s %5s %5s %7s %6s %4s | %10s %12s" % ("locus", "T", "R", "nnz", "N_f", "CTAs", "us/iter", "SM-us/iter"))
 for i in picks:
