@@ -89,7 +89,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("BAYES_B200_LIB") or LIB_PATH  # BAYES_B200_LIB: an experiment build of the same sources (debug bounds, phase clocks)
     if not os.path.exists(p):
         raise BayesError("CUDA extension %s is missing; build it with `python -m bayesembler_b200._build` "
                          "(there is no CPU fallback)" % p)

@@ -1331,7 +1331,7 @@ static int step_assignment(int device, const bayes_locus_desc *locus, const doub
     const KernelArgs args = kernel_args(ctx);
     const size_t smem = 12 * (size_t)T + 8 * (((size_t)T + 63) / 64) + 48 + 4 * kFastCtlWords;
     if ((rc = cuda_rc(cudaMemsetAsync(ctx->d_unit_err.p, 0, sizeof(int32_t), st), "memset"))) return fail(rc);
-    if (rows) rc = launch_step_assignment_rows(args, init, ctx->d_mean.p, iteration, ctx->d_occ.p, 12 * (size_t)T + 8 * (((size_t)T + 63) / 64) + 4 * kRowsCtlWords, st);
+    if (rows) rc = launch_step_assignment_rows(args, init, ctx->d_mean.p, iteration, ctx->d_occ.p, 12 * (size_t)T + 8 * (((size_t)T + 63) / 64) + 4 * kRowsCtlWords + 12 * (size_t)U.d.chain_max + 16, st);
     else if (fast) rc = launch_step_assignment_fast(args, init, tiles, ctx->d_mean.p, iteration, ctx->d_occ.p, smem, st);
     else rc = launch_step_assignment(args, init, ctx->d_mean.p, iteration, ctx->d_occ.p, smem, st);
     if (rc) return fail(rc);

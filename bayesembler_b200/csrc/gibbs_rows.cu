@@ -27,6 +27,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <float.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "internal.h"
@@ -54,18 +55,22 @@ constexpr int kCtlQ0 = 1, kCtlErr = 4, kCtlNAct = 5, kCtlB = 6;
 #define ROWS_CHECK(cond, code) do { } while (0)
 #endif
 
+// Development aid: -DBAYES_ROWS_PHASES makes thread 0 of the cluster's first CTA time the phases of every iteration (SM clock)
+// and print the averages when the unit ends.
+#ifdef BAYES_ROWS_PHASES
+struct PhaseClock {
+    long long t, a[10];
+};
+#define ROWS_PHASE(pc, i) do { if ((pc) && threadIdx.x == 0) { const long long now_ = clock64(); (pc)->a[i] += now_ - (pc)->t; (pc)->t = now_; } } while (0)
+#else
+struct PhaseClock;
+#define ROWS_PHASE(pc, i) do { } while (0)
+#endif
+
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
-}
-
-// index of the i-th (0-based) set bit of m
-__device__ __forceinline__ int nth_set_bit64(uint64_t m, int i) {
-    const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
-    const int pl = __popc(lo);
-    const bool up = i >= pl;
-    return (int)__fns(up ? hi : lo, 0, (up ? i - pl : i) + 1) + (up ? 32 : 0);
 }
 
 __device__ __forceinline__ int words_below(const u32x4 &w, int left, uint32_t t) {
@@ -89,6 +94,10 @@ struct RowsView {
     uint32_t *queue;           // two buffers of 3 * qcap words: fragments | node | row
     int qcap;
     const uint32_t *pool;      // this iteration's uniform words of the CTA's rows
+    double *ch_rz;             // rows with >= 20 fragments (row - row_begin): 1 / row sum of this iteration
+    int *ch_kk;                // their cells in play
+    const uint32_t *dtask;     // direct-draw tasks of the CTA: (row - row_begin) << 16 | block of 4 fragments
+    int n_dtask;
     int *ctl;
 };
 
@@ -264,11 +273,15 @@ __device__ __forceinline__ void rows_assign(const RowsView &V, const uint64_t *a
                 const uint32_t ma = w < n_w32 ? rm[w] : 0u;
                 G = mask_group(ma, w < n_w32 ? ma & amask[w] : 0u, w0, G.kbase + G.stored, lane);
             }
+            if (n <= kRowsDirectMax && lane == 0) {  // drawn fragment by fragment once all rows have their lists (rows_direct)
+                V.ch_kk[r - V.row_begin] = kk;
+                V.ch_rz[r - V.row_begin] = __drcp_rn(carry);
+            }
             if (kk == 0) {  // reference: assert(normalisation_constant >= double_underflow) (assignmentGenerator.cpp:284)
                 if (lane == 0) V.ctl[kCtlErr] = 1;
             } else if (kk == 1) {
                 if (lane == 0) atomicAdd(&acc[c_only], n);
-            } else {
+            } else if (n > kRowsDirectMax) {
                 // the row's fragments enter the tree as independent chunks of at most 64 (rows above 2048 fragments whole)
                 const int mch = n <= 2048 ? (n + 63) >> 6 : 1;
                 push_tasks(V, kCtlQ0, 0, lane < mch, (uint32_t)(n / mch + (lane < n % mch)), ((uint32_t)(kk - 1) << 12) | ((uint32_t)lane << 24),
@@ -345,7 +358,50 @@ __device__ __forceinline__ void rows_assign(const RowsView &V, const uint64_t *a
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// A-step, second part: the splitting trees of the rows with >= 20 fragments, level by level (the scheme of
+// A-step, second part: the rows with 20 .. kRowsDirectMax fragments, fragment by fragment.  One lane per block of four
+// fragments, whichever row they belong to: one Philox block of the row's own site, four binary searches (in step, for the
+// memory-level parallelism) of the words in the row's running sums -- the thresholds of the small rows, word <=
+// ceil(cum (1/Z) 2^32 - 1) -- and one shared-memory atomic per fragment.  Nothing here depends on anything but the lists the
+// first part left: no levels, no barriers, every lane of the CTA busy.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rows_direct(const RowsView &V, int32_t *acc, const uint64_t key, uint32_t iteration, const bool init) {
+    const uint32_t ph = init ? PH_INIT_DIRECT : PH_DIRECT;
+    for (int task = threadIdx.x; task < V.n_dtask; task += (int)blockDim.x) {
+        const uint32_t e = V.dtask[task];
+        const int rl = (int)(e >> 16);
+        const uint32_t blk = e & 0xffffu;
+        const int kk = V.ch_kk[rl];
+        if (kk < 2) continue;  // no cell in play (flagged) or a single one (took everything already)
+        const int ri = V.row_begin + rl - V.row_base;
+        const int n = V.row_n[ri];
+        const int sb = V.rcell[ri] - V.scr_base;
+        const double rZ = V.ch_rz[rl];
+        const double *sc = V.scr_cum + sb;
+        const u32x4 wv = make_site(key, ph, iteration, V.row_info[ri] & ((1u << kRowSlotShift) - 1u), blk >> 12).block(blk & 4095u);
+        const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
+        const int left = n - 4 * (int)blk < 4 ? n - 4 * (int)blk : 4;
+        // number of thresholds below the word = first cell whose threshold the word does not exceed (the last cell has none)
+        int lo[4] = {0, 0, 0, 0};
+        const int n_search = kk - 1;
+        for (int step = 1 << (31 - __clz(n_search)); step > 0; step >>= 1) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int cand = lo[q] + step;
+                if (cand <= n_search) {
+                    ROWS_CHECK(sb + cand - 1 >= 0 && sb + cand - 1 < V.scr_len, 205);
+                    const uint32_t t = __double2uint_ru(__fma_rn(sc[cand - 1] * rZ, 4294967296.0, -1.0));
+                    if (w[q] > t) lo[q] = cand;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (q < left) atomicAdd(&acc[V.scr_col[sb + lo[q]]], 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// A-step, third part: the splitting trees of the rows with >= 20 fragments, level by level (the scheme of
 // fast_tree_levels in gibbs_fast.cu: one lane per node of the level whichever row it belongs to, three rotating
 // counters, two queue buffers, one block barrier per level).
 // ------------------------------------------------------------------------------------------------------------------
@@ -456,7 +512,7 @@ struct RowsState {
 };
 
 __device__ __forceinline__ int rows_e_step(const RowsState &E, const uint64_t key, uint32_t iteration, bool sampling, int rank, int n_cta,
-                                           uint32_t *pool, const uint32_t *pool_desc, int pool_blocks) {
+                                           uint32_t *pool, const uint32_t *pool_desc, int pool_blocks, PhaseClock *pc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5, n_threads = blockDim.x;
     const int T = E.T, nch = E.nch;
     const uint32_t lt = lanemask_lt();
@@ -471,6 +527,7 @@ __device__ __forceinline__ int rows_e_step(const RowsState &E, const uint64_t ke
         if (t < T) E.theta[t] = 0.0;
     }
     __syncthreads();
+    ROWS_PHASE(pc, 0);
     // 2. warp 0: simplex size and the null candidates that join S+; the other warps: this iteration's uniform words
     if (warp == 0) {
         const int G = (nch + 31) >> 5;  // chunks per lane (<= 4: T <= 4096), lane l holds chunks [l G, (l + 1) G)
@@ -560,6 +617,7 @@ __device__ __forceinline__ int rows_e_step(const RowsState &E, const uint64_t ke
         rows_pool_gen(pool, pool_desc, pool_blocks, key, iteration, false, 32, n_threads - 32);
     }
     __syncthreads();
+    ROWS_PHASE(pc, 1);
     // 3. the members of the simplex, ascending, and the simplex mask the A-step ANDs the rows' masks with
     for (int c = warp; c < nch; c += n_warps) {
         const uint32_t m = E.mask[c] | E.mask[nch + c];
@@ -571,6 +629,7 @@ __device__ __forceinline__ int rows_e_step(const RowsState &E, const uint64_t ke
         E.amask[w] = ((uint64_t)hi << 32) | lo;
     }
     __syncthreads();
+    ROWS_PHASE(pc, 2);
     // 4. one Gamma(count + gamma) draw per member
     const int n_act = E.ctl[kCtlNAct];
     for (int i = threadIdx.x; i < n_act; i += n_threads) {
@@ -580,6 +639,7 @@ __device__ __forceinline__ int rows_e_step(const RowsState &E, const uint64_t ke
         E.theta[t] = gv;
     }
     __syncthreads();
+    ROWS_PHASE(pc, 3);
     // 5. the normalising sum, in the order it always had (per lane over the chunks, then across the lanes); fresh counts
     if (warp == 0) {
         double part = 0.0;
@@ -591,6 +651,7 @@ __device__ __forceinline__ int rows_e_step(const RowsState &E, const uint64_t ke
         if (lane == 0) *E.norm = norm;
     }
     __syncthreads();
+    ROWS_PHASE(pc, 4);
     for (int t = threadIdx.x; t < T; t += n_threads) E.counts[t] = E.base[t];  // fresh CountValueContainer (+ the folded rows)
     const double norm = *E.norm;
     for (int i = threadIdx.x; i < n_act; i += n_threads) {
@@ -612,6 +673,7 @@ __device__ __forceinline__ int rows_e_step(const RowsState &E, const uint64_t ke
         }
     }
     __syncthreads();
+    ROWS_PHASE(pc, 5);
     return E.ctl[kCtlB];
 }
 
@@ -626,7 +688,8 @@ __global__ void __maxnreg__(BAYES_ROWS_MAXNREG) gibbs_rows_kernel(const __grid_c
     const UnitDev &U = A.units[ui];
     const int T = U.T[0];
     const int n_threads = blockDim.x;
-    const RowsLayout lay = rows_layout(T, n_cta, U.rows_max, U.cells_max, U.ccells_max, U.qcap, U.pool_max, U.mat_smem != 0, U.scr_smem != 0, U.pool_smem != 0);
+    const RowsLayout lay = rows_layout(T, n_cta, U.rows_max, U.cells_max, U.ccells_max, U.chain_max, U.qcap, U.pool_max, U.mat_smem != 0, U.scr_smem != 0,
+                                       U.pool_smem != 0);
     RowsState E;
     E.theta = (double *)(smem + lay.theta);
     E.den = (double *)(smem + lay.den);
@@ -725,6 +788,10 @@ __global__ void __maxnreg__(BAYES_ROWS_MAXNREG) gibbs_rows_kernel(const __grid_c
     const int pool_blocks = U.cta_pool0[rank + 1] - U.cta_pool0[rank];
     if (threadIdx.x < 4) pool[4 * pool_blocks + threadIdx.x] = 0u;  // the spare block
     V.pool = pool;
+    V.ch_rz = (double *)(smem + lay.ch_rz);
+    V.ch_kk = (int *)(smem + lay.ch_kk);
+    V.dtask = A.chain_tab + U.ctab_off + U.cta_dtask0[rank];
+    V.n_dtask = U.cta_dtask0[rank + 1] - U.cta_dtask0[rank];
 
     const bool tracing = lead && A.trace_unit == ui;
     const int burn = U.burn;
@@ -733,6 +800,14 @@ __global__ void __maxnreg__(BAYES_ROWS_MAXNREG) gibbs_rows_kernel(const __grid_c
     int cur = 0;
     int32_t *acc = n_cta > 1 ? part : E.counts;
     __syncthreads();
+#ifdef BAYES_ROWS_PHASES
+    PhaseClock pclock;
+    PhaseClock *pc = lead ? &pclock : nullptr;
+    for (int i = 0; i < 10; i++) pclock.a[i] = 0;
+    pclock.t = clock64();
+#else
+    PhaseClock *pc = nullptr;
+#endif
 
     // it == -1 is initAssignment (gibbsSampler.cpp:90): the same A-step code on theta == 1, no E-step before it
     for (int it = -1; it < total; it++) {
@@ -748,7 +823,7 @@ __global__ void __maxnreg__(BAYES_ROWS_MAXNREG) gibbs_rows_kernel(const __grid_c
                 for (int t = threadIdx.x; t < T; t += n_threads) A.tr_init[t] = E.counts[t];
             if (tracing && it > 0 && it - 1 < A.trace_iters)
                 for (int t = threadIdx.x; t < T; t += n_threads) A.tr_counts[(size_t)(it - 1) * T + t] = E.counts[t];
-            const int b = rows_e_step(E, key, iter, it >= burn || (stamp_at >= 0 && it >= stamp_at), rank, n_cta, pool, pool_desc, pool_blocks);
+            const int b = rows_e_step(E, key, iter, it >= burn || (stamp_at >= 0 && it >= stamp_at), rank, n_cta, pool, pool_desc, pool_blocks, pc);
             if (tracing && it < A.trace_iters) {
                 for (int t = threadIdx.x; t < T; t += n_threads) A.tr_theta[(size_t)it * T + t] = E.theta[t];
                 if (threadIdx.x == 0) A.tr_b[it] = b;
@@ -758,18 +833,24 @@ __global__ void __maxnreg__(BAYES_ROWS_MAXNREG) gibbs_rows_kernel(const __grid_c
             rows_pool_gen(pool, pool_desc, pool_blocks, key, iter, true, 0, n_threads);
             __syncthreads();
         }
+        ROWS_PHASE(pc, 9);
         rows_assign(V, E.amask, E.theta, acc);
         __syncthreads();
+        ROWS_PHASE(pc, 6);
+        rows_direct(V, acc, key, iter, it < 0);
         rows_tree_levels(V, acc, key, iter, it < 0);
+        if (n_cta == 1) __syncthreads();  // the direct draws are in before the counts are read (a cluster meets at its barrier below)
+        ROWS_PHASE(pc, 7);
         if (n_cta > 1) {
             // every CTA adds up the partial counts of all CTAs (distributed shared memory); only members of the simplex got any
             cluster.sync();
+            // (one (member, CTA) pair per thread: the remote loads are all independent)
             const int n_act = ctl[kCtlNAct];
-            for (int i = threadIdx.x; i < n_act; i += n_threads) {
-                const int t = E.act[i];
-                int s = 0;
-                for (int j = 0; j < n_cta; j++) s += cluster.map_shared_rank(part, j)[cur * T + t];
-                E.counts[t] += s;
+            const int sh = 31 - __clz(n_cta);
+            for (int i = threadIdx.x; i < (n_act << sh); i += n_threads) {
+                const int t = E.act[i >> sh];
+                const int v = cluster.map_shared_rank(part, i & (n_cta - 1))[cur * T + t];
+                if (v) atomicAdd(&E.counts[t], v);
             }
             // the other buffer was read by the other CTAs one iteration ago (before the barrier above): clear it for the next one
             cur ^= 1;
@@ -777,7 +858,16 @@ __global__ void __maxnreg__(BAYES_ROWS_MAXNREG) gibbs_rows_kernel(const __grid_c
             acc = part + cur * T;
             __syncthreads();
         }
+        ROWS_PHASE(pc, 8);
     }
+#ifdef BAYES_ROWS_PHASES
+    if (lead && threadIdx.x == 0) {
+        const double k = 1.0 / (1.965 * (total + 1));  // ns per iteration at 1965 MHz
+        printf("rows phases, ns/iteration (T=%d, %d CTAs x %d threads): S+ %.0f | simplex+picks / pool %.0f | members %.0f | gamma %.0f | norm %.0f | theta+welford %.0f | "
+               "rows %.0f | trees %.0f | cluster reduce %.0f | other %.0f\n", T, n_cta, n_threads, pclock.a[0] * k, pclock.a[1] * k, pclock.a[2] * k, pclock.a[3] * k,
+               pclock.a[4] * k, pclock.a[5] * k, pclock.a[6] * k, pclock.a[7] * k, pclock.a[8] * k, pclock.a[9] * k);
+    }
+#endif
     if (tracing && total - 1 < A.trace_iters)
         for (int t = threadIdx.x; t < T; t += n_threads) A.tr_counts[(size_t)(total - 1) * T + t] = E.counts[t];
 
@@ -819,6 +909,8 @@ __global__ void step_assignment_rows_kernel(const __grid_constant__ KernelArgs A
     uint64_t *amask = (uint64_t *)(theta + T);
     int32_t *counts = (int32_t *)(amask + n_words);
     int *ctl = (int *)(counts + T);
+    int *ch_kk = ctl + kRowsCtlWords;
+    double *ch_rz = (double *)(smem + ((12 * (size_t)T + 8 * (size_t)n_words + 4 * (size_t)kRowsCtlWords + 4 * (size_t)U.chain_max + 7) & ~(size_t)7));
     for (int t = threadIdx.x; t < T; t += blockDim.x) {
         theta[t] = INIT ? 1.0 : theta_in[t];
         counts[t] = A.base_counts[U.lane_off + t];
@@ -858,9 +950,14 @@ __global__ void step_assignment_rows_kernel(const __grid_constant__ KernelArgs A
     rows_pool_gen(pool, A.pool_desc + U.pooldesc_off + U.cta_pool0[0], pool_blocks, key, iteration, INIT, 0, blockDim.x);
     if (threadIdx.x < 4) pool[4 * pool_blocks + threadIdx.x] = 0u;
     V.pool = pool;
+    V.ch_rz = ch_rz;
+    V.ch_kk = ch_kk;
+    V.dtask = A.chain_tab + U.ctab_off + U.cta_dtask0[0];
+    V.n_dtask = U.cta_dtask0[1] - U.cta_dtask0[0];
     __syncthreads();
     rows_assign(V, amask, theta, counts);
     __syncthreads();
+    rows_direct(V, counts, key, iteration, INIT);
     rows_tree_levels(V, counts, key, iteration, INIT);
     __syncthreads();
     for (int t = threadIdx.x; t < T; t += blockDim.x) counts_out[t] = counts[t];
@@ -887,8 +984,7 @@ int configure_rows_kernels() {
 
 // Largest cluster the device can co-schedule for the rows kernel at `block` threads and `smem_bytes` of shared memory per CTA.
 int rows_max_cluster(int block, size_t smem_bytes) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kMaxCluster, 1, 1);
     cfg.blockDim = dim3((unsigned)block, 1, 1);
     cfg.dynamicSmemBytes = smem_bytes;
@@ -904,8 +1000,7 @@ int rows_max_cluster(int block, size_t smem_bytes) {
 
 int launch_units_rows(const KernelArgs &args, int64_t unit_base, int64_t n_units, int block, int n_cta, size_t smem_bytes, void *stream) {
     if (n_units <= 0) return BAYES_OK;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_units * n_cta), 1, 1);
     cfg.blockDim = dim3((unsigned)block, 1, 1);
     cfg.dynamicSmemBytes = smem_bytes;

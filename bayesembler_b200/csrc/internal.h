@@ -22,6 +22,7 @@ constexpr int kMaxT = 4096;             // candidates per locus (per-candidate s
 constexpr int kMaxBlock = 512;          // threads per unit
 constexpr int kWarpsPerSM = 28;         // resident warps per SM at the kernels' 72 registers per thread
 constexpr int kMaxSlots = 16;           // slots per bundle (T = 2 -> Tpad = 2 -> 16 slots)
+constexpr int kRowsDirectMax = 4096;    // fast mode, T > 32: rows with 20 .. this many fragments are drawn fragment by fragment, larger ones by the splitting tree
 constexpr int kMaxCluster = 16;         // CTAs of the thread-block cluster a wide locus may be spread over (fast mode)
 constexpr int kSmallCount = 20;         // assignmentGenerator.cpp:289: rows with fewer fragments draw uniforms
 constexpr int kTableSmemEntries = 2048; // simplex CDF tables up to this many entries are staged in shared memory
@@ -81,8 +82,9 @@ struct UnitDev {
     // marks such a unit: n_slabs = rows, slab_h = 1 (slab_cell_off = first cell of every row), masks row-major; CTA j of the
     // cluster owns rows [cta_row0[j], cta_row0[j + 1]), the first cta_chain[j] of them with >= 20 fragments, and the Philox
     // blocks pool_desc[cta_pool0[j] .. cta_pool0[j + 1]) (row_woff = word within that pool).
-    int32_t n_cta, rows_max, cells_max, ccells_max, pool_max, gpool_pad;
+    int32_t n_cta, rows_max, cells_max, ccells_max, pool_max, chain_max;
     int32_t cta_row0[kMaxCluster + 1], cta_chain[kMaxCluster], cta_pool0[kMaxCluster + 1];
+    int32_t cta_dtask0[kMaxCluster + 1];  // -> chain_tab (from ctab_off): the CTA's direct-draw tasks, (row - first row of the CTA) << 16 | block of 4 fragments
     int64_t gpool_off;      // -> gpool (16-byte blocks), n_cta * (pool_max + 1) per unit whose pool is not in shared memory
     // per slot
     int32_t T[kMaxSlots];

@@ -159,16 +159,16 @@ BAYES_LAYOUT_HD TileLayout tile_layout(int n_slots, int Tpad, int n_tiles, int n
 // its pool of uniform words (`pool`) and, in a cluster of more than one CTA, two buffers of partial counts that the
 // other CTAs read through distributed shared memory.
 struct RowsLayout {
-    uint32_t theta, den, mean, m2, val, rmask, scr_cum, amask, norm;          // 8-byte
+    uint32_t theta, den, mean, m2, val, rmask, scr_cum, amask, norm, ch_rz;   // 8-byte
     uint32_t pool;                                                           // 16-byte
-    uint32_t counts, base, occ, part, mask, actoff, rcell, row_n, row_info, row_woff, pool_desc, queue, ctl;  // 4-byte
+    uint32_t counts, base, occ, part, mask, actoff, ch_kk, rcell, row_n, row_info, row_woff, pool_desc, queue, ctl;  // 4-byte
     uint32_t scr_col, act;                                                   // 2-byte
     uint32_t total;
 };
 
 constexpr int kRowsCtlWords = 16;
 
-BAYES_LAYOUT_HD RowsLayout rows_layout(int T, int n_cta, int rows_max, int cells_max, int ccells_max, int qcap, int pool_blocks,
+BAYES_LAYOUT_HD RowsLayout rows_layout(int T, int n_cta, int rows_max, int cells_max, int ccells_max, int chain_max, int qcap, int pool_blocks,
                                        bool mat, bool scr, bool pool) {
     RowsLayout L;
     const uint32_t uT = (uint32_t)T, nch = (uT + 31u) / 32u, nw = (uT + 63u) / 64u;
@@ -183,6 +183,7 @@ BAYES_LAYOUT_HD RowsLayout rows_layout(int T, int n_cta, int rows_max, int cells
     L.scr_cum = o; o += 8u * cc;
     L.amask = o; o += 8u * nw;
     L.norm = o; o += 8u;
+    L.ch_rz = o; o += 8u * (uint32_t)chain_max;  // rows with >= 20 fragments: 1 / row sum and cells in play of this iteration
     o = (o + 15u) & ~15u;
     L.pool = o; o += pool ? 16u * ((uint32_t)pool_blocks + 1u) : 0u;  // one spare block: a row reads its words four at a time
     L.counts = o; o += 4u * uT;
@@ -191,6 +192,7 @@ BAYES_LAYOUT_HD RowsLayout rows_layout(int T, int n_cta, int rows_max, int cells
     L.part = o; o += n_cta > 1 ? 8u * uT : 0u;
     L.mask = o; o += 4u * (2u * nch + 2u);
     L.actoff = o; o += 4u * (nch + 2u);
+    L.ch_kk = o; o += 4u * (uint32_t)chain_max;
     L.rcell = o; o += mat ? 4u * (rows + 1u) : 0u;
     L.row_n = o; o += 4u * rows;
     L.row_info = o; o += 4u * rows;

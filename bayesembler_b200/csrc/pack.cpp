@@ -457,11 +457,13 @@ void pack_unit_rows(const std::vector<SlotRef> &slots, int n_cta, PackedUnit *ou
     UnitDev &d = U.d;
     U.slab_cell_off.assign(1, 0);
     U.row_mask.assign((size_t)n_items * n_words * 2, 0u);
-    int rows_max = 0, cells_max = 0, ccells_max = 0, pool_max = 0;
+    int rows_max = 0, cells_max = 0, ccells_max = 0, pool_max = 0, chain_max = 0;
     int64_t qcap_max = 1;
     int row = 0;
     for (int j = 0; j < n_cta; j++) {
         d.cta_row0[j] = row;
+        d.cta_dtask0[j] = (int32_t)U.chain_tab.size();
+        chain_max = std::max(chain_max, chain_of[j]);
         d.cta_chain[j] = chain_of[j];
         d.cta_pool0[j] = (int32_t)U.pool_desc.size();
         const int cell_first = U.slab_cell_off.back();
@@ -474,7 +476,11 @@ void pack_unit_rows(const std::vector<SlotRef> &slots, int n_cta, PackedUnit *ou
             U.row_info.push_back((uint32_t)L.row_id[it.r]);
             int32_t woff = 0;
             if (it.chain) {
-                qcap += (int64_t)tree_chunks(it.n) * std::max(1, it.nnz / 2);  // nodes of the deepest tree level with two or more cells, per chunk
+                if (it.n <= kRowsDirectMax) {
+                    for (int b = 0; 4 * b < it.n; b++) U.chain_tab.push_back(((uint32_t)q << 16) | (uint32_t)b);  // q < 2^16: a CTA's rows with >= 20 fragments
+                } else {
+                    qcap += (int64_t)tree_chunks(it.n) * std::max(1, it.nnz / 2);  // nodes of the deepest tree level with two or more cells, per chunk
+                }
                 ccells += it.nnz;
             } else {
                 const int64_t w0 = L.row_woff[it.r], b0 = w0 / 4, b1 = (w0 + it.n - 1) / 4;
@@ -498,6 +504,7 @@ void pack_unit_rows(const std::vector<SlotRef> &slots, int n_cta, PackedUnit *ou
     for (int j = n_cta; j <= kMaxCluster; j++) d.cta_row0[j] = row;
     for (int j = n_cta; j < kMaxCluster; j++) d.cta_chain[j] = 0;
     for (int j = n_cta; j <= kMaxCluster; j++) d.cta_pool0[j] = (int32_t)U.pool_desc.size();
+    for (int j = n_cta; j <= kMaxCluster; j++) d.cta_dtask0[j] = (int32_t)U.chain_tab.size();
     pack_slots(slots, true, T, T, U);
     d.pool_first[0] = 0;
     d.n_cta = n_cta;
@@ -512,11 +519,12 @@ void pack_unit_rows(const std::vector<SlotRef> &slots, int n_cta, PackedUnit *ou
     d.cells_max = cells_max;
     d.ccells_max = ccells_max;
     d.pool_max = pool_max;
+    d.chain_max = chain_max;
     // Shared memory, in the order it pays: the scratch lists and task queues of the splitting trees (random access on the
     // critical path), the pool of uniform words, then the matrix itself (streamed reads; L2 serves them otherwise).
     const size_t limit = max_unit_smem();
     auto total = [&](bool mat, bool scr, bool pool) -> size_t {
-        return rows_layout(T, n_cta, rows_max, cells_max, ccells_max, d.qcap, pool_max, mat, scr, pool).total;
+        return rows_layout(T, n_cta, rows_max, cells_max, ccells_max, chain_max, d.qcap, pool_max, mat, scr, pool).total;
     };
     bool scr = total(false, true, false) <= limit;
     bool pool = total(false, scr, true) <= limit;

@@ -33,7 +33,9 @@ enum Phase : uint32_t {
     PH_POOL = 7,         // generateAssignment, words of the rows with < 20 fragments: block b of the iteration = block (b & 4095) of index (b >> 12)
     PH_INIT_POOL = 8,    // the same for initAssignment
     PH_TREE = 9,         // generateAssignment, one binomial per node of a row's splitting tree: index = row, phase word = PH_TREE | node << 8
-    PH_INIT_TREE = 10    // the same for initAssignment
+    PH_INIT_TREE = 10,   // the same for initAssignment
+    PH_DIRECT = 11,      // generateAssignment, rows with >= 20 fragments drawn fragment by fragment: index = row, word f of the row = word (f & 3) of block (f >> 2)
+    PH_INIT_DIRECT = 12  // the same for initAssignment
 };
 
 struct u32x4 {

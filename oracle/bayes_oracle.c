@@ -217,7 +217,9 @@ int orc_init_assignment(const orc_locus *loc, int rng_mode, uint64_t seed, int *
  *     (POOL, iteration, b >> 12)); word w lands in the first cell j < k with
  *     w * 2^-32 < cum_j * (1/Z), i.e. w <= ceil(cum_j (1/Z) 2^32 - 1), else in cell k (:302-334 with unsorted
  *     uniforms and one reciprocal per row);
- *   n >= 20: a balanced binary TREE over the cells in play instead of the chain of conditional binomials
+ *   20 <= n <= direct_max(T): fragment by fragment, one word each from the row's own site (DIRECT, iteration, row), located
+ *     like the words of the small rows;
+ *   n > direct_max(T): a balanced binary TREE over the cells in play instead of the chain of conditional binomials
  *     (:336-365): node (a, len) holds m fragments for cells [a, a + len); its left half [a, a + len/2) receives
  *     Binomial(m, (cum(a + len/2) - cum(a)) / (cum(a + len) - cum(a))), the right half the rest; one site per node
  *     (TREE | node << 8, iteration, row, chunk), node = a | (len - 1) << 12.  Depth log2 k instead of k dependent
@@ -251,8 +253,15 @@ static int tree_chunks(int n) {
     return m <= 32 ? m : 1;
 }
 
+/* Rows with >= 20 fragments and at most this many are drawn fragment by fragment (one uniform word each, located in the
+ * row's running sums like the words of the small rows), the larger ones by the splitting tree.  A tree costs about a binomial
+ * per cell in play and chunk of 64 fragments and is log2(cells) dependent levels deep; a fragment costs one binary search and
+ * depends on nothing, which is cheaper for all but the largest rows of a locus with hundreds of candidates. */
+static int direct_max(int T) { return T > 32 ? 4096 : 0; }
+
 static int assignment_fast(const orc_locus *L, const double *theta, orc_ws *ws, uint32_t iteration, int init, int *counts) {
     const uint32_t ph_pool = init ? ORC_PH_INIT_POOL : ORC_PH_POOL, ph_tree = init ? ORC_PH_INIT_TREE : ORC_PH_TREE;
+    const uint32_t ph_direct = init ? ORC_PH_INIT_DIRECT : ORC_PH_DIRECT;
     double *cum = (double *)malloc(sizeof(double) * (size_t)(L->T > 0 ? L->T : 1));
     int *cell_col = (int *)malloc(sizeof(int) * (size_t)(L->T > 0 ? L->T : 1));
     uint64_t pool_at = 0; /* next word of the pool */
@@ -322,6 +331,22 @@ static int assignment_fast(const orc_locus *L, const double *theta, orc_ws *ws, 
                 uint32_t b[4];
                 orc_ws_block(ws, b);
                 const uint32_t w = b[word & 3u];
+                int j = 0;
+                for (; j < kk - 1; j++)
+                    if (w <= sat_u32_ceil(fma(cum[j] * rZ, 4294967296.0, -1.0))) break;
+                counts[cell_col[j]] += 1;
+            }
+        } else if (n <= direct_max(L->T)) {
+            /* fragment by fragment: fragment f draws word (f & 3) of block (f >> 2) of the row's own site and lands like the
+             * words of a row with < 20 fragments do */
+            const double rZ = 1.0 / run;
+            for (int f = 0; f < n; f++) {
+                const uint32_t blk = (uint32_t)f >> 2;
+                orc_ws_site(ws, ph_direct, iteration, (uint32_t)i, blk >> 12);
+                ws->k = (blk & 4095u) << 2;
+                uint32_t b[4];
+                orc_ws_block(ws, b);
+                const uint32_t w = b[f & 3];
                 int j = 0;
                 for (; j < kk - 1; j++)
                     if (w <= sat_u32_ceil(fma(cum[j] * rZ, 4294967296.0, -1.0))) break;

@@ -112,7 +112,10 @@ enum {
     ORC_PH_INIT_POOL = 8,   /* the same for initAssignment                                                    */
     ORC_PH_TREE = 9,        /* generateAssignment, one binomial per node of a row's splitting tree: index = row,
                                phase word = ORC_PH_TREE | node << 8, node = first cell | (cells - 1) << 12       */
-    ORC_PH_INIT_TREE = 10   /* the same for initAssignment                                                    */
+    ORC_PH_INIT_TREE = 10,  /* the same for initAssignment                                                    */
+    ORC_PH_DIRECT = 11,     /* generateAssignment, rows with >= 20 fragments drawn fragment by fragment: index = row,
+                               fragment f takes word (f & 3) of block (f >> 2) of the row's site                  */
+    ORC_PH_INIT_DIRECT = 12 /* the same for initAssignment                                                    */
 };
 
 /* --------------------------------------------------------------- word source */
