@@ -30,6 +30,8 @@ EXPORTED_SYMBOLS = [
     "bayes_all_paths_build", "bayes_path_set_destroy", "bayes_path_set_num_candidates", "bayes_path_set_num_exons",
     "bayes_path_set_export", "bayes_path_set_stats", "bayes_path_set_graph_name", "bayes_path_set_reference",
     "bayes_path_set_strand", "bayes_path_set_candidate_name",
+    "bayes_bam_front_open", "bayes_bam_front_close", "bayes_bam_front_counts", "bayes_bam_front_num_alignments", "bayes_bam_front_write_sam",
+    "bayes_bam_front_graphs", "bayes_sequencing_probability",
 ]
 
 
@@ -159,6 +161,14 @@ def load_library(path=None):
         "bayes_path_set_reference": (C.c_char_p, [vp]),
         "bayes_path_set_strand": (C.c_char_p, [vp]),
         "bayes_path_set_candidate_name": (C.c_int, [vp, i32, C.c_char_p, i32]),
+        "bayes_bam_front_open": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(vp)]),
+        "bayes_bam_front_close": (None, [vp]),
+        "bayes_bam_front_counts": (C.c_int, [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl)]),
+        "bayes_bam_front_num_alignments": (i64, [vp, i32]),
+        "bayes_bam_front_write_sam": (C.c_int, [vp, i32, C.c_char_p, i32]),
+        "bayes_bam_front_graphs": (C.c_int, [vp, i32, C.c_char_p, C.c_char_p, dbl, i32, C.c_char_p, i32, C.POINTER(i32), C.POINTER(i32),
+                                             C.POINTER(i32), C.POINTER(i32)]),
+        "bayes_sequencing_probability": (C.c_int, [C.c_char_p, C.c_char_p, i32, C.c_char_p, vp, C.POINTER(dbl)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -549,3 +559,45 @@ def all_paths(dot, no_pre_mrna=False, max_candidate_number=100):
     finally:
         L.bayes_path_set_destroy(h)
     return out
+
+
+class BamFront(object):
+    """BAM front end (row f4, csrc/bamfront.cpp): duplicate removal and strand split of a coordinate-sorted paired-end BAM, SAM text
+    for CEM processsam, instance file -> graph file."""
+
+    def __init__(self, bam_path, strand_specific="unstranded"):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        _check(self.lib.bayes_bam_front_open(os.fsencode(bam_path), strand_specific.encode(), C.byref(self.h)), "bayes_bam_front_open")
+
+    def close(self):
+        if self.h:
+            self.lib.bayes_bam_front_close(self.h)
+            self.h = C.c_void_p()
+
+    def counts(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _check(self.lib.bayes_bam_front_counts(self.h, C.byref(a), C.byref(b), C.byref(c)), "bayes_bam_front_counts")
+        return dict(total_mapped_pairs=a.value, unique_pairs=b.value, pairs_written=c.value)
+
+    def num_alignments(self, strand_file=0):
+        return int(self.lib.bayes_bam_front_num_alignments(self.h, strand_file))
+
+    def write_sam(self, path, strand_file=0, with_header=False):
+        _check(self.lib.bayes_bam_front_write_sam(self.h, strand_file, os.fsencode(path), int(with_header)), "bayes_bam_front_write_sam")
+
+    def graphs(self, instance_path, graph_file_path, strand=".", strand_file=0, exon_base_coverage=0.05, no_pre_mrna=False, append=False):
+        n = [C.c_int32() for _ in range(4)]
+        _check(self.lib.bayes_bam_front_graphs(self.h, strand_file, os.fsencode(instance_path), strand.encode(), exon_base_coverage, int(no_pre_mrna),
+                                               os.fsencode(graph_file_path), int(append), *[C.byref(x) for x in n]), "bayes_bam_front_graphs")
+        return dict(zip(["graphs", "with_fragments", "excluded", "cem_graphs"], [x.value for x in n]))
+
+
+def sequencing_probability(md_tag, qualities, cigar):
+    """calculateSequencingProbability (assembler.cpp:1322-1417); cigar = [(op, length), ...]."""
+    L = load_library()
+    ops = "".join(o for o, _ in cigar).encode()
+    lens = np.asarray([l for _, l in cigar], np.int32)
+    out = C.c_double()
+    _check(L.bayes_sequencing_probability(md_tag.encode(), qualities.encode(), len(cigar), ops, _ptr(lens), C.byref(out)), "bayes_sequencing_probability")
+    return out.value

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbayesembler_b200.so")
 CLI = os.path.join(HERE, "bayesembler_b200_cli")
 CLI_SOURCES = [os.path.join(HERE, "host", f) for f in ("main.cpp", "assembler.hpp", "bayesembler_b200.hpp")]
-SOURCES = ["capi.cu", "gibbs_kernel.cu", "gibbs_fast.cu", "gibbs_rows.cu", "host_steps.cpp", "pack.cpp", "likelihood.cpp", "allpaths.cpp"]
+SOURCES = ["capi.cu", "gibbs_kernel.cu", "gibbs_fast.cu", "gibbs_rows.cu", "host_steps.cpp", "pack.cpp", "likelihood.cpp", "allpaths.cpp", "bamfront.cpp"]
 HEADERS = ["internal.h", "layout.h", "rng.cuh", "gibbs_common.cuh", os.path.join("..", "..", "include", "bayesembler_b200.h")]
 
 
@@ -35,6 +35,7 @@ def nvcc_command(out=LIB, extra=()):
         cmd += os.environ["BAYES_NVCC_FLAGS"].split()
     cmd += list(extra)
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += ["-lz"]  # the BAM front end inflates BGZF blocks with zlib
     return cmd
 
 

@@ -12,16 +12,20 @@
 //   assembly.gtf / candidates.gtf / graph_logs.txt /                 same files, same text (log lines carry no time stamps)
 //   fragment_lengths.txt  (:1748-1760, :1965-1978)
 //
-// What is NOT here is everything before the splice graphs (row f4): BAM parsing, duplicate removal, samtools, CEM
-// processsam (assembler.cpp:84-1417) need third-party tools that are absent.  The driver therefore starts from a "graph
-// file" holding what grapherCallback queues per graph (pair<list<string>, vector<FragmentAlignment*>>, :1167-1417):
+// The stages before the splice graphs (row f4, assembler.cpp:84-1417) are in the library too (csrc/bamfront.cpp, C ABI
+// bayes_bam_front_*): BAM reading, duplicate removal, strand split, instance file -> DOT strings, per-graph fragment fetch, read
+// probabilities -- everything but CEM processsam itself, which is not part of the reference's repository: with --bam-file the
+// driver either runs it (--cem-processsam-path, like the reference, :678-690) or takes the instance file(s) it wrote
+// (--instance-file / --instance-file-plus / --instance-file-minus).  Either way the front end writes a "graph file" holding what
+// grapherCallback queues per graph (pair<list<string>, vector<FragmentAlignment*>>, :1167-1417), which is also an input format
+// of its own (--graph-file):
 //
 //     fragments <unique non-redundant mapped read pairs> <all mapped read pairs>        (assembler.cpp:610-619)
 //     graph <dot strings> <fragments> <single-path 0|1>                                  (one block per graph)
 //     digraph <name> { ... }                                                             (DOT text, a line "}" ends it)
 //     <pos1> <cigar1> <pos2> <cigar2> <probability>                                      (0-based positions, CIGARs like 30M120N46M)
 //
-// --bam-file alone is refused with a message saying so.
+// --bam-file without processsam and without instance files is refused with a message saying so.
 #ifndef BAYESEMBLER_B200_ASSEMBLER_HPP
 #define BAYESEMBLER_B200_ASSEMBLER_HPP
 
@@ -44,6 +48,7 @@ namespace bayesembler_b200 {
 struct OptionsContainer {  // utils.h:140-170
     std::string bam_file;
     std::string graph_file;  // this driver's input (see header comment)
+    std::string instance_file, instance_file_plus, instance_file_minus;  // what CEM processsam wrote for the de-duplicated alignments
     std::string samtools_path;
     std::string cem_processsam_path;
     int num_threads = 1;
@@ -76,8 +81,12 @@ inline void printHelp(std::ostream &out, bool advanced) {
            "  -a [ --advanced ]                               produce help message for advanced options\n\n"
            "== Required arguments ==:\n"
            "  -b [ --bam-file ] arg                           TopHat2 bamfile containing the mapped paired-end reads to the reference genome\n"
-           "                                                  (needs the BAM front end, which this build does not have: use --graph-file)\n"
-           "  -g [ --graph-file ] arg                         splice graphs + fragment alignments, the stage after the BAM front end\n\n"
+           "                                                  (with --cem-processsam-path, or with the instance file(s) CEM processsam wrote)\n"
+           "  -g [ --graph-file ] arg                         splice graphs + fragment alignments, the stage after the BAM front end\n"
+           "  --instance-file arg                             CEM instance file of the de-duplicated alignments (unstranded data)\n"
+           "  --instance-file-plus / --instance-file-minus    the same for the two strand sets of strand-specific data\n"
+           "  --cem-processsam-path arg                       CEM processsam executable: run on the de-duplicated alignments when no\n"
+           "                                                  instance file is given\n\n"
            "== Optional arguments ==:\n"
            "  -o [ --output-prefix ] arg                      prefix to be used on all output filenames (OBS: to use output directory <dir>\n"
            "                                                  without any prefix on the output files, use <dir/>)\n"
@@ -126,7 +135,9 @@ inline int parseCommandLine(int argc, char *const argv[], OptionsContainer *opt,
                           {"keep-temp-files", 0, 4, &o.keep_temp_files}, {"max-candidate-number", 0, 2, &o.max_candidate_number},
                           {"dirichlet-parameter", 0, 3, &o.gamma}, {"frag-mean", 0, 3, &o.frag_mean}, {"frag-sd", 0, 3, &o.frag_sd},
                           {"gibbs-iteration-scaling", 0, 5, &o.gibbs_scale_iterations}, {"device", 0, 2, &o.device},
-                          {"devices", 0, 1, &o.devices}};
+                          {"devices", 0, 1, &o.devices}, {"instance-file", 0, 1, &o.instance_file},
+                          {"instance-file-plus", 0, 1, &o.instance_file_plus}, {"instance-file-minus", 0, 1, &o.instance_file_minus},
+                          {"cem-processsam-path", 0, 1, &o.cem_processsam_path}, {"samtools-path", 0, 1, &o.samtools_path}};
     const int n_specs = (int)(sizeof(specs) / sizeof(specs[0]));
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
@@ -166,11 +177,6 @@ inline int parseCommandLine(int argc, char *const argv[], OptionsContainer *opt,
     if (help || argc == 1) { printHelp(out, false); return 1; }
     if (advanced) { printHelp(out, true); return 1; }
     if (o.bam_file.empty() && o.graph_file.empty()) { err << "ERROR: the option '--bam-file' is required but missing" << std::endl; return -1; }
-    if (o.graph_file.empty()) {
-        err << "ERROR: --bam-file needs the BAM front end (samtools, CEM processsam, BamTools), which this build does not have; "
-               "give the splice graphs and fragment alignments with --graph-file" << std::endl;
-        return -1;
-    }
     if (o.strand_specific != "unstranded" && o.strand_specific != "first" && o.strand_specific != "second") {  // main.cpp:143-147
         err << "\nERROR: --strand-specific argument need to be either \"unstranded\", \"first\" or \"second\"" << std::endl;
         return -1;
@@ -184,6 +190,16 @@ inline int parseCommandLine(int argc, char *const argv[], OptionsContainer *opt,
         return -1;
     }
     o.estimate_fragment_length = !have_mean;  // main.cpp:155-166
+    if (o.graph_file.empty()) {
+        const bool stranded = o.strand_specific != "unstranded";
+        const bool have_instances = stranded ? (!o.instance_file_plus.empty() && !o.instance_file_minus.empty()) : !o.instance_file.empty();
+        if (!have_instances && o.cem_processsam_path.empty()) {
+            err << "ERROR: --bam-file needs the splice graphs of CEM processsam, which is not part of Bayesembler: give its path "
+                   "(--cem-processsam-path) or the instance file(s) it wrote for the de-duplicated alignments ("
+                << (stranded ? "--instance-file-plus and --instance-file-minus" : "--instance-file") << "), or start from --graph-file" << std::endl;
+            return -1;
+        }
+    }
     return 0;
 }
 
@@ -275,11 +291,65 @@ class Assembler {
    public:
     explicit Assembler(const OptionsContainer &o) : options_variables(o) {}
 
+    // generateSpliceGraphs + graphConstructorCallback + grapherCallback (assembler.cpp:272-1319) through the library's BAM front
+    // end: leaves the graphs with their fragments in <output-prefix>graphs.txt and points options_variables.graph_file at it
+    void generateSpliceGraphs(std::ostream &cout_) {
+        OptionsContainer &o = options_variables;
+        cout_ << "Removing duplicate reads" << std::endl;
+        bayes_bam_front *front = 0;
+        check(bayes_bam_front_open(o.bam_file.c_str(), o.strand_specific.c_str(), &front), "bayes_bam_front_open");
+        struct Closer {
+            bayes_bam_front *f;
+            ~Closer() { bayes_bam_front_close(f); }
+        } closer = {front};
+        double total = 0, unique = 0, written = 0;
+        check(bayes_bam_front_counts(front, &total, &unique, &written), "bayes_bam_front_counts");
+        cout_ << "Removed duplicates from " << total << " mapped read pairs" << std::endl;
+        cout_ << "Wrote " << written << " read pairs used for splice-graph construction" << std::endl;
+        // file names like the reference's (:274-300): <prefix><bam name without its last extension>_nd_<strand>
+        std::string stem = o.bam_file.substr(o.bam_file.rfind('/') == std::string::npos ? 0 : o.bam_file.rfind('/') + 1);
+        if (stem.rfind('.') != std::string::npos) stem = stem.substr(0, stem.rfind('.'));
+        const bool stranded = o.strand_specific != "unstranded";
+        const char *set_name[2] = {stranded ? "_nd_plus" : "_nd_unstranded", "_nd_minus"};
+        const char *set_strand[2] = {stranded ? "+" : ".", "-"};
+        const std::string given[2] = {stranded ? o.instance_file_plus : o.instance_file, o.instance_file_minus};
+        const std::string graph_file = o.output_prefix + "graphs.txt";
+        int graph_count = 0, cem_total = 0, excluded_total = 0;
+        for (int s = 0; s < (stranded ? 2 : 1); s++) {
+            std::string instance = given[s];
+            const std::string base = o.output_prefix + stem + set_name[s];
+            if (instance.empty()) {
+                // samtools view > .sam, then processsam (:662-690)
+                const std::string sam = base + ".sam", log = base + "_instance_log.txt";
+                cout_ << "Generating splice-graphs from " << base << " using cem" << std::endl;
+                check(bayes_bam_front_write_sam(front, s, sam.c_str(), 0), "bayes_bam_front_write_sam");
+                const std::string cmd = "nice " + o.cem_processsam_path + " --no-coverage -c 1 -g 1 -u 0.05 -d " + set_strand[s] + " -o " + base + " " + sam + " > " + log + " 2>&1";
+                if (system(cmd.c_str()) != 0) throw std::runtime_error("CEM processsam failed (see " + log + "): " + cmd);
+                instance = base + ".instance";
+                if (!o.keep_temp_files) remove(sam.c_str());
+            }
+            int32_t n_graphs = 0, n_with = 0, n_excluded = 0, cem = 0;
+            check(bayes_bam_front_graphs(front, s, instance.c_str(), set_strand[s], o.exon_base_coverage, o.no_pre_mrna ? 1 : 0, graph_file.c_str(), s > 0 ? 1 : 0,
+                                         &n_graphs, &n_with, &n_excluded, &cem), "bayes_bam_front_graphs");
+            cout_ << "Parsed " << cem << " graph(s) from cem instance file" << std::endl;
+            graph_count += n_graphs;
+            cem_total += cem;
+            excluded_total += n_excluded;
+        }
+        cout_ << "\nParsed " << cem_total << " splice graph(s) from cem instance file" << (stranded ? "s" : "") << " and collapsed them to " << graph_count
+              << " assembly graph(s)";
+        if (!stranded) cout_ << " (" << excluded_total << " graph(s) excluded due to inference issues resulting from unstranded data).";
+        cout_ << std::endl;
+        if (graph_count == 0) throw std::runtime_error("No graphs remaining after exclusion due to inference issues resulting from unstranded data");
+        o.graph_file = graph_file;
+    }
+
     // assembler.cpp:1841-2030 from the point where the splice graphs exist; returns the number of graphs assembled (code 0)
     int runBayesemblerBatched(std::ostream &cout_) {
         typedef std::chrono::steady_clock Clock;
         auto seconds = [](Clock::time_point a, Clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
         const Clock::time_point t_start = Clock::now();
+        if (options_variables.graph_file.empty()) generateSpliceGraphs(cout_);
         std::ifstream in(options_variables.graph_file.c_str());
         if (!in) throw std::runtime_error("cannot open graph file " + options_variables.graph_file);
         double unique_pairs = 0, mapped_pairs = 0;

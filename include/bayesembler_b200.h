@@ -274,6 +274,36 @@ const char *bayes_path_set_strand(const bayes_path_set *ps);
 /* Candidate::name of candidate i ("<graph>_seq<i>" or "<graph>_pre", allPaths.cpp:254, :270); returns its length */
 int bayes_path_set_candidate_name(const bayes_path_set *ps, int32_t i, char *buf, int32_t cap);
 
+/* ---- BAM front end (host, C++): TopHat2 BAM -> graphs with their fragment alignments -------------- */
+/* What the reference does before its graph queue exists (assembler.cpp:84-624, 627-1164, 1167-1417), without BamTools /
+ * samtools: a coordinate-sorted paired-end BAM is read (BGZF through zlib), the alignments the reference keeps are kept
+ * (mapped, primary, mate mapped, mates on opposite strands of one reference, |insert| <= 700 000; generateSpliceGraphs
+ * :329-352 / :400-470), duplicate pairs are removed (markDuplicates :157-249: same position, insert and CIGARs; a uniquely
+ * mapping pair replaces a multi-mapping one) and, for strand-specific data ("first" | "second"), split into a plus and a minus
+ * set (:424-470).  The de-duplicated alignments stay in memory in the order the reference writes them to its *_nd_*.bam. */
+typedef struct bayes_bam_front bayes_bam_front;
+int bayes_bam_front_open(const char *bam_path, const char *strand_specific, bayes_bam_front **out);
+void bayes_bam_front_close(bayes_bam_front *f);
+/* :384-388, :610-619: mapped read pairs, unique non-redundant (NH == 1) pairs, pairs written for graph construction */
+int bayes_bam_front_counts(bayes_bam_front *f, double *total_mapped_pairs, double *unique_pairs, double *pairs_written);
+/* alignments of a strand set: 0 = unstranded or plus, 1 = minus */
+int64_t bayes_bam_front_num_alignments(bayes_bam_front *f, int32_t strand_file);
+/* the strand set as SAM text, i.e. `samtools view` of the reference's *_nd_*.bam (:662-676): the input of CEM processsam,
+ * which is not part of the reference repository and not restated here */
+int bayes_bam_front_write_sam(bayes_bam_front *f, int32_t strand_file, const char *sam_path, int32_t with_header);
+/* graphConstructorCallback :692-1125 + grapherCallback :1167-1319: parse the instance file processsam wrote for this strand set
+ * (`strand` = "+", "-" or "." as passed to processsam -d), build the DOT strings, collapse overlapping graphs, fetch every
+ * graph's fragments (both mates inside the graph, NH == 1) with their read probabilities (calculateSequencingProbability
+ * :1322-1417) and write / append them to `graph_file_path` in the format `bayesembler_b200_cli --graph-file` reads.
+ * Counts out (any may be NULL): graphs after collapsing, those with fragments, instances dropped for lack of a strand,
+ * instances in the file. */
+int bayes_bam_front_graphs(bayes_bam_front *f, int32_t strand_file, const char *instance_path, const char *strand, double exon_base_coverage,
+                           int32_t no_pre_mrna, const char *graph_file_path, int32_t append, int32_t *n_graphs, int32_t *n_with_fragments,
+                           int32_t *n_excluded, int32_t *cem_graphs);
+/* calculateSequencingProbability (assembler.cpp:1322-1417): probability of the read's bases from its MD tag, its base
+ * qualities (phred + 33 text) and its CIGAR (operations / lengths) */
+int bayes_sequencing_probability(const char *md_tag, const char *qualities, int32_t n_cigar, const char *cigar_op, const int32_t *cigar_len, double *out);
+
 #ifdef __cplusplus
 }
 #endif
