@@ -49,7 +49,8 @@ def test_help_lists_the_reference_options(cli):
 @pytest.mark.parametrize("args,msg", [
     ((), None),
     (("--output-prefix", "x"), "'--bam-file' is required"),
-    (("-b", "reads.bam"), "BAM front end"),
+    (("-b", "reads.bam"), "--cem-processsam-path"),
+    (("-b", "reads.bam", "-s", "second", "--instance-file", "x.instance"), "--instance-file-plus and --instance-file-minus"),
     (("-g", "g.txt", "--strand-specific", "third"), "--strand-specific argument need to be either"),
     (("-g", "g.txt", "--output-mode", "verbose"), "--output_mode argument need to be either"),
     (("-g", "g.txt", "--frag-mean", "200"), "--frag-mean and --frag-sd must be given together"),
