@@ -583,7 +583,7 @@ class Assembler {
         P.burn_in = (int)(options_variables.gibbs_base_iterations + options_variables.gibbs_scale_iterations * max_subgraph_complexity);
         P.samples = (int)(10 * options_variables.gibbs_base_iterations + 10 * options_variables.gibbs_scale_iterations * max_subgraph_complexity);
         P.gibbs_output.reset(new GibbsOutput(P.samples, num_transcripts));
-        log << "Gibbs sampler: " << P.burn_in << " burn-in and " << P.samples << " sampling iterations" << std::endl;
+        GibbsSampler::writeSamplerLog(log, num_transcripts, P.burn_in, P.samples);  // the lines of runSampler (gibbsSampler.cpp:62, :99-143)
     }
 
     void finishGraph(Prepared *p, double adjusted_fragment_count) {  // :1604-1631

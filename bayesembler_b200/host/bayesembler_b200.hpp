@@ -108,7 +108,8 @@ class AssignmentGenerator {
         const int n = bayes_min_read_cover(&d, bayes_chain_key(mt_rng_pt->graph_seed, 0), 0);
         check(n, "calcMinimumReadCover");
         cover_size = n;
-        log_stream << "[bayesembler_b200] Minimum read cover size: " << cover_size << std::endl;
+        log_stream << "\nCalculating minimum read cover" << std::endl;                                               // :54
+        log_stream << "Number of candidates in minimum read cover: " << cover_size << "\n" << std::endl;              // :90
     }
     int getMinimumReadCoverSize() const { return cover_size; }  // :93-96
 
@@ -335,8 +336,24 @@ class GibbsSampler {
         std::string err = rc ? bayes_last_error() : "";
         bayes_gibbs_destroy(ctx);
         if (rc) throw std::runtime_error("runSampler: " + err);
-        log_stream << "[bayesembler_b200] Gibbs sampler: " << burn_in << " burn-in + " << samples << " sampling iterations on device " << device
-                   << std::endl;
+        writeSamplerLog(log_stream, num_transcripts, burn_in, samples);
+    }
+
+    // The lines runSampler writes to the graph's log (gibbsSampler.cpp:62, :99-143; assignmentGenerator.cpp:215), without the
+    // time stamps: on the GPU the iterations of all graphs run as one batch, so the text is written once the batch is back.
+    static void writeSamplerLog(std::ostream &log_stream, int num_transcripts, int burn_in, int samples) {
+        if (num_transcripts == 1) {
+            log_stream << "\nSingle candidate - skipping gibbs sampling" << std::endl;
+            return;
+        }
+        const int print_frequency = 2000;
+        log_stream << "Initialising read assignments uniformly" << std::endl;
+        log_stream << "\nPerforming " << burn_in << " burn-in iterations" << std::endl;
+        for (int i = print_frequency; i < burn_in; i += print_frequency) log_stream << "Completed " << i << " burn-in iterations" << std::endl;
+        log_stream << "Completed " << burn_in << " burn-in iterations" << std::endl;
+        log_stream << "\nPerforming " << samples << " gibbs iterations" << std::endl;
+        for (int i = print_frequency; i < samples; i += print_frequency) log_stream << "Completed " << i << " gibbs iterations" << std::endl;
+        log_stream << "Completed " << samples << " gibbs iterations" << std::endl;
     }
 
     int numTranscripts() const { return num_transcripts; }
@@ -451,8 +468,8 @@ class SequencingModel {
         GaussianFragmentLengthModel *g = dynamic_cast<GaussianFragmentLengthModel *>(fragment_length_model_pt);
         if (!g) throw std::invalid_argument("SequencingModel: only GaussianFragmentLengthModel is supported");
         check(bayes_seq_model_create_gaussian(g->getMean(), g->getSd(), max_transcript_length, &model), "bayes_seq_model_create_gaussian");
-        log_stream << "[bayesembler_b200] Tabulated fragment length and 3'-position probabilities up to transcript lengths of "
-                   << max_transcript_length << std::endl;
+        log_stream << "\nTabulating fragment length and 3'-position probabilities up to transcript lengths of " << max_transcript_length
+                   << std::endl;  // sequencingModel.cpp:36
     }
     ~SequencingModel() { bayes_seq_model_destroy(model); }
     double calculateThreePrimeProb(int three_prime_pos, int tran_length) { return bayes_seq_model_three_prime_prob(model, three_prime_pos, tran_length); }
@@ -522,8 +539,32 @@ class AlignmentParser {
             out.probability_matrix.row_ptr.assign(1, 0);
         }
         bayes_collapsed_map_destroy(cm);
-        log_stream << "[bayesembler_b200] " << st[0] << " fragment(s) parsed, " << st[1] << " matched a transcript, " << st[5]
-                   << " unique rows, " << st[6] << " of " << candidates.size() << " candidates excluded" << std::endl;
+        // the graph's log, as the reference words it (alignmentParser.cpp:273, :478, :484, :659, :668-684), without the time stamps
+        log_stream << "Matching fragments with candidates" << std::endl;
+        if (rc == 3) {
+            log_stream << "\nNo candidates had sufficient fragment coverage to continue - exiting!" << std::endl;
+        } else {
+            log_stream << "Excluding " << st[6] << " of " << candidates.size() << " candidates and renormalising conditional probability matrix " << std::endl;
+            if (rc == 4) {
+                log_stream << "\nNo rows in conditional probability matrix - exiting!" << std::endl;
+            } else {
+                log_stream << "\n=== BAM-FILE PARSING STATS ===\n" << std::endl;
+                log_stream << "  " << st[0] << " fragment(s) were parsed in total." << std::endl;
+                log_stream << "\n  - Fragment-candidate match stats:" << std::endl;
+                log_stream << "  " << st[1] << " fragment(s) matched a transcript." << std::endl;
+                log_stream << "  " << st[2] << " fragment(s) dit not match a transcript." << std::endl;
+                log_stream << "  " << st[3] << " fragments were removed due to probability underflow." << std::endl;
+                log_stream << "  " << st[4] << " fragment-candidate match(es) were found." << std::endl;
+                log_stream << "  " << st[5] << " unique rows in probability matrix." << std::endl;
+                log_stream << "\n  - Candidate exclusion stats:" << std::endl;
+                log_stream << "  " << st[6] << " candidates were excluded due to low fragment coverage." << std::endl;
+                log_stream << "  " << st[7] << " candidates were excluded due to lack of mapped fragments." << std::endl;
+                log_stream << "  " << st[8] << " candidates were excluded due to lack of internal fragment coverage." << std::endl;
+                log_stream << "  " << st[9] << " candidates were excluded due to lack of upstream fragment coverage." << std::endl;
+                log_stream << "  " << st[6] - st[7] - st[8] - st[9] << " candidates were excluded due to lack of downstream fragment coverage." << std::endl;
+                log_stream << std::endl;
+            }
+        }
         for (size_t i = 0; i < fragment_alignments->size(); i++) delete (*fragment_alignments)[i];
         return out;
     }

@@ -40,15 +40,23 @@ def test_config1_loci(lib, oracle, mode):
     _check(lib, oracle, batch, idx, 40, 400, mode=mode)
 
 
-@pytest.mark.parametrize("mode", ["fast", "replay"])
-def test_config3_wide_streaming_loci(lib, oracle, mode):
+@pytest.mark.parametrize("mode,ctas", [("fast", 0), ("fast", 1), ("replay", 0)])
+def test_config3_wide_streaming_loci(lib, oracle, monkeypatch, mode, ctas):
+    """ctas = 0: the library's own choice -- in the fast mode two loci alone on the GPU get a cluster of 16 CTAs each, every CTA with
+    its share of the matrix resident in shared memory; ctas = 1: one CTA per locus (what a batch of hundreds of such loci gets), the
+    largest matrices streamed from L2."""
     from bayesembler_b200 import synth
+    if ctas:
+        monkeypatch.setenv("BAYES_FORCE_CTAS", str(ctas))
     batch = synth.SynthBatch(3, n_loci=6)
     assert batch.T.min() >= 200 and batch.T.max() <= 1000
     idx = np.array([int(np.argmin(batch.T)), int(np.argmax(batch.T))])
     shape = _check(lib, oracle, batch, idx, 10, 60, mode=mode)
     assert np.all(shape[:, 0] == 1)              # wide units
-    assert np.any((shape[:, 7] & 1) == 0)        # at least one streams its matrix instead of staging it in shared memory
+    if mode == "fast" and ctas == 0:
+        assert np.all((shape[:, 7] & 1) == 1)    # spread over a cluster: resident
+    else:
+        assert np.any((shape[:, 7] & 1) == 0)    # at least one streams its matrix instead of staging it in shared memory
 
 
 @pytest.mark.parametrize("mode,pick", [("fast", [0, 9, 19, 29, 39]), ("replay", [0, 39])])
