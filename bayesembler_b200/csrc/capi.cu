@@ -404,7 +404,7 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         const double passes = tree_batches(S, 32 * warps, &levels);
         const double pool = warps > 1 ? 0.0 : kFastPoolUs * ceil(blocks_total / 32.0);
         return kTileEstepUs + pool + std::max(rows / warps, std::min(rows, kTileUniformUs)) + passes * kTileLevelUs +
-               (levels + 2) * kFastBarrierUs * (warps > 1 ? 1.0 : 0.2);
+               (levels + 2) * kFastBarrierUs * (warps > 1 ? 1.0 : 0.2) + (warps > 32 ? 3.0 : 0.0);  // (> 32 warps: a cluster, its barrier and count exchange)
     };
     // Cooperative rows (gibbs_rows.cu): the replicated E-step and the cluster barrier, one warp per row (the rows are dealt over
     // all warps of all CTAs of the cluster), the tree levels of the CTA with most of them.
@@ -532,9 +532,12 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         // (fast mode: the latency of a unit is in its tree levels, which all threads share whatever the slab height: more warps only)
         static const int ladder_replay[][2] = {{1, 32}, {2, 32}, {4, 32}, {8, 32}, {8, 16}, {16, 16}, {16, 8}};
         // (the tiled kernel runs at 64 registers per thread: a monster locus may take a whole SM's 32 warps)
-        static const int ladder_fast[][2] = {{1, 32}, {2, 32}, {4, 32}, {8, 32}, {16, 32}, {32, 32}};
+        // (beyond 32 warps a tiled unit is spread over a thread-block cluster of 2, 4 or 8 CTAs of 32 warps: gibbs_fast.cu)
+        static const int ladder_fast[][2] = {{1, 32}, {2, 32}, {4, 32}, {8, 32}, {16, 32}, {32, 32}, {64, 32}, {128, 32}, {256, 32}};
         const int (*ladder)[2] = fast ? ladder_fast : ladder_replay;
-        const int n_ladder_all = fast ? 6 : 7;
+        const char *mc = getenv("BAYES_MAX_BUNDLE_CTAS");  // experiment knob: 1 = no clusters for bundles
+        const int max_bundle_cta = mc ? std::max(1, std::min(8, atoi(mc))) : 8;
+        const int n_ladder_all = fast ? (max_bundle_cta >= 8 ? 9 : max_bundle_cta >= 4 ? 8 : max_bundle_cta >= 2 ? 7 : 6) : 7;
         const double capacity = (double)ctx->sm_count * kWarpsPerSM;  // resident warps at the kernels' register count
         const char *spw = getenv("BAYES_SMEM_PER_WARP");  // experiment knob
         const double smem_per_warp = spw ? atof(spw) : (fast ? 16384.0 : 8192.0);
@@ -588,7 +591,7 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         }
         const char *fw = getenv("BAYES_FORCE_WARPS"), *fh = getenv("BAYES_FORCE_H");  // experiment knobs
         for (int64_t i = 0; i < n_units; i++) {
-            unit_warps[i] = fw ? std::max(1, std::min(atoi(fw), (fast && !shapes[i].wide ? 1024 : kMaxBlock) / 32)) : ladder[step[i]][0];
+            unit_warps[i] = fw ? std::max(1, std::min(atoi(fw), (fast && !shapes[i].wide ? 8192 : kMaxBlock) / 32)) : ladder[step[i]][0];
             unit_h[i] = fh ? atoi(fh) : ladder[step[i]][1];
             // A locus with hundreds of candidates (config-3 class) is one long dependent chain of iterations that each walk
             // a thousand rows: all 16 warps, and the tallest slabs that still give every warp one -- its A-step is a scan of
@@ -629,9 +632,15 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         } else {
             if (!reuse || ctx->packed_h[i] != unit_h[i]) pack_unit(groups[i], group_wide[i] != 0, unit_h[i], fast, &packed[i]);
             ctx->packed_h[i] = unit_h[i];
+            // a tiled unit above 32 warps: a cluster of CTAs of 32 warps (its scratch lists and task queues are per CTA: shared memory only)
+            packed[i].d.n_cta = 0;
+            if (unit_warps[i] > 32) {
+                if (packed[i].d.scr_smem) packed[i].d.n_cta = unit_warps[i] / 32;
+                unit_warps[i] = 32;
+            }
         }
         packed[i].d.block = 32 * unit_warps[i];
-        packed[i].cost = unit_time(shapes[i], unit_warps[i], unit_h[i]);  // estimated duration: the launch-order key
+        packed[i].cost = unit_time(shapes[i], unit_warps[i] * std::max(1, unit_cta[i] > 0 ? 1 : packed[i].d.n_cta), unit_h[i]);  // estimated duration: the launch-order key
         unit_features(shapes[i], unit_h[i], packed[i].features);
     });
 
@@ -659,7 +668,8 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
     auto class_of = [&](const PackedUnit &u) {
         // (critical band: the largest blocks first -- a 1024-thread block needs a whole SM's registers and would wait, with
         // everything queued behind it, for an SM to drain completely if smaller blocks were spread over all SMs before it)
-        return ClassKey(-band_of(u), u.d.wide | (u.d.n_cta << 1), u.d.mat_smem | (u.d.scr_smem << 1), u.d.block >= 256 ? -u.d.block : u.d.block, smem_bucket(u.d.smem_bytes));
+        // (clusters first, the largest ahead: they need that many SMs of one GPC free at the same time)
+        return ClassKey(-band_of(u), u.d.wide + 2 * (kMaxCluster - u.d.n_cta), u.d.mat_smem | (u.d.scr_smem << 1), u.d.block >= 256 ? -u.d.block : u.d.block, smem_bucket(u.d.smem_bytes));
     };
     std::vector<ClassKey> key(n_units);
     for (int64_t i = 0; i < n_units; i++) key[i] = class_of(packed[i]);
@@ -677,7 +687,7 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
     for (int64_t i = 0; i < n_units; i++) {
         if ((rc = append_unit(ctx, packed[order[i]]))) return rc;
         ctx->unit_pred.push_back(packed[order[i]].cost);
-        ctx->unit_model_us.push_back(iteration_us(shapes[order[i]], unit_warps[order[i]], unit_h[order[i]]));
+        ctx->unit_model_us.push_back(iteration_us(shapes[order[i]], unit_warps[order[i]] * (unit_cta[order[i]] > 0 ? 1 : std::max(1, packed[order[i]].d.n_cta)), unit_h[order[i]]));
         for (int k = 0; k < 4; k++) ctx->unit_feat.push_back(packed[order[i]].features[k]);
     }
     const UnitDev *units = ctx->h_units.p;
@@ -998,8 +1008,8 @@ static int issue_launches(bayes_gibbs_ctx *ctx, int32_t iter_cap) {
             CU(cudaEventRecord(ctx->gate_ev[i], ctx->gate));
             CU(cudaStreamWaitEvent(st, ctx->gate_ev[i], 0));
         }
-        if (l.n_cta > 0) rc = launch_units_rows(args, l.unit_base, l.n_units, l.block, l.n_cta, l.smem, st);
-        else if (ctx->built_mode == BAYES_MODE_FAST) rc = launch_units_fast(args, l.unit_base, l.n_units, l.block, l.wide, l.mat_smem, l.scr_smem, l.smem, st);
+        if (l.n_cta > 0 && l.wide) rc = launch_units_rows(args, l.unit_base, l.n_units, l.block, l.n_cta, l.smem, st);
+        else if (ctx->built_mode == BAYES_MODE_FAST) rc = launch_units_fast(args, l.unit_base, l.n_units, l.block, l.wide, l.mat_smem, l.scr_smem, l.smem, st, std::max(1, l.n_cta));
         else rc = launch_units(args, l.unit_base, l.n_units, l.block, l.wide, l.mat_smem, l.smem, st);
         if (rc) return rc;
         if (n_l > 1) {

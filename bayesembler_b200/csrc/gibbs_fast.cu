@@ -28,8 +28,10 @@
 //    of warp 0 that every other thread had to allocate as well.
 // The CPU oracle restates this mode draw for draw (oracle/bayes_oracle.c, assignment_fast); tests compare the two.
 // No tensor cores: nothing here is a dense contraction.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <float.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "internal.h"
@@ -40,9 +42,8 @@
 #ifndef BAYES_FAST_MAXNREG
 #define BAYES_FAST_MAXNREG 64
 #endif
-#ifndef BAYES_FAST_WIDE_MAXNREG
-#define BAYES_FAST_WIDE_MAXNREG 128
-#endif
+
+namespace cg = cooperative_groups;
 
 namespace bayes {
 
@@ -65,47 +66,6 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
     return m;
 }
 
-struct FastView {
-    // packed matrix: shared memory (MAT_SMEM) or global
-    const double *val;
-    const uint16_t *col;
-    const int32_t *slab;
-    const int32_t *row_n;
-    const int32_t *row_nnz;
-    const uint32_t *row_info;
-    const int32_t *row_woff;
-    const uint64_t *row_mask;  // wide units, global
-    int n_words;
-    int n_slabs, n_chain_slabs, h, n_cells, n_chain_cells;
-    // per-iteration scratch of the chain rows and the task queues: where the matrix is
-    double *scr_cum;
-    uint16_t *scr_col;
-    uint32_t *queue;  // two buffers of 3 * qcap words: fragments | node | padded row
-    int qcap;
-    const uint32_t *pool;  // this iteration's uniform words (shared memory) or nullptr
-    const int32_t *pool_first;  // per slot: first block of the slot in the unit's pool (UnitDev, global)
-    int *ctl;
-};
-
-// Four consecutive words of a slot's pool starting at unit-level word `w`.
-__device__ __forceinline__ u32x4 pool_words4(const FastView &V, const uint64_t *skey, uint32_t slot, uint32_t ph_pool, uint32_t iteration, int w) {
-    u32x4 o;
-    if (V.pool) {
-        o.x = V.pool[w]; o.y = V.pool[w + 1]; o.z = V.pool[w + 2]; o.w = V.pool[w + 3];
-        return o;
-    }
-    // not staged (pool larger than shared memory): the blocks are computed where they are needed -- the same words
-    const int wl = w - 4 * V.pool_first[slot];  // word of the slot's own pool
-    const uint32_t b0 = (uint32_t)wl >> 2, off = (uint32_t)wl & 3u;
-    const uint64_t key = skey[slot];
-    const u32x4 A = make_site(key, ph_pool, iteration, b0 >> 12, 0).block(b0 & 4095u);
-    if (off == 0u) return A;
-    const u32x4 B = make_site(key, ph_pool, iteration, (b0 + 1u) >> 12, 0).block((b0 + 1u) & 4095u);
-    const uint32_t a[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
-    o.x = a[off]; o.y = a[off + 1]; o.z = a[off + 2]; o.w = a[off + 3];
-    return o;
-}
-
 // Pool of the iteration: block b of the unit = block (desc & 0xffffff) of the pool of slot (desc >> 24).
 __device__ __forceinline__ void fast_pool_gen(uint32_t *pool, const uint32_t *pool_desc, int pool_blocks, const uint64_t *skey, uint32_t iteration,
                                               bool init, int first_thread, int n_threads) {
@@ -114,24 +74,6 @@ __device__ __forceinline__ void fast_pool_gen(uint32_t *pool, const uint32_t *po
         const uint32_t desc = pool_desc[b], blk = desc & 0xffffffu;
         const u32x4 w = make_site(skey[desc >> 24], ph, iteration, blk >> 12, 0).block(blk & 4095u);
         reinterpret_cast<uint4 *>(pool)[b] = make_uint4(w.x, w.y, w.z, w.w);
-    }
-}
-
-// Warp-aggregated append of at most one task per lane to queue buffer `buf`, counted by ctl word `cnt`.  All 32 lanes call.
-__device__ __forceinline__ void push_tasks(const FastView &V, int cnt, int buf, bool want, uint32_t n, uint32_t node, uint32_t row) {
-    const uint32_t m = __ballot_sync(kFull, want);
-    if (m == 0u) return;
-    const int leader = __ffs(m) - 1;
-    int base = 0;
-    if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(&V.ctl[cnt], __popc(m));
-    base = __shfl_sync(kFull, base, leader);
-    if (want) {
-        const int idx = base + __popc(m & lanemask_lt());
-        BAYES_CHECK(idx < V.qcap, 101);
-        uint32_t *q = V.queue + (size_t)buf * 3 * V.qcap;
-        q[idx] = n;
-        q[V.qcap + idx] = node;
-        q[2 * V.qcap + idx] = row;
     }
 }
 
@@ -158,7 +100,7 @@ struct TileView {
     int n_tiles, n_chain_tiles;
     double *scr_cum;         // n_chain_tiles * 32: running sums of the cells in play of every chain row, compacted to the row's first cells
     uint16_t *scr_col;       // their candidate lanes
-    uint32_t *queue;         // two buffers of 2 * qcap words: fragments | ordinal | first cell << 20 | (cells - 1) << 25
+    uint32_t *queue;         // two buffers of 2 * qcap words: fragments | ordinal | chunk << 15 | first cell << 22 | (cells - 1) << 27
     int qcap;
     const uint32_t *pool;    // this iteration's uniform words (shared memory) or nullptr
     const int32_t *pool_first;
@@ -202,9 +144,11 @@ __device__ __forceinline__ u32x4 tile_pool_words4(const TileView &V, const uint6
 
 // A-step, first part: every tile in one pass.  Chain tiles compact the cells in play of their rows into the scratch
 // lists and queue the roots of the splitting trees; the other tiles locate their rows' pool words right away.
+// (a unit spread over a cluster of n_cta CTAs: tile t goes to CTA t mod n_cta, so the chain tiles -- the first ones -- and with them the
+// splitting trees are dealt over all CTAs)
 __device__ __forceinline__ void tile_rows(const TileView &V, const double *theta, int32_t *counts, const uint64_t *skey, uint32_t iteration,
-                                          const bool init) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+                                          const bool init, const int rank = 0, const int n_cta = 1) {
+    const int lane = threadIdx.x & 31, warp = (int)(threadIdx.x >> 5) * n_cta + rank, n_warps = (int)(blockDim.x >> 5) * n_cta;
     const uint32_t ph_pool = init ? PH_INIT_POOL : PH_POOL;
     const uint32_t le = lanemask_le(), lt = lanemask_lt();
     // Tiles cost about the same, so the warps take them round robin; the next tile of the warp is loaded while this one is
@@ -256,12 +200,13 @@ __device__ __forceinline__ void tile_rows(const TileView &V, const double *theta
             if (inplay && k == 1) atomicAdd(&counts[c], (int)n);
             if (head && k == 0) V.ctl[kCtlErr] = 1;  // reference: assert(normalisation_constant >= double_underflow) (:284)
             // the row's fragments enter the tree as independent chunks of at most 64: every binomial stays in the inversion regime
-            // (rows with more than 2048 fragments enter whole: their binomials are BTRD's either way)
-            const int m = head && k >= 2 ? (n <= 2048u ? ((int)n + 63) >> 6 : 1) : 0;
+            // (a row above 64 kTreeChunks fragments enters whole: its binomials are BTRD's either way.  Measured both ways on config 4:
+            // 128 chunks of such rows cost 5 % of the batch's throughput and make the largest locus slower, not faster)
+            const int m = head && k >= 2 ? (((int)n + 63) >> 6 <= kTreeChunks ? ((int)n + 63) >> 6 : 1) : 0;
             const int m_max = __reduce_max_sync(kFull, m);
             for (int ch = 0; ch < m_max; ch++)
                 tile_push(V, kCtlQ0, 0, ch < m, n / (uint32_t)max(m, 1) + (uint32_t)(ch < (int)(n % (uint32_t)max(m, 1))),
-                          ord | ((uint32_t)ch << 15) | ((uint32_t)(k - 1) << 25));
+                          ord | ((uint32_t)ch << 15) | ((uint32_t)(k - 1) << 27));
         } else {
             const int n = (int)((meta >> kMetaNShift) & 31u);  // 0: padding lane
             const int w0 = (int)(meta >> kMetaWoffShift);
@@ -293,8 +238,11 @@ __device__ __forceinline__ void tile_rows(const TileView &V, const double *theta
     }
 }
 
-// A-step, second part: the splitting trees, level by level (see fast_tree_levels below for the scheme)
-__device__ __forceinline__ void tile_tree_levels(const TileView &V, int32_t *counts, const uint64_t *skey, uint32_t iteration, const bool init) {
+// A-step, second part: the splitting trees, level by level.  One lane per node of the level, whichever row it belongs to; children
+// with two or more cells are queued for the next level, single cells receive their fragments.  Three rotating counters (this level,
+// next level, the one being reset) and two queue buffers need one block barrier per level.
+__device__ __forceinline__ void tile_tree_levels(const TileView &V, int32_t *counts, const uint64_t *skey, uint32_t iteration, const bool init,
+                                                 long long *n_levels = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t ph_tree = init ? PH_INIT_TREE : PH_TREE;
     const int qcap = V.qcap;
@@ -304,14 +252,15 @@ __device__ __forceinline__ void tile_tree_levels(const TileView &V, int32_t *cou
         if (Q == 0) break;
         if (threadIdx.x == 0) V.ctl[old] = 0;
         const uint32_t *q = V.queue + (size_t)buf * 2 * qcap;
+        if (n_levels) { n_levels[0] += 1; n_levels[1] += Q; }
         for (int i0 = warp * 32; i0 < Q; i0 += (int)blockDim.x) {
             const int i = i0 + lane;
             bool push_l = false, push_r = false;
             uint32_t n_l = 0, n_r = 0, w_l = 0, w_r = 0;
             if (i < Q) {
                 const uint32_t n = q[i], w1 = q[qcap + i];
-                const uint32_t ord = w1 & 0x7FFFu, och = w1 & 0xFFFFFu;  // och: ordinal and chunk, inherited by the children
-                const int a = (int)((w1 >> 20) & 31u), len = (int)(w1 >> 25) + 1, half = len >> 1, len_r = len - half;
+                const uint32_t ord = w1 & 0x7FFFu, och = w1 & 0x3FFFFFu;  // och: ordinal and chunk, inherited by the children
+                const int a = (int)((w1 >> 22) & 31u), len = (int)(w1 >> 27) + 1, half = len >> 1, len_r = len - half;
                 const int base = (int)V.ctab[3 * ord + 2];
                 BAYES_CHECK(base + a + len - 1 < 32 * V.n_chain_tiles, 116);
                 const double *sc = V.scr_cum + base;
@@ -320,197 +269,20 @@ __device__ __forceinline__ void tile_tree_levels(const TileView &V, int32_t *cou
                 const uint32_t info = V.ctab[3 * ord + 1];
                 const uint32_t node = (uint32_t)a | ((uint32_t)(len - 1) << 12);
                 const Site site = make_site(skey[info >> kRowSlotShift], ph_tree | (node << 8), iteration, info & ((1u << kRowSlotShift) - 1u),
-                                            (w1 >> 15) & 31u);
+                                            (w1 >> 15) & 127u);
                 n_l = (uint32_t)binomial_variate(site, (int)n, p_left);
                 n_r = n - n_l;
                 if (n_l) {
                     if (half == 1) atomicAdd(&counts[V.scr_col[base + a]], (int)n_l);
-                    else { push_l = true; w_l = och | ((uint32_t)a << 20) | ((uint32_t)(half - 1) << 25); }
+                    else { push_l = true; w_l = och | ((uint32_t)a << 22) | ((uint32_t)(half - 1) << 27); }
                 }
                 if (n_r) {
                     if (len_r == 1) atomicAdd(&counts[V.scr_col[base + a + half]], (int)n_r);
-                    else { push_r = true; w_r = och | ((uint32_t)(a + half) << 20) | ((uint32_t)(len_r - 1) << 25); }
+                    else { push_r = true; w_r = och | ((uint32_t)(a + half) << 22) | ((uint32_t)(len_r - 1) << 27); }
                 }
             }
             tile_push(V, nxt, buf ^ 1, push_l, n_l, w_l);
             tile_push(V, nxt, buf ^ 1, push_r, n_r, w_r);
-        }
-        __syncthreads();
-        const int t = old;
-        old = cur;
-        cur = nxt;
-        nxt = t;
-        buf ^= 1;
-    }
-}
-
-// Wide unit: a row stores hundreds of cells of which a few tens are in play; the cells in play are named by the row's
-// candidate mask ANDed with the simplex mask (ActiveCells, gibbs_common.cuh), never by visiting the stored cells.
-constexpr int kFastRowCache = 24;
-
-__device__ __forceinline__ void fast_rows_wide(const FastView &V, const uint64_t *amask, const double *theta, int32_t *counts, const uint64_t *skey,
-                                               uint32_t iteration, const bool init) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    const uint32_t ph_pool = init ? PH_INIT_POOL : PH_POOL;
-    const int H = V.h;
-    const bool dynamic = n_warps > 1;
-    uint32_t kc[kFastRowCache];  // candidates of the first cells in play of the row
-    double pc[kFastRowCache];    // their running sums
-    for (int s = warp;; s += n_warps) {
-        if (dynamic) {
-            if (lane == 0) s = atomicAdd(&V.ctl[kCtlSlab], 1);
-            s = __shfl_sync(kFull, s, 0);
-        }
-        if (s >= V.n_slabs) break;
-        const int r = s * H + lane;
-        const uint32_t item = lane < H ? (uint32_t)V.row_nnz[r] : 0u;
-        const int nnz = (int)(item & kItemNnzMask);
-        const bool live = nnz > 0;
-        const int n = live ? V.row_n[r] : 0;
-        const int cell0 = V.slab[s] + lane;
-        const double *val = V.val + cell0;
-        ActiveCells scan;
-        scan.rm = V.row_mask + (size_t)s * V.n_words * H + lane;
-        scan.amask = amask;
-        scan.h = H;
-        scan.n_words = V.n_words;
-        int k, c;
-        if (s < V.n_chain_slabs) {
-            double *sc = V.scr_cum + cell0;
-            uint16_t *scol = V.scr_col + cell0;
-            double cum = 0.0;
-            int k2 = 0, c_last = 0;
-            if (live) {
-                scan.start();
-                while (scan.next(k, c)) {
-                    BAYES_CHECK(k < nnz && cell0 + H * k < V.n_chain_cells, 104);
-                    const double p = val[H * k] * theta[c];
-                    if (p > 0.0) {
-                        cum += p;
-                        sc[H * k2] = cum;
-                        scol[H * k2] = (uint16_t)c;
-                        k2++;
-                        c_last = c;
-                    }
-                }
-                if (k2 == 1) atomicAdd(&counts[c_last], n);
-                else if (k2 == 0) V.ctl[kCtlErr] = 1;
-            }
-            {
-                const int m = live && k2 >= 2 ? (n <= 2048 ? (n + 63) >> 6 : 1) : 0;
-                const int m_max = __reduce_max_sync(kFull, m);
-                for (int ch = 0; ch < m_max; ch++)
-                    push_tasks(V, kCtlQ0, 0, ch < m, (uint32_t)(n / max(m, 1) + (ch < n % max(m, 1))),
-                               ((uint32_t)(k2 - 1) << 12) | ((uint32_t)ch << 24), (uint32_t)r);
-            }
-        } else if (live) {
-            double Z = 0.0;
-            int in_play = 0, c_last = 0;
-            scan.start();
-            while (scan.next(k, c)) {
-                BAYES_CHECK(k < nnz && cell0 + H * k < V.n_cells, 105);
-                const double p = val[H * k] * theta[c];
-                if (p > 0.0) {
-                    Z += p;
-                    if (in_play < kFastRowCache) {
-                        kc[in_play] = (uint32_t)c;
-                        pc[in_play] = Z;
-                    }
-                    in_play++;
-                    c_last = c;
-                }
-            }
-            if (in_play == 0) {
-                V.ctl[kCtlErr] = 1;
-            } else {
-                int rem = n;
-                if (in_play > 1) {
-                    const double rZ = __drcp_rn(Z);
-                    const int w0 = V.row_woff[r];
-                    for (int j0 = 0; j0 < n; j0 += 4) {
-                        const int left = n - j0 < 4 ? n - j0 : 4;
-                        const u32x4 w = pool_words4(V, skey, 0, ph_pool, iteration, w0 + j0);
-                        int prev = 0;
-                        if (in_play <= kFastRowCache) {
-                            for (int i = 0; i < in_play - 1; i++) {
-                                const uint32_t t = __double2uint_ru(__fma_rn(pc[i] * rZ, 4294967296.0, -1.0));
-                                const int below = words_below(w, left, t);
-                                if (below > prev) atomicAdd(&counts[kc[i]], below - prev);
-                                rem -= below - prev;
-                                prev = below;
-                                if (below >= left) break;
-                            }
-                        } else {
-                            double cum = 0.0;
-                            int seen = 0;
-                            scan.start();
-                            while (scan.next(k, c)) {
-                                const double p = val[H * k] * theta[c];
-                                if (!(p > 0.0)) continue;
-                                if (++seen == in_play) break;  // the last cell in play takes the rest
-                                cum += p;
-                                const uint32_t t = __double2uint_ru(__fma_rn(cum * rZ, 4294967296.0, -1.0));
-                                const int below = words_below(w, left, t);
-                                if (below > prev) atomicAdd(&counts[c], below - prev);
-                                rem -= below - prev;
-                                prev = below;
-                                if (below >= left) break;
-                            }
-                        }
-                    }
-                }
-                if (rem > 0) atomicAdd(&counts[c_last], rem);
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// A-step, second part: the splitting trees of the chain rows, level by level.  One lane per node of the level,
-// whichever row it belongs to; children with two or more cells are queued for the next level, single cells receive
-// their fragments.  Three rotating counters (this level, next level, the one being reset) and two queue buffers need
-// one block barrier per level.
-// ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fast_tree_levels(const FastView &V, int32_t *counts, const uint64_t *skey, uint32_t iteration, const bool init) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t ph_tree = init ? PH_INIT_TREE : PH_TREE;
-    const int H = V.h, hs = __ffs(H) - 1, qcap = V.qcap;
-    int cur = kCtlQ0, nxt = kCtlQ0 + 1, old = kCtlQ0 + 2, buf = 0;
-    for (;;) {
-        const int Q = V.ctl[cur];
-        if (Q == 0) break;
-        if (threadIdx.x == 0) V.ctl[old] = 0;
-        const uint32_t *q = V.queue + (size_t)buf * 3 * qcap;
-        for (int i0 = warp * 32; i0 < Q; i0 += (int)blockDim.x) {
-            const int i = i0 + lane;
-            bool push_l = false, push_r = false;
-            uint32_t n_l = 0, n_r = 0, node_l = 0, node_r = 0, row = 0;
-            if (i < Q) {
-                const uint32_t n = q[i], node = q[qcap + i];
-                row = q[2 * qcap + i];
-                const uint32_t chunk = node >> 24;
-                const int a = (int)(node & 4095u), len = (int)((node >> 12) & 4095u) + 1, half = len >> 1, len_r = len - half;
-                const int cell0 = V.slab[row >> hs] + (int)(row & (uint32_t)(H - 1));
-                BAYES_CHECK(cell0 + H * (a + len - 1) < V.n_chain_cells, 106);
-                const double *sc = V.scr_cum + cell0;
-                const double Pa = a ? sc[H * (a - 1)] : 0.0, Pm = sc[H * (a + half - 1)], Pb = sc[H * (a + len - 1)];
-                const double p_left = (Pm - Pa) / (Pb - Pa);
-                const uint32_t info = V.row_info[row];
-                const Site site = make_site(skey[info >> kRowSlotShift], ph_tree | ((node & 0xFFFFFFu) << 8), iteration,
-                                            info & ((1u << kRowSlotShift) - 1u), chunk);
-                n_l = (uint32_t)binomial_variate(site, (int)n, p_left);
-                n_r = n - n_l;
-                if (n_l) {
-                    if (half == 1) atomicAdd(&counts[V.scr_col[cell0 + H * a]], (int)n_l);
-                    else { push_l = true; node_l = (uint32_t)a | ((uint32_t)(half - 1) << 12) | (chunk << 24); }
-                }
-                if (n_r) {
-                    if (len_r == 1) atomicAdd(&counts[V.scr_col[cell0 + H * (a + half)]], (int)n_r);
-                    else { push_r = true; node_r = (uint32_t)(a + half) | ((uint32_t)(len_r - 1) << 12) | (chunk << 24); }
-                }
-            }
-            push_tasks(V, nxt, buf ^ 1, push_l, n_l, node_l, row);
-            push_tasks(V, nxt, buf ^ 1, push_r, n_r, node_r, row);
         }
         __syncthreads();
         const int t = old;
@@ -644,67 +416,19 @@ __device__ __forceinline__ TileView tile_stage(const KernelArgs &A, const UnitDe
     return V;
 }
 
-template <bool MAT_SMEM>
-__device__ __forceinline__ FastView fast_stage(const KernelArgs &A, const UnitDev &U, const FastLayout &lay, unsigned char *smem) {
-    FastView V;
-    V.n_slabs = U.n_slabs;
-    V.n_chain_slabs = U.n_chain_slabs;
-    V.h = U.slab_h;
-    V.n_cells = U.n_cells;
-    V.n_chain_cells = U.n_chain_cells;
-    V.qcap = U.qcap;
-    V.row_mask = (const uint64_t *)A.row_mask + U.mask_off;
-    V.n_words = (U.Tpad + 63) >> 6;
-    V.ctl = (int *)(smem + lay.ctl);
-    V.pool_first = U.pool_first;
-    const int Rp = U.n_slabs * U.slab_h;
-    if (MAT_SMEM) {
-        double *sv = (double *)(smem + lay.val);
-        uint16_t *sc = (uint16_t *)(smem + lay.col);
-        int32_t *ss = (int32_t *)(smem + lay.slab);
-        int32_t *rn = (int32_t *)(smem + lay.row_n);
-        int32_t *rz = (int32_t *)(smem + lay.row_nnz);
-        uint32_t *ri = (uint32_t *)(smem + lay.row_info);
-        int32_t *rw = (int32_t *)(smem + lay.row_woff);
-        block_copy(sv, A.val + U.cell_off, U.n_cells);
-        block_copy(sc, A.col + U.cell_off, U.n_cells);
-        block_copy(ss, A.slab_cell_off + U.slab_off, U.n_slabs + 1);
-        block_copy(rn, A.row_n + U.row_off, Rp);
-        block_copy(rz, A.row_nnz + U.row_off, Rp);
-        block_copy(ri, A.row_info + U.row_off, Rp);
-        block_copy(rw, A.row_woff + U.woff_off, Rp);
-        V.val = sv; V.col = sc; V.slab = ss; V.row_n = rn; V.row_nnz = rz; V.row_info = ri; V.row_woff = rw;
-        V.scr_cum = (double *)(smem + lay.scr_cum);
-        V.scr_col = (uint16_t *)(smem + lay.scr_col);
-        V.queue = (uint32_t *)(smem + lay.queue);
-    } else {
-        V.val = A.val + U.cell_off;
-        V.col = A.col + U.cell_off;
-        V.slab = A.slab_cell_off + U.slab_off;
-        V.row_n = A.row_n + U.row_off;
-        V.row_nnz = A.row_nnz + U.row_off;
-        V.row_info = A.row_info + U.row_off;
-        V.row_woff = A.row_woff + U.woff_off;
-        V.scr_cum = A.scr_cum + U.scr_off;
-        V.scr_col = A.scr_col + U.scr_off;
-        V.queue = A.queue + U.q_off;
-    }
-    uint32_t *pool = nullptr;
-    if (U.pool_smem) {
-        pool = (uint32_t *)(smem + lay.pool);
-        block_copy((uint32_t *)(smem + lay.pool_desc), A.pool_desc + U.pooldesc_off, U.pool_blocks);
-        if (threadIdx.x < 4) pool[4 * U.pool_blocks + threadIdx.x] = 0u;  // the spare block
-    }
-    V.pool = pool;
-    return V;
-}
-
 // ------------------------------------------------------------------------------------------------------------------
+// A latency-critical unit may be spread over a thread-block cluster (build_units, the ladder's last rungs): every CTA runs the
+// same E-step on the same counts (same theta, nothing to exchange), takes every n_cta-th tile -- and with its chain tiles their
+// splitting trees --, accumulates the fragments it places in a partial count vector of its own, and after one cluster barrier
+// per iteration adds up the partial vectors of all CTAs through distributed shared memory (double-buffered, like gibbs_rows.cu).
 template <bool MAT_SMEM, bool SCR_SMEM>
 __global__ void __maxnreg__(BAYES_FAST_MAXNREG) gibbs_fast_bundle_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int64_t ui = unit_base + blockIdx.x;
-    if (threadIdx.x == 0) A.unit_clock[3 * ui] = global_ns();
+    cg::cluster_group cluster = cg::this_cluster();
+    const int n_cta = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const bool lead = rank == 0;
+    const int64_t ui = unit_base + blockIdx.x / n_cta;
+    if (lead && threadIdx.x == 0) A.unit_clock[3 * ui] = global_ns();
     const UnitDev &U = A.units[ui];
     const int n_slots = U.n_slots, Tpad = U.Tpad;
     const TileLayout lay = tile_layout(n_slots, Tpad, U.n_tiles, U.n_chain_tiles, U.n_chain_rows, U.tab_len, U.tab_smem != 0, MAT_SMEM, SCR_SMEM,
@@ -768,7 +492,11 @@ __global__ void __maxnreg__(BAYES_FAST_MAXNREG) gibbs_fast_bundle_kernel(const _
     }
     if (threadIdx.x < kFastCtlWords) V.ctl[threadIdx.x] = 0;
 
-    const bool tracing = A.trace_unit == ui;
+    int32_t *part = (int32_t *)(smem + lay.part);  // cluster: two buffers of 32 partial counts
+    if (threadIdx.x < 64) part[threadIdx.x] = 0;
+    int cur = 0;
+    int32_t *acc = n_cta > 1 ? part : E.counts;
+    const bool tracing = lead && A.trace_unit == ui;
     const bool my_trace = tracing && threadIdx.x < 32 && g == A.trace_slot && valid;
     const int Tg = valid ? U.T[g] : 0;
     const int burn = U.burn;
@@ -776,6 +504,12 @@ __global__ void __maxnreg__(BAYES_FAST_MAXNREG) gibbs_fast_bundle_kernel(const _
     const int stamp_at = A.iter_cap > 0 ? total >> 1 : -2;  // calibration pass: time the second half only
     const int n_threads = blockDim.x;
     __syncthreads();
+#ifdef BAYES_TILE_PHASES  // development aid: thread 0 times the phases of every iteration (SM clock); large blocks print the averages
+    long long ph_t = clock64(), ph_a[3] = {0, 0, 0}, ph_levels[2] = {0, 0};
+#define TILE_PHASE(i) do { if (threadIdx.x == 0) { const long long now_ = clock64(); ph_a[i] += now_ - ph_t; ph_t = now_; } } while (0)
+#else
+#define TILE_PHASE(i) do { } while (0)
+#endif
 
     // it == -1 is initAssignment (gibbsSampler.cpp:90): the same A-step code on theta == 1, no E-step before it
     for (int it = -1; it < total; it++) {
@@ -785,7 +519,7 @@ __global__ void __maxnreg__(BAYES_FAST_MAXNREG) gibbs_fast_bundle_kernel(const _
             V.ctl[kCtlQ0] = 0;
             V.ctl[kCtlQ0 + 1] = 0;
             V.ctl[kCtlQ0 + 2] = 0;
-            if (it == stamp_at) A.unit_clock[3 * ui] = global_ns();
+            if (lead && it == stamp_at) A.unit_clock[3 * ui] = global_ns();
         }
         if (it >= 0 && threadIdx.x < 32) {
             if (my_trace && it == 0) A.tr_init[t] = E.counts[lane];
@@ -800,191 +534,61 @@ __global__ void __maxnreg__(BAYES_FAST_MAXNREG) gibbs_fast_bundle_kernel(const _
         if (it < 0 || n_threads == 32) fast_pool_gen(pool, pool_desc, pool_blocks, skey, iter, it < 0, 0, n_threads);
         else if (threadIdx.x >= 32) fast_pool_gen(pool, pool_desc, pool_blocks, skey, iter, false, 32, n_threads - 32);
         __syncthreads();
-        tile_rows(V, E.theta, E.counts, skey, iter, it < 0);
+        TILE_PHASE(0);
+        tile_rows(V, E.theta, acc, skey, iter, it < 0, rank, n_cta);
         __syncthreads();
-        tile_tree_levels(V, E.counts, skey, iter, it < 0);
+        TILE_PHASE(1);
+#ifdef BAYES_TILE_PHASES
+        tile_tree_levels(V, acc, skey, iter, it < 0, threadIdx.x == 0 ? ph_levels : nullptr);
+#else
+        tile_tree_levels(V, acc, skey, iter, it < 0);
+#endif
+        if (n_cta > 1) {
+            cluster.sync();
+            if (threadIdx.x < 32) {
+                int s = 0;
+                for (int j = 0; j < n_cta; j++) s += cluster.map_shared_rank(part, j)[cur * 32 + lane];
+                E.counts[lane] += s;
+                part[(cur ^ 1) * 32 + lane] = 0;  // read by the other CTAs one iteration ago, before the barrier above
+            }
+            cur ^= 1;
+            acc = part + cur * 32;
+            __syncthreads();
+        }
+        TILE_PHASE(2);
     }
+#ifdef BAYES_TILE_PHASES
+    if (threadIdx.x == 0 && n_threads >= 256) {
+        const double k = 1.0 / (1.965 * (total + 1));
+        printf("tile phases, ns/iteration (%d slots, T0=%d, %d tiles (%d chain), %d threads): E-step / pool %.0f | tiles %.0f | trees %.0f (%.1f levels, %.0f nodes per "
+               "iteration)\n", n_slots, U.T[0], U.n_tiles, U.n_chain_tiles, n_threads, ph_a[0] * k, ph_a[1] * k, ph_a[2] * k, (double)ph_levels[0] / (total + 1),
+               (double)ph_levels[1] / (total + 1));
+    }
+#endif
     if (my_trace && total - 1 < A.trace_iters) A.tr_counts[(size_t)(total - 1) * Tg + t] = E.counts[lane];
 
-    if (threadIdx.x < 32 && valid) {
+    if (lead && threadIdx.x < 32 && valid) {
         const int64_t o = U.out_off[g] + t;
         A.out_occ[o] = E.occ[lane];
         A.out_mean[o] = E.mean[lane];
         A.out_m2[o] = E.m2[lane];
         A.out_counts[o] = E.counts[lane];
     }
-    if (threadIdx.x == 0) {
-        A.unit_err[ui] = V.ctl[kCtlErr];
+    int err = V.ctl[kCtlErr];
+    if (n_cta > 1) {
+        cluster.sync();
+        if (lead && threadIdx.x == 0)
+            for (int j = 1; j < n_cta; j++) {
+                const int e = cluster.map_shared_rank(V.ctl, j)[kCtlErr];
+                if (e) err = e;
+            }
+        cluster.sync();  // nobody leaves while its shared memory may still be read
+    }
+    if (lead && threadIdx.x == 0) {
+        A.unit_err[ui] = err;
         A.unit_clock[3 * ui + 1] = global_ns();
         A.unit_clock[3 * ui + 2] = sm_id();
     }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-template <bool MAT_SMEM>
-__global__ void __maxnreg__(BAYES_FAST_WIDE_MAXNREG) gibbs_fast_wide_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int64_t ui = unit_base + blockIdx.x;
-    if (threadIdx.x == 0) A.unit_clock[3 * ui] = global_ns();
-    const UnitDev &U = A.units[ui];
-    const int T = U.T[0];
-    const FastLayout lay = fast_layout(true, T, 1, U.Tpad, U.n_slabs, U.slab_h, U.n_cells, U.tab_len, U.tab_smem != 0, MAT_SMEM, U.n_chain_cells,
-                                       U.qcap, U.pool_blocks, U.pool_smem != 0);
-    WideState E;
-    E.theta = (double *)(smem + lay.theta);
-    E.den = (double *)(smem + lay.den);
-    E.mean = (double *)(smem + lay.mean);
-    E.m2 = (double *)(smem + lay.m2);
-    E.counts = (int32_t *)(smem + lay.counts);
-    E.occ = (int32_t *)(smem + lay.occ);
-    int32_t *base = (int32_t *)(smem + lay.base);
-    E.base = base;
-    E.mask = (uint32_t *)(smem + lay.mask);
-    E.act = (uint16_t *)(smem + lay.act);
-    E.amask = (uint64_t *)(smem + lay.amask);
-    E.T = T;
-    E.nch = (T + 31) >> 5;
-    E.N_f = U.N_f[0];
-    E.gamma = U.gamma[0];
-    uint64_t *skey = (uint64_t *)(smem + lay.key);
-    const uint64_t key = U.key[0];
-    if (threadIdx.x == 0) skey[0] = key;
-
-    const double n_total = (double)U.N_total[0];
-    for (int t = threadIdx.x; t < T; t += blockDim.x) {
-        const int32_t bc = A.base_counts[U.lane_off + t];
-        base[t] = bc;
-        E.counts[t] = bc;
-        E.occ[t] = 0;
-        E.mean[t] = 0.0;
-        E.m2[t] = 0.0;
-        E.theta[t] = 1.0;  // initAssignment runs the A-step on P_ij itself
-        E.den[t] = A.efflen[U.lane_off + t] * n_total;  // valueContainer.cpp:235 denominator
-    }
-    // initAssignment (theta == 1): every candidate is "in the simplex"
-    for (int w = threadIdx.x; w < (T + 63) >> 6; w += blockDim.x)
-        E.amask[w] = w == ((T + 63) >> 6) - 1 && (T & 63) ? (1ull << (T & 63)) - 1ull : ~0ull;
-    if (U.tab_smem) {
-        double *tv = (double *)(smem + lay.tab_val);
-        int32_t *tr = (int32_t *)(smem + lay.tab_row);
-        block_copy(tv, A.tab_val + U.tab_off, U.tab_len);
-        block_copy(tr, A.tab_row + U.tabrow_off, T + 1);
-        E.tab_val = tv;
-        E.tab_row = tr;
-    } else {
-        E.tab_val = A.tab_val + U.tab_off;
-        E.tab_row = A.tab_row + U.tabrow_off;
-    }
-    FastView V = fast_stage<MAT_SMEM>(A, U, lay, smem);
-    uint32_t *pool = (uint32_t *)(smem + lay.pool);
-    const uint32_t *pool_desc = (const uint32_t *)(smem + lay.pool_desc);
-    const int pool_blocks = U.pool_smem ? U.pool_blocks : 0;
-    if (threadIdx.x < kFastCtlWords) V.ctl[threadIdx.x] = 0;
-
-    const bool tracing = A.trace_unit == ui;
-    const int burn = U.burn;
-    const int total = A.iter_cap > 0 && A.iter_cap < U.burn + U.samples ? A.iter_cap : U.burn + U.samples;
-    const int stamp_at = A.iter_cap > 0 ? total >> 1 : -2;
-    const int n_threads = blockDim.x;
-    __syncthreads();
-
-    for (int it = -1; it < total; it++) {
-        const uint32_t iter = (uint32_t)(it < 0 ? 0 : it);
-        if (threadIdx.x == 0) {
-            V.ctl[kCtlSlab] = 0;
-            V.ctl[kCtlQ0] = 0;
-            V.ctl[kCtlQ0 + 1] = 0;
-            V.ctl[kCtlQ0 + 2] = 0;
-            if (it == stamp_at) A.unit_clock[3 * ui] = global_ns();
-        }
-        if (it >= 0 && threadIdx.x < 32) {
-            const bool tr = tracing && it < A.trace_iters;
-            if (tracing && it == 0)
-                for (int t = threadIdx.x; t < T; t += 32) A.tr_init[t] = E.counts[t];
-            if (tracing && it > 0 && it - 1 < A.trace_iters)
-                for (int t = threadIdx.x; t < T; t += 32) A.tr_counts[(size_t)(it - 1) * T + t] = E.counts[t];
-            const int b = wide_e_step(E, key, iter, it >= burn || (stamp_at >= 0 && it >= stamp_at), tr ? A.tr_theta + (size_t)it * T : nullptr);
-            if (tr && threadIdx.x == 0) A.tr_b[it] = b;
-        }
-        if (it < 0 || n_threads == 32) fast_pool_gen(pool, pool_desc, pool_blocks, skey, iter, it < 0, 0, n_threads);
-        else if (threadIdx.x >= 32) fast_pool_gen(pool, pool_desc, pool_blocks, skey, iter, false, 32, n_threads - 32);
-        __syncthreads();
-        fast_rows_wide(V, E.amask, E.theta, E.counts, skey, iter, it < 0);
-        __syncthreads();
-        fast_tree_levels(V, E.counts, skey, iter, it < 0);
-    }
-    if (tracing && total - 1 < A.trace_iters)
-        for (int t = threadIdx.x; t < T; t += blockDim.x) A.tr_counts[(size_t)(total - 1) * T + t] = E.counts[t];
-
-    const int64_t o = U.out_off[0];
-    for (int t = threadIdx.x; t < T; t += blockDim.x) {
-        A.out_occ[o + t] = E.occ[t];
-        A.out_mean[o + t] = E.mean[t];
-        A.out_m2[o + t] = E.m2[t];
-        A.out_counts[o + t] = E.counts[t];
-    }
-    if (threadIdx.x == 0) {
-        A.unit_err[ui] = V.ctl[kCtlErr];
-        A.unit_clock[3 * ui + 1] = global_ns();
-        A.unit_clock[3 * ui + 2] = sm_id();
-    }
-}
-
-// ---- single A-step in fast mode (same device code, one block, wide layout, everything but theta / counts in global) ----
-template <bool INIT>
-__global__ void step_assignment_fast_kernel(const __grid_constant__ KernelArgs A, const double *theta_in, uint32_t iteration, int32_t *counts_out) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const UnitDev &U = A.units[0];
-    const int T = U.T[0];
-    double *theta = (double *)smem;
-    uint64_t *skey = (uint64_t *)(theta + T);
-    const int n_words = (T + 63) >> 6;
-    uint64_t *amask = (uint64_t *)(skey + 1);
-    int32_t *counts = (int32_t *)(amask + n_words);
-    int *ctl = (int *)(counts + T);
-    for (int t = threadIdx.x; t < T; t += blockDim.x) {
-        theta[t] = INIT ? 1.0 : theta_in[t];
-        counts[t] = A.base_counts[U.lane_off + t];
-    }
-    if (threadIdx.x == 0) skey[0] = U.key[0];
-    if (threadIdx.x < kFastCtlWords) ctl[threadIdx.x] = 0;
-    __syncthreads();
-    if (threadIdx.x < 32)
-        for (int w = 0; w < n_words; w++) {
-            const int t0 = w * 64 + (int)threadIdx.x;
-            const uint32_t lo = __ballot_sync(kFull, t0 < T && theta[t0] != 0.0);
-            const uint32_t hi = __ballot_sync(kFull, t0 + 32 < T && theta[t0 + 32] != 0.0);
-            if (threadIdx.x == 0) amask[w] = ((uint64_t)hi << 32) | lo;
-        }
-    FastView V;
-    V.n_slabs = U.n_slabs;
-    V.n_chain_slabs = U.n_chain_slabs;
-    V.h = U.slab_h;
-    V.n_cells = U.n_cells;
-    V.n_chain_cells = U.n_chain_cells;
-    V.qcap = U.qcap;
-    V.row_mask = (const uint64_t *)A.row_mask + U.mask_off;
-    V.n_words = n_words;
-    V.val = A.val + U.cell_off;
-    V.col = A.col + U.cell_off;
-    V.slab = A.slab_cell_off + U.slab_off;
-    V.row_n = A.row_n + U.row_off;
-    V.row_nnz = A.row_nnz + U.row_off;
-    V.row_info = A.row_info + U.row_off;
-    V.row_woff = A.row_woff + U.woff_off;
-    V.scr_cum = A.scr_cum + U.scr_off;
-    V.scr_col = A.scr_col + U.scr_off;
-    V.queue = A.queue + U.q_off;
-    V.pool = nullptr;  // the rows compute their pool blocks themselves
-    V.pool_first = U.pool_first;
-    V.ctl = ctl;
-    __syncthreads();
-    fast_rows_wide(V, amask, theta, counts, skey, iteration, INIT);
-    __syncthreads();
-    fast_tree_levels(V, counts, skey, iteration, INIT);
-    __syncthreads();
-    for (int t = threadIdx.x; t < T; t += blockDim.x) counts_out[t] = counts[t];
-    if (threadIdx.x == 0) A.unit_err[0] = ctl[kCtlErr];
 }
 
 // ---- single A-step in fast mode of a locus with up to 32 candidates: the tiles of a one-slot bundle, two warps ----------------
@@ -1038,30 +642,46 @@ int configure_fast_kernels() {
     int rc;
     const char *co = getenv("BAYES_CARVEOUT");  // experiment knob, percent (see configure_kernels)
     const int carveout = co ? atoi(co) : 65;
-    const void *fns[5] = {(const void *)gibbs_fast_bundle_kernel<true, true>, (const void *)gibbs_fast_bundle_kernel<false, true>,
-                          (const void *)gibbs_fast_bundle_kernel<false, false>, (const void *)gibbs_fast_wide_kernel<true>,
-                          (const void *)gibbs_fast_wide_kernel<false>};
+    const void *fns[3] = {(const void *)gibbs_fast_bundle_kernel<true, true>, (const void *)gibbs_fast_bundle_kernel<false, true>,
+                          (const void *)gibbs_fast_bundle_kernel<false, false>};
     for (const void *f : fns) {
         if ((rc = check_fast(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, carveout), "carveout"))) return rc;
         if ((rc = check_fast(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_unit_smem()), "cudaFuncSetAttribute"))) return rc;
     }
-    if ((rc = check_fast(cudaFuncSetAttribute(step_assignment_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "cudaFuncSetAttribute"))) return rc;
-    return check_fast(cudaFuncSetAttribute(step_assignment_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024), "cudaFuncSetAttribute");
+    return BAYES_OK;
 }
 
 int launch_units_fast(const KernelArgs &args, int64_t unit_base, int64_t n_units, int block, bool wide, bool mat_smem, bool scr_smem,
-                      size_t smem_bytes, void *stream) {
+                      size_t smem_bytes, void *stream, int n_cta) {
     if (n_units <= 0) return BAYES_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)n_units;
-    if (wide) {
-        if (mat_smem) gibbs_fast_wide_kernel<true><<<grid, block, smem_bytes, st>>>(args, unit_base);
-        else gibbs_fast_wide_kernel<false><<<grid, block, smem_bytes, st>>>(args, unit_base);
-    } else {
-        if (mat_smem) gibbs_fast_bundle_kernel<true, true><<<grid, block, smem_bytes, st>>>(args, unit_base);
-        else if (scr_smem) gibbs_fast_bundle_kernel<false, true><<<grid, block, smem_bytes, st>>>(args, unit_base);
-        else gibbs_fast_bundle_kernel<false, false><<<grid, block, smem_bytes, st>>>(args, unit_base);
+    if (!wide && n_cta > 1) {  // critical bundles spread over a thread-block cluster
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(n_units * n_cta), 1, 1);
+        cfg.blockDim = dim3((unsigned)block, 1, 1);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)n_cta;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t e;
+        if (mat_smem) e = cudaLaunchKernelEx(&cfg, gibbs_fast_bundle_kernel<true, true>, args, unit_base);
+        else if (scr_smem) e = cudaLaunchKernelEx(&cfg, gibbs_fast_bundle_kernel<false, true>, args, unit_base);
+        else e = cudaLaunchKernelEx(&cfg, gibbs_fast_bundle_kernel<false, false>, args, unit_base);
+        return check_fast(e, "gibbs fast kernel launch (cluster)");
     }
+    if (wide) {  // loci with more than 32 candidates run in gibbs_rows.cu (launch_units_rows)
+        set_error("launch_units_fast: wide units belong to the cooperative-rows kernel");
+        return BAYES_E_STATE;
+    }
+    if (mat_smem) gibbs_fast_bundle_kernel<true, true><<<grid, block, smem_bytes, st>>>(args, unit_base);
+    else if (scr_smem) gibbs_fast_bundle_kernel<false, true><<<grid, block, smem_bytes, st>>>(args, unit_base);
+    else gibbs_fast_bundle_kernel<false, false><<<grid, block, smem_bytes, st>>>(args, unit_base);
     return check_fast(cudaGetLastError(), "gibbs fast kernel launch");
 }
 
@@ -1073,9 +693,9 @@ int launch_step_assignment_fast(const KernelArgs &args, bool init, bool tiles, c
         else step_assignment_tiles_kernel<false><<<1, 64, 0, st>>>(args, d_theta, iteration, d_counts_out);
         return check_fast(cudaGetLastError(), "step_assignment_tiles_kernel launch");
     }
-    if (init) step_assignment_fast_kernel<true><<<1, 128, smem_bytes, st>>>(args, d_theta, iteration, d_counts_out);
-    else step_assignment_fast_kernel<false><<<1, 128, smem_bytes, st>>>(args, d_theta, iteration, d_counts_out);
-    return check_fast(cudaGetLastError(), "step_assignment_fast_kernel launch");
+    (void)smem_bytes;
+    set_error("launch_step_assignment_fast: loci with more than 32 candidates take launch_step_assignment_rows");
+    return BAYES_E_STATE;
 }
 
 }  // namespace bayes

@@ -282,10 +282,12 @@ __device__ __forceinline__ void rows_assign(const RowsView &V, const uint64_t *a
             } else if (kk == 1) {
                 if (lane == 0) atomicAdd(&acc[c_only], n);
             } else if (n > kRowsDirectMax) {
-                // the row's fragments enter the tree as independent chunks of at most 64 (rows above 2048 fragments whole)
-                const int mch = n <= 2048 ? (n + 63) >> 6 : 1;
-                push_tasks(V, kCtlQ0, 0, lane < mch, (uint32_t)(n / mch + (lane < n % mch)), ((uint32_t)(kk - 1) << 12) | ((uint32_t)lane << 24),
-                           (uint32_t)r);
+                // the row's fragments enter the tree as ceil(n / 64) independent chunks while that is at most kTreeChunks, else whole
+                const int mch = (n + 63) >> 6 <= kTreeChunks ? (n + 63) >> 6 : 1;
+                for (int c0 = 0; c0 < mch; c0 += 32) {
+                    const int ch = c0 + lane;
+                    push_tasks(V, kCtlQ0, 0, ch < mch, (uint32_t)(n / mch + (ch < n % mch)), ((uint32_t)(kk - 1) << 12) | ((uint32_t)ch << 24), (uint32_t)r);
+                }
             }
             continue;
         }

@@ -22,6 +22,7 @@ constexpr int kMaxT = 4096;             // candidates per locus (per-candidate s
 constexpr int kMaxBlock = 512;          // threads per unit
 constexpr int kWarpsPerSM = 28;         // resident warps per SM at the kernels' 72 registers per thread
 constexpr int kMaxSlots = 16;           // slots per bundle (T = 2 -> Tpad = 2 -> 16 slots)
+constexpr int kTreeChunks = 32;         // fast mode: a row enters its splitting tree in ceil(n / 64) independent chunks of fragments while that is at most kTreeChunks, else whole
 constexpr int kRowsDirectMax = 4096;    // fast mode, T > 32: rows with 20 .. this many fragments are drawn fragment by fragment, larger ones by the splitting tree
 constexpr int kMaxCluster = 16;         // CTAs of the thread-block cluster a wide locus may be spread over (fast mode)
 constexpr int kSmallCount = 20;         // assignmentGenerator.cpp:289: rows with fewer fragments draw uniforms
@@ -212,7 +213,7 @@ int launch_units(const KernelArgs &args, int64_t unit_base, int64_t n_units, int
                  void *stream);
 // gibbs_fast.cu
 int launch_units_fast(const KernelArgs &args, int64_t unit_base, int64_t n_units, int block, bool wide, bool mat_smem, bool scr_smem,
-                      size_t smem_bytes, void *stream);
+                      size_t smem_bytes, void *stream, int n_cta = 1);
 int launch_step_assignment_fast(const KernelArgs &args, bool init, bool tiles, const double *d_theta, uint32_t iteration, int32_t *d_counts_out,
                                 size_t smem_bytes, void *stream);
 int configure_fast_kernels();

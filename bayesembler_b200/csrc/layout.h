@@ -113,7 +113,7 @@ BAYES_LAYOUT_HD FastLayout fast_layout(bool wide, int nT, int n_slots, int Tpad,
 // ---- fast mode, bundles: lane-per-cell tiles --------------------------------------------------------------------------
 struct TileLayout {
     uint32_t theta, den, mean, m2, tab_val, val, scr_cum, key, sgamma, pool;  // 8-byte (pool: 16)
-    uint32_t counts, base, occ, tab_row, meta, ctab, pool_desc, queue, sT, sNf, ctl;  // 4-byte
+    uint32_t counts, base, occ, part, tab_row, meta, ctab, pool_desc, queue, sT, sNf, ctl;  // 4-byte
     uint32_t scr_col;  // 2-byte
     uint32_t total;
 };
@@ -140,6 +140,7 @@ BAYES_LAYOUT_HD TileLayout tile_layout(int n_slots, int Tpad, int n_tiles, int n
     L.counts = o; o += 4u * 32u;
     L.base = o; o += 4u * 32u;
     L.occ = o; o += 4u * 32u;
+    L.part = o; o += 4u * 64u;  // a critical unit spread over a cluster: two buffers of partial counts (gibbs_fast.cu)
     L.tab_row = o; o += tab_smem ? 4u * n_tabrow : 0u;
     L.meta = o; o += 4u * cells;
     L.ctab = o; o += scr_smem ? 12u * (uint32_t)n_chain_rows : 0u;

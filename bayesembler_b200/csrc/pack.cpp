@@ -46,7 +46,7 @@ int validate_locus(const bayes_locus_desc &in, std::string *err) {
 }
 
 size_t max_unit_smem() { return 227 * 1024; }
-int tree_chunks(int n) { return (n + 63) / 64 <= 32 ? (n + 63) / 64 : 1; }
+int tree_chunks(int n) { return (n + 63) / 64 <= kTreeChunks ? (n + 63) / 64 : 1; }
 bool g_tile_stream = true;
 
 int slot_lanes(int T) {

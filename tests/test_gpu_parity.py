@@ -303,3 +303,37 @@ def test_cluster_rows_full_chain(lib, oracle, monkeypatch, T, R, mc, n_cta):
     np.testing.assert_allclose(g["mean"], o["mean"], rtol=RTOL)
     np.testing.assert_allclose(g["m2"], o["m2"], rtol=1e-7, atol=1e-9 * np.abs(o["mean"]).max() ** 2)
     assert np.array_equal(g["final_counts"], o["counts_trace"][-1])
+
+
+@pytest.mark.parametrize("warps", [64, 128, 256])
+def test_cluster_bundle_full_chain(lib, oracle, monkeypatch, warps):
+    """A latency-critical bundle (loci with up to 32 candidates) spread over a thread-block cluster of 2, 4 or 8 CTAs of 32 warps
+    (gibbs_fast.cu): tiles and splitting trees dealt over the CTAs, partial counts summed through distributed shared memory.
+    Same chain as the oracle's, whatever the cluster size; a several-slot bundle rides along."""
+    monkeypatch.setenv("BAYES_FORCE_WARPS", str(warps))
+    rng = np.random.default_rng(warps)
+    loci = [random_locus(rng, 30, 900, max_count=4000), random_locus(rng, 5, 60, max_count=300), random_locus(rng, 5, 40, max_count=50),
+            random_locus(rng, 5, 80, max_count=900)]
+    seeds = [int(s) for s in rng.integers(1, 2 ** 62, len(loci))]
+    burn, samples = 50, 450
+    total = burn + samples
+    ctx = lib.GibbsContext(0, mode="fast")
+    ctx.submit(lib.make_desc_array(loci, [burn] * len(loci), [samples] * len(loci), seeds))
+    ctx.set_trace(0, 0, total)
+    ctx.upload(); ctx.run(); ctx.download(); ctx.sync()
+    tr = ctx.fetch_trace()
+    shape, _ = ctx.unit_stats()
+    assert np.all(shape[:, 1] == 1024)  # blocks of 32 warps, the cluster on top
+    for i, loc in enumerate(loci):
+        g = ctx.fetch(i)
+        o = oracle.run_sampler(loc, burn, samples, FAST, lib.chain_key(seeds[i], 0), trace_iters=total if i == 0 else 0)
+        if i == 0:
+            assert np.array_equal(tr["init_counts"], o["init_counts"])
+            assert np.array_equal(tr["b_trace"], o["b_trace"])
+            assert np.array_equal(tr["counts_trace"], o["counts_trace"])
+            np.testing.assert_allclose(tr["theta_trace"], o["theta_trace"], rtol=RTOL, atol=0)
+        assert np.array_equal(g["occ"], o["occ"]), i
+        np.testing.assert_allclose(g["mean"], o["mean"], rtol=RTOL)
+        np.testing.assert_allclose(g["m2"], o["m2"], rtol=1e-7, atol=1e-9 * np.abs(o["mean"]).max() ** 2)
+        assert g["final_counts"].sum() == loc.n_frag
+    ctx.close()
