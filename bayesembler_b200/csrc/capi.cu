@@ -536,13 +536,21 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         static const int ladder_fast[][2] = {{1, 32}, {2, 32}, {4, 32}, {8, 32}, {16, 32}, {32, 32}, {64, 32}, {128, 32}, {256, 32}};
         const int (*ladder)[2] = fast ? ladder_fast : ladder_replay;
         const char *mc = getenv("BAYES_MAX_BUNDLE_CTAS");  // experiment knob: 1 = no clusters for bundles
-        const int max_bundle_cta = mc ? std::max(1, std::min(8, atoi(mc))) : 8;
+        const int max_bundle_cta = mc ? std::max(1, std::min(8, atoi(mc))) : (n_units < 12 * (int64_t)ctx->sm_count ? 8 : 1);
         const int n_ladder_all = fast ? (max_bundle_cta >= 8 ? 9 : max_bundle_cta >= 4 ? 8 : max_bundle_cta >= 2 ? 7 : 6) : 7;
         const double capacity = (double)ctx->sm_count * kWarpsPerSM;  // resident warps at the kernels' register count
         const char *spw = getenv("BAYES_SMEM_PER_WARP");  // experiment knob
         const double smem_per_warp = spw ? atof(spw) : (fast ? 16384.0 : 8192.0);
         const char *ce = getenv("BAYES_CRIT");  // experiment knob
-        const double crit = ce ? atof(ce) : (fast ? 0.5 : 0.75);
+        // Fast mode, two regimes (measured on config 4 and on its eighth, the share of one GPU of eight; profiles/README.md):
+        //  * a batch of many more units than the SMs hold at once is bound by throughput, and the SMs hold about 17 tiled units each
+        //    (shared memory): units of two or four warps are what fills the warp slots, so units are widened generously (0.5: 4 980 ms per
+        //    step of config 4 against 5 520 ms at 1.0);
+        //  * a batch the GPU holds at once is bound by its longest units, and widening costs throughput (a unit on 32 warps runs an
+        //    iteration 1.6 times faster than on one, for 32 times the issue slots): only the units that would outlast the batch are
+        //    widened, those as far as a cluster of eight CTAs (1.0 with clusters: 1 040 ms for 5 000 loci against 1 213 ms at 0.5 without).
+        const bool small_batch = fast && n_units < 12 * (int64_t)ctx->sm_count;
+        const double crit = ce ? atof(ce) : (fast ? (small_batch ? 1.0 : 0.5) : 0.75);
         std::vector<int> step(n_units, 0);
         std::vector<double> t(n_units);
         double occupied = 0;  // sum of warps * time
@@ -632,10 +640,14 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         } else {
             if (!reuse || ctx->packed_h[i] != unit_h[i]) pack_unit(groups[i], group_wide[i] != 0, unit_h[i], fast, &packed[i]);
             ctx->packed_h[i] = unit_h[i];
-            // a tiled unit above 32 warps: a cluster of CTAs of 32 warps (its scratch lists and task queues are per CTA: shared memory only)
+            // a tiled unit above 32 warps: a cluster of CTAs of 32 warps
+            if (packed[i].d.n_cta > 1) packed[i].d.smem_bytes -= kTileClusterBytes;  // (a cached unit that was a cluster in the first build)
             packed[i].d.n_cta = 0;
             if (unit_warps[i] > 32) {
-                if (packed[i].d.scr_smem) packed[i].d.n_cta = unit_warps[i] / 32;
+                if (packed[i].d.smem_bytes + kTileClusterBytes <= (int32_t)max_unit_smem()) {
+                    packed[i].d.n_cta = unit_warps[i] / 32;
+                    packed[i].d.smem_bytes += kTileClusterBytes;
+                }
                 unit_warps[i] = 32;
             }
         }

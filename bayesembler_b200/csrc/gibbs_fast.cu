@@ -402,9 +402,9 @@ __device__ __forceinline__ TileView tile_stage(const KernelArgs &A, const UnitDe
         V.queue = (uint32_t *)(smem + lay.queue);
     } else {
         V.ctab = A.chain_tab + U.ctab_off;
-        V.scr_cum = A.scr_cum + U.scr_off;
+        V.scr_cum = A.scr_cum + U.scr_off;  // (a cluster shares the lists: every CTA writes and reads the rows of its own tiles only)
         V.scr_col = A.scr_col + U.scr_off;
-        V.queue = A.queue + U.q_off;
+        V.queue = A.queue + U.q_off + (size_t)cg::this_cluster().block_rank() * 6 * U.qcap;  // (its own task queues)
     }
     uint32_t *pool = nullptr;
     if (U.pool_smem) {
@@ -492,8 +492,8 @@ __global__ void __maxnreg__(BAYES_FAST_MAXNREG) gibbs_fast_bundle_kernel(const _
     }
     if (threadIdx.x < kFastCtlWords) V.ctl[threadIdx.x] = 0;
 
-    int32_t *part = (int32_t *)(smem + lay.part);  // cluster: two buffers of 32 partial counts
-    if (threadIdx.x < 64) part[threadIdx.x] = 0;
+    int32_t *part = (int32_t *)(smem + lay.total);  // cluster: two buffers of 32 partial counts (kTileClusterBytes, only then)
+    if (n_cta > 1 && threadIdx.x < 64) part[threadIdx.x] = 0;
     int cur = 0;
     int32_t *acc = n_cta > 1 ? part : E.counts;
     const bool tracing = lead && A.trace_unit == ui;

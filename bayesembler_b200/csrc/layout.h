@@ -66,6 +66,7 @@ struct FastLayout {
 };
 
 constexpr int kFastCtlWords = 8;  // ctl: next slab, three rotating task counters, error flag
+constexpr int kTileClusterBytes = 256;  // a tiled unit spread over a cluster: two buffers of 32 partial counts, after TileLayout::total
 
 BAYES_LAYOUT_HD FastLayout fast_layout(bool wide, int nT, int n_slots, int Tpad, int n_slabs, int slab_h, int n_cells, int tab_len,
                                        bool tab_smem, bool mat_smem, int n_chain_cells, int qcap, int pool_blocks, bool pool_smem) {
@@ -113,7 +114,7 @@ BAYES_LAYOUT_HD FastLayout fast_layout(bool wide, int nT, int n_slots, int Tpad,
 // ---- fast mode, bundles: lane-per-cell tiles --------------------------------------------------------------------------
 struct TileLayout {
     uint32_t theta, den, mean, m2, tab_val, val, scr_cum, key, sgamma, pool;  // 8-byte (pool: 16)
-    uint32_t counts, base, occ, part, tab_row, meta, ctab, pool_desc, queue, sT, sNf, ctl;  // 4-byte
+    uint32_t counts, base, occ, tab_row, meta, ctab, pool_desc, queue, sT, sNf, ctl;  // 4-byte
     uint32_t scr_col;  // 2-byte
     uint32_t total;
 };
@@ -140,7 +141,6 @@ BAYES_LAYOUT_HD TileLayout tile_layout(int n_slots, int Tpad, int n_tiles, int n
     L.counts = o; o += 4u * 32u;
     L.base = o; o += 4u * 32u;
     L.occ = o; o += 4u * 32u;
-    L.part = o; o += 4u * 64u;  // a critical unit spread over a cluster: two buffers of partial counts (gibbs_fast.cu)
     L.tab_row = o; o += tab_smem ? 4u * n_tabrow : 0u;
     L.meta = o; o += 4u * cells;
     L.ctab = o; o += scr_smem ? 12u * (uint32_t)n_chain_rows : 0u;

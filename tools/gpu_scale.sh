@@ -1,6 +1,16 @@
+# bench.py on N GPUs of one box, launched like the driver does: tools/gpu_scale.sh <tag> <N> [extra bench flags]
 set -u
+TAG=$1; N=$2; shift 2
 mkdir -p gpurun_out
-for N in 2 4 8; do
-  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500+N)) bench.py --gpus $N --steps 2 --warmup 1 > gpurun_out/r2_scale_n$N.json 2> gpurun_out/r2_scale_n$N.err
-  echo "N=$N rc=$?"; cut -c1-330 gpurun_out/r2_scale_n$N.json; tail -2 gpurun_out/r2_scale_n$N.err | cut -c1-300
-done
+if [ "$N" = "1" ]; then
+  python bench.py --gpus 1 "$@" > gpurun_out/${TAG}_n1.json 2> gpurun_out/${TAG}_n1.err
+else
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N "$@" > gpurun_out/${TAG}_n${N}.json 2> gpurun_out/${TAG}_n${N}.err
+fi
+echo "rc=$?"; tail -2 gpurun_out/${TAG}_n${N}.err
+python - <<PY
+import json
+for ln in open('gpurun_out/${TAG}_n${N}.json'):
+    if ln.startswith('{'):
+        l=json.loads(ln); print('N=%d: %.1f ms/step (device), %.1f ms/step (e2e), %.4g draws/s, launches %d' % (l['n_gpus'], l['ms_per_step'], l['e2e']['ms_per_step'], l['value'], l['gpu_launches']))
+PY
