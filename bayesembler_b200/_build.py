@@ -74,7 +74,24 @@ def build_cli(force=False):
     return CLI
 
 
+# development builds of the same sources, loaded instead of the product library through BAYES_B200_LIB=<path>
+VARIANTS = {"debug": ("-DBAYES_DEBUG_BOUNDS",),                       # every index derived from packed data is checked on the device
+            "phases": ("-DBAYES_ROWS_PHASES", "-DBAYES_TILE_PHASES")}  # per-phase clocks of an iteration, printed when a unit ends
+
+
+def build_variant(name):
+    out = os.path.join(HERE, "libbayes_%s.so" % name)
+    res = subprocess.run(nvcc_command(out=out, extra=VARIANTS[name]), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout)
+        raise RuntimeError("nvcc failed building %s" % out)
+    return out
+
+
 if __name__ == "__main__":
-    build(force=True, verbose=True)
-    build_cli(force=True)
-    print(LIB)
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":
+        print(build_variant(sys.argv[2]))
+    else:
+        build(force=True, verbose=True)
+        build_cli(force=True)
+        print(LIB)

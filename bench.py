@@ -398,7 +398,8 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "note": "dominant kernel = gibbs_fast_bundle_kernel (sampling mode fast; gibbs_bundle_kernel in replay mode); one step "
+                         "note": "dominant kernel = gibbs_fast_bundle_kernel (sampling mode fast; gibbs_bundle_kernel in replay mode; loci with more "
+                                 "than 32 candidates -- config 3 -- run in gibbs_rows_kernel); one step "
                                  "issues its unit classes as concurrent launches of that kernel, so 'per launch' here means per step: achieved = "
                                  "algorithmic bytes of the step (sum over jobs of iters*(12 nnz + 8 R + 24 T) + samples*40 T, f64/u32 "
                                  "reference-equivalent CSR) / CUDA-event time of the step, per GPU; traffic = DRAM bytes summed over the same "
