@@ -370,7 +370,7 @@ __device__ __forceinline__ int fast_bundle_e_step(const FastBundleE &E, uint32_t
 }
 
 template <bool MAT_SMEM, bool SCR_SMEM>
-__device__ __forceinline__ TileView tile_stage(const KernelArgs &A, const UnitDev &U, const TileLayout &lay, unsigned char *smem) {
+__device__ __forceinline__ TileView tile_stage(const KernelArgs &A, const UnitDev &U, const TileLayout &lay, unsigned char *smem, const int rank) {
     TileView V;
     V.n_tiles = U.n_tiles;
     V.n_chain_tiles = U.n_chain_tiles;
@@ -404,7 +404,7 @@ __device__ __forceinline__ TileView tile_stage(const KernelArgs &A, const UnitDe
         V.ctab = A.chain_tab + U.ctab_off;
         V.scr_cum = A.scr_cum + U.scr_off;  // (a cluster shares the lists: every CTA writes and reads the rows of its own tiles only)
         V.scr_col = A.scr_col + U.scr_off;
-        V.queue = A.queue + U.q_off + (size_t)cg::this_cluster().block_rank() * 6 * U.qcap;  // (its own task queues)
+        V.queue = A.queue + U.q_off + (size_t)rank * 6 * U.qcap;  // (its own task queues)
     }
     uint32_t *pool = nullptr;
     if (U.pool_smem) {
@@ -421,11 +421,12 @@ __device__ __forceinline__ TileView tile_stage(const KernelArgs &A, const UnitDe
 // same E-step on the same counts (same theta, nothing to exchange), takes every n_cta-th tile -- and with its chain tiles their
 // splitting trees --, accumulates the fragments it places in a partial count vector of its own, and after one cluster barrier
 // per iteration adds up the partial vectors of all CTAs through distributed shared memory (double-buffered, like gibbs_rows.cu).
-template <bool MAT_SMEM, bool SCR_SMEM>
+// (CLUSTER is a template parameter so that the thousands of one-CTA units of a batch carry none of this: it cost them 3 % otherwise)
+template <bool MAT_SMEM, bool SCR_SMEM, bool CLUSTER>
 __global__ void __maxnreg__(BAYES_FAST_MAXNREG) gibbs_fast_bundle_kernel(const __grid_constant__ KernelArgs A, const int64_t unit_base) {
     extern __shared__ __align__(16) unsigned char smem[];
     cg::cluster_group cluster = cg::this_cluster();
-    const int n_cta = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int n_cta = CLUSTER ? (int)cluster.num_blocks() : 1, rank = CLUSTER ? (int)cluster.block_rank() : 0;
     const bool lead = rank == 0;
     const int64_t ui = unit_base + blockIdx.x / n_cta;
     if (lead && threadIdx.x == 0) A.unit_clock[3 * ui] = global_ns();
@@ -466,7 +467,7 @@ __global__ void __maxnreg__(BAYES_FAST_MAXNREG) gibbs_fast_bundle_kernel(const _
         E.tab_val = A.tab_val + U.tab_off;
         E.tab_row = A.tab_row + U.tabrow_off;
     }
-    TileView V = tile_stage<MAT_SMEM, SCR_SMEM>(A, U, lay, smem);
+    TileView V = tile_stage<MAT_SMEM, SCR_SMEM>(A, U, lay, smem, rank);
     E.ctl = V.ctl;
     uint32_t *pool = (uint32_t *)(smem + lay.pool);
     const uint32_t *pool_desc = (const uint32_t *)(smem + lay.pool_desc);
@@ -543,7 +544,7 @@ __global__ void __maxnreg__(BAYES_FAST_MAXNREG) gibbs_fast_bundle_kernel(const _
 #else
         tile_tree_levels(V, acc, skey, iter, it < 0);
 #endif
-        if (n_cta > 1) {
+        if (CLUSTER && n_cta > 1) {
             cluster.sync();
             if (threadIdx.x < 32) {
                 int s = 0;
@@ -575,7 +576,7 @@ __global__ void __maxnreg__(BAYES_FAST_MAXNREG) gibbs_fast_bundle_kernel(const _
         A.out_counts[o] = E.counts[lane];
     }
     int err = V.ctl[kCtlErr];
-    if (n_cta > 1) {
+    if (CLUSTER && n_cta > 1) {
         cluster.sync();
         if (lead && threadIdx.x == 0)
             for (int j = 1; j < n_cta; j++) {
@@ -642,8 +643,9 @@ int configure_fast_kernels() {
     int rc;
     const char *co = getenv("BAYES_CARVEOUT");  // experiment knob, percent (see configure_kernels)
     const int carveout = co ? atoi(co) : 65;
-    const void *fns[3] = {(const void *)gibbs_fast_bundle_kernel<true, true>, (const void *)gibbs_fast_bundle_kernel<false, true>,
-                          (const void *)gibbs_fast_bundle_kernel<false, false>};
+    const void *fns[6] = {(const void *)gibbs_fast_bundle_kernel<true, true, false>, (const void *)gibbs_fast_bundle_kernel<false, true, false>,
+                          (const void *)gibbs_fast_bundle_kernel<false, false, false>, (const void *)gibbs_fast_bundle_kernel<true, true, true>,
+                          (const void *)gibbs_fast_bundle_kernel<false, true, true>, (const void *)gibbs_fast_bundle_kernel<false, false, true>};
     for (const void *f : fns) {
         if ((rc = check_fast(cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, carveout), "carveout"))) return rc;
         if ((rc = check_fast(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_unit_smem()), "cudaFuncSetAttribute"))) return rc;
@@ -670,18 +672,18 @@ int launch_units_fast(const KernelArgs &args, int64_t unit_base, int64_t n_units
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         cudaError_t e;
-        if (mat_smem) e = cudaLaunchKernelEx(&cfg, gibbs_fast_bundle_kernel<true, true>, args, unit_base);
-        else if (scr_smem) e = cudaLaunchKernelEx(&cfg, gibbs_fast_bundle_kernel<false, true>, args, unit_base);
-        else e = cudaLaunchKernelEx(&cfg, gibbs_fast_bundle_kernel<false, false>, args, unit_base);
+        if (mat_smem) e = cudaLaunchKernelEx(&cfg, gibbs_fast_bundle_kernel<true, true, true>, args, unit_base);
+        else if (scr_smem) e = cudaLaunchKernelEx(&cfg, gibbs_fast_bundle_kernel<false, true, true>, args, unit_base);
+        else e = cudaLaunchKernelEx(&cfg, gibbs_fast_bundle_kernel<false, false, true>, args, unit_base);
         return check_fast(e, "gibbs fast kernel launch (cluster)");
     }
     if (wide) {  // loci with more than 32 candidates run in gibbs_rows.cu (launch_units_rows)
         set_error("launch_units_fast: wide units belong to the cooperative-rows kernel");
         return BAYES_E_STATE;
     }
-    if (mat_smem) gibbs_fast_bundle_kernel<true, true><<<grid, block, smem_bytes, st>>>(args, unit_base);
-    else if (scr_smem) gibbs_fast_bundle_kernel<false, true><<<grid, block, smem_bytes, st>>>(args, unit_base);
-    else gibbs_fast_bundle_kernel<false, false><<<grid, block, smem_bytes, st>>>(args, unit_base);
+    if (mat_smem) gibbs_fast_bundle_kernel<true, true, false><<<grid, block, smem_bytes, st>>>(args, unit_base);
+    else if (scr_smem) gibbs_fast_bundle_kernel<false, true, false><<<grid, block, smem_bytes, st>>>(args, unit_base);
+    else gibbs_fast_bundle_kernel<false, false, false><<<grid, block, smem_bytes, st>>>(args, unit_base);
     return check_fast(cudaGetLastError(), "gibbs fast kernel launch");
 }
 

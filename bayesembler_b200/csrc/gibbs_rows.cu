@@ -481,6 +481,36 @@ __device__ __forceinline__ int sample_simplex_warp(const double *tab_val, const 
     return (lo - first) + n_plus;
 }
 
+// The CTA's share of the matrix goes to shared memory as ONE bulk asynchronous copy (cp.async.bulk, the TMA unit's 1-D form),
+// completion counted in bytes by an mbarrier.  Source and destination have to be 16-byte aligned and the size a multiple of 16:
+// the destination is shifted by one entry when needed so that both agree modulo 16, an odd first / last entry is copied by hand.
+__device__ __forceinline__ const double *stage_values_bulk(double *dst, const double *src, int n, uint64_t *bar) {
+    if ((((uintptr_t)src) ^ ((uintptr_t)dst)) & 8u) dst += 1;
+    const int head = (((uintptr_t)src) & 8u) ? 1 : 0;
+    const int bulk = n > head ? (n - head) & ~1 : 0;
+    const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_addr), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (head && n > 0) dst[0] = src[0];
+        if (n > 0 && head + bulk < n) dst[n - 1] = src[n - 1];
+        const uint32_t bytes = (uint32_t)bulk * 8u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+        if (bytes)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             (uint32_t)__cvta_generic_to_shared(dst + head)),
+                         "l"(src + head), "r"(bytes), "r"(bar_addr)
+                         : "memory");
+    }
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar_addr), "r"(0) : "memory");
+    return dst;
+}
+
 // the iteration's uniform words of this CTA's rows: block b of the CTA's pool = Philox block (desc & 0xffffff) of the locus' pool
 __device__ __forceinline__ void rows_pool_gen(uint32_t *pool, const uint32_t *pool_desc, int pool_blocks, const uint64_t key, uint32_t iteration,
                                               bool init, int first_thread, int n_threads) {
@@ -753,13 +783,13 @@ __global__ void __maxnreg__(BAYES_ROWS_MAXNREG) gibbs_rows_kernel(const __grid_c
         uint64_t *sm = (uint64_t *)(smem + lay.rmask);
         int32_t *rc = (int32_t *)(smem + lay.rcell), *rn = (int32_t *)(smem + lay.row_n), *rw = (int32_t *)(smem + lay.row_woff);
         uint32_t *rinfo = (uint32_t *)(smem + lay.row_info);
-        block_copy(sv, A.val + U.cell_off + cell_begin, cell_end - cell_begin);
+        const double *staged = stage_values_bulk(sv, A.val + U.cell_off + cell_begin, cell_end - cell_begin, (uint64_t *)(smem + lay.bar));
         block_copy(sm, (const uint64_t *)A.row_mask + U.mask_off + (size_t)V.row_begin * V.n_words, rows * V.n_words);
         block_copy(rc, g_rcell + V.row_begin, rows + 1);
         block_copy(rn, A.row_n + U.row_off + V.row_begin, rows);
         block_copy(rinfo, A.row_info + U.row_off + V.row_begin, rows);
         block_copy(rw, A.row_woff + U.woff_off + V.row_begin, rows);
-        V.val = sv; V.rmask = sm; V.rcell = rc; V.row_n = rn; V.row_info = rinfo; V.row_woff = rw;
+        V.val = staged; V.rmask = sm; V.rcell = rc; V.row_n = rn; V.row_info = rinfo; V.row_woff = rw;
         V.row_base = V.row_begin;
         V.cell_base = cell_begin;
     } else {

@@ -160,7 +160,7 @@ BAYES_LAYOUT_HD TileLayout tile_layout(int n_slots, int Tpad, int n_tiles, int n
 // its pool of uniform words (`pool`) and, in a cluster of more than one CTA, two buffers of partial counts that the
 // other CTAs read through distributed shared memory.
 struct RowsLayout {
-    uint32_t theta, den, mean, m2, val, rmask, scr_cum, amask, norm, ch_rz;   // 8-byte
+    uint32_t theta, den, mean, m2, val, rmask, scr_cum, amask, norm, bar, ch_rz;   // 8-byte
     uint32_t pool;                                                           // 16-byte
     uint32_t counts, base, occ, part, mask, actoff, ch_kk, rcell, row_n, row_info, row_woff, pool_desc, queue, ctl;  // 4-byte
     uint32_t scr_col, act;                                                   // 2-byte
@@ -179,11 +179,12 @@ BAYES_LAYOUT_HD RowsLayout rows_layout(int T, int n_cta, int rows_max, int cells
     L.den = o; o += 8u * uT;
     L.mean = o; o += 8u * uT;
     L.m2 = o; o += 8u * uT;
-    L.val = o; o += 8u * cells;
+    L.val = o; o += mat ? 8u * (cells + 1u) : 0u;  // (one spare entry: the copy lands 16-byte congruent with its source)
     L.rmask = o; o += 8u * rows * nw;
     L.scr_cum = o; o += 8u * cc;
     L.amask = o; o += 8u * nw;
     L.norm = o; o += 8u;
+    L.bar = o; o += 8u;  // mbarrier of the bulk copy that stages the matrix
     L.ch_rz = o; o += 8u * (uint32_t)chain_max;  // rows with >= 20 fragments: 1 / row sum and cells in play of this iteration
     o = (o + 15u) & ~15u;
     L.pool = o; o += pool ? 16u * ((uint32_t)pool_blocks + 1u) : 0u;  // one spare block: a row reads its words four at a time
