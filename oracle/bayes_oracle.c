@@ -42,6 +42,10 @@ typedef struct {
  * ORC_WS_FAST is the product's production sampling mode: the same conditional distributions drawn in an order that
  * suits the GPU.  It replaces exactly two functions (init_assignment / generate_assignment -> assignment_fast) and
  * draws from sites like ORC_WS_SITE; everything else is shared.
+ *
+ * RULE: no function below may branch on the word-source mode except through orc_ws_site() / orc_ws_next() (and the
+ * two dispatch points that select assignment_fast).  The parity argument reference(SEQ) == oracle(SEQ) and
+ * oracle(SITE) == GPU(SITE) needs the two modes to run the SAME statements, differing only in where the words come from.
  */
 static void rng_init(rng_t *r, int mode, uint64_t seed) {
     if (mode == ORC_WS_SEQ) {
