@@ -949,11 +949,12 @@ int bayes_gibbs_upload(bayes_gibbs_ctx *ctx) {
         (rc = ctx->h_m2.resize(n_out)))
         return rc;
     ctx->phase_s[2] = now_s() - t1;
-    // calibration pass (see calibrate_units): worth it once the batch is several times what the GPU holds at once
+    // calibration pass (see calibrate_units): worth it once units have to share SMs
     ctx->calibrated = false;
     int32_t calib = ctx->calibration;
     if (const char *e = getenv("BAYES_CALIB_ITERS")) calib = atoi(e);  // experiment knob
-    if (calib < 0) calib = (int64_t)ctx->h_units.n >= 8 * (int64_t)ctx->sm_count ? 256 : 0;
+    // (from two units per SM on: below that nothing waits for anything; at 8 units per SM -- one eighth of config 4 -- it is worth 9 % of the step)
+    if (calib < 0) calib = (int64_t)ctx->h_units.n >= 2 * (int64_t)ctx->sm_count ? 256 : 0;
     if (calib > 0 && ctx->h_units.n > 0 && ctx->trace_locus < 0) {
         t1 = now_s();
         std::vector<double> scale;
