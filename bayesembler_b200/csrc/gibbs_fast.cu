@@ -200,13 +200,31 @@ __device__ __forceinline__ void tile_rows(const TileView &V, const double *theta
             if (inplay && k == 1) atomicAdd(&counts[c], (int)n);
             if (head && k == 0) V.ctl[kCtlErr] = 1;  // reference: assert(normalisation_constant >= double_underflow) (:284)
             // the row's fragments enter the tree as independent chunks of at most 64: every binomial stays in the inversion regime
-            // (a row above 64 kTreeChunks fragments enters whole: its binomials are BTRD's either way.  Measured both ways on config 4:
-            // 128 chunks of such rows cost 5 % of the batch's throughput and make the largest locus slower, not faster)
+            // (a row above 64 kTreeChunks = 8 192 fragments enters whole: its binomials are BTRD's either way, and 128 larger chunks of
+            // it were measured slower.  Below that every binomial stays in the inversion regime: a single row of 2 500 fragments
+            // entering whole put one BTRD binomial per level on the critical path of its locus, 20 us of a 28 us iteration)
             const int m = head && k >= 2 ? (((int)n + 63) >> 6 <= kTreeChunks ? ((int)n + 63) >> 6 : 1) : 0;
             const int m_max = __reduce_max_sync(kFull, m);
-            for (int ch = 0; ch < m_max; ch++)
-                tile_push(V, kCtlQ0, 0, ch < m, n / (uint32_t)max(m, 1) + (uint32_t)(ch < (int)(n % (uint32_t)max(m, 1))),
-                          ord | ((uint32_t)ch << 15) | ((uint32_t)(k - 1) << 27));
+            if (m_max <= 4) {
+                // the usual tile: a few rows of a few chunks each, the heads push side by side
+                for (int ch = 0; ch < m_max; ch++)
+                    tile_push(V, kCtlQ0, 0, ch < m, n / (uint32_t)max(m, 1) + (uint32_t)(ch < (int)(n % (uint32_t)max(m, 1))),
+                              ord | ((uint32_t)ch << 15) | ((uint32_t)(k - 1) << 27));
+            } else {
+                // a row of many chunks: all lanes push its roots, 32 chunks at a time
+                uint32_t heads = __ballot_sync(kFull, m > 0);
+                while (heads) {
+                    const int src = __ffs(heads) - 1;
+                    heads &= heads - 1u;
+                    const int mb = __shfl_sync(kFull, m, src);
+                    const uint32_t nb = __shfl_sync(kFull, n, src);
+                    const uint32_t wb = __shfl_sync(kFull, ord | ((uint32_t)(k - 1) << 27), src);
+                    for (int c0 = 0; c0 < mb; c0 += 32) {
+                        const int ch = c0 + lane;
+                        tile_push(V, kCtlQ0, 0, ch < mb, nb / (uint32_t)mb + (uint32_t)(ch < (int)(nb % (uint32_t)mb)), wb | ((uint32_t)ch << 15));
+                    }
+                }
+            }
         } else {
             const int n = (int)((meta >> kMetaNShift) & 31u);  // 0: padding lane
             const int w0 = (int)(meta >> kMetaWoffShift);

@@ -227,7 +227,7 @@ int orc_init_assignment(const orc_locus *loc, int rng_mode, uint64_t seed, int *
  *     (:336-365): node (a, len) holds m fragments for cells [a, a + len); its left half [a, a + len/2) receives
  *     Binomial(m, (cum(a + len/2) - cum(a)) / (cum(a + len) - cum(a))), the right half the rest; one site per node
  *     (TREE | node << 8, iteration, row, chunk), node = a | (len - 1) << 12.  Depth log2 k instead of k dependent
- *     draws.  The row's fragments enter the tree in ceil(n / 64) independent chunks of equal size +- 1 (n <= 2048; a
+ *     draws.  The row's fragments enter the tree in ceil(n / 64) independent chunks of equal size +- 1 (n <= 8192; a
  *     larger row enters whole).
  * ---------------------------------------------------------------------------------------------- */
 static uint32_t sat_u32_ceil(double x) { /* __double2uint_ru */
@@ -249,12 +249,12 @@ static void tree_split(orc_ws *ws, uint32_t phase, uint32_t iteration, uint32_t 
     tree_split(ws, phase, iteration, row, chunk, cum, cell_col, a + half, len - half, m - left, counts);
 }
 
-/* chunks a row with n >= 20 fragments is drawn in: ceil(n / 64) while that is at most 32 (every binomial then has
- * n <= 64, the inversion regime); a larger row is drawn whole (its binomials are BTRD's either way, and one is cheaper
- * than 32; 128 chunks were tried on the GPU and cost throughput) */
+/* chunks a row with n >= 20 fragments is drawn in: ceil(n / 64) while that is at most 128 (every binomial then has
+ * n <= 64, the inversion regime); a row above 8192 fragments is drawn whole (its binomials are BTRD's either way, and
+ * one is cheaper than 128) */
 static int tree_chunks(int n) {
     const int m = (n + 63) / 64;
-    return m <= 32 ? m : 1;
+    return m <= 128 ? m : 1;
 }
 
 /* Rows with >= 20 fragments and at most this many are drawn fragment by fragment (one uniform word each, located in the
