@@ -20,7 +20,7 @@ namespace bayes {
 
 constexpr int kMaxT = 4096;             // candidates per locus (per-candidate state lives in shared memory)
 constexpr int kMaxBlock = 512;          // threads per unit
-constexpr int kWarpsPerSM = 28;         // resident warps per SM at the kernels' 72 registers per thread
+constexpr int kWarpsPerSM = 28;         // warps an SM keeps resident in a full batch (replay kernels: 72 registers per thread; fast mode: shared memory of ~17 tiled units): the scheduler's capacity
 constexpr int kMaxSlots = 16;           // slots per bundle (T = 2 -> Tpad = 2 -> 16 slots)
 constexpr int kTreeChunks = 128;        // fast mode: a row enters its splitting tree in ceil(n / 64) independent chunks of fragments while that is at most kTreeChunks, else whole
 constexpr int kRowsDirectMax = 4096;    // fast mode, T > 32: rows with 20 .. this many fragments are drawn fragment by fragment, larger ones by the splitting tree
