@@ -22,7 +22,10 @@ constexpr int kMaxT = 4096;             // candidates per locus (per-candidate s
 constexpr int kMaxBlock = 512;          // threads per unit
 constexpr int kWarpsPerSM = 28;         // warps an SM keeps resident in a full batch (replay kernels: 72 registers per thread; fast mode: shared memory of ~17 tiled units): the scheduler's capacity
 constexpr int kMaxSlots = 16;           // slots per bundle (T = 2 -> Tpad = 2 -> 16 slots)
-constexpr int kTreeChunks = 128;        // fast mode: a row enters its splitting tree in ceil(n / 64) independent chunks of fragments while that is at most kTreeChunks, else whole
+#ifndef BAYES_TREE_CHUNKS
+#define BAYES_TREE_CHUNKS 128
+#endif
+constexpr int kTreeChunks = BAYES_TREE_CHUNKS;        // fast mode: a row enters its splitting tree in ceil(n / 64) independent chunks of fragments while that is at most kTreeChunks, else whole
 constexpr int kRowsDirectMax = 4096;    // fast mode, T > 32: rows with 20 .. this many fragments are drawn fragment by fragment, larger ones by the splitting tree
 constexpr int kMaxCluster = 16;         // CTAs of the thread-block cluster a wide locus may be spread over (fast mode)
 constexpr int kSmallCount = 20;         // assignmentGenerator.cpp:289: rows with fewer fragments draw uniforms
