@@ -181,7 +181,7 @@ def load_library(path=None):
 
 def _check(rc, what):
     if rc < 0:
-        raise BayesError("%s failed (%d): %s" % (what, rc, load_library().bayes_last_error().decode()))
+        raise BayesError("%s failed (%d): %s" % (what, rc, load_library().bayes_last_error().decode("utf-8", "replace")))  # (messages may quote bytes of a corrupt input file)
     return rc
 
 

@@ -59,3 +59,80 @@ def test_fuzz_raw_locus(lib):
             seen.add("invalid")
             assert "bayes_" in str(e)
     assert 0 in seen and "invalid" in seen
+
+
+def test_fuzz_bam_and_instance_files(tmp_path):
+    """Row f4: byte mutations of a BAM file's decompressed stream (re-compressed into valid BGZF, so the record decoder sees them) and
+    line mutations of a CEM instance file.  The reference asserts all over this stage (assembler.cpp:329-352, :700-1010); the library
+    answers BAYES_E_INVALID / BAYES_E_NUMERIC or a valid result, and never takes the process down."""
+    import gzip
+    import bayesembler_b200 as bb
+    from oracle import f4_py
+    rng = np.random.default_rng(2)
+    refs, recs, instance, _ = f4_py.synth_dataset(rng, n_loci=3, pairs_per_locus=25)
+    good = str(tmp_path / "good.bam")
+    f4_py.write_bam(good, refs, recs)
+    raw = bytearray(gzip.open(good, "rb").read())
+    inst_path = str(tmp_path / "good.instance")
+    open(inst_path, "w").write(instance)
+    outcomes = {"ok": 0, "invalid": 0}
+    for trial in range(300):
+        b = bytearray(raw)
+        for _ in range(int(rng.integers(1, 4))):
+            k, i = int(rng.integers(0, 4)), int(rng.integers(0, len(b)))
+            if k == 0:
+                b[i] = int(rng.integers(0, 256))
+            elif k == 1:
+                b[i:i + 4] = int(rng.choice([0, 1, 0x7FFFFFFF, 0xFFFFFFFF, 0x80000000, 65536])).to_bytes(4, "little")
+            elif k == 2:
+                del b[i:i + int(rng.integers(1, 40))]
+            else:
+                b = b[:max(8, i)]
+        p = str(tmp_path / "m.bam")
+        with open(p, "wb") as f:
+            for j in range(0, len(b), 60000):
+                f.write(f4_py._bgzf_block(bytes(b[j:j + 60000])))
+            f.write(f4_py._bgzf_block(b""))
+        try:
+            front = bb.BamFront(p, str(rng.choice(["unstranded", "first", "second"])))
+            c = front.counts()
+            assert c["unique_pairs"] <= c["total_mapped_pairs"] + 1
+            try:
+                front.graphs(inst_path, str(tmp_path / "g.txt"))
+            except bb.BayesError as e:
+                assert "bayes_bam_front_graphs" in str(e)
+            front.close()
+            outcomes["ok"] += 1
+        except bb.BayesError as e:
+            assert "bayes_bam_front_open" in str(e)
+            outcomes["invalid"] += 1
+    assert outcomes["ok"] > 5 and outcomes["invalid"] > 100, outcomes
+    front = bb.BamFront(good)
+    lines = instance.split("\n")
+    alphabet = list("0123456789\t +-.ISRBPT")
+    seen = {"ok": 0, "invalid": 0}
+    for trial in range(300):
+        ls = list(lines)
+        for _ in range(int(rng.integers(1, 4))):
+            k, i = int(rng.integers(0, 4)), int(rng.integers(0, len(ls)))
+            if k == 0:
+                del ls[i]
+            elif k == 1:
+                ls.insert(i, ls[int(rng.integers(0, len(ls)))])
+            elif k == 2 and ls[i]:
+                c = list(ls[i])
+                c[int(rng.integers(0, len(c)))] = alphabet[int(rng.integers(0, len(alphabet)))]
+                ls[i] = "".join(c)
+            else:
+                ls[i] = ls[i][:int(rng.integers(0, len(ls[i]) + 1))]
+        ip = str(tmp_path / "m.instance")
+        open(ip, "w").write("\n".join(ls))
+        try:
+            n = front.graphs(ip, str(tmp_path / "g2.txt"))
+            assert n["graphs"] >= n["with_fragments"] >= 0
+            seen["ok"] += 1
+        except bb.BayesError as e:
+            assert "bayes_bam_front_graphs" in str(e)
+            seen["invalid"] += 1
+    front.close()
+    assert seen["ok"] > 20 and seen["invalid"] > 20, seen
