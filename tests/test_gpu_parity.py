@@ -337,3 +337,45 @@ def test_cluster_bundle_full_chain(lib, oracle, monkeypatch, warps):
         np.testing.assert_allclose(g["m2"], o["m2"], rtol=1e-7, atol=1e-9 * np.abs(o["mean"]).max() ** 2)
         assert g["final_counts"].sum() == loc.n_frag
     ctx.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_full_run_at_the_candidate_limit(lib, oracle, mode):
+    """T = 4096 (kMaxT) with a 40-90 KB matrix, the whole chain, both modes: the per-candidate state alone is ~190 KB of shared memory,
+    so everything else has to stay in global memory / L2 -- decided on the unit's whole footprint, never a launch that does not fit."""
+    rng = np.random.default_rng(4096)
+    T = 4096
+    loc = random_locus(rng, T, 48, max_count=90, density=0.045)
+    assert 40_000 <= 10 * loc.nnz <= 110_000
+    seed = int(rng.integers(1, 2 ** 62))
+    burn, samples = 6, 40
+    ctx = lib.GibbsContext(0, mode=mode)
+    ctx.submit(lib.make_desc_array([loc], [burn], [samples], [seed]))
+    ctx.set_trace(0, 0, burn + samples)
+    ctx.upload(); ctx.run(); ctx.download(); ctx.sync()
+    g, tr = ctx.fetch(0), ctx.fetch_trace()
+    ctx.close()
+    o = oracle.run_sampler(loc, burn, samples, ORACLE_MODE[mode], lib.chain_key(seed, 0), trace_iters=burn + samples)
+    assert np.array_equal(tr["b_trace"], o["b_trace"])
+    assert np.array_equal(tr["counts_trace"], o["counts_trace"])
+    np.testing.assert_allclose(tr["theta_trace"], o["theta_trace"], rtol=RTOL, atol=0)
+    assert np.array_equal(g["occ"], o["occ"])
+    np.testing.assert_allclose(g["mean"], o["mean"], rtol=RTOL)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("T", [33, 200])
+def test_wide_locus_whose_rows_all_fold(lib, oracle, mode, T):
+    """A locus with more than 32 candidates in which every row has a single cell: all fragments are folded into base counts, the
+    unit has no rows at all (no matrix, no pool, no trees) and the chain is the E-step alone."""
+    rng = np.random.default_rng(T)
+    loc = random_locus(rng, T, 40, max_count=50, single_frac=1.0)
+    seed = int(rng.integers(1, 2 ** 62))
+    ctx = lib.GibbsContext(0, mode=mode)
+    ctx.run_batch(lib.make_desc_array([loc], [20], [200], [seed]))
+    g = ctx.fetch(0)
+    ctx.close()
+    o = oracle.run_sampler(loc, 20, 200, ORACLE_MODE[mode], lib.chain_key(seed, 0))
+    assert np.array_equal(g["occ"], o["occ"])
+    np.testing.assert_allclose(g["mean"], o["mean"], rtol=RTOL)
+    assert g["final_counts"].sum() == loc.n_frag
