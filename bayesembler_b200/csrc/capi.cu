@@ -668,6 +668,11 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         return std::min(smem_limit, (bytes + step - 1) / step * step);
     };
     for (int64_t i = 0; i < n_units; i++)
+        if (unit_cta[i] > 0 && packed[i].d.chain_max >= (1 << 16)) {  // direct-draw tasks name a row of their CTA in 16 bits
+            set_error("a locus with more than 32 candidates has more than 65 535 rows of 20 or more fragments per CTA: more than the fast sampling mode addresses (use BAYES_MODE_REPLAY)");
+            return BAYES_E_INVALID;
+        }
+    for (int64_t i = 0; i < n_units; i++)
         if (packed[i].d.smem_bytes > smem_limit) {
             set_error("a unit needs " + std::to_string(packed[i].d.smem_bytes) + " bytes of shared memory, more than the device offers");
             return BAYES_E_INVALID;
