@@ -152,6 +152,11 @@ struct bayes_gibbs_ctx {
     std::vector<double> unit_model_us;  // time model's per-iteration estimate at the unit's shape, before calibration
     int32_t calibration = -1;           // iterations of the calibration pass: -1 = automatic, 0 = off
     bool calibrated = false;
+    // the per-unit corrections of the last calibration pass and a fingerprint of the batch they belong to: a caller that uploads the
+    // same batch again (other seeds, the next pass of a pipeline over the same library) does not pay for the pass, and its upload stays
+    // asynchronous
+    std::vector<double> calib_scale;
+    uint64_t calib_fp = 0;
     std::vector<double> unit_pred;  // time model's estimate per unit (seconds), launch order
     std::vector<double> unit_feat;  // 4 per unit: chain columns, uniform slabs, uniform blocks, uniform block-columns
     int32_t last_launches = 0;
@@ -321,6 +326,7 @@ int build_units(bayes_gibbs_ctx *ctx, const std::vector<double> *group_scale) {
         }
     }
     const int64_t n_units = (int64_t)groups.size();
+    if (group_scale && (int64_t)group_scale->size() != n_units) group_scale = nullptr;  // (corrections of another batch: none)
     std::vector<int> unit_cta(n_units, 0);  // > 0: cooperative-rows unit (fast mode, T > 32), CTAs of its cluster
 
     // ---- shape of every unit before it is packed: its A-step items in processing order (chain items, then uniform
@@ -929,13 +935,34 @@ int bayes_gibbs_submit(bayes_gibbs_ctx *ctx, int32_t n_loci, const bayes_locus_d
 
 static int calibrate_units(bayes_gibbs_ctx *ctx, int32_t iters, std::vector<double> *group_scale);
 
+// what the unit time model sees of a batch (shapes, iteration counts, mode, calibration length), hashed
+static uint64_t batch_fingerprint(const bayes_gibbs_ctx *ctx, int32_t calib) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&h](uint64_t v) { h = (h ^ v) * 1099511628211ull; };
+    mix((uint64_t)ctx->mode);
+    mix((uint64_t)calib);
+    mix((uint64_t)ctx->loci.size());
+    for (const PreLocus &L : ctx->loci) {
+        mix((uint64_t)L.T | ((uint64_t)L.n_chains << 32));
+        mix((uint64_t)(uint32_t)L.burn | ((uint64_t)(uint32_t)L.samples << 32));
+        mix((uint64_t)L.row_id.size() | ((uint64_t)L.cell_val.size() << 24));
+        mix((uint64_t)L.n_frag | ((uint64_t)L.pool_words << 32));
+    }
+    return h ? h : 1;
+}
+
 int bayes_gibbs_upload(bayes_gibbs_ctx *ctx) {
     if (!ctx) return BAYES_E_INVALID;
     int rc = use_device(ctx);
     if (rc) return rc;
     if (ctx->uploaded) CU(cudaStreamSynchronize(ctx->stream));  // a second upload rewrites the pinned staging buffers
     const double t0 = now_s();
-    if ((rc = build_units(ctx, nullptr))) return rc;
+    // the same batch as last time (as far as the time model can tell): its calibration still holds, no timing pass, no synchronisation
+    int32_t calib_want = ctx->calibration;
+    if (const char *e = getenv("BAYES_CALIB_ITERS")) calib_want = atoi(e);
+    const uint64_t fp = batch_fingerprint(ctx, calib_want);
+    const bool cached = calib_want != 0 && ctx->trace_locus < 0 && fp == ctx->calib_fp && !ctx->calib_scale.empty();
+    if ((rc = build_units(ctx, cached ? &ctx->calib_scale : nullptr))) return rc;
     double t1 = now_s();
     ctx->phase_s[1] = t1 - t0;
     if (ctx->trace_locus >= 0) {
@@ -960,10 +987,14 @@ int bayes_gibbs_upload(bayes_gibbs_ctx *ctx) {
     if (const char *e = getenv("BAYES_CALIB_ITERS")) calib = atoi(e);  // experiment knob
     // (from two units per SM on: below that nothing waits for anything; at 8 units per SM -- one eighth of config 4 -- it is worth 9 % of the step)
     if (calib < 0) calib = (int64_t)ctx->h_units.n >= 2 * (int64_t)ctx->sm_count ? 256 : 0;
-    if (calib > 0 && ctx->h_units.n > 0 && ctx->trace_locus < 0) {
+    if (cached) {
+        ctx->calibrated = true;
+    } else if (calib > 0 && ctx->h_units.n > 0 && ctx->trace_locus < 0) {
         t1 = now_s();
         std::vector<double> scale;
         if ((rc = calibrate_units(ctx, calib, &scale))) return rc;
+        ctx->calib_scale = scale;
+        ctx->calib_fp = fp;
         const double t2 = now_s();
         if ((rc = build_units(ctx, &scale))) return rc;
         const double t3 = now_s();

@@ -101,8 +101,9 @@ const char *bayes_last_error(void);
 int bayes_gibbs_submit(bayes_gibbs_ctx *ctx, int32_t n_loci, const bayes_locus_desc *loci, int64_t *first_id);
 /* Forms the units, packs them and enqueues their H2D copies on the context stream.  For a batch of several units per SM it also
  * runs the calibration pass (bayes_gibbs_set_calibration): the first iterations of every unit are timed on the device and the
- * batch is re-formed, which SYNCHRONISES the context stream before it returns; a second upload of the same batch synchronises
- * first as well (it rewrites the pinned staging buffers). */
+ * batch is re-formed, which SYNCHRONISES the context stream before it returns -- unless the context has calibrated the same batch
+ * (same shapes, iteration counts and mode) before: then the corrections are reused and the call only enqueues.  An upload while
+ * the previous batch of the context is still uploaded synchronises first (it rewrites the pinned staging buffers). */
 int bayes_gibbs_upload(bayes_gibbs_ctx *ctx);
 /* initAssignment (assignmentGenerator.cpp:213-260), initSimplexSize (simplexSizeGenerator.cpp:201-206) and
  * burn_in + samples iterations of generateExpression / generateAssignment / generateSimplexSize / addSample
