@@ -248,3 +248,46 @@ def test_cli_from_a_bam_file(tmp_path):
     assert gtf == open(str(tmp_path) + "/b_assembly.gtf").read()
     assert gtf.count("\ttranscript\t") >= 3 or gtf.count("\texon\t") >= 6
     assert open(str(tmp_path) + "/a_candidates.gtf").read() == open(str(tmp_path) + "/b_candidates.gtf").read()
+
+
+@pytest.mark.parametrize("strand_specific", ["unstranded", "first"])
+def test_cli_front_end_writes_the_graph_file(tmp_path, strand_specific):
+    """The command line's BAM stage runs on the host: whatever happens afterwards (here, on a box without a GPU, the sampler refuses
+    to start), <prefix>graphs.txt holds the graphs of every strand set, equal to what the C ABI writes when called directly."""
+    import torch
+    cli = os.path.join(os.path.dirname(bb.__file__), "bayesembler_b200_cli")
+    if not os.path.exists(cli):
+        from bayesembler_b200 import _build
+        _build.build_cli()
+    rng = np.random.default_rng(31)
+    stranded = strand_specific != "unstranded"
+    refs, recs, instance, loci = f4_py.synth_dataset(rng, n_loci=6, pairs_per_locus=60, stranded=stranded)
+    bam = str(tmp_path / "lib.bam")
+    f4_py.write_bam(bam, refs, recs)
+    # one instance file per strand set, as processsam -d + / -d - would write them
+    blocks = instance.strip("\n").split("Instance\t")[1:]
+    args = ["--bam-file", bam, "-s", strand_specific, "-o", str(tmp_path) + "/o_", "--frag-mean", "220", "--frag-sd", "25", "--seed", "3"]
+    front = bb.BamFront(bam, strand_specific)
+    want = str(tmp_path / "want.txt")
+    if stranded:
+        files = {}
+        for sign, name in (("+", "plus"), ("-", "minus")):
+            files[name] = str(tmp_path / (name + ".instance"))
+            open(files[name], "w").write("".join("Instance\t" + b for b in blocks if "\t%s\n" % sign in b.split("\n")[1] + "\n"))
+            args += ["--instance-file-" + name, files[name]]
+        front.graphs(files["plus"], want, strand="+", strand_file=0)
+        front.graphs(files["minus"], want, strand="-", strand_file=1, append=True)
+    else:
+        inst = str(tmp_path / "lib.instance")
+        open(inst, "w").write(instance)
+        args += ["--instance-file", inst]
+        front.graphs(inst, want, strand=".")
+    front.close()
+    r = subprocess.run([cli] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert "Removed duplicates from" in r.stdout and "collapsed them to" in r.stdout, (r.stdout, r.stderr)
+    if not torch.cuda.is_available():
+        assert r.returncode == 1 and "no CUDA device" in r.stderr
+    else:
+        assert r.returncode == 0, r.stderr
+    got = open(str(tmp_path) + "/o_graphs.txt").read()
+    assert got == open(want).read() and got.count("\ngraph ") >= 3
