@@ -25,6 +25,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <fstream>
 #include <functional>
 #include <limits>
@@ -33,6 +34,7 @@
 #include <regex>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <tr1/unordered_map>
 #include <tr1/unordered_set>
 #include <vector>
@@ -49,6 +51,9 @@ struct FrontError {
 [[noreturn]] void fail(int code, const std::string &msg) { throw FrontError{code, msg}; }
 
 // ---- BGZF: a series of gzip members (RFC 1952), each at most 64 KB of data -------------------------------------------------
+// Every BGZF member says how long it is (extra subfield "BC"), so a batch of members is cut out of the file without
+// inflating anything and inflated by a pool of host threads, one member each; the records are then parsed in file order.
+// A gzip stream without the subfield (not BGZF proper) is inflated as one sequential stream instead.
 class BgzfStream {
    public:
     explicit BgzfStream(const char *path) : f_(fopen(path, "rb")) {
@@ -57,6 +62,12 @@ class BgzfStream {
         if (inflateInit2(&zs_, 15 + 16) != Z_OK) fail(BAYES_E_NOMEM, "inflateInit2 failed");
         in_.resize(1 << 16);
         out_.resize(1 << 17);
+        n_threads_ = (int)std::min<unsigned>(16u, std::max<unsigned>(1u, std::thread::hardware_concurrency()));
+        // BGZF proper?  (peek at the first member's header)
+        unsigned char h[18];
+        const size_t k = fread(h, 1, sizeof h, f_);
+        rewind(f_);
+        blocked_ = k == sizeof h && h[0] == 31 && h[1] == 139 && (h[3] & 4) && h[12] == 'B' && h[13] == 'C' && h[14] == 2 && h[15] == 0;
     }
     ~BgzfStream() {
         inflateEnd(&zs_);
@@ -67,7 +78,7 @@ class BgzfStream {
         unsigned char *d = (unsigned char *)dst;
         size_t got = 0;
         while (got < n) {
-            if (out_pos_ == out_len_ && !refill()) {
+            if (out_pos_ == out_len_ && !(blocked_ ? refill_blocks() : refill())) {
                 if (got == 0) return false;
                 fail(BAYES_E_INVALID, "truncated BAM file");
             }
@@ -80,6 +91,74 @@ class BgzfStream {
     }
 
    private:
+    // a batch of members: cut, inflated in parallel, concatenated
+    bool refill_blocks() {
+        const int kBatch = 64 * n_threads_;
+        struct Member {
+            size_t in_off, in_len, out_off, out_len;
+        };
+        std::vector<Member> members;
+        comp_.clear();
+        size_t out_total = 0;
+        for (int m = 0; m < kBatch; m++) {
+            unsigned char h[12];
+            const size_t k = fread(h, 1, sizeof h, f_);
+            if (k == 0) break;
+            if (k != sizeof h || h[0] != 31 || h[1] != 139 || h[2] != 8 || !(h[3] & 4)) fail(BAYES_E_INVALID, "not a BGZF block (header)");
+            const size_t xlen = (size_t)h[10] | ((size_t)h[11] << 8);
+            std::vector<unsigned char> extra(xlen);
+            if (xlen && fread(extra.data(), 1, xlen, f_) != xlen) fail(BAYES_E_INVALID, "truncated BGZF block");
+            long bsize = -1;
+            for (size_t i = 0; i + 4 <= xlen;) {
+                const size_t slen = (size_t)extra[i + 2] | ((size_t)extra[i + 3] << 8);
+                if (extra[i] == 'B' && extra[i + 1] == 'C' && slen == 2 && i + 6 <= xlen) bsize = (long)extra[i + 4] | ((long)extra[i + 5] << 8);
+                i += 4 + slen;
+            }
+            const long cdata = bsize - (long)xlen - 19;
+            if (bsize < 0 || cdata < 0) fail(BAYES_E_INVALID, "not a BGZF block (no length)");
+            const size_t at = comp_.size();
+            comp_.resize(at + (size_t)cdata + 8);
+            if (fread(comp_.data() + at, 1, (size_t)cdata + 8, f_) != (size_t)cdata + 8) fail(BAYES_E_INVALID, "truncated BGZF block");
+            const size_t isize = le32(comp_.data() + at + cdata + 4);
+            if (isize > (1u << 16)) fail(BAYES_E_INVALID, "BGZF block larger than 64 KB");
+            members.push_back(Member{at, (size_t)cdata, out_total, isize});
+            out_total += isize;
+        }
+        if (members.empty()) return false;
+        if (out_.size() < out_total) out_.resize(out_total);
+        std::atomic<size_t> next(0);
+        std::atomic<int> bad(0);
+        auto work = [&]() {
+            z_stream z;
+            memset(&z, 0, sizeof z);
+            if (inflateInit2(&z, -15) != Z_OK) { bad = 1; return; }
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= members.size()) break;
+                const Member &mb = members[i];
+                inflateReset(&z);
+                z.next_in = comp_.data() + mb.in_off;
+                z.avail_in = (uInt)mb.in_len;
+                z.next_out = out_.data() + mb.out_off;
+                z.avail_out = (uInt)mb.out_len;
+                const int rc = mb.out_len == 0 && mb.in_len <= 2 ? Z_STREAM_END : inflate(&z, Z_FINISH);
+                if (rc != Z_STREAM_END || z.avail_out != 0 ||
+                    (uint32_t)crc32(crc32(0L, Z_NULL, 0), out_.data() + mb.out_off, (uInt)mb.out_len) != le32(comp_.data() + mb.in_off + mb.in_len))
+                    bad = 1;
+            }
+            inflateEnd(&z);
+        };
+        const int n_thr = (int)std::min<size_t>((size_t)n_threads_, members.size());
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_thr; t++) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+        if (bad) fail(BAYES_E_INVALID, "corrupt BGZF block (inflate or CRC failed)");
+        out_pos_ = 0;
+        out_len_ = out_total;
+        return out_total > 0 || refill_blocks();  // (a batch of empty members, e.g. the end-of-file marker alone: look further)
+    }
+    static uint32_t le32(const unsigned char *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
     bool refill() {
         out_pos_ = out_len_ = 0;
         while (out_len_ == 0) {
@@ -104,9 +183,10 @@ class BgzfStream {
     }
     FILE *f_;
     z_stream zs_;
-    std::vector<unsigned char> in_, out_;
+    std::vector<unsigned char> in_, out_, comp_;
     size_t out_pos_ = 0, out_len_ = 0;
-    bool mid_member_ = false;
+    bool mid_member_ = false, blocked_ = false;
+    int n_threads_ = 1;
 };
 
 // ---- BAM records ---------------------------------------------------------------------------------------------------------------
@@ -119,9 +199,10 @@ struct BamRec {
     int32_t ref_id = -1, pos = -1, mate_ref = -1, mate_pos = -1, tlen = 0;
     uint16_t flag = 0;
     uint8_t mapq = 0;
-    std::string name, seq, qual, md;  // qual: phred + 33 text like BamTools' Qualities
+    std::string name, qual, md;  // qual: phred + 33 text like BamTools' Qualities
     std::vector<CigarOp> cigar;
-    std::string tags_sam;  // the optional fields as SAM text (tab separated)
+    std::string seq_packed, tags_raw;  // 4-bit bases and the optional fields as they are in the file: turned into SAM text only when written
+    int32_t l_seq = 0;
     uint32_t nh = 0, hi = 0;
     bool has_nh = false, has_hi = false, has_md = false;
     bool paired() const { return flag & 0x1; }
@@ -222,12 +303,35 @@ void append_tag_value(std::string *out, char type, const unsigned char *&p, cons
     out->append("i:").append(std::to_string(*ival));
 }
 
-bool read_bam_record(BgzfStream &in, BamRec *r) {
+// the optional fields of a record as SAM text (tab separated), from their raw bytes
+std::string tags_sam_text(const std::string &raw) {
+    std::string out;
+    const unsigned char *p = (const unsigned char *)raw.data(), *end = p + raw.size();
+    while (p < end) {
+        if (end - p < 3) fail(BAYES_E_INVALID, "truncated optional field");
+        const char t0 = (char)p[0], t1 = (char)p[1], type = (char)p[2];
+        p += 3;
+        std::string text;
+        long long ival = 0;
+        bool is_int = false;
+        append_tag_value(&text, type, p, end, &ival, &is_int);
+        if (!out.empty()) out.push_back('\t');
+        out.push_back(t0);
+        out.push_back(t1);
+        out.push_back(':');
+        out.append(text);
+    }
+    return out;
+}
+
+std::string seq_text(const BamRec &r);
+
+bool read_bam_record(BgzfStream &in, BamRec *r, std::vector<unsigned char> &buf) {
     unsigned char b4[4];
     if (!in.read(b4, 4)) return false;
     const int32_t block = le<int32_t>(b4);
     if (block < 32 || block > (1 << 28)) fail(BAYES_E_INVALID, "bad BAM record size");
-    std::vector<unsigned char> buf(block);
+    buf.resize(block);
     if (!in.read(buf.data(), block)) fail(BAYES_E_INVALID, "truncated BAM record");
     const unsigned char *p = buf.data(), *end = p + block;
     *r = BamRec();
@@ -251,31 +355,54 @@ bool read_bam_record(BgzfStream &in, BamRec *r) {
         if ((v & 15u) > 8u) fail(BAYES_E_INVALID, "unknown CIGAR operation");
         r->cigar.push_back(CigarOp{ops[v & 15u], v >> 4});
     }
-    static const char bases[] = "=ACMGRSVTWYHKDBN";
-    r->seq.resize(l_seq);
-    for (int32_t i = 0; i < l_seq; i++) r->seq[i] = bases[(p[i >> 1] >> ((~i & 1) << 2)) & 15];
+    r->l_seq = l_seq;
+    r->seq_packed.assign((const char *)p, (size_t)(l_seq + 1) / 2);
     p += (l_seq + 1) / 2;
     r->qual.resize(l_seq);
     for (int32_t i = 0; i < l_seq; i++) r->qual[i] = (char)(p[i] + 33);
     p += l_seq;
+    r->tags_raw.assign((const char *)p, (size_t)(end - p));
+    // the three tags the front end itself reads: NH, HI (integers of any width), MD (string); the others are only walked over
     while (p < end) {
         if (end - p < 3) fail(BAYES_E_INVALID, "truncated optional field");
         const char t0 = (char)p[0], t1 = (char)p[1], type = (char)p[2];
         p += 3;
-        std::string text;
-        long long ival = 0;
-        bool is_int = false;
-        append_tag_value(&text, type, p, end, &ival, &is_int);
-        if (!r->tags_sam.empty()) r->tags_sam.push_back('\t');
-        r->tags_sam.push_back(t0);
-        r->tags_sam.push_back(t1);
-        r->tags_sam.push_back(':');
-        r->tags_sam.append(text);
-        if (t0 == 'N' && t1 == 'H' && is_int) { r->nh = (uint32_t)ival; r->has_nh = true; }
-        if (t0 == 'H' && t1 == 'I' && is_int) { r->hi = (uint32_t)ival; r->has_hi = true; }
-        if (t0 == 'M' && t1 == 'D' && type == 'Z') { r->md = text.substr(2); r->has_md = true; }
+        const bool nh = t0 == 'N' && t1 == 'H', hi = t0 == 'H' && t1 == 'I', md = t0 == 'M' && t1 == 'D' && type == 'Z';
+        if (nh || hi || md || type == 'B') {
+            std::string text;
+            long long ival = 0;
+            bool is_int = false;
+            append_tag_value(&text, type, p, end, &ival, &is_int);
+            if (nh && is_int) { r->nh = (uint32_t)ival; r->has_nh = true; }
+            if (hi && is_int) { r->hi = (uint32_t)ival; r->has_hi = true; }
+            if (md) { r->md = text.substr(2); r->has_md = true; }
+        } else {
+            size_t skip = 0;
+            switch (type) {
+                case 'A': case 'c': case 'C': skip = 1; break;
+                case 's': case 'S': skip = 2; break;
+                case 'i': case 'I': case 'f': skip = 4; break;
+                case 'Z': case 'H': {
+                    const unsigned char *q = (const unsigned char *)memchr(p, 0, end - p);
+                    if (!q) fail(BAYES_E_INVALID, "unterminated string field");
+                    skip = (size_t)(q - p) + 1;
+                    break;
+                }
+                default: fail(BAYES_E_INVALID, std::string("unknown optional field type '") + type + "'");
+            }
+            if ((size_t)(end - p) < skip) fail(BAYES_E_INVALID, "truncated optional field");
+            p += skip;
+        }
     }
     return true;
+}
+
+std::string seq_text(const BamRec &r) {
+    static const char bases[] = "=ACMGRSVTWYHKDBN";
+    std::string s((size_t)r.l_seq, 'N');
+    const unsigned char *p = (const unsigned char *)r.seq_packed.data();
+    for (int32_t i = 0; i < r.l_seq; i++) s[i] = bases[(p[i >> 1] >> ((~i & 1) << 2)) & 15];
+    return s;
 }
 
 // ---- duplicate removal (assembler.cpp:84-249) -------------------------------------------------------------------------------
@@ -312,13 +439,17 @@ typedef std::tr1::unordered_map<PairInfo, ReadPair, PairInfoHasher> ReadPairs;
 typedef std::multimap<uint32_t, BamRec *> UniqueReads;
 
 std::string dedup_cigar_string(const std::vector<CigarOp> &cigar) {  // generateCigarString, assembler.cpp:130-154
-    std::stringstream s;
+    std::string s;
+    char num[16];
     for (const CigarOp &c : cigar) {
-        if (c.type == 'M' || c.type == 'D') s << c.length << "M";
-        else if (c.type == 'N') s << c.length << "N";
-        else if (c.type != 'I') fail(BAYES_E_INVALID, std::string("Unhandled cigar string symbol '") + c.type + "'!");
+        if (c.type == 'M' || c.type == 'D' || c.type == 'N') {
+            s.append(num, (size_t)snprintf(num, sizeof num, "%u", c.length));
+            s.push_back(c.type == 'N' ? 'N' : 'M');
+        } else if (c.type != 'I') {
+            fail(BAYES_E_INVALID, std::string("Unhandled cigar string symbol '") + c.type + "'!");
+        }
     }
-    return s.str();
+    return s;
 }
 
 struct Strand {
@@ -344,24 +475,25 @@ struct Strand {
             if (!a->has_nh) fail(BAYES_E_INVALID, "alignment " + a->name + " has no NH tag");
             if (!a->has_hi && a->nh != 1) fail(BAYES_E_INVALID, "multi-mapping alignment " + a->name + " has no HI tag");
             if (a->nh == 1) nd_nm_reads += 1;
-            written.push_back(*a);
+            written.push_back(std::move(*a));
             delete a;
             unique_reads.erase(unique_reads.begin());
         }
     }
-    void mark_duplicates(const BamRec &cur) {  // assembler.cpp:157-249
+    void mark_duplicates(BamRec &cur) {  // assembler.cpp:157-249 (the record is moved into the containers, not copied: the caller reads the next one into it)
         ReadId ri;
         ri.name = cur.name;
         ri.hi_tag = cur.has_hi ? cur.hi : 0;
         FirstReads::iterator fit = first_reads.find((uint32_t)cur.mate_pos);
         if (fit == first_reads.end()) {
-            if (!first_reads[(uint32_t)cur.pos].insert(std::make_pair(ri, new BamRec(cur))).second) fail(BAYES_E_INVALID, "alignment " + cur.name + " seen twice at one position");
+            if (first_reads[(uint32_t)cur.pos].count(ri)) fail(BAYES_E_INVALID, "alignment " + cur.name + " seen twice at one position");
+            first_reads[(uint32_t)cur.pos].insert(std::make_pair(ri, new BamRec(std::move(cur))));
             return;
         }
         ReadIDs::iterator pit = fit->second.find(ri);
         if (pit == fit->second.end()) {
             if (cur.pos != cur.mate_pos) fail(BAYES_E_INVALID, "mate of " + cur.name + " not found where it should be (is the BAM sorted by coordinate?)");
-            if (!fit->second.insert(std::make_pair(ri, new BamRec(cur))).second) fail(BAYES_E_INVALID, "alignment " + cur.name + " seen twice at one position");
+            fit->second.insert(std::make_pair(ri, new BamRec(std::move(cur))));
             return;
         }
         BamRec *first = pit->second;
@@ -373,14 +505,14 @@ struct Strand {
         if ((uint32_t)cur.mate_pos != pi.pos) fail(BAYES_E_INVALID, "mate position of " + cur.name + " does not match its mate");
         ReadPairs::iterator rit = read_pairs.find(pi);
         if (rit == read_pairs.end()) {
-            read_pairs.insert(std::make_pair(pi, ReadPair(first, new BamRec(cur))));
+            read_pairs.insert(std::make_pair(pi, ReadPair(first, new BamRec(std::move(cur)))));
         } else {
             if (!first->has_nh || !cur.has_nh || !rit->second.first->has_nh) fail(BAYES_E_INVALID, "alignment " + cur.name + " has no NH tag");
             if (first->nh != cur.nh) fail(BAYES_E_INVALID, "mates of " + cur.name + " disagree on NH");
             if (first->nh == 1 && rit->second.first->nh > 1) {  // a unique pair replaces a multi-mapping duplicate
                 delete rit->second.first;
                 delete rit->second.second;
-                rit->second = ReadPair(first, new BamRec(cur));
+                rit->second = ReadPair(first, new BamRec(std::move(cur)));
             } else {
                 delete first;
             }
@@ -388,7 +520,7 @@ struct Strand {
         fit->second.erase(pit);
         if (fit->second.empty()) first_reads.erase(fit);
     }
-    void take(const BamRec &cur) {  // assembler.cpp:343-368
+    void take(BamRec &cur) {  // assembler.cpp:343-368
         if (current_position != cur.pos || cur_reference != cur.ref_id) {
             num_reads_paired += read_pairs.size();
             add_unique_reads();
@@ -400,8 +532,9 @@ struct Strand {
                 fail(BAYES_E_INVALID, "BAM file is not sorted by coordinate");
             }
         }
+        const int32_t pos = cur.pos;
         mark_duplicates(cur);
-        current_position = cur.pos;
+        current_position = pos;
     }
     void finish() {  // assembler.cpp:371-379
         num_reads_paired += read_pairs.size();
@@ -768,7 +901,8 @@ void scan(bayes_bam_front *F, const char *path) {
     Strand *plus = &F->strand[0], *minus = &F->strand[1];
     Strand *w_first = F->strand_specific == "first" ? plus : minus, *w_second = F->strand_specific == "first" ? minus : plus;
     BamRec cur;
-    while (read_bam_record(in, &cur)) {
+    std::vector<unsigned char> buf;
+    while (read_bam_record(in, &cur, buf)) {
         if (!cur.paired()) fail(BAYES_E_INVALID, "alignment " + cur.name + " is not from a paired-end read");
         if (cur.failed_qc()) fail(BAYES_E_INVALID, "alignment " + cur.name + " failed quality control");
         if (!(cur.mapped() && cur.primary() && cur.mate_mapped())) continue;
@@ -858,8 +992,8 @@ int bayes_bam_front_write_sam(bayes_bam_front *f, int32_t strand_file, const cha
         for (const BamRec &r : f->strand[strand_file].written) {
             out << r.name << '\t' << r.flag << '\t' << ref(r.ref_id) << '\t' << r.pos + 1 << '\t' << (int)r.mapq << '\t' << cigar_text(r.cigar) << '\t'
                 << (r.mate_ref < 0 ? std::string("*") : r.mate_ref == r.ref_id ? std::string("=") : ref(r.mate_ref)) << '\t' << r.mate_pos + 1 << '\t' << r.tlen << '\t'
-                << (r.seq.empty() ? std::string("*") : r.seq) << '\t' << (r.qual.empty() || (unsigned char)(r.qual[0] - 33) == 0xff ? std::string("*") : r.qual);
-            if (!r.tags_sam.empty()) out << '\t' << r.tags_sam;
+                << (r.l_seq == 0 ? std::string("*") : seq_text(r)) << '\t' << (r.qual.empty() || (unsigned char)(r.qual[0] - 33) == 0xff ? std::string("*") : r.qual);
+            if (!r.tags_raw.empty()) out << '\t' << tags_sam_text(r.tags_raw);
             out << '\n';
         }
     });

@@ -67,11 +67,12 @@ def write_bam(path, refs, records, header_text=None):
     ref_index = {n: i for i, (n, _) in enumerate(refs)}
     text = (header_text if header_text is not None else
             "@HD\tVN:1.0\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % (n, l) for n, l in refs)).encode()
-    raw = b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(refs))
+    parts = [b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(refs))]
     for n, l in refs:
-        raw += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", l)
+        parts.append(struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", l))
     for r in records:
-        raw += encode_record(r, ref_index)
+        parts.append(encode_record(r, ref_index))
+    raw = b"".join(parts)
     with open(path, "wb") as f:
         for i in range(0, len(raw), 60000):
             f.write(_bgzf_block(raw[i:i + 60000]))
