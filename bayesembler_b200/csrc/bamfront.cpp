@@ -551,6 +551,16 @@ struct Strand {
 };
 
 // ---- read probability (assembler.cpp:1322-1417) -------------------------------------------------------------------------------
+// 10^(-q / 10) for every phred score a quality character can hold: the reference calls pow() per base (:1381, :1397), the same
+// expression evaluated once per score gives the same doubles
+struct PhredTable {
+    double err[256];
+    PhredTable() {
+        for (int c = 0; c < 256; c++) err[c] = pow(10, -((int)(signed char)c - 33) / (double)10);  // ((int) qualities[i] - 33 on a signed char, like the reference)
+    }
+};
+const PhredTable g_phred;
+
 double sequencing_probability(const std::string &md_tag, const std::string &qualities, const std::vector<CigarOp> &cigar) {
     double probability = 1;
     std::vector<unsigned short> deletions, insertions;
@@ -583,14 +593,14 @@ double sequencing_probability(const std::string &md_tag, const std::string &qual
         }
     }
     unsigned short q_idx = 0;
-    auto qual_at = [&](unsigned short i) -> int {
+    auto err_at = [&](unsigned short i) -> double {
         if (i >= qualities.size()) fail(BAYES_E_INVALID, "MD tag runs past the end of the read");
-        return (int)qualities[i] - 33;
+        return g_phred.err[(unsigned char)qualities[i]];
     };
     for (size_t k = 0; k < numbers.size(); k++) {
         for (unsigned short i = 0; i < numbers[k]; i++) {
             while (insertions[ins_it] == q_idx) { ins_it++; q_idx++; }
-            probability *= (1 - pow(10, -qual_at(q_idx) / (double)10));
+            probability *= (1 - err_at(q_idx));
             q_idx++;
         }
         while (insertions[ins_it] == q_idx) { ins_it++; q_idx++; }
@@ -598,7 +608,7 @@ double sequencing_probability(const std::string &md_tag, const std::string &qual
             if (deletions[del_it] == q_idx) {
                 del_it++;
             } else {
-                probability *= pow(10, -qual_at(q_idx) / (double)10) / 3;
+                probability *= err_at(q_idx) / 3;
                 q_idx++;
             }
         } else if (k + 1 != numbers.size()) {
