@@ -1035,21 +1035,53 @@ int bayes_bam_front_graphs(bayes_bam_front *f, int32_t strand_file, const char *
         }
         std::map<std::string, int> ref_id;
         for (size_t r = 0; r < f->header.ref_name.size(); r++) ref_id[f->header.ref_name[r]] = (int)r;
-        int with = 0;
-        std::vector<Fragment> frags;
+        // the graphs are independent: host threads fetch and format them, the file is written in graph order
+        std::vector<const GraphInfo *> gv;
+        std::vector<int> gref;
         for (const GraphInfo &g : graphs) {
             std::map<std::string, int>::iterator it = ref_id.find(g.reference);
             if (it == ref_id.end()) fail(BAYES_E_INVALID, "instance file names a reference sequence the BAM header does not have: " + g.reference);
-            fetch_fragments(f->strand[strand_file].written, f->ref_first[strand_file], it->second, g, &frags);
-            if (frags.empty()) continue;  // assembler.cpp:1262-1280: a graph without fragments is dropped
-            with++;
-            out << "graph " << g.dot_strings.size() << " " << frags.size() << " " << (g.single_path_graph ? 1 : 0) << "\n";
-            for (const std::string &d : g.dot_strings) out << d;
+            gv.push_back(&g);
+            gref.push_back(it->second);
+        }
+        std::vector<std::string> text(gv.size());
+        std::vector<std::string> errors(gv.size());
+        std::vector<int> codes(gv.size(), 0);
+        std::atomic<size_t> next(0);
+        auto work = [&]() {
+            std::vector<Fragment> frags;
             char num[64];
-            for (const Fragment &fr : frags) {
-                snprintf(num, sizeof num, "%.17g", fr.probability);
-                out << fr.pos1 << " " << cigar_text(fr.cigar1) << " " << fr.pos2 << " " << cigar_text(fr.cigar2) << " " << num << "\n";
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= gv.size()) return;
+                try {
+                    const GraphInfo &g = *gv[i];
+                    fetch_fragments(f->strand[strand_file].written, f->ref_first[strand_file], gref[i], g, &frags);
+                    if (frags.empty()) continue;  // assembler.cpp:1262-1280: a graph without fragments is dropped
+                    std::string &t = text[i];
+                    t = "graph " + std::to_string(g.dot_strings.size()) + " " + std::to_string(frags.size()) + " " + (g.single_path_graph ? "1" : "0") + "\n";
+                    for (const std::string &d : g.dot_strings) t += d;
+                    for (const Fragment &fr : frags) {
+                        snprintf(num, sizeof num, "%.17g", fr.probability);
+                        t += std::to_string(fr.pos1) + " " + cigar_text(fr.cigar1) + " " + std::to_string(fr.pos2) + " " + cigar_text(fr.cigar2) + " " + num + "\n";
+                    }
+                } catch (const FrontError &e) {
+                    codes[i] = e.code;
+                    errors[i] = e.msg;
+                }
             }
+        };
+        const int n_thr = (int)std::min<size_t>(std::min<unsigned>(16u, std::max<unsigned>(1u, std::thread::hardware_concurrency())), std::max<size_t>(1, gv.size()));
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_thr; t++) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+        int with = 0;
+        for (size_t i = 0; i < gv.size(); i++) {
+            if (codes[i]) fail(codes[i], errors[i]);
+            if (text[i].empty()) continue;
+            with++;
+            out << text[i];
         }
         if (n_graphs) *n_graphs = (int32_t)graphs.size();
         if (n_with_fragments) *n_with_fragments = with;
