@@ -198,7 +198,8 @@ def run_reference_arm(args, cfg, total_loci, n_chains):
                              "sample": sample_note(sample, batch, cfg, n_threads) + " per step (a rate: draws of the sample / its wall time)",
                              "notes": "inputs from the repo's synthetic generator (libbayessynth.so, no sampler code); reference TUs compiled "
                                       "unmodified (-O3, asserts on) against stand-in Eigen/Boost headers whose variate transforms are "
-                                      "oracle/orc_rng.h (Boost absent): inversion binomial below n*q = 32, BTRD above"},
+                                      "oracle/orc_rng.h (Boost absent): inversion binomial below n*q = 32, BTRD above (switching at 11, about where Boost "
+                                      "does, is 2 % slower on the CPU: profiles/cpu_binomial_switch.txt)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
