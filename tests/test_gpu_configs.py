@@ -1,4 +1,4 @@
-"""The other BASELINE.json configurations as parity cases (bench.py measures configs[1] only): loci of the synthetic
+"""The BASELINE.json configurations as parity cases (bench.py measures their throughput): loci of the synthetic
 config 1 (the CPU-runnable case), config 3 (200-1000 candidates: wide units whose matrix is streamed from L2/HBM),
 config 4 (heavy-tailed fragments per locus) and config 5 (many chains per locus) run through the C ABI with shortened
 iteration counts and are compared draw for draw with the CPU oracle."""
